@@ -1,0 +1,204 @@
+// C ABI (include/pvsr.h): library info, host-side packing logic and the per-op entry points.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/pvsr.h"
+#include "conv.h"
+#include "internal.h"
+#include "simt.h"
+
+namespace pvsr {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int check_cuda(int e, const char* what) {
+  if (e == 0) return 0;
+  return set_error(e, "%s: %s", what, cudaGetErrorString(static_cast<cudaError_t>(e)));
+}
+
+int device_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+int fill_conv_params(const pvsr_conv_desc* d, ConvParams* p) {
+  memset(p, 0, sizeof(*p));
+  if (d->n_src < 1 || d->n_src > kMaxSrc) return set_error(-2, "n_src %d out of range", d->n_src);
+  if (d->taps != 9 && d->taps != 1) return set_error(-2, "taps must be 9 or 1");
+  if (d->k16_last < 1 || d->k16_last > 4) return set_error(-2, "k16_last must be 1..4");
+  p->H = d->H;
+  p->W = d->W;
+  choose_tile(d->H, d->W, &p->tw_log2);
+  const int tw = 1 << p->tw_log2, th = kTileM >> p->tw_log2;
+  p->tiles_x = (d->W + tw - 1) / tw;
+  p->tiles_y = (d->H + th - 1) / th;
+  p->n_img = static_cast<int>(d->n_img);
+  p->n_prob = 1;
+  p->taps = d->taps;
+  p->kb_per_src = d->kb_per_src;
+  p->k16_last = d->k16_last;
+  p->n_tiles_n = d->n_tiles_n;
+  p->n_total = d->n_tiles_n * d->bn;
+  p->n_store = d->n_store;
+  p->out_ch = d->out_ch;
+  p->ps_r = d->ps_r;
+  ConvProblem& pr = p->prob[0];
+  pr.n_src = d->n_src;
+  for (int i = 0; i < d->n_src; ++i) pr.src_img_base[i] = d->src_img_base[i];
+  pr.w_row_base = d->w_row_base;
+  pr.bias = d->bias;
+  pr.out_bf16 = static_cast<__nv_bfloat16*>(d->out_bf16);
+  pr.out_f32 = d->out_f32;
+  pr.res = static_cast<const __nv_bfloat16*>(d->res);
+  pr.posterm = d->posterm;
+  pr.c_in = d->c_in;
+  pr.c_out = d->c_out;
+  pr.h_out = static_cast<__nv_bfloat16*>(d->h_out);
+  pr.gates_out = static_cast<__nv_bfloat16*>(d->gates_out);
+  return 0;
+}
+
+}  // namespace pvsr
+
+using namespace pvsr;
+
+extern "C" {
+
+int pvsr_version(void) { return PVSR_VERSION; }
+const char* pvsr_last_error(void) { return g_err; }
+
+int pvsr_device_check(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error(-10, "no CUDA device");
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return set_error(-11, "compute capability %d.x is not sm_100", major);
+  return 0;
+}
+
+int pvsr_choose_tile(int H, int W, int* tw_log2_out) {
+  if (H <= 0 || W <= 0 || !tw_log2_out) return set_error(-2, "bad image size");
+  choose_tile(H, W, tw_log2_out);
+  return 0;
+}
+
+int64_t pvsr_pack_index_count(const pvsr_pack_spec* s) {
+  return static_cast<int64_t>(s->n_src) * s->taps * s->kb_per_src * s->n_total * 64;
+}
+
+static int spec_out_channel(const pvsr_pack_spec* s, int n) {
+  if (s->ps_r == 0) return n;
+  const int r2 = s->ps_r * s->ps_r;
+  const int q = n / 64, c = n % 64;
+  if (q >= r2) return -1;
+  return c * r2 + q;
+}
+
+int pvsr_pack_index_host(const pvsr_pack_spec* s, int32_t* idx) {
+  if (s->taps != 9 && s->taps != 1) return set_error(-2, "taps must be 9 or 1");
+  if (s->taps == 9 && (s->kh != 3 || s->kw != 3)) return set_error(-2, "taps=9 needs a 3x3 parameter");
+  if (s->n_src < 1 || s->n_src > PVSR_MAX_SRC) return set_error(-2, "n_src out of range");
+  const int centre = (s->kh * s->kw == 1) ? 0 : (s->kh / 2) * s->kw + s->kw / 2;
+  int64_t e = 0;
+  for (int src = 0; src < s->n_src; ++src)
+    for (int ti = 0; ti < s->taps; ++ti) {
+      const int tap = s->taps == 9 ? ti : centre;
+      int ky = tap / s->kw, kx = tap % s->kw;
+      if (s->transpose_flip) { ky = s->kh - 1 - ky; kx = s->kw - 1 - kx; }
+      for (int cb = 0; cb < s->kb_per_src; ++cb)
+        for (int n = 0; n < s->n_total; ++n) {
+          const int col = spec_out_channel(s, n);
+          for (int c = 0; c < 64; ++c, ++e) {
+            const int ic = cb * 64 + c;
+            int v = -1;
+            if (ic < s->src_ch && col >= 0) {
+              const int gin = s->src_ch_off[src] + ic;  // GEMM K channel
+              const int o = s->transpose_flip ? gin : col;
+              const int i = s->transpose_flip ? col : gin;
+              if (o < s->c_out && i < s->c_in) v = ((o * s->c_in + i) * s->kh + ky) * s->kw + kx;
+            }
+            idx[e] = v;
+          }
+        }
+    }
+  return 0;
+}
+
+int pvsr_pack_bias_index_host(const pvsr_pack_spec* s, int32_t* idx) {
+  const int lim = s->transpose_flip ? s->c_in : s->c_out;
+  for (int n = 0; n < s->n_total; ++n) {
+    const int col = spec_out_channel(s, n);
+    idx[n] = (col >= 0 && col < lim) ? col : -1;
+  }
+  return 0;
+}
+
+int pvsr_pack_weights(const float* w, const int32_t* idx, const int32_t* idx2, void* out, int64_t n, void* stream) {
+  return check_cuda(launch_pack_weights(w, idx, idx2, out, n, static_cast<cudaStream_t>(stream)), "pack_weights");
+}
+int pvsr_gather_f32(const float* src, const int32_t* idx, float* out, int64_t n, void* stream) {
+  return check_cuda(launch_gather_f32(src, idx, out, n, static_cast<cudaStream_t>(stream)), "gather_f32");
+}
+
+int pvsr_in_conv_prelu_fwd(const float* x, const float* w, const float* b, const float* slope, void* out,
+                           int64_t n_img, int H, int W, void* stream) {
+  return check_cuda(launch_in_conv_prelu(x, w, b, slope, out, n_img, H, W, static_cast<cudaStream_t>(stream)),
+                    "in_conv_prelu");
+}
+
+int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream) {
+  ConvParams p;
+  int rc = fill_conv_params(d, &p);
+  if (rc) return rc;
+  if (d->act_channels % 8 != 0) return set_error(-2, "act_channels must be a multiple of 8");
+  CUtensorMap tm_act, tm_w;
+  const int tw = 1 << p.tw_log2, th = kTileM >> p.tw_log2;
+  rc = make_act_tmap(&tm_act, d->act, d->act_channels, d->W, d->H, d->act_images, tw, th);
+  if (rc) return set_error(rc, "activation tensor map encode failed (%d)", rc);
+  rc = make_weight_tmap(&tm_w, d->w_packed, d->w_rows, d->bn);
+  if (rc) return set_error(rc, "weight tensor map encode failed (%d)", rc);
+  return check_cuda(launch_conv3x3(d->bn, d->epi, tm_act, tm_w, p, device_num_sms(), static_cast<cudaStream_t>(stream)),
+                    "conv3x3");
+}
+
+int64_t pvsr_lstm_state_elems(int64_t n_img, int H, int W) {
+  int l;
+  choose_tile(H, W, &l);
+  const int tw = 1 << l, th = kTileM >> l;
+  return n_img * ((W + tw - 1) / tw) * ((H + th - 1) / th) * 64 * kTileM;
+}
+
+int pvsr_refine_posterm(const float* w1, const float* b1, const float* pos, float* table, int n_frames_out, int B,
+                        int L, int window, int c_out, int c_in, int feat2, int n_total, void* stream) {
+  return check_cuda(launch_posterm(w1, b1, pos, table, n_frames_out, B, L, window, c_out, c_in, feat2, n_total,
+                                   static_cast<cudaStream_t>(stream)),
+                    "posterm");
+}
+
+int pvsr_head_conv_last_fwd(const void* in, const float* w, const float* b, float* out, const float* target,
+                            float* l1_partial, int64_t n_img, int H, int W, void* stream) {
+  return check_cuda(
+      launch_head_conv_last(in, w, b, out, target, l1_partial, n_img, H, W, static_cast<cudaStream_t>(stream)),
+      "head_conv_last");
+}
+
+int pvsr_add_bf16(const void* a, const void* b, void* out, int64_t n_elems, void* stream) {
+  return check_cuda(launch_add_bf16(a, b, out, n_elems, static_cast<cudaStream_t>(stream)), "add_bf16");
+}
+
+}  // extern "C"

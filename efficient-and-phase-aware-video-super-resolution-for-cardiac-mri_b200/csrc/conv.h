@@ -1,0 +1,82 @@
+// Host/device shared definitions of the implicit-GEMM 3x3 convolution launch.
+//
+// One launch computes, for every output image `img` of every problem `z`:
+//   D[pixel, n] = sum_{src, tap, c} A_src[pixel + tap, c] * Wp[(src, tap, cblock), n, c]
+// with A read by TMA from NHWC bf16 activation tensors (zero fill outside the image = padding 1)
+// and Wp the packed bf16 weight matrix (see pvsr/packing.py).  This is the GEMM view of
+// torch.nn.Conv2d(k=3, padding=1) at reference src/model/nets/refine_net.py:149,151,199-205,235.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pvsr {
+
+constexpr int kMaxSrc = 10;   // refine conv1: 5 frames x {forward h, backward h}
+constexpr int kMaxProb = 6;   // one ConvLSTM wavefront: up to 3 layers x 2 directions share one launch
+constexpr int kTileM = 128;   // output pixels per tile (UMMA M)
+constexpr int kBlockK = 64;   // bf16 channels per K block (one 128-byte swizzle row)
+
+enum EpiKind : int {
+  EPI_STORE = 0,  // bias (+ border-class term) (+ residual) -> NHWC bf16 and/or fp32
+  EPI_PS = 1,     // bias -> pixel-shuffled NHWC bf16 (columns grouped per sub-pixel)
+  EPI_LSTM = 2,   // ConvLSTM gates + state update (refine_net.py:258-265)
+};
+
+struct ConvProblem {
+  int n_src;                  // A sources of this problem (each 64*kb_per_src channels)
+  int src_img_base[kMaxSrc];  // image index of source s that pairs with output image 0
+  int w_row_base;             // first row of this problem's weights in the packed weight matrix
+  const float* bias;          // [n_total] fp32 in packed column order (nullptr = none)
+  // EPI_STORE / EPI_PS
+  __nv_bfloat16* out_bf16;    // NHWC, out_ch channels per pixel (nullptr = skip)
+  float* out_f32;             // NHWC fp32 (nullptr = skip)
+  const __nv_bfloat16* res;   // optional residual, same shape as out_bf16
+  const float* posterm;       // optional [n_img][16][n_total] border-class additive term
+  // EPI_LSTM
+  const float* c_in;          // cell state, tile-transposed [tile][64][128] fp32 (nullptr = zeros)
+  float* c_out;               // same layout (may alias c_in)
+  __nv_bfloat16* h_out;       // NHWC [n_img][H][W][64]
+  __nv_bfloat16* gates_out;   // optional, tile-transposed [tile][256][128] bf16 post-activation i,f,o,g
+};
+
+struct ConvParams {
+  int H, W;          // image height/width (input == output resolution)
+  int tw_log2;       // tile is TH x TW pixels, TW = 1 << tw_log2, TH = 128 / TW
+  int tiles_x, tiles_y;
+  int n_img;         // output images per problem
+  int n_prob;        // 1..kMaxProb
+  int taps;          // 9 (3x3) or 1 (centre tap only: 1x1 conv)
+  int kb_per_src;    // 64-channel K blocks per source per tap
+  int k16_last;      // number of K=16 MMAs issued for the last K block of a source (1..4)
+  int n_tiles_n;     // N tiles of BN columns
+  int n_total;       // packed weight rows per K block (= n_tiles_n * BN)
+  int n_store;       // columns per N tile that are real outputs (<= BN, multiple of 16)
+  int out_ch;        // channels per pixel of the output tensor
+  int ps_r;          // pixel-shuffle factor for EPI_PS
+  ConvProblem prob[kMaxProb];
+};
+
+// Launches the tcgen05 kernel. `tm_act` is a 4D map (C, W, H, images) with box (64, TW, TH, 1) and
+// 128B swizzle; `tm_w` a 2D map (64, rows) with box (64, BN).  Returns a cudaError_t as int.
+int launch_conv3x3(int bn, int epi, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvParams& p,
+                   int num_sms, cudaStream_t stream);
+
+// Host helpers (tensormap.cpp)
+int make_act_tmap(CUtensorMap* out, const void* base, int channels, int W, int H, long long images, int tw, int th);
+int make_weight_tmap(CUtensorMap* out, const void* base, long long rows, int bn);
+
+inline void choose_tile(int H, int W, int* tw_log2_out) {
+  // Pick TW in {8,...,128} (TH = 128/TW) minimising padded work; ties -> wider tiles (longer TMA rows).
+  long long best = -1;
+  int best_l = 7;
+  for (int l = 7; l >= 3; --l) {
+    int tw = 1 << l, th = 128 >> l;
+    long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+    if (best < 0 || tiles < best) { best = tiles; best_l = l; }
+  }
+  *tw_log2_out = best_l;
+}
+
+}  // namespace pvsr

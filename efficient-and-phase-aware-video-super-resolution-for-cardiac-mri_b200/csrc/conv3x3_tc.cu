@@ -1,0 +1,341 @@
+// 3x3 convolution (padding 1) as an implicit GEMM on the sm_100a tensor cores.
+//
+//   warp 0      : TMA producer  - per K block one 4D box (64 ch x TW x TH px, shifted by the tap; TMA zero-fills
+//                 outside the image, which *is* the conv padding) + one 2D box of packed weights (BN x 64).
+//   warp 1      : MMA issuer    - tcgen05.mma (M=128, N=BN, K=16) x 4 per K block, fp32 accumulator in TMEM,
+//                 two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps 2..9  : epilogue      - tcgen05.ld -> bias / ConvLSTM gates / residual / pixel-shuffle -> global.
+// Persistent: grid = min(#tiles, #SMs); tiles are walked round-robin.
+//
+// Reference semantics reproduced (file:line in /root/reference/src/model/nets/refine_net.py):
+//   ConvLSTMCell.forward 247-267 (EPI_LSTM), _RefineBlock.body 147-155 (EPI_STORE), _OutBlock 194-205 (EPI_PS).
+#include "conv.h"
+#include "ptx.cuh"
+
+namespace pvsr {
+
+using namespace ptx;
+
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = 64 + kNumEpiWarps * 32;  // 320
+constexpr int kABytes = kTileM * kBlockK * 2;        // 16384
+constexpr int kAccStride = 256;                      // TMEM columns between the two accumulator stages
+constexpr int kTmemCols = 512;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment for the 128B swizzle");
+  static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint for M=128");
+};
+
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_fast(float x) { return 2.f * __frcp_rn(1.f + __expf(-2.f * x)) - 1.f; }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+struct TileCoord {
+  int z, img, y0, x0, nt, tile_lin;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
+  TileCoord c;
+  c.nt = t % p.n_tiles_n;
+  t /= p.n_tiles_n;
+  int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  int ty = t % p.tiles_y;
+  t /= p.tiles_y;
+  c.img = t % p.n_img;
+  c.z = t / p.n_img;
+  c.x0 = tx << p.tw_log2;
+  c.y0 = ty * (kTileM >> p.tw_log2);
+  c.tile_lin = (c.img * p.tiles_y + ty) * p.tiles_x + tx;
+  return c;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
+                  const __grid_constant__ ConvParams p) {
+  using C = Cfg<BN>;
+  constexpr int S = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + S * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * C::kStageBytes);
+  uint64_t* full = bars;            // [S]  TMA -> MMA
+  uint64_t* empty = bars + S;       // [S]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * S;   // [2]  MMA -> epilogue
+  uint64_t* tempty = tfull + 2;     // [2]  epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.n_prob * p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tm_act);
+    prefetch_tmap(&tm_w);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], kNumEpiWarps * 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const ConvProblem& pr = p.prob[tc.z];
+        int wrow = pr.w_row_base + tc.nt * BN;
+        for (int s = 0; s < pr.n_src; ++s) {
+          const int img = pr.src_img_base[s] + tc.img;
+          for (int ti = 0; ti < p.taps; ++ti) {
+            const int tap = (p.taps == 9) ? ti : 4;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            for (int cb = 0; cb < p.kb_per_src; ++cb) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
+              tma_load_4d(smem_a + stage * kABytes, &tm_act, &full[stage], cb * kBlockK, tc.x0 + dx, tc.y0 + dy, img);
+              tma_load_2d(smem_b + stage * C::kBBytes, &tm_w, &full[stage], 0, wrow);
+              wrow += p.n_total;
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * kAccStride;
+      const int kb_per_tile = p.prob[decode_tile(p, t).z].n_src * p.taps * p.kb_per_src;
+      int cb = 0;
+      for (int kb = 0; kb < kb_per_tile; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const int nk16 = (cb == p.kb_per_src - 1) ? p.k16_last : 4;
+        if (elect_one()) {
+          const uint64_t adesc = make_desc_k_sw128(smem_u32(smem_a + stage * kABytes));
+          const uint64_t bdesc = make_desc_k_sw128(smem_u32(smem_b + stage * C::kBBytes));
+          for (int k = 0; k < nk16; ++k) {
+            // +32 bytes per K=16 slice inside the 128-byte swizzle row (address field is in 16-byte units)
+            mma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          mma_commit(&empty[stage]);
+          if (kb == kb_per_tile - 1) mma_commit(&tfull[as]);
+        }
+        __syncwarp();
+        if (++cb == p.kb_per_src) cb = 0;
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 2;
+    const int quad = warp & 3;       // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;        // which half of the column chunks this warp handles
+    const int row = quad * 32 + lane;
+    const int TW = 1 << p.tw_log2;
+    const int ly = row >> p.tw_log2, lx = row & (TW - 1);
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const TileCoord tc = decode_tile(p, t);
+      const ConvProblem& pr = p.prob[tc.z];
+      const int y = tc.y0 + ly, x = tc.x0 + lx;
+      const bool valid = (y < p.H) && (x < p.W);
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * kAccStride + (static_cast<uint32_t>(quad * 32) << 16);
+
+      if constexpr (EPI == EPI_LSTM) {
+        // Columns: [i | f | o | g] x 64 channels (refine_net.py:258). This warp: channels [32*half, 32*half+32).
+        const size_t cbase = (static_cast<size_t>(tc.tile_lin) * 64) * kTileM + row;
+        const size_t pix = (static_cast<size_t>(tc.img) * p.H + y) * p.W + x;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int ch0 = half * 32 + cc * 16;
+          uint32_t vi[16], vf[16], vo[16], vg[16];
+          tmem_ld16(taddr + ch0, vi);
+          tmem_ld16(taddr + 64 + ch0, vf);
+          tmem_ld16(taddr + 128 + ch0, vo);
+          tmem_ld16(taddr + 192 + ch0, vg);
+          float cprev[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            cprev[j] = pr.c_in ? pr.c_in[cbase + static_cast<size_t>(ch0 + j) * kTileM] : 0.f;
+          tmem_ld_wait();
+          uint32_t hp[8];
+          float hprev = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ch = ch0 + j;
+            const float gi = sigmoidf_fast(__uint_as_float(vi[j]) + pr.bias[ch]);
+            const float gf = sigmoidf_fast(__uint_as_float(vf[j]) + pr.bias[64 + ch]);
+            const float go = sigmoidf_fast(__uint_as_float(vo[j]) + pr.bias[128 + ch]);
+            const float gg = tanhf_fast(__uint_as_float(vg[j]) + pr.bias[192 + ch]);
+            const float cn = gf * cprev[j] + gi * gg;
+            const float hn = go * tanhf_fast(cn);
+            pr.c_out[cbase + static_cast<size_t>(ch) * kTileM] = cn;
+            if (pr.gates_out) {
+              __nv_bfloat16* g = pr.gates_out + (static_cast<size_t>(tc.tile_lin) * 256) * kTileM + row;
+              g[static_cast<size_t>(ch) * kTileM] = __float2bfloat16(gi);
+              g[static_cast<size_t>(64 + ch) * kTileM] = __float2bfloat16(gf);
+              g[static_cast<size_t>(128 + ch) * kTileM] = __float2bfloat16(go);
+              g[static_cast<size_t>(192 + ch) * kTileM] = __float2bfloat16(gg);
+            }
+            if (j & 1) hp[j >> 1] = pack_bf16x2(hprev, hn);
+            hprev = hn;
+          }
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(pr.h_out + pix * 64 + ch0);
+            dst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            dst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+          }
+        }
+      } else {
+        // EPI_STORE / EPI_PS: 16-column chunks, alternating between the two warp halves.
+        const int nchunks = p.n_store >> 4;
+        const int cls = (y > 0 ? 1 : 0) | (y < p.H - 1 ? 2 : 0) | (x > 0 ? 4 : 0) | (x < p.W - 1 ? 8 : 0);
+        const float* pterm =
+            pr.posterm ? pr.posterm + (static_cast<size_t>(tc.img) * 16 + cls) * p.n_total + tc.nt * BN : nullptr;
+        const float* bias = pr.bias ? pr.bias + tc.nt * BN : nullptr;
+#pragma unroll 1
+        for (int ck = half; ck < nchunks; ck += 2) {
+          uint32_t v[16];
+          tmem_ld16(taddr + ck * 16, v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += bias[ck * 16 + j];
+          }
+          if (valid) {
+            if (pterm) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] += pterm[ck * 16 + j];
+            }
+            size_t off;
+            if constexpr (EPI == EPI_PS) {
+              // column = q*64 + c with q = i*r + j  ->  HR pixel (y*r+i, x*r+j), channel c (PixelShuffle, :200,204)
+              const int col = tc.nt * BN + ck * 16;
+              const int q = col >> 6, c0 = col & 63;
+              const int r = p.ps_r;
+              const int qi = q / r, qj = q - qi * r;
+              off = ((static_cast<size_t>(tc.img) * p.H * r + (y * r + qi)) * (p.W * r) + (x * r + qj)) * 64 + c0;
+            } else {
+              off = ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * p.out_ch + tc.nt * BN + ck * 16;
+            }
+            if (pr.res) {
+              const uint4* rp = reinterpret_cast<const uint4*>(pr.res + off);
+              float rf[16];
+              unpack_bf16x8(rp[0], rf);
+              unpack_bf16x8(rp[1], rf + 8);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] += rf[j];
+            }
+            if (pr.out_bf16) {
+              uint4* dst = reinterpret_cast<uint4*>(pr.out_bf16 + off);
+              dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                  pack_bf16x2(f[6], f[7]));
+              dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                                  pack_bf16x2(f[14], f[15]));
+            }
+            if (pr.out_f32) {
+              float4* dst = reinterpret_cast<float4*>(pr.out_f32 + off);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            }
+          }
+        }
+      }
+      // All TMEM reads of this accumulator stage are complete (wait::ld above): hand it back to the MMA warp.
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+template <int BN, int EPI>
+static int launch_t(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvParams& p, int num_sms,
+                    cudaStream_t stream) {
+  using C = Cfg<BN>;
+  auto kern = conv3x3_tc_kernel<BN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  const long long total = 1LL * p.n_prob * p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
+  if (total <= 0) return 0;
+  const int grid = static_cast<int>(total < num_sms ? total : num_sms);
+  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(tm_act, tm_w, p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_conv3x3(int bn, int epi, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvParams& p,
+                   int num_sms, cudaStream_t stream) {
+  if (epi == EPI_LSTM && bn == 256) return launch_t<256, EPI_LSTM>(tm_act, tm_w, p, num_sms, stream);
+  if (epi == EPI_STORE) {
+    switch (bn) {
+      case 64: return launch_t<64, EPI_STORE>(tm_act, tm_w, p, num_sms, stream);
+      case 144: return launch_t<144, EPI_STORE>(tm_act, tm_w, p, num_sms, stream);
+      case 256: return launch_t<256, EPI_STORE>(tm_act, tm_w, p, num_sms, stream);
+    }
+  }
+  if (epi == EPI_PS) {
+    switch (bn) {
+      case 192: return launch_t<192, EPI_PS>(tm_act, tm_w, p, num_sms, stream);
+      case 256: return launch_t<256, EPI_PS>(tm_act, tm_w, p, num_sms, stream);
+    }
+  }
+  return static_cast<int>(cudaErrorInvalidValue);
+}
+
+}  // namespace pvsr

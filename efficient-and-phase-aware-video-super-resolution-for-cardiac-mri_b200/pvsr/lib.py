@@ -1,0 +1,120 @@
+"""ctypes binding of libpvsr.so (include/pvsr.h).
+
+The product path is CUDA only: if the shared library is missing this module raises at import of the
+symbols (no CPU fallback, no oracle on this path).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
+LIB_PATH = os.path.join(CSRC, "libpvsr.so")
+
+MAX_SRC = 10
+MAX_LAYERS = 8
+MAX_HEAD_CONVS = 4
+EPI_STORE, EPI_PS, EPI_LSTM = 0, 1, 2
+
+c_void_p, c_int, c_int64, c_float_p, c_int32_p = C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p
+
+
+class PackSpec(C.Structure):
+    _fields_ = [("c_out", c_int), ("c_in", c_int), ("kh", c_int), ("kw", c_int), ("n_src", c_int),
+                ("src_ch_off", c_int * MAX_SRC), ("src_ch", c_int), ("kb_per_src", c_int), ("taps", c_int),
+                ("n_total", c_int), ("ps_r", c_int), ("transpose_flip", c_int)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("epi", c_int), ("bn", c_int), ("H", c_int), ("W", c_int), ("n_img", c_int64),
+                ("act", c_void_p), ("act_channels", c_int), ("act_images", c_int64), ("n_src", c_int),
+                ("src_img_base", c_int * MAX_SRC), ("kb_per_src", c_int), ("k16_last", c_int), ("taps", c_int),
+                ("w_packed", c_void_p), ("w_rows", c_int64), ("w_row_base", c_int), ("n_tiles_n", c_int),
+                ("bias", c_void_p), ("out_bf16", c_void_p), ("out_f32", c_void_p), ("res", c_void_p),
+                ("posterm", c_void_p), ("out_ch", c_int), ("n_store", c_int), ("ps_r", c_int),
+                ("c_in", c_void_p), ("c_out", c_void_p), ("h_out", c_void_p), ("gates_out", c_void_p)]
+
+
+class NetConfig(C.Structure):
+    _fields_ = [("batch", c_int), ("n_frames", c_int), ("n_updated", c_int), ("h", c_int), ("w", c_int),
+                ("scale", c_int), ("n_stages", c_int), ("window", c_int), ("n_layers", c_int), ("pos_enc", c_int),
+                ("memory", c_int), ("all_heads", c_int), ("save_for_backward", c_int)]
+
+
+class NetParams(C.Structure):
+    _fields_ = [("in_w", c_void_p), ("in_b", c_void_p), ("in_slope", c_void_p),
+                ("lstm_w", (c_void_p * MAX_LAYERS) * 2), ("lstm_b", (c_void_p * MAX_LAYERS) * 2),
+                ("ref_w1", c_void_p), ("ref_b1", c_void_p), ("ref_w2", c_void_p), ("ref_b2", c_void_p),
+                ("head_w", c_void_p * MAX_HEAD_CONVS), ("head_b", c_void_p * MAX_HEAD_CONVS)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/pvsr.h
+SIGNATURES = {
+    "pvsr_version": (c_int, []),
+    "pvsr_last_error": (C.c_char_p, []),
+    "pvsr_device_check": (c_int, []),
+    "pvsr_choose_tile": (c_int, [c_int, c_int, C.POINTER(c_int)]),
+    "pvsr_pack_index_count": (c_int64, [C.POINTER(PackSpec)]),
+    "pvsr_pack_index_host": (c_int, [C.POINTER(PackSpec), c_void_p]),
+    "pvsr_pack_bias_index_host": (c_int, [C.POINTER(PackSpec), c_void_p]),
+    "pvsr_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pvsr_gather_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pvsr_in_conv_prelu_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                       c_void_p]),
+    "pvsr_conv3x3_fwd": (c_int, [C.POINTER(ConvDesc), c_void_p]),
+    "pvsr_lstm_state_elems": (c_int64, [c_int64, c_int, c_int]),
+    "pvsr_refine_posterm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, c_int, c_int, c_void_p]),
+    "pvsr_head_conv_last_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                        c_int, c_void_p]),
+    "pvsr_add_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pvsr_plan_create": (c_int, [C.POINTER(NetConfig), C.POINTER(c_void_p)]),
+    "pvsr_plan_destroy": (None, [c_void_p]),
+    "pvsr_plan_workspace_bytes": (c_int64, [c_void_p]),
+    "pvsr_plan_packed_bytes": (c_int64, [c_void_p]),
+    "pvsr_plan_output_elems": (c_int64, [c_void_p]),
+    "pvsr_plan_num_lists": (c_int, [c_void_p]),
+    "pvsr_plan_num_launches": (c_int64, [c_void_p]),
+    "pvsr_plan_flops": (C.c_double, [c_void_p]),
+    "pvsr_plan_pack": (c_int, [c_void_p, C.POINTER(NetParams), c_void_p, c_void_p]),
+    "pvsr_plan_forward": (c_int, [c_void_p, C.POINTER(NetParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_void_p]),
+}
+
+_lib = None
+
+
+class PvsrError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libpvsr.so (once). Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PvsrError(f"{LIB_PATH} is missing - build it with `python {os.path.join(CSRC, 'build.py')}` "
+                        "(or __graft_entry__.build()); the CUDA extension is the only compute path")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().pvsr_last_error()
+        raise PvsrError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / None."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,176 @@
+"""Per-op Python wrappers over the C ABI (torch tensors in, torch tensors out).
+
+Used by the unit tests and by tools; the network itself runs through the plan API (pvsr/engine.py).
+Layouts: activations are bf16 NHWC stacked frame-major as [images, H, W, C].
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+
+# ------------------------------------------------------------------------------------------------ pack specs
+def _spec(c_out, c_in, k, n_src, offs, src_ch, kb_per_src, taps, n_total, ps_r=0, transpose_flip=0):
+    s = L.PackSpec()
+    s.c_out, s.c_in, s.kh, s.kw = c_out, c_in, k, k
+    s.n_src = n_src
+    for i, o in enumerate(offs):
+        s.src_ch_off[i] = o
+    s.src_ch, s.kb_per_src, s.taps, s.n_total = src_ch, kb_per_src, taps, n_total
+    s.ps_r, s.transpose_flip = ps_r, transpose_flip
+    return s
+
+
+def spec_lstm(feat=64):
+    """ConvLSTMCell.conv (refine_net.py:235): in = [x | h], out = [i | f | o | g]."""
+    return _spec(4 * feat, 2 * feat, 3, 2, [0, feat], feat, 1, 9, 4 * feat)
+
+
+def spec_refine_conv1(window=5, feat=64):
+    """_RefineBlock.body.conv1 with positional encoding (refine_net.py:149): per frame [fwd 64 | bwd 64 | pos 1].
+    Sources are ordered (frame 0 fwd, frame 0 bwd, frame 1 fwd, ...); the pos channel is handled by posterm."""
+    per = 2 * feat + 1
+    offs = [per * (s // 2) + feat * (s % 2) for s in range(2 * window)]
+    return _spec(per, per * window, 3, 2 * window, offs, feat, 1, 9, 144)
+
+
+def spec_refine_conv2(feat=64):
+    """_RefineBlock.body.conv2 (refine_net.py:151): 129 -> 64; the 129-channel input is stored with 144 channels."""
+    return _spec(feat, 2 * feat + 1, 3, 1, [0], 2 * feat + 1, 3, 9, feat)
+
+
+def spec_refine_conv1x1(window=5, feat=64):
+    """_RefineBlock.body.conv1 without positional encoding (refine_net.py:154): 1x1 conv over [fwd | bwd] x window."""
+    offs = [2 * feat * (s // 2) + feat * (s % 2) for s in range(2 * window)]
+    return _spec(feat, 2 * feat * window, 1, 2 * window, offs, feat, 1, 1, feat)
+
+
+def spec_head_ps(r, feat=64):
+    """_OutBlock conv + PixelShuffle(r) (refine_net.py:199-204): columns regrouped per sub-pixel."""
+    return _spec(feat * r * r, feat, 3, 1, [0], feat, 1, 9, feat * r * r, ps_r=r)
+
+
+def pack_index(spec):
+    lib = L.load()
+    n = lib.pvsr_pack_index_count(C.byref(spec))
+    idx = np.empty(n, dtype=np.int32)
+    L.check(lib.pvsr_pack_index_host(C.byref(spec), idx.ctypes.data_as(C.c_void_p)), "pack_index")
+    return idx
+
+
+def pack_bias_index(spec):
+    lib = L.load()
+    idx = np.empty(spec.n_total, dtype=np.int32)
+    L.check(lib.pvsr_pack_bias_index_host(C.byref(spec), idx.ctypes.data_as(C.c_void_p)), "pack_bias_index")
+    return idx
+
+
+def pack_weight(weight, spec, weight_sum_spec=None):
+    """fp32 Conv2d weight (cuda) -> packed bf16 [rows, 64]."""
+    lib = L.load()
+    idx = torch.from_numpy(pack_index(spec)).to(weight.device)
+    idx2 = torch.from_numpy(pack_index(weight_sum_spec)).to(weight.device) if weight_sum_spec is not None else None
+    out = torch.empty(idx.numel() // 64, 64, dtype=torch.bfloat16, device=weight.device)
+    w = weight.detach().contiguous().float()
+    L.check(lib.pvsr_pack_weights(L.ptr(w), L.ptr(idx), L.ptr(idx2), L.ptr(out), idx.numel(), L.current_stream()),
+            "pack_weights")
+    return out
+
+
+def pack_bias(bias, spec):
+    lib = L.load()
+    idx = torch.from_numpy(pack_bias_index(spec)).to(bias.device)
+    out = torch.empty(spec.n_total, dtype=torch.float32, device=bias.device)
+    b = bias.detach().contiguous().float()
+    L.check(lib.pvsr_gather_f32(L.ptr(b), L.ptr(idx), L.ptr(out), idx.numel(), L.current_stream()), "gather_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ ops
+def in_conv_prelu(x, w, b, slope):
+    """x fp32 [n_img, H, W] -> bf16 [n_img, H, W, 64]   (_InBlock, refine_net.py:188-192)."""
+    lib = L.load()
+    n, H, W = x.shape
+    out = torch.empty(n, H, W, 64, dtype=torch.bfloat16, device=x.device)
+    L.check(lib.pvsr_in_conv_prelu_fwd(L.ptr(x.contiguous()), L.ptr(w.contiguous()), L.ptr(b.contiguous()),
+                                       L.ptr(slope.contiguous()), L.ptr(out), n, H, W, L.current_stream()),
+            "in_conv_prelu")
+    return out
+
+
+def conv3x3(act, src_img_base, n_img, w_packed, bn, epi=L.EPI_STORE, kb_per_src=1, k16_last=4, taps=9, bias=None,
+            n_tiles_n=1, w_row_base=0, out_bf16=None, out_f32=None, res=None, posterm=None, out_ch=None,
+            n_store=None, ps_r=0, c_in=None, c_out=None, h_out=None, gates_out=None):
+    """Generic launch of the tcgen05 implicit-GEMM conv. `act` is [images, H, W, C] bf16 holding all sources."""
+    lib = L.load()
+    d = L.ConvDesc()
+    d.epi, d.bn = epi, bn
+    d.H, d.W = act.shape[1], act.shape[2]
+    d.n_img = n_img
+    d.act = act.data_ptr()
+    d.act_channels = act.shape[3]
+    d.act_images = act.shape[0]
+    d.n_src = len(src_img_base)
+    for i, v in enumerate(src_img_base):
+        d.src_img_base[i] = v
+    d.kb_per_src, d.k16_last, d.taps = kb_per_src, k16_last, taps
+    d.w_packed = w_packed.data_ptr()
+    d.w_rows = w_packed.shape[0]
+    d.w_row_base = w_row_base
+    d.n_tiles_n = n_tiles_n
+    for name, t in (("bias", bias), ("out_bf16", out_bf16), ("out_f32", out_f32), ("res", res),
+                    ("posterm", posterm), ("c_in", c_in), ("c_out", c_out), ("h_out", h_out),
+                    ("gates_out", gates_out)):
+        setattr(d, name, None if t is None else t.data_ptr())
+    d.out_ch = out_ch if out_ch is not None else bn * n_tiles_n
+    d.n_store = n_store if n_store is not None else bn
+    d.ps_r = ps_r
+    L.check(lib.pvsr_conv3x3_fwd(C.byref(d), L.current_stream()), "conv3x3")
+
+
+def lstm_state(n_img, H, W, device):
+    n = L.load().pvsr_lstm_state_elems(n_img, H, W)
+    return torch.zeros(n, dtype=torch.float32, device=device)
+
+
+def lstm_state_to_nchw(state, n_img, H, W):
+    """Tile-transposed cell state -> [n_img, 64, H, W] fp32 (test helper)."""
+    lib = L.load()
+    l = C.c_int()
+    lib.pvsr_choose_tile(H, W, C.byref(l))
+    tw, th = 1 << l.value, 128 >> l.value
+    tx, ty = (W + tw - 1) // tw, (H + th - 1) // th
+    s = state.view(n_img, ty, tx, 64, th, tw).permute(0, 3, 1, 4, 2, 5).reshape(n_img, 64, ty * th, tx * tw)
+    return s[:, :, :H, :W].contiguous()
+
+
+def refine_posterm(w1, b1, pos, n_frames_out, window=5, feat=64, n_total=144):
+    """pos fp32 [B, L] -> table fp32 [n_frames_out * B, 16, n_total]."""
+    lib = L.load()
+    B, Lf = pos.shape
+    c_out, c_in = w1.shape[0], w1.shape[1]
+    table = torch.empty(n_frames_out * B, 16, n_total, dtype=torch.float32, device=pos.device)
+    L.check(lib.pvsr_refine_posterm(L.ptr(w1.contiguous()), L.ptr(b1.contiguous()), L.ptr(pos.contiguous()),
+                                    L.ptr(table), n_frames_out, B, Lf, window, c_out, c_in, 2 * feat, n_total,
+                                    L.current_stream()), "posterm")
+    return table
+
+
+def head_conv_last(x, w, b, target=None, l1_partial=None):
+    """bf16 [n_img, H, W, 64] -> fp32 [n_img, H, W]   (_OutBlock last conv, refine_net.py:203/205)."""
+    lib = L.load()
+    n, H, W, _ = x.shape
+    out = torch.empty(n, H, W, dtype=torch.float32, device=x.device)
+    L.check(lib.pvsr_head_conv_last_fwd(L.ptr(x), L.ptr(w.contiguous()), L.ptr(b.contiguous()), L.ptr(out),
+                                        L.ptr(target), L.ptr(l1_partial), n, H, W, L.current_stream()),
+            "head_conv_last")
+    return out
+
+
+def add_bf16(a, b):
+    lib = L.load()
+    out = torch.empty_like(a)
+    L.check(lib.pvsr_add_bf16(L.ptr(a), L.ptr(b), L.ptr(out), a.numel(), L.current_stream()), "add_bf16")
+    return out

@@ -1,0 +1,167 @@
+/*
+ * pvsr.h - C ABI of the B200-native RefineNet hot path (phase-aware cardiac cine-MRI video super-resolution).
+ *
+ * The reference (cmlab-mira/Efficient-and-Phase-aware-Video-Super-resolution-for-Cardiac-MRI) has NO FFI on this
+ * path: its boundary is the Python nn.Module `RefineNet` (src/model/nets/refine_net.py:10-135) whose arithmetic is
+ * done by torch.nn layers.  This header is the boundary a maintainer would bind instead of those layers; every entry
+ * point names the reference call site it replaces.  Host side: Python (ctypes), see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, no torch types; all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - bf16 tensors are passed as `void*` (16-bit storage), activations are NHWC, images are stacked frame-major:
+ *     image index = frame * batch + sample;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
+ *   - return value: 0 = OK, >0 = cudaError_t, <0 = pvsr error (see pvsr_last_error()); no C++ exception crosses;
+ *   - buffers are borrowed: the caller keeps them alive until the stream work has completed.
+ */
+#ifndef PVSR_H_
+#define PVSR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVSR_VERSION 100
+#define PVSR_MAX_SRC 10
+#define PVSR_MAX_LAYERS 8
+#define PVSR_MAX_HEAD_CONVS 4
+
+enum { PVSR_EPI_STORE = 0, PVSR_EPI_PS = 1, PVSR_EPI_LSTM = 2 };
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+int pvsr_version(void);
+const char* pvsr_last_error(void);
+/* 0 when the current CUDA device can run the kernels (compute capability 10.x); negative otherwise. */
+int pvsr_device_check(void);
+
+/* ---- host-side packing logic (pure CPU; usable without a GPU) ------------------------------------------------ */
+/* Tile choice of the implicit GEMM: tile = (128 >> tw_log2) x (1 << tw_log2) output pixels. */
+int pvsr_choose_tile(int H, int W, int* tw_log2_out);
+
+/* Gather index of a packed conv weight operand.  The packed operand is bf16 [n_src*taps*kb_per_src][n_total][64]
+ * (K block major; K block = (source, tap, 64-channel block)); element e takes parameter element idx[e] of the fp32
+ * (c_out, c_in, kh, kw) Conv2d weight (refine_net.py:149,151,154,199-205,235), or 0 when idx[e] < 0.
+ *   src_ch_off[s] : first input channel of source s in the Conv2d weight
+ *   src_ch        : real channels per source (<= 64*kb_per_src; the rest is zero padding)
+ *   taps          : 9 (3x3) or 1 (1x1 conv, or centre tap)
+ *   ps_r          : 0 = column n is output channel n; r>0 = pixel-shuffle order: column q*64+c is channel c*r*r+q
+ *   transpose_flip: 1 = data-gradient operand (swap c_out/c_in roles, spatially flipped taps)                    */
+typedef struct pvsr_pack_spec {
+  int c_out, c_in, kh, kw;
+  int n_src;
+  int src_ch_off[PVSR_MAX_SRC];
+  int src_ch;
+  int kb_per_src;
+  int taps;
+  int n_total;
+  int ps_r;
+  int transpose_flip;
+} pvsr_pack_spec;
+int64_t pvsr_pack_index_count(const pvsr_pack_spec* spec);
+int pvsr_pack_index_host(const pvsr_pack_spec* spec, int32_t* idx_host);
+/* Column -> output-channel index (or -1) for biases in packed order. */
+int pvsr_pack_bias_index_host(const pvsr_pack_spec* spec, int32_t* idx_host);
+
+/* ---- per-op entry points ------------------------------------------------------------------------------------- */
+/* out[e] = bf16(w[idx[e]] (+ w[idx2[e]]))  -- parameter -> tensor-core operand (idx2 may be NULL). */
+int pvsr_pack_weights(const float* w, const int32_t* idx, const int32_t* idx2, void* out_bf16, int64_t n,
+                      void* stream);
+int pvsr_gather_f32(const float* src, const int32_t* idx, float* out, int64_t n, void* stream);
+
+/* _InBlock (refine_net.py:188-192): conv3x3 1->64 + bias + PReLU.  x fp32 [n_img][H][W] -> bf16 [n_img][H][W][64]. */
+int pvsr_in_conv_prelu_fwd(const float* x, const float* w, const float* b, const float* slope, void* out_bf16,
+                           int64_t n_img, int H, int W, void* stream);
+
+/* Generic tcgen05 implicit-GEMM conv3x3 (padding 1).  One descriptor = one problem. */
+typedef struct pvsr_conv_desc {
+  int epi;                 /* PVSR_EPI_* */
+  int bn;                  /* N tile: 64, 144, 192 or 256 (LSTM: 256) */
+  int H, W;
+  int64_t n_img;           /* output images */
+  const void* act;         /* bf16 NHWC activation tensor holding every source image */
+  int act_channels;        /* channels per pixel of `act` (64 or 144) */
+  int64_t act_images;      /* images in `act` */
+  int n_src;
+  int src_img_base[PVSR_MAX_SRC];
+  int kb_per_src;          /* 64-channel K blocks per source */
+  int k16_last;            /* K=16 slices used in the last K block of a source (4 = all) */
+  int taps;                /* 9 or 1 */
+  const void* w_packed;    /* bf16 [rows][64] */
+  int64_t w_rows;
+  int w_row_base;
+  int n_tiles_n;
+  const float* bias;       /* packed order, n_tiles_n*bn entries, or NULL */
+  /* PVSR_EPI_STORE / PVSR_EPI_PS */
+  void* out_bf16;
+  float* out_f32;
+  const void* res;         /* bf16 residual with the shape of out_bf16, or NULL */
+  const float* posterm;    /* [n_img][16][n_tiles_n*bn] or NULL */
+  int out_ch;
+  int n_store;
+  int ps_r;
+  /* PVSR_EPI_LSTM (ConvLSTMCell.forward, refine_net.py:247-267) */
+  const float* c_in;       /* tile-transposed fp32 state or NULL (= zeros) */
+  float* c_out;
+  void* h_out;             /* bf16 [n_img][H][W][64] */
+  void* gates_out;         /* optional bf16 [tiles][256][128] */
+} pvsr_conv_desc;
+int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream);
+/* Number of fp32 elements of a tile-transposed ConvLSTM cell-state buffer for n_img images of H x W. */
+int64_t pvsr_lstm_state_elems(int64_t n_img, int H, int W);
+
+/* _RefineBlock positional-code term (refine_net.py:168-172) as a border-class table, bias included. */
+int pvsr_refine_posterm(const float* w1, const float* b1, const float* pos, float* table, int n_frames_out, int B,
+                        int L, int window, int c_out, int c_in, int feat2, int n_total, void* stream);
+
+/* _OutBlock last conv (refine_net.py:203/205): bf16 [n_img][H][W][64] -> fp32 [n_img][H][W].
+ * If l1_partial != NULL also accumulates sum|out - target| per image (nn.L1Loss numerator). */
+int pvsr_head_conv_last_fwd(const void* in_bf16, const float* w, const float* b, float* out, const float* target,
+                            float* l1_partial, int64_t n_img, int H, int W, void* stream);
+
+int pvsr_add_bf16(const void* a, const void* b, void* out, int64_t n_elems, void* stream);
+
+/* ---- whole-network plan: RefineNet.forward (refine_net.py:61-135) --------------------------------------------- */
+typedef struct pvsr_net_config {
+  int batch;              /* N: cine sequences processed together */
+  int n_frames;           /* L = T + 2U input frames */
+  int n_updated;          /* U = num_updated_frames */
+  int h, w;               /* LR frame size */
+  int scale;              /* upscale_factor: 2, 3, 4 or 8 */
+  int n_stages;           /* num_stages */
+  int window;             /* refine_window_size (odd) */
+  int n_layers;           /* len(num_features); every entry must be 64 */
+  int pos_enc;            /* positional_encoding */
+  int memory;             /* ConvLSTMCell memory flag */
+  int all_heads;          /* 1: all 3*n_stages output lists (reference behaviour); 0: only the last list */
+  int save_for_backward;  /* 1: keep per-step states for pvsr_plan_backward */
+} pvsr_net_config;
+
+typedef struct pvsr_net_params { /* fp32 device pointers, reference state_dict layout */
+  const float* in_w; const float* in_b; const float* in_slope;
+  const float* lstm_w[2][PVSR_MAX_LAYERS]; const float* lstm_b[2][PVSR_MAX_LAYERS]; /* [0]=forward,[1]=backward */
+  const float* ref_w1; const float* ref_b1; const float* ref_w2; const float* ref_b2;
+  const float* head_w[PVSR_MAX_HEAD_CONVS]; const float* head_b[PVSR_MAX_HEAD_CONVS];
+} pvsr_net_params;
+
+typedef struct pvsr_plan pvsr_plan;
+int pvsr_plan_create(const pvsr_net_config* cfg, pvsr_plan** out);      /* host only */
+void pvsr_plan_destroy(pvsr_plan* p);
+int64_t pvsr_plan_workspace_bytes(const pvsr_plan* p);
+int64_t pvsr_plan_packed_bytes(const pvsr_plan* p);
+int64_t pvsr_plan_output_elems(const pvsr_plan* p);    /* fp32 elements: [lists][T][N][H*s][W*s] */
+int pvsr_plan_num_lists(const pvsr_plan* p);
+int64_t pvsr_plan_num_launches(const pvsr_plan* p);    /* kernels launched by one pvsr_plan_forward */
+double pvsr_plan_flops(const pvsr_plan* p);            /* conv FLOPs executed by one forward */
+/* fp32 parameters -> packed bf16 operands (+ biases in packed order); call after every parameter update. */
+int pvsr_plan_pack(pvsr_plan* p, const pvsr_net_params* params, void* packed, void* stream);
+/* lr: fp32 [L][N][h][w]; pos: fp32 [N][L]; out: fp32 [lists][T][N][H*s][W*s].
+ * use_graph != 0 replays a CUDA graph captured on first use for this (workspace, packed, lr, pos, out) tuple. */
+int pvsr_plan_forward(pvsr_plan* p, const pvsr_net_params* params, const void* packed, const float* lr,
+                      const float* pos, float* out, void* workspace, int use_graph, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVSR_H_ */

@@ -1,0 +1,256 @@
+"""Kernel-level parity (GPU): every sm_100a kernel against a plain PyTorch fp32 reference of the same op.
+
+Inputs and weights are made exactly bf16-representable, so the only differences are the fp32 accumulation
+order and the final bf16 rounding of the stored activations.  Tolerances are written at each comparison.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def nhwc(x):  # [n, C, H, W] fp32 -> [n, H, W, C] bf16
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(x):  # [n, H, W, C] -> [n, C, H, W] fp32
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def rel_l2(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def _rand(*shape, gen, scale=1.0):
+    return bf16r(torch.randn(*shape, generator=gen, device="cuda") * scale)
+
+
+@pytest.mark.parametrize("n,H,W", [(3, 10, 13), (2, 54, 63), (1, 63, 48), (2, 32, 32), (1, 5, 130)])
+def test_conv_store_256(pvsr_lib, n, H, W):
+    from pvsr import ops, lib as L
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = _rand(n, 64, H, W, gen=g)
+    w = _rand(256, 64, 3, 3, gen=g, scale=0.05)
+    b = torch.randn(256, generator=g, device="cuda")
+    spec = ops._spec(256, 64, 3, 1, [0], 64, 1, 9, 256)
+    wp = ops.pack_weight(w, spec)
+    out = torch.zeros(n, H, W, 256, dtype=torch.float32, device="cuda")
+    ops.conv3x3(nhwc(x), [0], n, wp, 256, bias=ops.pack_bias(b, spec), out_f32=out)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, w, b, padding=1)
+    assert torch.allclose(nchw(out), ref, atol=2e-4, rtol=1e-4), (nchw(out) - ref).abs().max()
+
+
+def test_conv_store_64_residual_144in(pvsr_lib):
+    """refine conv2 shape: 129 (stored as 144) -> 64 channels, + bias + bf16 residual."""
+    from pvsr import ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    n, H, W = 4, 54, 63
+    x = _rand(n, 129, H, W, gen=g)
+    xs = torch.zeros(n, 144, H, W, device="cuda")
+    xs[:, :129] = x
+    w = _rand(64, 129, 3, 3, gen=g, scale=0.03)
+    b = torch.randn(64, generator=g, device="cuda")
+    r = _rand(n, 64, H, W, gen=g)
+    spec = ops.spec_refine_conv2()
+    wp = ops.pack_weight(w, spec)
+    out = torch.zeros(n, H, W, 64, dtype=torch.bfloat16, device="cuda")
+    ops.conv3x3(nhwc(xs), [0], n, wp, 64, kb_per_src=3, k16_last=1, bias=ops.pack_bias(b, spec), out_bf16=out,
+                res=nhwc(r))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, w, b, padding=1) + r
+    # bf16 output rounding: 2^-9 relative
+    assert torch.allclose(nchw(out), ref, atol=1e-2, rtol=8e-3), (nchw(out) - ref).abs().max()
+    assert rel_l2(nchw(out), ref) < 3e-3
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 54, 63), (3, 9, 17)])
+def test_refine_conv1_posterm(pvsr_lib, B, H, W):
+    """645 -> 129 conv over a 5-frame window of (fwd h | bwd h | pos plane), refine_net.py:166-180."""
+    from pvsr import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    Lf, win = 9, 5
+    nf = Lf - win + 1
+    hf = _rand(Lf * B, 64, H, W, gen=g)
+    hb = _rand(Lf * B, 64, H, W, gen=g)
+    pos = torch.randn(B, Lf, generator=g, device="cuda")
+    w1 = _rand(129, 645, 3, 3, gen=g, scale=0.02)
+    b1 = torch.randn(129, generator=g, device="cuda")
+    spec = ops.spec_refine_conv1()
+    wp = ops.pack_weight(w1, spec)
+    table = ops.refine_posterm(w1, b1, pos, nf)
+    act = torch.cat([nhwc(hf), nhwc(hb)], dim=0)  # images: [hf frames | hb frames]
+    src = []
+    for j in range(win):
+        src += [j * B, Lf * B + j * B]
+    out = torch.zeros(nf * B, H, W, 144, dtype=torch.bfloat16, device="cuda")
+    ops.conv3x3(act, src, nf * B, wp, 144, posterm=table, out_bf16=out, out_ch=144, n_store=144)
+    torch.cuda.synchronize()
+    # reference: build the 645-channel window input exactly like the reference does
+    hf5 = hf.view(Lf, B, 64, H, W)
+    hb5 = hb.view(Lf, B, 64, H, W)
+    refs = []
+    for i in range(nf):
+        chans = []
+        for j in range(win):
+            p = pos[:, i + j].view(B, 1, 1, 1).expand(B, 1, H, W)
+            chans += [hf5[i + j], hb5[i + j], p]
+        refs.append(F.conv2d(torch.cat(chans, dim=1), w1, b1, padding=1))
+    ref = torch.stack(refs).view(nf * B, 129, H, W)
+    got = nchw(out)
+    assert torch.allclose(got[:, :129], ref, atol=2e-2, rtol=8e-3), (got[:, :129] - ref).abs().max()
+    assert rel_l2(got[:, :129], ref) < 3e-3
+    assert got[:, 129:].abs().max().item() == 0.0
+
+
+def test_conv1x1_window(pvsr_lib):
+    """_RefineBlock without positional encoding: 1x1 conv 640 -> 64 (refine_net.py:154)."""
+    from pvsr import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    B, H, W, Lf, win = 2, 20, 23, 7, 5
+    nf = Lf - win + 1
+    hf = _rand(Lf * B, 64, H, W, gen=g)
+    hb = _rand(Lf * B, 64, H, W, gen=g)
+    w = _rand(64, 640, 1, 1, gen=g, scale=0.05)
+    b = torch.randn(64, generator=g, device="cuda")
+    spec = ops.spec_refine_conv1x1()
+    wp = ops.pack_weight(w, spec)
+    act = torch.cat([nhwc(hf), nhwc(hb)], dim=0)
+    src = []
+    for j in range(win):
+        src += [j * B, Lf * B + j * B]
+    out = torch.zeros(nf * B, H, W, 64, dtype=torch.float32, device="cuda")
+    ops.conv3x3(act, src, nf * B, wp, 64, taps=1, bias=ops.pack_bias(b, spec), out_f32=out)
+    torch.cuda.synchronize()
+    hf5, hb5 = hf.view(Lf, B, 64, H, W), hb.view(Lf, B, 64, H, W)
+    refs = []
+    for i in range(nf):
+        chans = []
+        for j in range(win):
+            chans += [hf5[i + j], hb5[i + j]]
+        refs.append(F.conv2d(torch.cat(chans, dim=1), w, b))
+    ref = torch.stack(refs).view(nf * B, 64, H, W)
+    assert torch.allclose(nchw(out), ref, atol=3e-4, rtol=1e-4), (nchw(out) - ref).abs().max()
+
+
+@pytest.mark.parametrize("r,H,W", [(2, 54, 63), (3, 24, 28), (2, 7, 9)])
+def test_head_conv_pixel_shuffle(pvsr_lib, r, H, W):
+    from pvsr import ops, lib as L
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 3
+    x = _rand(n, 64, H, W, gen=g)
+    w = _rand(64 * r * r, 64, 3, 3, gen=g, scale=0.05)
+    b = torch.randn(64 * r * r, generator=g, device="cuda")
+    spec = ops.spec_head_ps(r)
+    wp = ops.pack_weight(w, spec)
+    out = torch.zeros(n, H * r, W * r, 64, dtype=torch.bfloat16, device="cuda")
+    bn, nt = (256, 1) if r == 2 else (192, 3)
+    ops.conv3x3(nhwc(x), [0], n, wp, bn, epi=L.EPI_PS, bias=ops.pack_bias(b, spec), n_tiles_n=nt, out_bf16=out,
+                out_ch=64, ps_r=r)
+    torch.cuda.synchronize()
+    ref = F.pixel_shuffle(F.conv2d(x, w, b, padding=1), r)
+    assert torch.allclose(nchw(out), ref, atol=1e-2, rtol=8e-3), (nchw(out) - ref).abs().max()
+    assert rel_l2(nchw(out), ref) < 3e-3
+
+
+@pytest.mark.parametrize("n,H,W", [(2, 54, 63), (5, 12, 20)])
+def test_convlstm_cell(pvsr_lib, n, H, W):
+    """Two consecutive ConvLSTMCell steps (refine_net.py:247-267), first with h = c = 0."""
+    from pvsr import ops, lib as L
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x0 = _rand(n, 64, H, W, gen=g)
+    x1 = _rand(n, 64, H, W, gen=g)
+    w = _rand(256, 128, 3, 3, gen=g, scale=0.04)
+    b = torch.randn(256, generator=g, device="cuda") * 0.5
+    spec = ops.spec_lstm()
+    wp = ops.pack_weight(w, spec)
+    bias = ops.pack_bias(b, spec)
+
+    def ref_cell(x, h, c):
+        cc = F.conv2d(torch.cat([x, h], dim=1), w, b, padding=1)
+        i, f, o, gg = torch.split(cc, 64, dim=1)
+        c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        return torch.sigmoid(o) * torch.tanh(c2), c2
+
+    z = torch.zeros(n, 64, H, W, device="cuda")
+    h1r, c1r = ref_cell(x0, z, z)
+    h1r_b = bf16r(h1r)
+    h2r, c2r = ref_cell(x1, h1r_b, c1r)
+
+    # images: [x0 | x1 | h1]
+    act = torch.zeros(3 * n, H, W, 64, dtype=torch.bfloat16, device="cuda")
+    act[:n] = nhwc(x0)
+    act[n:2 * n] = nhwc(x1)
+    cst = ops.lstm_state(n, H, W, "cuda")
+    gates = torch.zeros(cst.numel() * 4, dtype=torch.bfloat16, device="cuda")
+    # step 0: only the x source (h = 0), c_in = None
+    ops.conv3x3(act, [0], n, wp, 256, epi=L.EPI_LSTM, bias=bias, c_in=None, c_out=cst, h_out=act[2 * n:],
+                gates_out=gates)
+    torch.cuda.synchronize()
+    h1 = nchw(act[2 * n:])
+    c1 = ops.lstm_state_to_nchw(cst, n, H, W)
+    assert torch.allclose(c1, c1r, atol=2e-4, rtol=1e-4), (c1 - c1r).abs().max()
+    assert torch.allclose(h1, h1r, atol=5e-3, rtol=8e-3), (h1 - h1r).abs().max()
+    # step 1: sources x1 and h1 (as produced by the kernel), state updated in place
+    ops.conv3x3(act, [n, 2 * n], n, wp, 256, epi=L.EPI_LSTM, bias=bias, c_in=cst, c_out=cst,
+                h_out=act[:n])
+    torch.cuda.synchronize()
+    h2r, c2r = ref_cell(x1, h1, c1)
+    c2 = ops.lstm_state_to_nchw(cst, n, H, W)
+    h2 = nchw(act[:n])
+    assert torch.allclose(c2, c2r, atol=3e-4, rtol=1e-4), (c2 - c2r).abs().max()
+    assert torch.allclose(h2, h2r, atol=5e-3, rtol=8e-3), (h2 - h2r).abs().max()
+
+
+def test_in_conv_prelu(pvsr_lib):
+    from pvsr import ops
+    g = torch.Generator(device="cuda").manual_seed(7)
+    n, H, W = 5, 54, 63
+    x = torch.randn(n, H, W, generator=g, device="cuda")
+    w = torch.randn(64, 1, 3, 3, generator=g, device="cuda") * 0.3
+    b = torch.randn(64, generator=g, device="cuda") * 0.1
+    a = torch.tensor([0.2], device="cuda")
+    out = ops.in_conv_prelu(x, w, b, a)
+    torch.cuda.synchronize()
+    ref = F.prelu(F.conv2d(x.unsqueeze(1), w, b, padding=1), a)
+    assert torch.allclose(nchw(out), ref, atol=1e-2, rtol=8e-3), (nchw(out) - ref).abs().max()
+    assert rel_l2(nchw(out), ref) < 3e-3
+
+
+@pytest.mark.parametrize("H,W", [(216, 252), (24, 28), (9, 33)])
+def test_head_conv_last_and_l1(pvsr_lib, H, W):
+    from pvsr import ops
+    g = torch.Generator(device="cuda").manual_seed(8)
+    n = 3
+    x = _rand(n, 64, H, W, gen=g)
+    w = torch.randn(1, 64, 3, 3, generator=g, device="cuda") * 0.05
+    b = torch.randn(1, generator=g, device="cuda")
+    tgt = torch.randn(n, H, W, generator=g, device="cuda")
+    part = torch.zeros(n, device="cuda")
+    out = ops.head_conv_last(nhwc(x), w, b, target=tgt, l1_partial=part)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, w, b, padding=1)[:, 0]
+    assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4), (out - ref).abs().max()
+    l1 = (ref - tgt).abs().sum(dim=(1, 2))
+    assert torch.allclose(part, l1, rtol=1e-4)
+
+
+def test_add_bf16(pvsr_lib):
+    from pvsr import ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    a = torch.randn(3, 54, 63, 64, generator=g, device="cuda").to(torch.bfloat16)
+    b = torch.randn(3, 54, 63, 64, generator=g, device="cuda").to(torch.bfloat16)
+    out = ops.add_bf16(a, b)
+    torch.cuda.synchronize()
+    assert torch.equal(out, (a.float() + b.float()).to(torch.bfloat16))
