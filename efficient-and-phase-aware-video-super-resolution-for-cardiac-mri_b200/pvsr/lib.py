@@ -78,6 +78,9 @@ SIGNATURES = {
     "pvsr_plan_pack": (c_int, [c_void_p, C.POINTER(NetParams), c_void_p, c_void_p]),
     "pvsr_plan_forward": (c_int, [c_void_p, C.POINTER(NetParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_void_p]),
+    "pvsr_plan_class_stats": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "pvsr_plan_profile": (c_int, [c_void_p, C.POINTER(NetParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
 }
 
 _lib = None

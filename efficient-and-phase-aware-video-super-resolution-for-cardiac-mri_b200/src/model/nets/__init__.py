@@ -1,0 +1,3 @@
+# Net registry: names resolved by `getattr(src.model.nets, config.net.name)` (reference src/main.py:59,128,179).
+from .base_net import BaseNet
+from .refine_net import RefineNet

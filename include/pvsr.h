@@ -161,6 +161,14 @@ int pvsr_plan_pack(pvsr_plan* p, const pvsr_net_params* params, void* packed, vo
 int pvsr_plan_forward(pvsr_plan* p, const pvsr_net_params* params, const void* packed, const float* lr,
                       const float* pos, float* out, void* workspace, int use_graph, void* stream);
 
+/* Launch classes for accounting: 0 in_conv, 1 ConvLSTM cells, 2 refine conv1, 3 refine conv2, 4 head conv+shuffle,
+ * 5 head last conv, 6 misc (adds, posterm).  Arrays must hold PVSR_NUM_CLASSES entries. */
+#define PVSR_NUM_CLASSES 7
+int pvsr_plan_class_stats(const pvsr_plan* p, int64_t* launches, double* flops);
+/* One eager forward with CUDA events around every launch (synchronises `stream`); summed ms per launch class. */
+int pvsr_plan_profile(pvsr_plan* p, const pvsr_net_params* params, const void* packed, const float* lr,
+                      const float* pos, float* out, void* workspace, double* ms_by_class, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

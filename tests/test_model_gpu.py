@@ -1,0 +1,148 @@
+"""Model-level parity (GPU): the drop-in RefineNet (CUDA kernels through the C ABI) against
+ (a) fixtures produced by the unmodified reference (tests/golden, small shapes, all 3*S output lists), and
+ (b) the pinned CPU oracle at the full ACDCSR shape (LR 54x63, T=30, U=6), incl. PSNR/SSIM parity.
+
+Tolerances (SURVEY.md section 8c error budget for bf16 operands with fp32 accumulation/state):
+  outputs max-abs <= 2e-2 and rel-L2 <= 1.5e-2;  PSNR delta <= 0.01 dB, SSIM delta <= 1e-4.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_net, golden_cases, load_golden, oracle_kwargs
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS, REL_L2 = 2e-2, 1.5e-2
+
+
+def _run(net, inputs, pos):
+    with torch.no_grad():
+        out = net([x.cuda() for x in inputs], pos.cuda())
+    torch.cuda.synchronize()
+    return out
+
+
+def _stack(out):
+    return torch.stack([torch.stack(list(o)) for o in out]).float().cpu()
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_forward_matches_reference_fixture(pvsr_lib, name):
+    z, meta = load_golden(name)
+    net = build_net(meta["kwargs"]).cuda().eval()
+    inputs = [torch.from_numpy(x) for x in z["inputs"]]
+    pos = torch.from_numpy(z["pos"])
+    out = _run(net, inputs, pos)
+    assert isinstance(out, tuple) and len(out) == 3 * meta["kwargs"]["num_stages"]
+    assert all(isinstance(o, list) and len(o) == meta["T"] for o in out)
+    got, ref = _stack(out), torch.from_numpy(z["outputs_eval"])
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item()
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert err <= MAX_ABS and rel <= REL_L2, (name, err, rel)
+    # per-list check: every head of every stage, not just the last one
+    for l in range(got.shape[0]):
+        rl = ((got[l] - ref[l]).norm() / ref[l].norm()).item()
+        assert rl <= REL_L2, (name, l, rl)
+
+
+def test_last_head_fast_path_and_graph_replay(pvsr_lib):
+    z, meta = load_golden("x4_pos")
+    net = build_net(meta["kwargs"]).cuda().eval()
+    inputs = [torch.from_numpy(x) for x in z["inputs"]]
+    pos = torch.from_numpy(z["pos"])
+    full = _stack(_run(net, inputs, pos))
+    net.only_last_head = True
+    a = _stack(_run(net, inputs, pos))          # first call: eager + capture
+    b = _stack(_run(net, inputs, pos))          # second call: CUDA-graph replay
+    assert a.shape[0] == 1
+    assert torch.equal(a, b)
+    assert torch.equal(a[0], full[-1])
+    # inputs must not be mutated and outputs are fresh tensors by default
+    assert all(torch.equal(x, torch.from_numpy(y)) for x, y in zip(inputs, z["inputs"]))
+
+
+def test_parameter_update_is_picked_up(pvsr_lib):
+    """Packed bf16 operands are refreshed when the fp32 master parameters change (e.g. optimizer.step)."""
+    z, meta = load_golden("x2_pos")
+    net = build_net(meta["kwargs"]).cuda().eval()
+    inputs = [torch.from_numpy(x) for x in z["inputs"]]
+    pos = torch.from_numpy(z["pos"])
+    a = _stack(_run(net, inputs, pos))
+    with torch.no_grad():
+        net.out_block.conv2.bias.add_(1.0)
+    b = _stack(_run(net, inputs, pos))
+    assert torch.allclose(b, a + 1.0, atol=1e-5)
+    with torch.no_grad():
+        net.forward_lstm_block.cell_list[0].conv.weight.mul_(0.5)
+    c = _stack(_run(net, inputs, pos))
+    assert (c - b).abs().max().item() > 1e-4
+
+
+def test_errors_like_reference(pvsr_lib):
+    from src.model.nets import RefineNet
+    with pytest.raises(ValueError):
+        RefineNet(1, 1, [64, 64, 64], upscale_factor=5)
+    with pytest.raises(ValueError):
+        RefineNet(1, 1, [64, 64, 64], update_memory=False, num_updated_frames=6)
+    net = RefineNet(1, 1, [64, 64, 64], num_stages=1, update_memory=False, num_updated_frames=0).cuda().eval()
+    with pytest.raises(IndexError):
+        with torch.no_grad():
+            net([torch.zeros(1, 1, 8, 8, device="cuda")] * 5, torch.zeros(1, 5, 1, device="cuda"))
+    net2 = build_net(dict(in_channels=1, out_channels=1, num_features=[64, 64, 64], num_stages=1, update_memory=True,
+                          num_updated_frames=2, upscale_factor=2))
+    from pvsr.lib import PvsrError
+    with pytest.raises(PvsrError):
+        with torch.no_grad():
+            net2.eval()([torch.zeros(1, 1, 8, 8)] * 6, torch.zeros(1, 6, 1))   # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("scale,h,w,pos", [(4, 54, 63, True), (4, 63, 48, True), (3, 72, 84, True)])
+def test_full_size_sequence_vs_oracle(pvsr_lib, scale, h, w, pos):
+    """One ACDCSR / DSB15SR-shaped cine sequence (T=30, U=6): SR frames and PSNR/SSIM against the CPU oracle."""
+    from oracle import refinenet_oracle as O
+    T, U = 30, 6
+    kw = dict(in_channels=1, out_channels=1, num_features=[64, 64, 64], num_stages=3, update_memory=True,
+              num_updated_frames=U, refine_window_size=5, upscale_factor=scale, positional_encoding=pos)
+    net = build_net(kw)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(1234)
+    frames = [torch.randn(1, 1, h, w, generator=g) for _ in range(T)]
+    inputs = O.circular_window(frames, T, U)
+    code = torch.from_numpy(O.positional_code(T, 11))
+    pos_codes = torch.stack(O.circular_window(list(code), T, U)).view(1, T + 2 * U, 1)
+    hr = [torch.randn(1, 1, h * scale, w * scale, generator=g) for _ in range(T)]
+    with torch.no_grad():
+        ref = O.refinenet_forward(sd, inputs, pos_codes, **oracle_kwargs(kw))[-1]
+    net = net.cuda().eval()
+    net.only_last_head = True
+    got = _run(net, inputs, pos_codes)[-1]
+    got = [o.cpu() for o in got]
+    errs = [(a - b).abs().max().item() for a, b in zip(got, ref)]
+    rels = [((a - b).norm() / b.norm()).item() for a, b in zip(got, ref)]
+    assert max(errs) <= MAX_ABS and max(rels) <= REL_L2, (max(errs), max(rels))
+    # metric parity on denormalised frames (reference metrics.py / utils.py semantics)
+    dataset = "acdc"
+    dp, ds = [], []
+    for a, b, t in zip(got, ref, hr):
+        ta = O.denormalize(t, dataset)
+        dp.append(abs(float(O.psnr(O.denormalize(a, dataset), ta)) - float(O.psnr(O.denormalize(b, dataset), ta))))
+        ds.append(abs(float(O.ssim(O.denormalize(a, dataset), ta)) - float(O.ssim(O.denormalize(b, dataset), ta))))
+    assert max(dp) <= 0.01 and max(ds) <= 1e-4, (max(dp), max(ds))
+
+
+def test_batched_sequences_are_independent(pvsr_lib):
+    """Batching N sequences (the inference sharding unit) gives the same frames as running them one by one."""
+    kw = dict(in_channels=1, out_channels=1, num_features=[64, 64, 64], num_stages=3, update_memory=True,
+              num_updated_frames=3, refine_window_size=5, upscale_factor=4, positional_encoding=True)
+    net = build_net(kw).cuda().eval()
+    net.only_last_head = True
+    g = torch.Generator().manual_seed(5)
+    N, L, h, w = 3, 10, 20, 17
+    inputs = [torch.randn(N, 1, h, w, generator=g) for _ in range(L)]
+    pos = torch.randn(N, L, 1, generator=g)
+    full = _stack(_run(net, inputs, pos))[0]
+    for n in range(N):
+        one = _stack(_run(net, [x[n:n + 1] for x in inputs], pos[n:n + 1]))[0]
+        assert torch.allclose(one[:, 0], full[:, n], atol=1e-6), n
