@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py - SR frames/s of the RefineNet x4 hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+A step = one RefineNet x4 inference pass (only the consumed output list, i.e. what the reference predictor
+reads through `[-1]`) over B synthetic ACDCSR-shaped cine sequences per GPU (LR 54x63, T=30 phases, U=6 warm-up
+frames each side -> 42 LR frames in, 30 SR frames 216x252 out, random-init weights, seed 0).
+N > 1: one process per GPU (torchrun), sequences sharded by rank, no data-path collective (weak scaling).
+
+Printed JSON (one line, rank 0): value = device-timed frames/s with inputs resident in HBM; e2e = same metric
+through the public module call with pinned host inputs (H2D) and the SR frames read back (D2H) every step;
+roofline = ConvLSTM-cell tcgen05 kernel (dominant launch class) FLOP/s vs the measured bf16 peak;
+cpu_baseline = the pinned CPU oracle (torch fp32 restatement of the reference) on this box's host cores.
+`--impl reference` times that CPU implementation alone (the reference itself cannot be installed: see DESIGN.md).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "efficient-and-phase-aware-video-super-resolution-for-cardiac-mri_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+T_FRAMES, U_FRAMES, LR_H, LR_W, SCALE = 30, 6, 54, 63, 4
+NET_KW = dict(in_channels=1, out_channels=1, num_features=[64, 64, 64], upscale_factor=SCALE, num_stages=3,
+              update_memory=True, num_updated_frames=U_FRAMES, refine_window_size=5, positional_encoding=True)
+METRIC = "SR frames/s at x4"
+UNIT = "frames/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        d["_source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback (B200_PROFILING.md)"
+    return d
+
+
+def synthetic_sequences(batch, seed):
+    """ACDCSR-shaped synthetic cine sequences: circular padding and positional code as the reference dataset
+    builds them (acdc_vsr_refinenet_dataset.py:74-87, gen_positional_encoding.py:35-38)."""
+    from pvsr.synthetic import cine_batch
+    return cine_batch(batch, T=T_FRAMES, U=U_FRAMES, h=LR_H, w=LR_W, scale=SCALE, seed=seed)
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.index = None, index
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = sorted(sm)[len(sm) // 2:]  # upper half = samples under load
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_time(n_seq_steps, warmup, threads):
+    """Times the CPU oracle (all 3*S heads, as the reference predictor executes them) on one sequence per step."""
+    from oracle import refinenet_oracle as O
+    torch.set_num_threads(threads)
+    sd = O.init_state_dict(upscale_factor=SCALE, positional_encoding=True, seed=0)
+    inputs, pos = synthetic_sequences(1, 1234)
+    kw = dict(num_stages=3, num_updated_frames=U_FRAMES, refine_window_size=5, upscale_factor=SCALE,
+              positional_encoding=True, memory=True, num_layers=3)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + n_seq_steps):
+            t0 = time.perf_counter()
+            O.refinenet_forward(sd, inputs, pos, **kw)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    times = cpu_oracle_time(args.steps, args.warmup, cores)
+    total = sum(times)
+    value = T_FRAMES * len(times) / total
+    sample = f"{len(times)} step(s) x 1 ACDCSR x4 sequence (42 LR frames 54x63 -> 30 SR frames), all 9 heads, fp32"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "RefineNet x4 inference, synthetic ACDCSR-shaped cine sequences (LR 54x63, T=30, U=6), "
+                                   "1 sequence per step on the host CPU", "sequences_per_step": 1},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="cine sequences per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(PKG, "csrc"))
+    import build as pvsr_build
+    pvsr_build.build()
+    from src.model.nets import RefineNet
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (the path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    net = RefineNet(**NET_KW).to(dev).eval()
+    net.only_last_head = True
+    net.reuse_output_buffers = True
+    net.engine.use_graph = not args.no_graph
+    B = args.batch
+
+    # this rank's shard of the synthetic job: B sequences, host-resident (pinned) for the e2e leg
+    inputs_h, pos_h = synthetic_sequences(B, 1234 + rank)
+    inputs_h = [x.pin_memory() for x in inputs_h]
+    pos_h = pos_h.pin_memory()
+    inputs_d = [x.to(dev) for x in inputs_h]
+    pos_d = pos_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out_h = torch.empty(T_FRAMES, B, 1, LR_H * SCALE, LR_W * SCALE, dtype=torch.float32).pin_memory()
+
+    eng = net.engine
+    plan = eng.plan_for(B, len(inputs_d), LR_H, LR_W, False, dev)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        flush.fill_(1)                      # L2 flush: 256 MiB write between steps
+        eng.run(plan)                       # inputs already staged in HBM
+
+    def e2e_step():
+        flush.fill_(1)
+        xs = [x.to(dev, non_blocking=True) for x in inputs_h]           # H2D from pinned host memory
+        ps = pos_h.to(dev, non_blocking=True)
+        with torch.no_grad():
+            frames = net(xs, ps)[-1]                                     # the public module call
+        for t, f in enumerate(frames):
+            out_h[t].copy_(f, non_blocking=True)                        # D2H read of the SR frames
+        return frames
+
+    with torch.no_grad():
+        eng.stage_inputs(plan, inputs_d, pos_d)
+        for _ in range(args.warmup):
+            device_step()
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            device_step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+
+        # per-class kernel times (eager pass with events around every launch), averaged over 2 passes
+        prof = None
+        for _ in range(2):
+            pr = eng.profile(plan)
+            prof = pr if prof is None else {k: (prof[k][0] + v[0], v[1], v[2]) for k, v in pr.items()}
+        prof = {k: (v[0] / 2, v[1], v[2]) for k, v in prof.items()}
+
+        # end-to-end leg through the public API with host buffers
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    if rank == 0:
+        peaks = measured_peaks()
+        frames_per_step = world * B * T_FRAMES
+        value = frames_per_step * args.steps / (ms / 1e3)
+        e2e_value = frames_per_step * args.steps / (ms_e2e / 1e3)
+        lstm_ms, lstm_launches, lstm_flops = prof["convlstm_cell"]
+        achieved = lstm_flops / (lstm_ms / 1e3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        step_flops = sum(v[2] for v in prof.values())
+        h2d = sum(x.numel() * 4 for x in inputs_h) + pos_h.numel() * 4
+        d2h = out_h.numel() * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"RefineNet x4 inference, {B} synthetic ACDCSR-shaped cine sequences per GPU per step "
+                                   "(LR 54x63, T=30, U=6 -> 42 LR frames in, 30 SR frames 216x252 out), last output list only",
+                       "sequences_per_gpu": B, "frames_per_step": frames_per_step, "parallelism": f"sequence-sharded x{world}",
+                       "l2": "256 MiB flush write between steps; per-step working set >> 126 MB L2",
+                       "cuda_graph": not args.no_graph, "algorithmic_tflop_per_step_per_gpu": step_flops / 1e12},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(plan.launches * args.steps),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel<256, EPI_LSTM> (ConvLSTM cell wavefront)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peaks["_source"] + ", sustained bf16",
+                         "launches_per_step": lstm_launches, "avg_launch_ms": lstm_ms / max(lstm_launches, 1),
+                         "share_of_step": lstm_ms / sum(v[0] for v in prof.values()),
+                         "whole_step_tflops": step_flops / (ms / args.steps / 1e3) / 1e12},
+            "kernel_ms_per_step": {k: round(v[0], 3) for k, v in prof.items()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            times = cpu_oracle_time(1, 1, cores)
+            line["cpu_baseline"] = {"value": T_FRAMES * len(times) / sum(times), "unit": UNIT, "cores": cores,
+                                    "kind": "port",
+                                    "sample": "1 ACDCSR x4 sequence (30 SR frames), all 9 heads as the reference "
+                                              "executes them, fp32 torch CPU oracle, 1 warm-up + 1 timed run"}
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
