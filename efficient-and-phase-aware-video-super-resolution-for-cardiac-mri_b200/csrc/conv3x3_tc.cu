@@ -27,13 +27,28 @@ struct Cfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
+                                    kMaxProb * 256 * 4 /*pre-scaled LSTM biases*/;
   static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment for the 128B swizzle");
   static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint for M=128");
 };
 
-__device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(1.f + __expf(-x)); }
-__device__ __forceinline__ float tanhf_fast(float x) { return 2.f * __frcp_rn(1.f + __expf(-2.f * x)) - 1.f; }
+// MUFU-only transcendental building blocks (ex2.approx / rcp.approx: ~1 ulp, no slow paths, no branches).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+// sigmoid(x) with t = -log2(e) * x precomputed:  1 / (1 + 2^t)
+__device__ __forceinline__ float sigmoid_from_scaled(float t) { return rcp_approx(1.f + ex2_approx(t)); }
+// tanh(x) with t = 2 * log2(e) * x precomputed:  1 - 2 / (1 + 2^t)   (saturates correctly at +-inf)
+__device__ __forceinline__ float tanh_from_scaled(float t) { return fmaf(-2.f, rcp_approx(1.f + ex2_approx(t)), 1.f); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -84,6 +99,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
   uint64_t* tfull = bars + 2 * S;   // [2]  MMA -> epilogue
   uint64_t* tempty = tfull + 2;     // [2]  epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + S * C::kStageBytes + 256);  // [n_prob][256], LSTM only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -103,6 +119,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if constexpr (EPI == EPI_LSTM) {
+    // Gate biases, pre-multiplied so that each gate costs one FFMA + ex2 + add + rcp:
+    // i, f, o: -log2(e) * b (sigmoid);  g: 2 * log2(e) * b (tanh).
+    for (int i = threadIdx.x; i < p.n_prob * 256; i += kNumThreads) {
+      const int z = i >> 8, n = i & 255;
+      bias_s[i] = p.prob[z].bias[n] * (n < 192 ? -kLog2e : 2.f * kLog2e);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -189,8 +213,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
 
       if constexpr (EPI == EPI_LSTM) {
         // Columns: [i | f | o | g] x 64 channels (refine_net.py:258). This warp: channels [32*half, 32*half+32).
-        const size_t cbase = (static_cast<size_t>(tc.tile_lin) * 64) * kTileM + row;
-        const size_t pix = (static_cast<size_t>(tc.img) * p.H + y) * p.W + x;
+        const float* cin = pr.c_in ? pr.c_in + (static_cast<size_t>(tc.tile_lin) * 64) * kTileM + row : nullptr;
+        float* cout = pr.c_out + (static_cast<size_t>(tc.tile_lin) * 64) * kTileM + row;
+        __nv_bfloat16* gout =
+            pr.gates_out ? pr.gates_out + (static_cast<size_t>(tc.tile_lin) * 256) * kTileM + row : nullptr;
+        __nv_bfloat16* hrow = pr.h_out + ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * 64;
+        const float4* bs4 = reinterpret_cast<const float4*>(bias_s + tc.z * 256);
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
           const int ch0 = half * 32 + cc * 16;
@@ -200,34 +228,44 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
           tmem_ld16(taddr + 128 + ch0, vo);
           tmem_ld16(taddr + 192 + ch0, vg);
           float cprev[16];
+          if (cin) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            cprev[j] = pr.c_in ? pr.c_in[cbase + static_cast<size_t>(ch0 + j) * kTileM] : 0.f;
+            for (int j = 0; j < 16; ++j) cprev[j] = cin[(ch0 + j) * kTileM];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cprev[j] = 0.f;
+          }
           tmem_ld_wait();
           uint32_t hp[8];
-          float hprev = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int ch = ch0 + j;
-            const float gi = sigmoidf_fast(__uint_as_float(vi[j]) + pr.bias[ch]);
-            const float gf = sigmoidf_fast(__uint_as_float(vf[j]) + pr.bias[64 + ch]);
-            const float go = sigmoidf_fast(__uint_as_float(vo[j]) + pr.bias[128 + ch]);
-            const float gg = tanhf_fast(__uint_as_float(vg[j]) + pr.bias[192 + ch]);
-            const float cn = gf * cprev[j] + gi * gg;
-            const float hn = go * tanhf_fast(cn);
-            pr.c_out[cbase + static_cast<size_t>(ch) * kTileM] = cn;
-            if (pr.gates_out) {
-              __nv_bfloat16* g = pr.gates_out + (static_cast<size_t>(tc.tile_lin) * 256) * kTileM + row;
-              g[static_cast<size_t>(ch) * kTileM] = __float2bfloat16(gi);
-              g[static_cast<size_t>(64 + ch) * kTileM] = __float2bfloat16(gf);
-              g[static_cast<size_t>(128 + ch) * kTileM] = __float2bfloat16(go);
-              g[static_cast<size_t>(192 + ch) * kTileM] = __float2bfloat16(gg);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bi = bs4[(ch0 >> 2) + j4], bf = bs4[16 + (ch0 >> 2) + j4];
+            const float4 bo = bs4[32 + (ch0 >> 2) + j4], bg = bs4[48 + (ch0 >> 2) + j4];
+            const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, bfa[4] = {bf.x, bf.y, bf.z, bf.w};
+            const float boa[4] = {bo.x, bo.y, bo.z, bo.w}, bga[4] = {bg.x, bg.y, bg.z, bg.w};
+            float hn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j4 * 4 + u;
+              const float gi = sigmoid_from_scaled(fmaf(__uint_as_float(vi[j]), -kLog2e, bia[u]));
+              const float gf = sigmoid_from_scaled(fmaf(__uint_as_float(vf[j]), -kLog2e, bfa[u]));
+              const float go = sigmoid_from_scaled(fmaf(__uint_as_float(vo[j]), -kLog2e, boa[u]));
+              const float gg = tanh_from_scaled(fmaf(__uint_as_float(vg[j]), 2.f * kLog2e, bga[u]));
+              const float cn = fmaf(gf, cprev[j], gi * gg);
+              hn[u] = go * tanh_from_scaled(cn * (2.f * kLog2e));
+              cout[(ch0 + j) * kTileM] = cn;
+              if (gout) {
+                gout[(ch0 + j) * kTileM] = __float2bfloat16(gi);
+                gout[(64 + ch0 + j) * kTileM] = __float2bfloat16(gf);
+                gout[(128 + ch0 + j) * kTileM] = __float2bfloat16(go);
+                gout[(192 + ch0 + j) * kTileM] = __float2bfloat16(gg);
+              }
             }
-            if (j & 1) hp[j >> 1] = pack_bf16x2(hprev, hn);
-            hprev = hn;
+            hp[j4 * 2] = pack_bf16x2(hn[0], hn[1]);
+            hp[j4 * 2 + 1] = pack_bf16x2(hn[2], hn[3]);
           }
           if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(pr.h_out + pix * 64 + ch0);
+            uint4* dst = reinterpret_cast<uint4*>(hrow + ch0);
             dst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
             dst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
           }
@@ -248,13 +286,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
           if (bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + ck * 16);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += bias[ck * 16 + j];
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = __ldg(b4 + j);
+              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+            }
           }
           if (valid) {
             if (pterm) {
+              const float4* t4 = reinterpret_cast<const float4*>(pterm + ck * 16);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] += pterm[ck * 16 + j];
+              for (int j = 0; j < 4; ++j) {
+                const float4 b = __ldg(t4 + j);
+                f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+              }
             }
             size_t off;
             if constexpr (EPI == EPI_PS) {
