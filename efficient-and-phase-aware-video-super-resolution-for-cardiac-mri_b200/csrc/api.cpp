@@ -40,11 +40,14 @@ int device_num_sms() {
 int fill_conv_params(const pvsr_conv_desc* d, ConvParams* p) {
   memset(p, 0, sizeof(*p));
   if (d->n_src < 1 || d->n_src > kMaxSrc) return set_error(-2, "n_src %d out of range", d->n_src);
+  if (d->n_views < 1 || d->n_views > kMaxMaps) return set_error(-2, "n_views %d out of range", d->n_views);
   if (d->taps != 9 && d->taps != 1) return set_error(-2, "taps must be 9 or 1");
   if (d->k16_last < 1 || d->k16_last > 4) return set_error(-2, "k16_last must be 1..4");
   p->H = d->H;
   p->W = d->W;
-  choose_tile(d->H, d->W, &p->tw_log2);
+  int max_mul = 1;
+  for (int v = 0; v < d->n_views; ++v) max_mul = d->views[v].mul > max_mul ? d->views[v].mul : max_mul;
+  choose_tile(d->H, d->W, &p->tw_log2, max_mul == 1 ? 128 : (max_mul == 2 ? 128 : 64));
   const int tw = 1 << p->tw_log2, th = kTileM >> p->tw_log2;
   p->tiles_x = (d->W + tw - 1) / tw;
   p->tiles_y = (d->H + th - 1) / th;
@@ -58,15 +61,22 @@ int fill_conv_params(const pvsr_conv_desc* d, ConvParams* p) {
   p->n_store = d->n_store;
   p->out_ch = d->out_ch;
   p->ps_r = d->ps_r;
+  p->grad_split = d->grad_split;
   ConvProblem& pr = p->prob[0];
   pr.n_src = d->n_src;
-  for (int i = 0; i < d->n_src; ++i) pr.src_img_base[i] = d->src_img_base[i];
+  for (int i = 0; i < d->n_src; ++i) {
+    const int v = d->src_view[i];
+    if (v < 0 || v >= d->n_views) return set_error(-2, "src_view out of range");
+    pr.src[i] = SrcView{v, d->src_img_base[i], d->src_ch0[i], d->views[v].mul, d->src_off_x[i], d->src_off_y[i]};
+  }
   pr.w_row_base = d->w_row_base;
   pr.bias = d->bias;
   pr.out_bf16 = static_cast<__nv_bfloat16*>(d->out_bf16);
   pr.out_f32 = d->out_f32;
   pr.res = static_cast<const __nv_bfloat16*>(d->res);
   pr.posterm = d->posterm;
+  pr.grad0 = d->grad0;
+  pr.grad1 = d->grad1;
   pr.c_in = d->c_in;
   pr.c_out = d->c_out;
   pr.h_out = static_cast<__nv_bfloat16*>(d->h_out);
@@ -127,7 +137,9 @@ int pvsr_pack_index_host(const pvsr_pack_spec* s, int32_t* idx) {
             const int ic = cb * 64 + c;
             int v = -1;
             if (ic < s->src_ch && col >= 0) {
-              const int gin = s->src_ch_off[src] + ic;  // GEMM K channel
+              // GEMM K channel -> parameter channel
+              const int gin = (s->transpose_flip && s->k_ps_r > 0) ? ic * s->k_ps_r * s->k_ps_r + src
+                                                                     : s->src_ch_off[src] + ic;
               const int o = s->transpose_flip ? gin : col;
               const int i = s->transpose_flip ? col : gin;
               if (o < s->c_out && i < s->c_in) v = ((o * s->c_in + i) * s->kh + ky) * s->kw + kx;
@@ -165,14 +177,18 @@ int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream) {
   ConvParams p;
   int rc = fill_conv_params(d, &p);
   if (rc) return rc;
-  if (d->act_channels % 8 != 0) return set_error(-2, "act_channels must be a multiple of 8");
-  CUtensorMap tm_act, tm_w;
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
   const int tw = 1 << p.tw_log2, th = kTileM >> p.tw_log2;
-  rc = make_act_tmap(&tm_act, d->act, d->act_channels, d->W, d->H, d->act_images, tw, th);
-  if (rc) return set_error(rc, "activation tensor map encode failed (%d)", rc);
-  rc = make_weight_tmap(&tm_w, d->w_packed, d->w_rows, d->bn);
+  for (int v = 0; v < d->n_views; ++v) {
+    const pvsr_act_view& a = d->views[v];
+    if (a.channels % 8 != 0) return set_error(-2, "view channels must be a multiple of 8");
+    rc = make_act_tmap(&maps.act[v], a.ptr, a.channels, a.W, a.H, a.images, tw, th, a.mul);
+    if (rc) return set_error(rc, "activation tensor map encode failed (%d)", rc);
+  }
+  rc = make_weight_tmap(&maps.w, d->w_packed, d->w_rows, d->bn);
   if (rc) return set_error(rc, "weight tensor map encode failed (%d)", rc);
-  return check_cuda(launch_conv3x3(d->bn, d->epi, tm_act, tm_w, p, device_num_sms(), static_cast<cudaStream_t>(stream)),
+  return check_cuda(launch_conv3x3(d->bn, d->epi, maps, p, device_num_sms(), static_cast<cudaStream_t>(stream)),
                     "conv3x3");
 }
 

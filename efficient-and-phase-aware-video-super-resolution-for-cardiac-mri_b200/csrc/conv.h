@@ -3,8 +3,9 @@
 // One launch computes, for every output image `img` of every problem `z`:
 //   D[pixel, n] = sum_{src, tap, c} A_src[pixel + tap, c] * Wp[(src, tap, cblock), n, c]
 // with A read by TMA from NHWC bf16 activation tensors (zero fill outside the image = padding 1)
-// and Wp the packed bf16 weight matrix (see pvsr/packing.py).  This is the GEMM view of
-// torch.nn.Conv2d(k=3, padding=1) at reference src/model/nets/refine_net.py:149,151,199-205,235.
+// and Wp the packed bf16 weight matrix (api.cpp: pvsr_pack_index_host).  This is the GEMM view of
+// torch.nn.Conv2d(k=3, padding=1) at reference src/model/nets/refine_net.py:149,151,199-205,235, and - with
+// transposed/flipped packed weights - of its data gradient.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -15,6 +16,7 @@ namespace pvsr {
 
 constexpr int kMaxSrc = 10;   // refine conv1: 5 frames x {forward h, backward h}
 constexpr int kMaxProb = 6;   // one ConvLSTM wavefront: up to 3 layers x 2 directions share one launch
+constexpr int kMaxMaps = 4;   // distinct activation tensors (TMA descriptors) one launch may read
 constexpr int kTileM = 128;   // output pixels per tile (UMMA M)
 constexpr int kBlockK = 64;   // bf16 channels per K block (one 128-byte swizzle row)
 
@@ -22,11 +24,23 @@ enum EpiKind : int {
   EPI_STORE = 0,  // bias (+ border-class term) (+ residual) -> NHWC bf16 and/or fp32
   EPI_PS = 1,     // bias -> pixel-shuffled NHWC bf16 (columns grouped per sub-pixel)
   EPI_LSTM = 2,   // ConvLSTM gates + state update (refine_net.py:258-265)
+  EPI_GRAD = 3,   // fp32 accumulation (+=) into one or two NHWC 64-channel gradient tensors
+};
+
+// One 64-channel-block source of the A operand.  TMA coordinates of output pixel (x, y) of image `img`, tap
+// (dx, dy), channel block cb:  (ch0 + 64*cb, mul*(x+dx) + off_x, mul*(y+dy) + off_y, img_base + img).
+// mul > 1 reads a pixel-UNshuffled view of a higher-resolution tensor (element stride `mul` in the map).
+struct SrcView {
+  int map;       // index into ConvMaps::act
+  int img_base;
+  int ch0;
+  int mul;
+  int off_x, off_y;
 };
 
 struct ConvProblem {
   int n_src;                  // A sources of this problem (each 64*kb_per_src channels)
-  int src_img_base[kMaxSrc];  // image index of source s that pairs with output image 0
+  SrcView src[kMaxSrc];
   int w_row_base;             // first row of this problem's weights in the packed weight matrix
   const float* bias;          // [n_total] fp32 in packed column order (nullptr = none)
   // EPI_STORE / EPI_PS
@@ -34,6 +48,9 @@ struct ConvProblem {
   float* out_f32;             // NHWC fp32 (nullptr = skip)
   const __nv_bfloat16* res;   // optional residual, same shape as out_bf16
   const float* posterm;       // optional [n_img][16][n_total] border-class additive term
+  // EPI_GRAD: fp32 [n_img][H][W][64]; split: cols [0,64) -> grad0, [64,128) -> grad1; else cols [0,64) -> both
+  float* grad0;
+  float* grad1;
   // EPI_LSTM
   const float* c_in;          // cell state, tile-transposed [tile][64][128] fp32 (nullptr = zeros)
   float* c_out;               // same layout (may alias c_in)
@@ -55,24 +72,30 @@ struct ConvParams {
   int n_store;       // columns per N tile that are real outputs (<= BN, multiple of 16)
   int out_ch;        // channels per pixel of the output tensor
   int ps_r;          // pixel-shuffle factor for EPI_PS
+  int grad_split;    // EPI_GRAD column routing (see ConvProblem)
   ConvProblem prob[kMaxProb];
 };
 
-// Launches the tcgen05 kernel. `tm_act` is a 4D map (C, W, H, images) with box (64, TW, TH, 1) and
-// 128B swizzle; `tm_w` a 2D map (64, rows) with box (64, BN).  Returns a cudaError_t as int.
-int launch_conv3x3(int bn, int epi, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvParams& p,
-                   int num_sms, cudaStream_t stream);
+struct ConvMaps {
+  CUtensorMap act[kMaxMaps];  // 4D (C, W, H, images), box (64, TW*mul, TH*mul, 1), element strides (1,mul,mul,1)
+  CUtensorMap w;              // 2D (64, rows), box (64, BN)
+};
+
+// Launches the tcgen05 kernel.  Returns a cudaError_t as int.
+int launch_conv3x3(int bn, int epi, const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream);
 
 // Host helpers (tensormap.cpp)
-int make_act_tmap(CUtensorMap* out, const void* base, int channels, int W, int H, long long images, int tw, int th);
+int make_act_tmap(CUtensorMap* out, const void* base, int channels, int W, int H, long long images, int tw, int th,
+                  int mul = 1);
 int make_weight_tmap(CUtensorMap* out, const void* base, long long rows, int bn);
 
-inline void choose_tile(int H, int W, int* tw_log2_out) {
-  // Pick TW in {8,...,128} (TH = 128/TW) minimising padded work; ties -> wider tiles (longer TMA rows).
+inline void choose_tile(int H, int W, int* tw_log2_out, int max_tw = 128) {
+  // Pick TW in {8,...,max_tw} (TH = 128/TW) minimising padded work; ties -> wider tiles (longer TMA rows).
   long long best = -1;
-  int best_l = 7;
+  int best_l = 3;
   for (int l = 7; l >= 3; --l) {
     int tw = 1 << l, th = 128 >> l;
+    if (tw > max_tw) continue;
     long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
     if (best < 0 || tiles < best) { best = tiles; best_l = l; }
   }

@@ -85,8 +85,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
-                  const __grid_constant__ ConvParams p) {
+conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
   using C = Cfg<BN>;
   constexpr int S = C::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -106,8 +105,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
   const int total_tiles = p.n_prob * p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
 
   if (warp == 0 && elect_one()) {
-    prefetch_tmap(&tm_act);
-    prefetch_tmap(&tm_w);
+    prefetch_tmap(&maps.act[0]);
+    prefetch_tmap(&maps.w);
     for (int i = 0; i < S; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -142,15 +141,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
         const ConvProblem& pr = p.prob[tc.z];
         int wrow = pr.w_row_base + tc.nt * BN;
         for (int s = 0; s < pr.n_src; ++s) {
-          const int img = pr.src_img_base[s] + tc.img;
+          const SrcView& sv = pr.src[s];
+          const int img = sv.img_base + tc.img;
+          const CUtensorMap* tm = &maps.act[sv.map];
           for (int ti = 0; ti < p.taps; ++ti) {
             const int tap = (p.taps == 9) ? ti : 4;
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const int cx = sv.mul * (tc.x0 + tap % 3 - 1) + sv.off_x;
+            const int cy = sv.mul * (tc.y0 + tap / 3 - 1) + sv.off_y;
             for (int cb = 0; cb < p.kb_per_src; ++cb) {
               mbar_wait(&empty[stage], phase ^ 1);
               mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
-              tma_load_4d(smem_a + stage * kABytes, &tm_act, &full[stage], cb * kBlockK, tc.x0 + dx, tc.y0 + dy, img);
-              tma_load_2d(smem_b + stage * C::kBBytes, &tm_w, &full[stage], 0, wrow);
+              tma_load_4d(smem_a + stage * kABytes, tm, &full[stage], sv.ch0 + cb * kBlockK, cx, cy, img);
+              tma_load_2d(smem_b + stage * C::kBBytes, &maps.w, &full[stage], 0, wrow);
               wrow += p.n_total;
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
@@ -270,6 +272,41 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
             dst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
           }
         }
+      } else if constexpr (EPI == EPI_GRAD) {
+        // fp32 accumulation into NHWC 64-channel gradient tensors (data gradients of the convs).
+        const int nchunks = p.n_store >> 4;
+        const size_t pixoff = ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * 64;
+#pragma unroll 1
+        for (int ck = half; ck < nchunks; ck += 2) {
+          uint32_t v[16];
+          tmem_ld16(taddr + ck * 16, v);
+          tmem_ld_wait();
+          if (valid) {
+            float* d0 = p.grad_split ? ((ck < 4) ? pr.grad0 : pr.grad1) : pr.grad0;
+            float* d1 = p.grad_split ? nullptr : pr.grad1;
+            const int c0 = (ck & 3) * 16;
+            if (d0) {
+              float4* q = reinterpret_cast<float4*>(d0 + pixoff + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float4 o = q[j];
+                o.x += __uint_as_float(v[4 * j]); o.y += __uint_as_float(v[4 * j + 1]);
+                o.z += __uint_as_float(v[4 * j + 2]); o.w += __uint_as_float(v[4 * j + 3]);
+                q[j] = o;
+              }
+            }
+            if (d1) {
+              float4* q = reinterpret_cast<float4*>(d1 + pixoff + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float4 o = q[j];
+                o.x += __uint_as_float(v[4 * j]); o.y += __uint_as_float(v[4 * j + 1]);
+                o.z += __uint_as_float(v[4 * j + 2]); o.w += __uint_as_float(v[4 * j + 3]);
+                q[j] = o;
+              }
+            }
+          }
+        }
       } else {
         // EPI_STORE / EPI_PS: 16-column chunks, alternating between the two warp halves.
         const int nchunks = p.n_store >> 4;
@@ -348,8 +385,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
 }
 
 template <int BN, int EPI>
-static int launch_t(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvParams& p, int num_sms,
-                    cudaStream_t stream) {
+static int launch_t(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<BN>;
   auto kern = conv3x3_tc_kernel<BN, EPI>;
   static bool attr_set = false;
@@ -361,24 +397,29 @@ static int launch_t(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const Co
   const long long total = 1LL * p.n_prob * p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
   if (total <= 0) return 0;
   const int grid = static_cast<int>(total < num_sms ? total : num_sms);
-  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(tm_act, tm_w, p);
+  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(maps, p);
   return static_cast<int>(cudaGetLastError());
 }
 
-int launch_conv3x3(int bn, int epi, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvParams& p,
-                   int num_sms, cudaStream_t stream) {
-  if (epi == EPI_LSTM && bn == 256) return launch_t<256, EPI_LSTM>(tm_act, tm_w, p, num_sms, stream);
+int launch_conv3x3(int bn, int epi, const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
+  if (epi == EPI_LSTM && bn == 256) return launch_t<256, EPI_LSTM>(maps, p, num_sms, stream);
   if (epi == EPI_STORE) {
     switch (bn) {
-      case 64: return launch_t<64, EPI_STORE>(tm_act, tm_w, p, num_sms, stream);
-      case 144: return launch_t<144, EPI_STORE>(tm_act, tm_w, p, num_sms, stream);
-      case 256: return launch_t<256, EPI_STORE>(tm_act, tm_w, p, num_sms, stream);
+      case 64: return launch_t<64, EPI_STORE>(maps, p, num_sms, stream);
+      case 144: return launch_t<144, EPI_STORE>(maps, p, num_sms, stream);
+      case 256: return launch_t<256, EPI_STORE>(maps, p, num_sms, stream);
     }
   }
   if (epi == EPI_PS) {
     switch (bn) {
-      case 192: return launch_t<192, EPI_PS>(tm_act, tm_w, p, num_sms, stream);
-      case 256: return launch_t<256, EPI_PS>(tm_act, tm_w, p, num_sms, stream);
+      case 192: return launch_t<192, EPI_PS>(maps, p, num_sms, stream);
+      case 256: return launch_t<256, EPI_PS>(maps, p, num_sms, stream);
+    }
+  }
+  if (epi == EPI_GRAD) {
+    switch (bn) {
+      case 64: return launch_t<64, EPI_GRAD>(maps, p, num_sms, stream);
+      case 128: return launch_t<128, EPI_GRAD>(maps, p, num_sms, stream);
     }
   }
   return static_cast<int>(cudaErrorInvalidValue);

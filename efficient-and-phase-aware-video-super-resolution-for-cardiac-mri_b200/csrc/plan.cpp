@@ -89,7 +89,7 @@ struct pvsr_plan {
   int num_sms = 0;
   const void* maps_ws = nullptr;
   const void* maps_pk = nullptr;
-  CUtensorMap tm_act, tm_mid, tm_head_in[PVSR_MAX_HEAD_CONVS], tm_w_lstm, tm_w_c1, tm_w_c2, tm_w_head[PVSR_MAX_HEAD_CONVS];
+  ConvMaps maps_lstm, maps_c1, maps_c2, maps_head[PVSR_MAX_HEAD_CONVS];   // act[0] + packed weights of each launch kind
   std::map<GraphKey, cudaGraphExec_t> graphs;
   cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's stream may be the legacy stream)
 
@@ -137,6 +137,7 @@ pvsr_pack_spec make_spec(int c_out, int c_in, int k, int n_src, const int* offs,
   s.c_out = c_out; s.c_in = c_in; s.kh = k; s.kw = k; s.n_src = n_src;
   for (int i = 0; i < n_src; ++i) s.src_ch_off[i] = offs[i];
   s.src_ch = src_ch; s.kb_per_src = kb; s.taps = taps; s.n_total = n_total; s.ps_r = ps_r; s.transpose_flip = 0;
+  s.k_ps_r = 0;
   return s;
 }
 
@@ -203,12 +204,13 @@ void base_params(const pvsr_plan* p, const Tiling& t, int H, int W, ConvParams* 
   (void)p;
 }
 
-void run_conv(Ctx& c, int cls, int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tw, const ConvParams& cp,
-              double fl) {
+inline SrcView view0(long long img_base) { return SrcView{0, static_cast<int>(img_base), 0, 1, 0, 0}; }
+
+void run_conv(Ctx& c, int cls, int bn, int epi, const ConvMaps& maps, const ConvParams& cp, double fl) {
   if (c.rc) return;
   c.begin(cls);
   if (!c.dry) {
-    int e = launch_conv3x3(bn, epi, ta, tw, cp, c.p->num_sms, c.stream);
+    int e = launch_conv3x3(bn, epi, maps, cp, c.p->num_sms, c.stream);
     if (e) c.rc = check_cuda(e, "conv3x3 launch");
   }
   c.end(cls, fl);
@@ -268,10 +270,10 @@ void schedule(Ctx& c) {
           const int jp = dir == 0 ? j - 1 : j + 1;
           ConvProblem& pr = cp.prob[np++];
           const long long xin = (l == 0 ? p->img_x[s] : p->img_h[dir][l - 1]) + static_cast<long long>(j) * B;
-          pr.src_img_base[0] = static_cast<int>(xin);
+          pr.src[0] = view0(xin);
           pr.n_src = 1;
           if (p->lstm_src == 2 && t > 0) {
-            pr.src_img_base[1] = static_cast<int>(p->img_h[dir][l] + static_cast<long long>(jp) * B);
+            pr.src[1] = view0(p->img_h[dir][l] + static_cast<long long>(jp) * B);
             pr.n_src = 2;
           }
           const int ci = dir * NL + l;
@@ -283,7 +285,7 @@ void schedule(Ctx& c) {
           pr.h_out = act_img(c, p->img_h[dir][l] + static_cast<long long>(j) * B);
         }
       cp.n_prob = np;
-      run_conv(c, CLS_LSTM, 256, EPI_LSTM, p->tm_act, p->tm_w_lstm, cp, lstm_fl * px * B * np);
+      run_conv(c, CLS_LSTM, 256, EPI_LSTM, p->maps_lstm, cp, lstm_fl * px * B * np);
     }
 
     // ---------------------------------------------------------------- refine block -> next-stage features
@@ -296,8 +298,8 @@ void schedule(Ctx& c) {
       cp.n_prob = 1;
       pr.n_src = 2 * p->Wn;
       for (int jw = 0; jw < p->Wn; ++jw) {
-        pr.src_img_base[2 * jw] = static_cast<int>(hf_top + static_cast<long long>(jw) * B);
-        pr.src_img_base[2 * jw + 1] = static_cast<int>(hb_top + static_cast<long long>(jw) * B);
+        pr.src[2 * jw] = view0(hf_top + static_cast<long long>(jw) * B);
+        pr.src[2 * jw + 1] = view0(hb_top + static_cast<long long>(jw) * B);
       }
       const __nv_bfloat16* res = act_img(c, p->img_x[s] + static_cast<long long>(half) * B);
       __nv_bfloat16* xnext = act_img(c, p->img_x[s + 1] + static_cast<long long>(half) * B);
@@ -305,7 +307,7 @@ void schedule(Ctx& c) {
         cp.n_total = 144; cp.n_store = 144; cp.out_ch = 144;
         pr.posterm = posterm;
         pr.out_bf16 = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_mid);
-        run_conv(c, CLS_CONV1, 144, EPI_STORE, p->tm_act, p->tm_w_c1, cp,
+        run_conv(c, CLS_CONV1, 144, EPI_STORE, p->maps_c1, cp,
                  2.0 * 9 * (2 * kFeat + 1) * p->Wn * (2 * kFeat + 1) * px * cp.n_img);
         ConvParams c2;
         base_params(p, p->lr, p->h, p->w, &c2);
@@ -315,11 +317,11 @@ void schedule(Ctx& c) {
         c2.n_total = 64; c2.n_store = 64; c2.out_ch = 64;
         ConvProblem& p2 = c2.prob[0];
         p2.n_src = 1;
-        p2.src_img_base[0] = 0;
+        p2.src[0] = view0(0);
         p2.bias = reinterpret_cast<const float*>(c.pk + p->pk_c2_b);
         p2.res = res;
         p2.out_bf16 = xnext;
-        run_conv(c, CLS_CONV2, 64, EPI_STORE, p->tm_mid, p->tm_w_c2, c2,
+        run_conv(c, CLS_CONV2, 64, EPI_STORE, p->maps_c2, c2,
                  2.0 * 9 * (2 * kFeat + 1) * kFeat * px * c2.n_img);
       } else {
         cp.taps = 1;
@@ -327,7 +329,7 @@ void schedule(Ctx& c) {
         pr.bias = reinterpret_cast<const float*>(c.pk + p->pk_c2_b);
         pr.res = res;
         pr.out_bf16 = xnext;
-        run_conv(c, CLS_CONV1, 64, EPI_STORE, p->tm_act, p->tm_w_c1, cp,
+        run_conv(c, CLS_CONV1, 64, EPI_STORE, p->maps_c1, cp,
                  2.0 * (2 * kFeat) * p->Wn * kFeat * px * cp.n_img);
       }
     }
@@ -359,10 +361,10 @@ void schedule(Ctx& c) {
         cp.ps_r = p->ps_r[q];
         ConvProblem& pr = cp.prob[0];
         pr.n_src = 1;
-        pr.src_img_base[0] = q == 0 ? static_cast<int>(in_img) : 0;
+        pr.src[0] = view0(q == 0 ? in_img : 0);
         pr.bias = reinterpret_cast<const float*>(c.pk + p->pk_head_b[q]);
         pr.out_bf16 = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_head[q]);
-        run_conv(c, CLS_HEAD_PS, p->ps_bn[q], EPI_PS, q == 0 ? p->tm_act : p->tm_head_in[q], p->tm_w_head[q], cp,
+        run_conv(c, CLS_HEAD_PS, p->ps_bn[q], EPI_PS, p->maps_head[q], cp,
                  2.0 * 9 * kFeat * (kFeat * p->ps_r[q] * p->ps_r[q]) * p->ps_h[q] * p->ps_w[q] * n_head);
       }
       c.begin(CLS_HEAD_LAST);
@@ -389,18 +391,23 @@ int build_maps(pvsr_plan* p, const void* ws, const void* pk) {
   const uint8_t* w = static_cast<const uint8_t*>(ws);
   const uint8_t* k = static_cast<const uint8_t*>(pk);
   int rc = 0;
-  rc |= make_act_tmap(&p->tm_act, w + p->off_act, kFeat, p->w, p->h, p->act_images, p->lr.tw, p->lr.th);
+  CUtensorMap tm_act;
+  rc |= make_act_tmap(&tm_act, w + p->off_act, kFeat, p->w, p->h, p->act_images, p->lr.tw, p->lr.th);
+  p->maps_lstm.act[0] = tm_act;
+  p->maps_c1.act[0] = tm_act;
+  p->maps_head[0].act[0] = tm_act;
   if (p->cfg.pos_enc)
-    rc |= make_act_tmap(&p->tm_mid, w + p->off_mid, 144, p->w, p->h, static_cast<long long>(p->n_win) * p->B, p->lr.tw,
-                        p->lr.th);
+    rc |= make_act_tmap(&p->maps_c2.act[0], w + p->off_mid, 144, p->w, p->h, static_cast<long long>(p->n_win) * p->B,
+                        p->lr.tw, p->lr.th);
   for (int q = 1; q < p->n_ps; ++q)
-    rc |= make_act_tmap(&p->tm_head_in[q], w + p->off_head[q - 1], kFeat, p->ps_w[q], p->ps_h[q],
+    rc |= make_act_tmap(&p->maps_head[q].act[0], w + p->off_head[q - 1], kFeat, p->ps_w[q], p->ps_h[q],
                         static_cast<long long>(p->T) * p->B, p->ps_tile[q].tw, p->ps_tile[q].th);
-  rc |= make_weight_tmap(&p->tm_w_lstm, k + p->pk_lstm_w, static_cast<long long>(2 * p->NL) * p->lstm_rows_per_cell, 256);
-  rc |= make_weight_tmap(&p->tm_w_c1, k + p->pk_c1_w, p->c1_rows, p->cfg.pos_enc ? 144 : 64);
-  if (p->cfg.pos_enc) rc |= make_weight_tmap(&p->tm_w_c2, k + p->pk_c2_w, p->c2_rows, 64);
+  rc |= make_weight_tmap(&p->maps_lstm.w, k + p->pk_lstm_w, static_cast<long long>(2 * p->NL) * p->lstm_rows_per_cell,
+                         256);
+  rc |= make_weight_tmap(&p->maps_c1.w, k + p->pk_c1_w, p->c1_rows, p->cfg.pos_enc ? 144 : 64);
+  if (p->cfg.pos_enc) rc |= make_weight_tmap(&p->maps_c2.w, k + p->pk_c2_w, p->c2_rows, 64);
   for (int q = 0; q < p->n_ps; ++q)
-    rc |= make_weight_tmap(&p->tm_w_head[q], k + p->pk_head_w[q], p->head_rows[q], p->ps_bn[q]);
+    rc |= make_weight_tmap(&p->maps_head[q].w, k + p->pk_head_w[q], p->head_rows[q], p->ps_bn[q]);
   if (rc) return set_error(-20, "tensor map encode failed");
   p->maps_ws = ws;
   p->maps_pk = pk;

@@ -24,13 +24,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // NHWC bf16 activation tensor viewed as (C, W, H, images); box = (64 channels, tw, th, 1 image).
-int make_act_tmap(CUtensorMap* out, const void* base, int channels, int W, int H, long long images, int tw, int th) {
+// mul > 1: pixel-unshuffled view - every mul-th pixel in x and y (element strides), box spans tw*mul x th*mul.
+int make_act_tmap(CUtensorMap* out, const void* base, int channels, int W, int H, long long images, int tw, int th,
+                  int mul) {
   auto fn = get_encode_fn();
   if (!fn) return -100;
   cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)images};
   cuuint64_t strides[3] = {(cuuint64_t)channels * 2, (cuuint64_t)W * channels * 2, (cuuint64_t)H * W * channels * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (tw * mul > 256 || th * mul > 256) return -101;
+  cuuint32_t box[4] = {64, (cuuint32_t)(tw * mul), (cuuint32_t)(th * mul), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)mul, (cuuint32_t)mul, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(CSRC, "libpvsr.so")
 MAX_SRC = 10
 MAX_LAYERS = 8
 MAX_HEAD_CONVS = 4
-EPI_STORE, EPI_PS, EPI_LSTM = 0, 1, 2
+MAX_VIEWS = 4
+EPI_STORE, EPI_PS, EPI_LSTM, EPI_GRAD = 0, 1, 2, 3
 
 c_void_p, c_int, c_int64, c_float_p, c_int32_p = C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p
 
@@ -21,16 +22,24 @@ c_void_p, c_int, c_int64, c_float_p, c_int32_p = C.c_void_p, C.c_int, C.c_int64,
 class PackSpec(C.Structure):
     _fields_ = [("c_out", c_int), ("c_in", c_int), ("kh", c_int), ("kw", c_int), ("n_src", c_int),
                 ("src_ch_off", c_int * MAX_SRC), ("src_ch", c_int), ("kb_per_src", c_int), ("taps", c_int),
-                ("n_total", c_int), ("ps_r", c_int), ("transpose_flip", c_int)]
+                ("n_total", c_int), ("ps_r", c_int), ("transpose_flip", c_int), ("k_ps_r", c_int)]
+
+
+class ActView(C.Structure):
+    _fields_ = [("ptr", c_void_p), ("channels", c_int), ("W", c_int), ("H", c_int), ("images", c_int64),
+                ("mul", c_int)]
 
 
 class ConvDesc(C.Structure):
     _fields_ = [("epi", c_int), ("bn", c_int), ("H", c_int), ("W", c_int), ("n_img", c_int64),
-                ("act", c_void_p), ("act_channels", c_int), ("act_images", c_int64), ("n_src", c_int),
-                ("src_img_base", c_int * MAX_SRC), ("kb_per_src", c_int), ("k16_last", c_int), ("taps", c_int),
+                ("n_views", c_int), ("views", ActView * MAX_VIEWS), ("n_src", c_int),
+                ("src_view", c_int * MAX_SRC), ("src_img_base", c_int * MAX_SRC), ("src_ch0", c_int * MAX_SRC),
+                ("src_off_x", c_int * MAX_SRC), ("src_off_y", c_int * MAX_SRC),
+                ("kb_per_src", c_int), ("k16_last", c_int), ("taps", c_int),
                 ("w_packed", c_void_p), ("w_rows", c_int64), ("w_row_base", c_int), ("n_tiles_n", c_int),
                 ("bias", c_void_p), ("out_bf16", c_void_p), ("out_f32", c_void_p), ("res", c_void_p),
                 ("posterm", c_void_p), ("out_ch", c_int), ("n_store", c_int), ("ps_r", c_int),
+                ("grad0", c_void_p), ("grad1", c_void_p), ("grad_split", c_int),
                 ("c_in", c_void_p), ("c_out", c_void_p), ("h_out", c_void_p), ("gates_out", c_void_p)]
 
 

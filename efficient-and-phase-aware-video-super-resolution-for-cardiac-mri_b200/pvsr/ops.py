@@ -12,14 +12,14 @@ from . import lib as L
 
 
 # ------------------------------------------------------------------------------------------------ pack specs
-def _spec(c_out, c_in, k, n_src, offs, src_ch, kb_per_src, taps, n_total, ps_r=0, transpose_flip=0):
+def _spec(c_out, c_in, k, n_src, offs, src_ch, kb_per_src, taps, n_total, ps_r=0, transpose_flip=0, k_ps_r=0):
     s = L.PackSpec()
     s.c_out, s.c_in, s.kh, s.kw = c_out, c_in, k, k
     s.n_src = n_src
     for i, o in enumerate(offs):
         s.src_ch_off[i] = o
     s.src_ch, s.kb_per_src, s.taps, s.n_total = src_ch, kb_per_src, taps, n_total
-    s.ps_r, s.transpose_flip = ps_r, transpose_flip
+    s.ps_r, s.transpose_flip, s.k_ps_r = ps_r, transpose_flip, k_ps_r
     return s
 
 
@@ -100,21 +100,36 @@ def in_conv_prelu(x, w, b, slope):
     return out
 
 
-def conv3x3(act, src_img_base, n_img, w_packed, bn, epi=L.EPI_STORE, kb_per_src=1, k16_last=4, taps=9, bias=None,
+def conv3x3(act, srcs, n_img, w_packed, bn, epi=L.EPI_STORE, kb_per_src=1, k16_last=4, taps=9, bias=None,
             n_tiles_n=1, w_row_base=0, out_bf16=None, out_f32=None, res=None, posterm=None, out_ch=None,
-            n_store=None, ps_r=0, c_in=None, c_out=None, h_out=None, gates_out=None):
-    """Generic launch of the tcgen05 implicit-GEMM conv. `act` is [images, H, W, C] bf16 holding all sources."""
+            n_store=None, ps_r=0, c_in=None, c_out=None, h_out=None, gates_out=None, grad0=None, grad1=None,
+            grad_split=0, out_hw=None):
+    """Generic launch of the tcgen05 implicit-GEMM conv.
+
+    act  : one bf16 tensor [images, H, W, C], or a list of views (tensor, mul) - mul > 1 reads the pixel-unshuffled
+           image of a tensor mul x larger than the output.
+    srcs : per source either an image base (view 0) or a tuple (view, img_base, ch0, off_x, off_y).
+    """
     lib = L.load()
+    views = act if isinstance(act, (list, tuple)) else [(act, 1)]
     d = L.ConvDesc()
     d.epi, d.bn = epi, bn
-    d.H, d.W = act.shape[1], act.shape[2]
+    if out_hw is None:
+        t0, m0 = views[0]
+        out_hw = (t0.shape[1] // m0, t0.shape[2] // m0)
+    d.H, d.W = out_hw
     d.n_img = n_img
-    d.act = act.data_ptr()
-    d.act_channels = act.shape[3]
-    d.act_images = act.shape[0]
-    d.n_src = len(src_img_base)
-    for i, v in enumerate(src_img_base):
-        d.src_img_base[i] = v
+    d.n_views = len(views)
+    for i, (t, mul) in enumerate(views):
+        d.views[i].ptr = t.data_ptr()
+        d.views[i].channels = t.shape[3]
+        d.views[i].H, d.views[i].W = t.shape[1], t.shape[2]
+        d.views[i].images = t.shape[0]
+        d.views[i].mul = mul
+    d.n_src = len(srcs)
+    for i, v in enumerate(srcs):
+        view, base, ch0, ox, oy = v if isinstance(v, (list, tuple)) else (0, v, 0, 0, 0)
+        d.src_view[i], d.src_img_base[i], d.src_ch0[i], d.src_off_x[i], d.src_off_y[i] = view, base, ch0, ox, oy
     d.kb_per_src, d.k16_last, d.taps = kb_per_src, k16_last, taps
     d.w_packed = w_packed.data_ptr()
     d.w_rows = w_packed.shape[0]
@@ -122,11 +137,12 @@ def conv3x3(act, src_img_base, n_img, w_packed, bn, epi=L.EPI_STORE, kb_per_src=
     d.n_tiles_n = n_tiles_n
     for name, t in (("bias", bias), ("out_bf16", out_bf16), ("out_f32", out_f32), ("res", res),
                     ("posterm", posterm), ("c_in", c_in), ("c_out", c_out), ("h_out", h_out),
-                    ("gates_out", gates_out)):
+                    ("gates_out", gates_out), ("grad0", grad0), ("grad1", grad1)):
         setattr(d, name, None if t is None else t.data_ptr())
     d.out_ch = out_ch if out_ch is not None else bn * n_tiles_n
     d.n_store = n_store if n_store is not None else bn
     d.ps_r = ps_r
+    d.grad_split = grad_split
     L.check(lib.pvsr_conv3x3_fwd(C.byref(d), L.current_stream()), "conv3x3")
 
 

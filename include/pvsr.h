@@ -28,7 +28,7 @@ extern "C" {
 #define PVSR_MAX_LAYERS 8
 #define PVSR_MAX_HEAD_CONVS 4
 
-enum { PVSR_EPI_STORE = 0, PVSR_EPI_PS = 1, PVSR_EPI_LSTM = 2 };
+enum { PVSR_EPI_STORE = 0, PVSR_EPI_PS = 1, PVSR_EPI_LSTM = 2, PVSR_EPI_GRAD = 3 };
 
 /* ---- library ------------------------------------------------------------------------------------------------ */
 int pvsr_version(void);
@@ -58,6 +58,8 @@ typedef struct pvsr_pack_spec {
   int n_total;
   int ps_r;
   int transpose_flip;
+  int k_ps_r;   /* transpose_flip only: K channel ic of source s is parameter output channel ic*k_ps_r^2 + s
+                   (sources = sub-pixels of a pixel-unshuffled gradient); 0 = src_ch_off[s] + ic */
 } pvsr_pack_spec;
 int64_t pvsr_pack_index_count(const pvsr_pack_spec* spec);
 int pvsr_pack_index_host(const pvsr_pack_spec* spec, int32_t* idx_host);
@@ -74,17 +76,32 @@ int pvsr_gather_f32(const float* src, const int32_t* idx, float* out, int64_t n,
 int pvsr_in_conv_prelu_fwd(const float* x, const float* w, const float* b, const float* slope, void* out_bf16,
                            int64_t n_img, int H, int W, void* stream);
 
-/* Generic tcgen05 implicit-GEMM conv3x3 (padding 1).  One descriptor = one problem. */
+/* Generic tcgen05 implicit-GEMM conv3x3 (padding 1).  One descriptor = one problem.
+ * Sources are 64-channel-block views of up to PVSR_MAX_VIEWS bf16 NHWC tensors.  A view with mul > 1 reads the
+ * pixel-UNshuffled image (every mul-th pixel starting at (off_x, off_y)) of a tensor that is mul x larger than the
+ * output - the adjoint of nn.PixelShuffle (refine_net.py:200,204), used by the data/weight gradients of the head. */
+#define PVSR_MAX_VIEWS 4
+typedef struct pvsr_act_view {
+  const void* ptr;         /* bf16 [images][H][W][channels] */
+  int channels;
+  int W, H;
+  int64_t images;
+  int mul;                 /* 1, or the pixel-shuffle factor for unshuffled views */
+} pvsr_act_view;
+
 typedef struct pvsr_conv_desc {
   int epi;                 /* PVSR_EPI_* */
-  int bn;                  /* N tile: 64, 144, 192 or 256 (LSTM: 256) */
-  int H, W;
+  int bn;                  /* N tile: 64, 128, 144, 192 or 256 (LSTM: 256) */
+  int H, W;                /* output image size */
   int64_t n_img;           /* output images */
-  const void* act;         /* bf16 NHWC activation tensor holding every source image */
-  int act_channels;        /* channels per pixel of `act` (64 or 144) */
-  int64_t act_images;      /* images in `act` */
+  int n_views;
+  pvsr_act_view views[PVSR_MAX_VIEWS];
   int n_src;
+  int src_view[PVSR_MAX_SRC];
   int src_img_base[PVSR_MAX_SRC];
+  int src_ch0[PVSR_MAX_SRC];
+  int src_off_x[PVSR_MAX_SRC];
+  int src_off_y[PVSR_MAX_SRC];
   int kb_per_src;          /* 64-channel K blocks per source */
   int k16_last;            /* K=16 slices used in the last K block of a source (4 = all) */
   int taps;                /* 9 or 1 */
@@ -101,6 +118,11 @@ typedef struct pvsr_conv_desc {
   int out_ch;
   int n_store;
   int ps_r;
+  /* PVSR_EPI_GRAD: fp32 [n_img][H][W][64] accumulated in place.  grad_split: columns [0,64) -> grad0 and
+   * [64,128) -> grad1; otherwise columns [0,64) are added to both (NULL = skip). */
+  float* grad0;
+  float* grad1;
+  int grad_split;
   /* PVSR_EPI_LSTM (ConvLSTMCell.forward, refine_net.py:247-267) */
   const float* c_in;       /* tile-transposed fp32 state or NULL (= zeros) */
   float* c_out;

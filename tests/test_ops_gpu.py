@@ -254,3 +254,79 @@ def test_add_bf16(pvsr_lib):
     out = ops.add_bf16(a, b)
     torch.cuda.synchronize()
     assert torch.equal(out, (a.float() + b.float()).to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------ data gradients
+def _autograd_dx(fn, x, gy):
+    x = x.clone().requires_grad_(True)
+    y = fn(x)
+    (gx,) = torch.autograd.grad(y, x, gy)
+    return gx
+
+
+def test_dgrad_plain_conv_accumulates(pvsr_lib):
+    """dX of a 64->256 conv = conv of dY with the transposed, spatially flipped weights; EPI_GRAD does +=."""
+    from pvsr import ops, lib as L
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n, H, W = 3, 20, 27
+    w = _rand(256, 64, 3, 3, gen=g, scale=0.05)
+    gy = _rand(n, 256, H, W, gen=g)
+    x = torch.randn(n, 64, H, W, generator=g, device="cuda")
+    ref = _autograd_dx(lambda t: F.conv2d(t, w, None, padding=1), x, gy)
+    spec = ops._spec(256, 64, 3, 1, [0], 256, 4, 9, 64, transpose_flip=1)
+    wp = ops.pack_weight(w, spec)
+    acc0 = torch.randn(n, H, W, 64, generator=g, device="cuda")
+    acc = acc0.clone()
+    ops.conv3x3(nhwc(gy), [0], n, wp, 64, epi=L.EPI_GRAD, kb_per_src=4, grad0=acc, n_store=64)
+    torch.cuda.synchronize()
+    got = (acc - acc0).permute(0, 3, 1, 2)
+    assert torch.allclose(got, ref, atol=3e-3, rtol=1e-3), (got - ref).abs().max()
+
+
+def test_dgrad_lstm_split(pvsr_lib):
+    """ConvLSTM gate conv (128 -> 256): d[x | h] in one launch, routed to two gradient tensors."""
+    from pvsr import ops, lib as L
+    g = torch.Generator(device="cuda").manual_seed(12)
+    n, H, W = 2, 32, 32
+    w = _rand(256, 128, 3, 3, gen=g, scale=0.04)
+    gy = _rand(n, 256, H, W, gen=g)
+    xin = torch.randn(n, 128, H, W, generator=g, device="cuda")
+    ref = _autograd_dx(lambda t: F.conv2d(t, w, None, padding=1), xin, gy)
+    spec = ops._spec(256, 128, 3, 1, [0], 256, 4, 9, 128, transpose_flip=1)
+    wp = ops.pack_weight(w, spec)
+    d0 = torch.zeros(n, H, W, 64, device="cuda")
+    d1 = torch.zeros(n, H, W, 64, device="cuda")
+    ops.conv3x3(nhwc(gy), [0], n, wp, 128, epi=L.EPI_GRAD, kb_per_src=4, grad0=d0, grad1=d1, grad_split=1,
+                n_store=128)
+    torch.cuda.synchronize()
+    got = torch.cat([d0, d1], dim=3).permute(0, 3, 1, 2)
+    assert torch.allclose(got, ref, atol=3e-3, rtol=1e-3), (got - ref).abs().max()
+    # dual (non-split) routing: the same 64 columns added to two tensors
+    spec64 = ops._spec(256, 64, 3, 1, [0], 256, 4, 9, 64, transpose_flip=1)
+    w64 = _rand(256, 64, 3, 3, gen=g, scale=0.04)
+    a, b = torch.zeros(n, H, W, 64, device="cuda"), torch.ones(n, H, W, 64, device="cuda")
+    ops.conv3x3(nhwc(gy), [0], n, ops.pack_weight(w64, spec64), 64, epi=L.EPI_GRAD, kb_per_src=4, grad0=a, grad1=b,
+                n_store=64)
+    torch.cuda.synchronize()
+    assert torch.equal(a + 1.0, b)
+
+
+@pytest.mark.parametrize("r,H,W", [(2, 27, 31), (3, 12, 14), (2, 64, 126)])
+def test_dgrad_pixel_shuffle_conv(pvsr_lib, r, H, W):
+    """dX of PixelShuffle(conv(x)): the pixel-unshuffle is done by TMA element strides on the HR gradient."""
+    from pvsr import ops, lib as L
+    g = torch.Generator(device="cuda").manual_seed(13)
+    n = 2
+    w = _rand(64 * r * r, 64, 3, 3, gen=g, scale=0.05)
+    ghr = _rand(n, 64, H * r, W * r, gen=g)
+    x = torch.randn(n, 64, H, W, generator=g, device="cuda")
+    ref = _autograd_dx(lambda t: F.pixel_shuffle(F.conv2d(t, w, None, padding=1), r), x, ghr)
+    spec = ops._spec(64 * r * r, 64, 3, r * r, [0] * (r * r), 64, 1, 9, 64, transpose_flip=1, k_ps_r=r)
+    wp = ops.pack_weight(w, spec)
+    out = torch.zeros(n, H, W, 64, dtype=torch.bfloat16, device="cuda")
+    srcs = [(0, 0, 0, q % r, q // r) for q in range(r * r)]
+    ops.conv3x3([(nhwc(ghr), r)], srcs, n, wp, 64, out_bf16=out, out_hw=(H, W))
+    torch.cuda.synchronize()
+    got = nchw(out)
+    assert rel_l2(got, ref) < 3e-3, rel_l2(got, ref)
+    assert torch.allclose(got, ref, atol=3e-2, rtol=1e-2), (got - ref).abs().max()
