@@ -4,7 +4,9 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "../../include/pvsr.h"
 #include "conv.h"
@@ -82,6 +84,50 @@ int fill_conv_params(const pvsr_conv_desc* d, ConvParams* p) {
   pr.h_out = static_cast<__nv_bfloat16*>(d->h_out);
   pr.gates_out = static_cast<__nv_bfloat16*>(d->gates_out);
   return 0;
+}
+
+void build_wgrad_jobs(const std::vector<WgSource>& srcs, int kb_per_src, int taps, const std::vector<WgChunk>& chunks,
+                      int n_total, bool with_bias, long long dw_off, long long db_off, std::vector<WgJob>* out) {
+  std::vector<WgUnit> units;
+  int kb = 0;
+  for (size_t s = 0; s < srcs.size(); ++s)
+    for (int ti = 0; ti < taps; ++ti) {
+      const int tap = taps == 9 ? ti : 4;
+      for (int cb = 0; cb < kb_per_src; ++cb, ++kb) {
+        WgUnit u{};
+        u.kind = 0;
+        u.view = srcs[s].view;
+        u.view.ch0 += cb * 64;
+        u.dx = tap % 3 - 1;
+        u.dy = tap / 3 - 1;
+        u.out_kb = kb;
+        units.push_back(u);
+      }
+    }
+  if (with_bias) {
+    WgUnit u{};
+    u.kind = 1;
+    units.push_back(u);
+  }
+  for (size_t u0 = 0; u0 < units.size(); u0 += kWgUnits)
+    for (size_t c0 = 0; c0 < chunks.size(); c0 += kWgChunks) {
+      WgJob j{};
+      j.n_units = static_cast<int>(std::min<size_t>(kWgUnits, units.size() - u0));
+      j.n_chunks = static_cast<int>(std::min<size_t>(kWgChunks, chunks.size() - c0));
+      for (int i = 0; i < j.n_units; ++i) j.unit[i] = units[u0 + i];
+      for (int i = 0; i < j.n_chunks; ++i) { j.dy[i] = chunks[c0 + i].view; j.col0[i] = chunks[c0 + i].col0; }
+      j.n_total = n_total;
+      j.dw_off = dw_off;
+      j.db_off = db_off;
+      out->push_back(j);
+    }
+}
+
+int auto_wgrad_splits(int n_jobs, long long total_tiles, int num_sms) {
+  long long s = (2LL * num_sms + n_jobs - 1) / n_jobs;
+  if (s < 1) s = 1;
+  if (s > total_tiles) s = total_tiles;
+  return static_cast<int>(s);
 }
 
 }  // namespace pvsr
@@ -190,6 +236,61 @@ int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream) {
   if (rc) return set_error(rc, "weight tensor map encode failed (%d)", rc);
   return check_cuda(launch_conv3x3(d->bn, d->epi, maps, p, device_num_sms(), static_cast<cudaStream_t>(stream)),
                     "conv3x3");
+}
+
+int64_t pvsr_wgrad_scratch_bytes(void) { return 256 * static_cast<int64_t>(sizeof(WgJob)); }
+
+int pvsr_conv3x3_wgrad(const pvsr_wgrad_desc* d, void* stream) {
+  if (d->n_views < 1 || d->n_views > kMaxMaps) return set_error(-2, "n_views out of range");
+  if (d->n_src < 1 || d->n_src > kMaxSrc || d->n_dy < 1 || d->n_dy > PVSR_MAX_DY) return set_error(-2, "bad source count");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  WgParams p{};
+  p.H = d->H; p.W = d->W;
+  int max_mul = 1;
+  for (int v = 0; v < d->n_views; ++v) max_mul = d->views[v].mul > max_mul ? d->views[v].mul : max_mul;
+  choose_tile(d->H, d->W, &p.tw_log2, max_mul <= 2 ? 128 : 64);
+  const int tw = 1 << p.tw_log2, th = kTileM >> p.tw_log2;
+  p.tiles_x = (d->W + tw - 1) / tw;
+  p.tiles_y = (d->H + th - 1) / th;
+  p.n_img = static_cast<int>(d->n_img);
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int v = 0; v < d->n_views; ++v) {
+    const pvsr_act_view& a = d->views[v];
+    int rc = make_act_tmap(&maps.act[v], a.ptr, a.channels, a.W, a.H, a.images, tw, th, a.mul);
+    if (rc) return set_error(rc, "tensor map encode failed (%d)", rc);
+  }
+  std::vector<WgSource> srcs;
+  for (int i = 0; i < d->n_src; ++i) {
+    const int v = d->src_view[i];
+    srcs.push_back(WgSource{SrcView{v, d->src_img_base[i], d->src_ch0[i], d->views[v].mul, d->src_off_x[i], d->src_off_y[i]}});
+  }
+  std::vector<WgChunk> chunks;
+  for (int i = 0; i < d->n_dy; ++i) {
+    const int v = d->dy_view[i];
+    chunks.push_back(WgChunk{SrcView{v, d->dy_img_base[i], d->dy_ch0[i], d->views[v].mul, d->dy_off_x[i], d->dy_off_y[i]}, 64 * i});
+  }
+  std::vector<WgJob> jobs;
+  build_wgrad_jobs(srcs, d->kb_per_src, d->taps, chunks, d->n_total, d->with_bias != 0, 0,
+                   d->with_bias ? static_cast<long long>(d->db_packed - d->dw_packed) : 0, &jobs);
+  if (jobs.size() > 256) return set_error(-2, "too many wgrad jobs");
+  int e = cudaMemcpyAsync(d->job_scratch, jobs.data(), jobs.size() * sizeof(WgJob), cudaMemcpyHostToDevice, s);
+  if (e) return check_cuda(e, "job upload");
+  e = cudaStreamSynchronize(s);   // the host vector dies at return (test/tool entry point; the plan pre-uploads)
+  if (e) return check_cuda(e, "job upload sync");
+  p.n_jobs = static_cast<int>(jobs.size());
+  const long long total_tiles = static_cast<long long>(p.n_img) * p.tiles_x * p.tiles_y;
+  p.n_splits = d->n_splits > 0 ? d->n_splits : auto_wgrad_splits(p.n_jobs, total_tiles, device_num_sms());
+  if (p.n_splits > total_tiles) p.n_splits = static_cast<int>(total_tiles);
+  p.jobs = static_cast<const WgJob*>(d->job_scratch);
+  p.grad = d->dw_packed;
+  return check_cuda(launch_wgrad(maps, p, s), "wgrad");
+}
+
+int pvsr_scatter_add(float* param_grad, const int32_t* idx, const int32_t* idx2, const float* packed, int64_t n,
+                     void* stream) {
+  return check_cuda(launch_scatter_add(param_grad, idx, idx2, packed, n, static_cast<cudaStream_t>(stream)),
+                    "scatter_add");
 }
 
 int64_t pvsr_lstm_state_elems(int64_t n_img, int H, int W) {

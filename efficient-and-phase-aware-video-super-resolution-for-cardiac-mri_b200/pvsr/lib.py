@@ -43,6 +43,19 @@ class ConvDesc(C.Structure):
                 ("c_in", c_void_p), ("c_out", c_void_p), ("h_out", c_void_p), ("gates_out", c_void_p)]
 
 
+MAX_DY = 9
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("H", c_int), ("W", c_int), ("n_img", c_int64), ("n_views", c_int), ("views", ActView * MAX_VIEWS),
+                ("n_src", c_int), ("src_view", c_int * MAX_SRC), ("src_img_base", c_int * MAX_SRC),
+                ("src_ch0", c_int * MAX_SRC), ("src_off_x", c_int * MAX_SRC), ("src_off_y", c_int * MAX_SRC),
+                ("kb_per_src", c_int), ("taps", c_int), ("n_dy", c_int), ("dy_view", c_int * MAX_DY),
+                ("dy_img_base", c_int * MAX_DY), ("dy_ch0", c_int * MAX_DY), ("dy_off_x", c_int * MAX_DY),
+                ("dy_off_y", c_int * MAX_DY), ("n_total", c_int), ("with_bias", c_int), ("dw_packed", c_void_p),
+                ("db_packed", c_void_p), ("n_splits", c_int), ("job_scratch", c_void_p)]
+
+
 class NetConfig(C.Structure):
     _fields_ = [("batch", c_int), ("n_frames", c_int), ("n_updated", c_int), ("h", c_int), ("w", c_int),
                 ("scale", c_int), ("n_stages", c_int), ("window", c_int), ("n_layers", c_int), ("pos_enc", c_int),
@@ -71,6 +84,9 @@ SIGNATURES = {
                                        c_void_p]),
     "pvsr_conv3x3_fwd": (c_int, [C.POINTER(ConvDesc), c_void_p]),
     "pvsr_lstm_state_elems": (c_int64, [c_int64, c_int, c_int]),
+    "pvsr_wgrad_scratch_bytes": (c_int64, []),
+    "pvsr_conv3x3_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
+    "pvsr_scatter_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "pvsr_refine_posterm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_int, c_void_p]),
     "pvsr_head_conv_last_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,

@@ -190,3 +190,49 @@ def add_bf16(a, b):
     out = torch.empty_like(a)
     L.check(lib.pvsr_add_bf16(L.ptr(a), L.ptr(b), L.ptr(out), a.numel(), L.current_stream()), "add_bf16")
     return out
+
+
+def conv3x3_wgrad(views, srcs, dys, n_img, out_hw, n_total, kb_per_src=1, taps=9, with_bias=True, n_splits=0,
+                  dw=None, db=None):
+    """Weight/bias gradient in packed layout (fp32, accumulated).
+    views: list of (tensor [images,H,W,C] bf16, mul); srcs / dys: tuples (view, img_base, ch0, off_x, off_y)."""
+    lib = L.load()
+    dev = views[0][0].device
+    d = L.WgradDesc()
+    d.H, d.W = out_hw
+    d.n_img = n_img
+    d.n_views = len(views)
+    for i, (t, mul) in enumerate(views):
+        d.views[i].ptr = t.data_ptr()
+        d.views[i].channels = t.shape[3]
+        d.views[i].H, d.views[i].W = t.shape[1], t.shape[2]
+        d.views[i].images = t.shape[0]
+        d.views[i].mul = mul
+    d.n_src = len(srcs)
+    for i, (v, base, ch0, ox, oy) in enumerate(srcs):
+        d.src_view[i], d.src_img_base[i], d.src_ch0[i], d.src_off_x[i], d.src_off_y[i] = v, base, ch0, ox, oy
+    d.n_dy = len(dys)
+    for i, (v, base, ch0, ox, oy) in enumerate(dys):
+        d.dy_view[i], d.dy_img_base[i], d.dy_ch0[i], d.dy_off_x[i], d.dy_off_y[i] = v, base, ch0, ox, oy
+    d.kb_per_src, d.taps, d.n_total, d.with_bias, d.n_splits = kb_per_src, taps, n_total, int(with_bias), n_splits
+    n_kb = len(srcs) * taps * kb_per_src
+    buf = torch.zeros(n_kb * n_total * 64 + n_total, dtype=torch.float32, device=dev) if dw is None else None
+    if dw is None:
+        dw, db = buf[:n_kb * n_total * 64], buf[n_kb * n_total * 64:]
+    d.dw_packed, d.db_packed = dw.data_ptr(), db.data_ptr()
+    scratch = torch.empty(lib.pvsr_wgrad_scratch_bytes(), dtype=torch.uint8, device=dev)
+    d.job_scratch = scratch.data_ptr()
+    L.check(lib.pvsr_conv3x3_wgrad(C.byref(d), L.current_stream()), "conv3x3_wgrad")
+    return dw.view(n_kb, n_total, 64), db
+
+
+def scatter_add(param_grad, spec, packed, bias_grad=None, packed_bias=None):
+    """Packed fp32 gradient -> parameter-layout gradient (+=) through the packing index."""
+    lib = L.load()
+    idx = torch.from_numpy(pack_index(spec)).to(packed.device)
+    L.check(lib.pvsr_scatter_add(L.ptr(param_grad), L.ptr(idx), None, L.ptr(packed), idx.numel(), L.current_stream()),
+            "scatter_add")
+    if bias_grad is not None:
+        bidx = torch.from_numpy(pack_bias_index(spec)).to(packed.device)
+        L.check(lib.pvsr_scatter_add(L.ptr(bias_grad), L.ptr(bidx), None, L.ptr(packed_bias), bidx.numel(),
+                                     L.current_stream()), "scatter_add")

@@ -130,6 +130,43 @@ typedef struct pvsr_conv_desc {
   void* gates_out;         /* optional bf16 [tiles][256][128] */
 } pvsr_conv_desc;
 int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream);
+/* Weight (+ bias) gradient of a conv described like pvsr_conv_desc: X sources (source, tap, channel block) against
+ * the output gradient dY given as `n_dy` 64-column chunks (views; pixel-unshuffled views for conv+PixelShuffle).
+ * Result: fp32, ACCUMULATED, in the layout of the forward packed operand [n_src*taps*kb_per_src][n_total][64]
+ * (scatter to the parameter with the packing index: pvsr_scatter_add) and [n_total] for the bias. */
+#define PVSR_MAX_DY 9
+typedef struct pvsr_wgrad_desc {
+  int H, W;
+  int64_t n_img;
+  int n_views;
+  pvsr_act_view views[PVSR_MAX_VIEWS];
+  int n_src;
+  int src_view[PVSR_MAX_SRC];
+  int src_img_base[PVSR_MAX_SRC];
+  int src_ch0[PVSR_MAX_SRC];
+  int src_off_x[PVSR_MAX_SRC];
+  int src_off_y[PVSR_MAX_SRC];
+  int kb_per_src;
+  int taps;
+  int n_dy;
+  int dy_view[PVSR_MAX_DY];
+  int dy_img_base[PVSR_MAX_DY];
+  int dy_ch0[PVSR_MAX_DY];
+  int dy_off_x[PVSR_MAX_DY];
+  int dy_off_y[PVSR_MAX_DY];
+  int n_total;
+  int with_bias;
+  float* dw_packed;
+  float* db_packed;
+  int n_splits;            /* 0 = automatic */
+  void* job_scratch;       /* device scratch of pvsr_wgrad_scratch_bytes() bytes */
+} pvsr_wgrad_desc;
+int64_t pvsr_wgrad_scratch_bytes(void);
+int pvsr_conv3x3_wgrad(const pvsr_wgrad_desc* d, void* stream);
+/* param_grad[idx[e]] += packed[e] for idx[e] >= 0 (idx2 optional second target). */
+int pvsr_scatter_add(float* param_grad, const int32_t* idx, const int32_t* idx2, const float* packed, int64_t n,
+                     void* stream);
+
 /* Number of fp32 elements of a tile-transposed ConvLSTM cell-state buffer for n_img images of H x W. */
 int64_t pvsr_lstm_state_elems(int64_t n_img, int H, int W);
 

@@ -330,3 +330,120 @@ def test_dgrad_pixel_shuffle_conv(pvsr_lib, r, H, W):
     got = nchw(out)
     assert rel_l2(got, ref) < 3e-3, rel_l2(got, ref)
     assert torch.allclose(got, ref, atol=3e-2, rtol=1e-2), (got - ref).abs().max()
+
+
+# ------------------------------------------------------------------------------------------------ weight gradients
+def _autograd_dw(fn, w, b, gy):
+    w = w.clone().requires_grad_(True)
+    b = b.clone().requires_grad_(True)
+    y = fn(w, b)
+    gw, gb = torch.autograd.grad(y, (w, b), gy)
+    return gw, gb
+
+
+def _check_wgrad(got_w, got_b, ref_w, ref_b):
+    # bf16 operands (exact products), fp32 accumulation in a different order
+    assert rel_l2(got_w, ref_w) < 2e-4, rel_l2(got_w, ref_w)
+    assert rel_l2(got_b, ref_b) < 2e-4, rel_l2(got_b, ref_b)
+
+
+@pytest.mark.parametrize("n,H,W,splits", [(3, 20, 27, 0), (2, 54, 63, 5), (1, 9, 130, 1)])
+def test_wgrad_lstm_shape(pvsr_lib, n, H, W, splits):
+    """dW, db of the ConvLSTM gate conv: two 64-channel sources [x | h], 256 output columns."""
+    from pvsr import ops
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = _rand(n, 64, H, W, gen=g)
+    h = _rand(n, 64, H, W, gen=g)
+    gy = _rand(n, 256, H, W, gen=g)
+    w = torch.randn(256, 128, 3, 3, generator=g, device="cuda") * 0.05
+    b = torch.zeros(256, device="cuda")
+    ref_w, ref_b = _autograd_dw(lambda ww, bb: F.conv2d(torch.cat([x, h], 1), ww, bb, padding=1), w, b, gy)
+    act = torch.cat([nhwc(x), nhwc(h)], dim=0)
+    dy = nhwc(gy)
+    srcs = [(0, 0, 0, 0, 0), (0, n, 0, 0, 0)]
+    dys = [(1, 0, 64 * c, 0, 0) for c in range(4)]
+    dwp, dbp = ops.conv3x3_wgrad([(act, 1), (dy, 1)], srcs, dys, n, (H, W), 256, n_splits=splits)
+    spec = ops.spec_lstm()
+    gw, gb = torch.zeros_like(w), torch.zeros_like(b)
+    ops.scatter_add(gw, spec, dwp, gb, dbp)
+    torch.cuda.synchronize()
+    _check_wgrad(gw, gb, ref_w, ref_b)
+
+
+def test_wgrad_refine_conv2_shape(pvsr_lib):
+    """129 (stored 144) -> 64 conv: three channel blocks per tap, the last one mostly padding."""
+    from pvsr import ops
+    g = torch.Generator(device="cuda").manual_seed(22)
+    n, H, W = 3, 24, 31
+    x = _rand(n, 129, H, W, gen=g)
+    xs = torch.zeros(n, 144, H, W, device="cuda")
+    xs[:, :129] = x
+    gy = _rand(n, 64, H, W, gen=g)
+    w = torch.randn(64, 129, 3, 3, generator=g, device="cuda") * 0.05
+    b = torch.zeros(64, device="cuda")
+    ref_w, ref_b = _autograd_dw(lambda ww, bb: F.conv2d(x, ww, bb, padding=1), w, b, gy)
+    dwp, dbp = ops.conv3x3_wgrad([(nhwc(xs), 1), (nhwc(gy), 1)], [(0, 0, 0, 0, 0)], [(1, 0, 0, 0, 0)], n, (H, W), 64,
+                                 kb_per_src=3)
+    gw, gb = torch.zeros_like(w), torch.zeros_like(b)
+    ops.scatter_add(gw, ops.spec_refine_conv2(), dwp, gb, dbp)
+    torch.cuda.synchronize()
+    _check_wgrad(gw, gb, ref_w, ref_b)
+
+
+def test_wgrad_refine_conv1_shape(pvsr_lib):
+    """10 sources (5-frame window of fwd/bwd hidden maps) against a 129 (stored 144) channel gradient."""
+    from pvsr import ops
+    g = torch.Generator(device="cuda").manual_seed(23)
+    B, H, W, Lf, win = 2, 16, 19, 7, 5
+    nf = Lf - win + 1
+    hf = _rand(Lf * B, 64, H, W, gen=g)
+    hb = _rand(Lf * B, 64, H, W, gen=g)
+    gy = _rand(nf * B, 129, H, W, gen=g)
+    gys = torch.zeros(nf * B, 144, H, W, device="cuda")
+    gys[:, :129] = gy
+    w = torch.randn(129, 645, 3, 3, generator=g, device="cuda") * 0.02
+    b = torch.zeros(129, device="cuda")
+    hf5, hb5 = hf.view(Lf, B, 64, H, W), hb.view(Lf, B, 64, H, W)
+
+    def fwd(ww, bb):
+        outs = []
+        for i in range(nf):
+            chans = []
+            for j in range(win):
+                chans += [hf5[i + j], hb5[i + j], torch.zeros(B, 1, H, W, device="cuda")]
+            outs.append(F.conv2d(torch.cat(chans, 1), ww, bb, padding=1))
+        return torch.stack(outs).view(nf * B, 129, H, W)
+
+    ref_w, ref_b = _autograd_dw(fwd, w, b, gy)
+    act = torch.cat([nhwc(hf), nhwc(hb)], dim=0)
+    srcs = []
+    for j in range(win):
+        srcs += [(0, j * B, 0, 0, 0), (0, Lf * B + j * B, 0, 0, 0)]
+    dys = [(1, 0, 64 * c, 0, 0) for c in range(3)]
+    dwp, dbp = ops.conv3x3_wgrad([(act, 1), (nhwc(gys), 1)], srcs, dys, nf * B, (H, W), 192)
+    spec = ops.spec_refine_conv1()
+    spec.n_total = 192
+    gw, gb = torch.zeros_like(w), torch.zeros_like(b)
+    ops.scatter_add(gw, spec, dwp, gb, dbp)
+    torch.cuda.synchronize()
+    pos_ch = [129 * j + 128 for j in range(win)]
+    keep = [c for c in range(645) if c not in pos_ch]
+    _check_wgrad(gw[:, keep], gb, ref_w[:, keep], ref_b)
+
+
+@pytest.mark.parametrize("r,H,W", [(2, 27, 31), (3, 12, 14)])
+def test_wgrad_pixel_shuffle_conv(pvsr_lib, r, H, W):
+    from pvsr import ops
+    g = torch.Generator(device="cuda").manual_seed(24)
+    n = 2
+    x = _rand(n, 64, H, W, gen=g)
+    ghr = _rand(n, 64, H * r, W * r, gen=g)
+    w = torch.randn(64 * r * r, 64, 3, 3, generator=g, device="cuda") * 0.05
+    b = torch.zeros(64 * r * r, device="cuda")
+    ref_w, ref_b = _autograd_dw(lambda ww, bb: F.pixel_shuffle(F.conv2d(x, ww, bb, padding=1), r), w, b, ghr)
+    dys = [(1, 0, 0, q % r, q // r) for q in range(r * r)]
+    dwp, dbp = ops.conv3x3_wgrad([(nhwc(x), 1), (nhwc(ghr), r)], [(0, 0, 0, 0, 0)], dys, n, (H, W), 64 * r * r)
+    gw, gb = torch.zeros_like(w), torch.zeros_like(b)
+    ops.scatter_add(gw, ops.spec_head_ps(r), dwp, gb, dbp)
+    torch.cuda.synchronize()
+    _check_wgrad(gw, gb, ref_w, ref_b)
