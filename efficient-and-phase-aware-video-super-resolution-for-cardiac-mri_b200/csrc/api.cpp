@@ -187,7 +187,7 @@ int pvsr_pack_index_host(const pvsr_pack_spec* s, int32_t* idx) {
               const int gin = (s->transpose_flip && s->k_ps_r > 0) ? ic * s->k_ps_r * s->k_ps_r + src
                                                                      : s->src_ch_off[src] + ic;
               const int o = s->transpose_flip ? gin : col;
-              const int i = s->transpose_flip ? col : gin;
+              const int i = s->transpose_flip ? col + s->src_col_off[src] : gin;
               if (o < s->c_out && i < s->c_in) v = ((o * s->c_in + i) * s->kh + ky) * s->kw + kx;
             }
             idx[e] = v;
@@ -316,6 +316,65 @@ int pvsr_head_conv_last_fwd(const void* in, const float* w, const float* b, floa
 
 int pvsr_add_bf16(const void* a, const void* b, void* out, int64_t n_elems, void* stream) {
   return check_cuda(launch_add_bf16(a, b, out, n_elems, static_cast<cudaStream_t>(stream)), "add_bf16");
+}
+
+int pvsr_lstm_cell_bwd_pointwise(const float* dh, const void* gates, const float* c, const float* c_prev, float* dc,
+                                 int dc_zero, void* dgates, int64_t n_img, int H, int W, void* stream) {
+  LstmBwdParams p{};
+  p.H = H; p.W = W;
+  choose_tile(H, W, &p.tw_log2);
+  const int tw = 1 << p.tw_log2, th = kTileM >> p.tw_log2;
+  p.tiles_x = (W + tw - 1) / tw;
+  p.tiles_y = (H + th - 1) / th;
+  p.n_img = static_cast<int>(n_img);
+  p.n_prob = 1;
+  p.prob[0] = LstmBwdProb{dh, gates, c, c_prev, dc, dc_zero, dgates};
+  return check_cuda(launch_lstm_bwd_pointwise(p, static_cast<cudaStream_t>(stream)), "lstm_bwd_pointwise");
+}
+
+int pvsr_l1_multistage(const float* out, const float* target, const float* w, int n_lists, int64_t n_per_list,
+                       float* loss, float* dout, void* stream) {
+  if (n_per_list % 4 != 0) return set_error(-2, "n_per_list must be a multiple of 4");
+  return check_cuda(launch_l1_multistage(out, target, w, n_lists, n_per_list, loss, dout, device_num_sms(),
+                                         static_cast<cudaStream_t>(stream)), "l1_multistage");
+}
+
+int pvsr_head_conv_last_bwd_data(const float* dout, const float* w, void* din, int64_t n_img, int H, int W,
+                                 void* stream) {
+  return check_cuda(launch_head_last_bwd_data(dout, w, din, n_img, H, W, static_cast<cudaStream_t>(stream)),
+                    "head_last_bwd_data");
+}
+
+int pvsr_head_conv_last_bwd_weight(const void* in, const float* dout, float* dw, float* db, int64_t n_img, int H,
+                                   int W, void* stream) {
+  return check_cuda(launch_head_last_bwd_weight(in, dout, dw, db, n_img, H, W, device_num_sms(),
+                                                static_cast<cudaStream_t>(stream)), "head_last_bwd_weight");
+}
+
+int pvsr_in_conv_prelu_bwd(const float* x, const float* w, const float* b, const float* slope, const float* g,
+                           float* dw, float* db, float* dslope, int64_t n_img, int H, int W, void* stream) {
+  return check_cuda(launch_in_conv_prelu_bwd(x, w, b, slope, g, dw, db, dslope, n_img, H, W, device_num_sms(),
+                                             static_cast<cudaStream_t>(stream)), "in_conv_prelu_bwd");
+}
+
+int pvsr_refine_posterm_bwd(const void* g, const float* pos, float* sums, float* dw1, int n_frames, int B, int L,
+                            int frame0, int window, int H, int W, int c_out, int c_in, int feat2, int ch,
+                            void* stream) {
+  if (ch > 192) return set_error(-2, "posterm_bwd supports at most 192 channels");
+  return check_cuda(launch_posterm_bwd(g, pos, sums, dw1, n_frames, B, L, frame0, window, H, W, c_out, c_in, feat2, ch,
+                                       static_cast<cudaStream_t>(stream)), "posterm_bwd");
+}
+
+int pvsr_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream) {
+  if (n % 8 != 0) return set_error(-2, "cast needs a multiple of 8 elements");
+  return check_cuda(launch_cast_f32_bf16(in, out, n, static_cast<cudaStream_t>(stream)), "cast_f32_bf16");
+}
+
+int pvsr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, float grad_scale, float* state, void* stream) {
+  if (n % 4 != 0) return set_error(-2, "adam needs a multiple of 4 elements (pad the flat buffer)");
+  return check_cuda(launch_adam(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, state,
+                                device_num_sms(), static_cast<cudaStream_t>(stream)), "adam");
 }
 
 }  // extern "C"

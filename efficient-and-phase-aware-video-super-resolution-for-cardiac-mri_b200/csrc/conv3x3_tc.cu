@@ -50,6 +50,9 @@ __device__ __forceinline__ float sigmoid_from_scaled(float t) { return rcp_appro
 // tanh(x) with t = 2 * log2(e) * x precomputed:  1 - 2 / (1 + 2^t)   (saturates correctly at +-inf)
 __device__ __forceinline__ float tanh_from_scaled(float t) { return fmaf(-2.f, rcp_approx(1.f + ex2_approx(t)), 1.f); }
 
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -285,25 +288,21 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
             float* d0 = p.grad_split ? ((ck < 4) ? pr.grad0 : pr.grad1) : pr.grad0;
             float* d1 = p.grad_split ? nullptr : pr.grad1;
             const int c0 = (ck & 3) * 16;
+            // Fire-and-forget vector reductions: several tiles of one launch (cells of a reverse wavefront) may add
+            // into the same gradient pixels, so a plain read-modify-write would race.
             if (d0) {
-              float4* q = reinterpret_cast<float4*>(d0 + pixoff + c0);
+              float* q = d0 + pixoff + c0;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float4 o = q[j];
-                o.x += __uint_as_float(v[4 * j]); o.y += __uint_as_float(v[4 * j + 1]);
-                o.z += __uint_as_float(v[4 * j + 2]); o.w += __uint_as_float(v[4 * j + 3]);
-                q[j] = o;
-              }
+              for (int j = 0; j < 4; ++j)
+                red_add_v4(q + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
             }
             if (d1) {
-              float4* q = reinterpret_cast<float4*>(d1 + pixoff + c0);
+              float* q = d1 + pixoff + c0;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float4 o = q[j];
-                o.x += __uint_as_float(v[4 * j]); o.y += __uint_as_float(v[4 * j + 1]);
-                o.z += __uint_as_float(v[4 * j + 2]); o.w += __uint_as_float(v[4 * j + 3]);
-                q[j] = o;
-              }
+              for (int j = 0; j < 4; ++j)
+                red_add_v4(q + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
             }
           }
         }

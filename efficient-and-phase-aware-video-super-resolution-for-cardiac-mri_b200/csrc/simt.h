@@ -14,4 +14,35 @@ int launch_pack_weights(const float* w, const int* idx, const int* idx2, void* o
 int launch_gather_f32(const float* src, const int* idx, float* out, long long n, cudaStream_t s);
 int launch_add_bf16(const void* a, const void* b, void* out, long long n_elems, cudaStream_t s);
 
+
+// ---- backward / optimiser kernels (simt_bwd.cu)
+struct LstmBwdProb {
+  const float* dh;          // fp32 NHWC [n_img][H][W][64]: total gradient wrt h_t
+  const void* gates;        // bf16 tile-transposed [tile][256][128]: post-activation i, f, o, g of the forward pass
+  const float* c;           // fp32 tile-transposed [tile][64][128]: c_t
+  const float* c_prev;      // c_{t-1} (nullptr = zeros)
+  float* dc;                // in: gradient wrt c_t from the later step; out: gradient wrt c_{t-1}
+  int dc_zero;              // 1: the incoming dc is zero (first backward step of the cell)
+  void* dgates;             // bf16 NHWC [n_img][H][W][256]: pre-activation gate gradients
+};
+struct LstmBwdParams {
+  int H, W, tw_log2, tiles_x, tiles_y, n_img, n_prob;
+  LstmBwdProb prob[6];
+};
+int launch_lstm_bwd_pointwise(const LstmBwdParams& p, cudaStream_t s);
+int launch_l1_multistage(const float* out, const float* target, const float* w, int n_lists, long long n_per_list,
+                         float* loss, float* dout, int num_sms, cudaStream_t s);
+int launch_head_last_bwd_data(const float* dout, const float* w, void* din_bf16, long long n_img, int H, int W,
+                              cudaStream_t s);
+int launch_head_last_bwd_weight(const void* in_bf16, const float* dout, float* dw, float* db, long long n_img, int H,
+                                int W, int num_sms, cudaStream_t s);
+int launch_in_conv_prelu_bwd(const float* x, const float* w, const float* b, const float* slope, const float* g,
+                             float* dw, float* db, float* dslope, long long n_img, int H, int W, int num_sms,
+                             cudaStream_t s);
+int launch_posterm_bwd(const void* g_bf16, const float* pos, float* sums, float* dw1, int n_frames, int B, int L,
+                       int frame0, int window, int H, int W, int c_out, int c_in, int feat2, int ch, cudaStream_t s);
+int launch_cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t s);
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                float wd, float grad_scale, float* state, int num_sms, cudaStream_t s);
+
 }  // namespace pvsr

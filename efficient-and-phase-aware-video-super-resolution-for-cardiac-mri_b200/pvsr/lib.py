@@ -22,7 +22,8 @@ c_void_p, c_int, c_int64, c_float_p, c_int32_p = C.c_void_p, C.c_int, C.c_int64,
 class PackSpec(C.Structure):
     _fields_ = [("c_out", c_int), ("c_in", c_int), ("kh", c_int), ("kw", c_int), ("n_src", c_int),
                 ("src_ch_off", c_int * MAX_SRC), ("src_ch", c_int), ("kb_per_src", c_int), ("taps", c_int),
-                ("n_total", c_int), ("ps_r", c_int), ("transpose_flip", c_int), ("k_ps_r", c_int)]
+                ("n_total", c_int), ("ps_r", c_int), ("transpose_flip", c_int), ("k_ps_r", c_int),
+                ("src_col_off", c_int * MAX_SRC)]
 
 
 class ActView(C.Structure):
@@ -69,6 +70,13 @@ class NetParams(C.Structure):
                 ("head_w", c_void_p * MAX_HEAD_CONVS), ("head_b", c_void_p * MAX_HEAD_CONVS)]
 
 
+class NetGrads(C.Structure):
+    """fp32 gradient buffers in the parameter layouts (accumulated by pvsr_plan_backward)."""
+    _fields_ = NetParams._fields_
+
+
+NUM_CLASSES, NUM_CLASSES_BWD = 7, 9
+
 # name -> (restype, argtypes); every symbol declared in include/pvsr.h
 SIGNATURES = {
     "pvsr_version": (c_int, []),
@@ -92,6 +100,25 @@ SIGNATURES = {
     "pvsr_head_conv_last_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                         c_int, c_void_p]),
     "pvsr_add_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pvsr_lstm_cell_bwd_pointwise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64,
+                                             c_int, c_int, c_void_p]),
+    "pvsr_l1_multistage": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "pvsr_head_conv_last_bwd_data": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "pvsr_head_conv_last_bwd_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                               c_void_p]),
+    "pvsr_in_conv_prelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int64, c_int, c_int, c_void_p]),
+    "pvsr_refine_posterm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 11 + [c_void_p]),
+    "pvsr_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "pvsr_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, C.c_float, C.c_float, C.c_float,
+                               C.c_float, C.c_float, C.c_float, c_void_p, c_void_p]),
+    "pvsr_plan_backward": (c_int, [c_void_p, C.POINTER(NetParams), c_void_p, c_void_p, c_void_p, c_void_p,
+                                   C.POINTER(NetGrads), c_void_p, c_int, c_void_p]),
+    "pvsr_plan_num_launches_bwd": (c_int64, [c_void_p]),
+    "pvsr_plan_flops_bwd": (C.c_double, [c_void_p]),
+    "pvsr_plan_class_stats_bwd": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "pvsr_plan_profile_bwd": (c_int, [c_void_p, C.POINTER(NetParams), c_void_p, c_void_p, c_void_p, c_void_p,
+                                      C.POINTER(NetGrads), c_void_p, c_void_p, c_void_p]),
     "pvsr_plan_create": (c_int, [C.POINTER(NetConfig), C.POINTER(c_void_p)]),
     "pvsr_plan_destroy": (None, [c_void_p]),
     "pvsr_plan_workspace_bytes": (c_int64, [c_void_p]),

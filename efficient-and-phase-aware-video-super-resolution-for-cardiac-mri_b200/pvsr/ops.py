@@ -236,3 +236,85 @@ def scatter_add(param_grad, spec, packed, bias_grad=None, packed_bias=None):
         bidx = torch.from_numpy(pack_bias_index(spec)).to(packed.device)
         L.check(lib.pvsr_scatter_add(L.ptr(bias_grad), L.ptr(bidx), None, L.ptr(packed_bias), bidx.numel(),
                                      L.current_stream()), "scatter_add")
+
+
+# ------------------------------------------------------------------------------------------------ backward ops
+def lstm_cell_bwd_pointwise(dh, gates, c, c_prev, dc, dc_zero, n_img, H, W):
+    """dh fp32 [n_img,H,W,64]; gates bf16 / c, c_prev, dc fp32 tile-transposed -> dgates bf16 [n_img,H,W,256]."""
+    lib = L.load()
+    dg = torch.zeros(n_img, H, W, 256, dtype=torch.bfloat16, device=dh.device)
+    L.check(lib.pvsr_lstm_cell_bwd_pointwise(L.ptr(dh), L.ptr(gates), L.ptr(c), L.ptr(c_prev), L.ptr(dc), int(dc_zero),
+                                             L.ptr(dg), n_img, H, W, L.current_stream()), "lstm_cell_bwd_pointwise")
+    return dg
+
+
+def nchw_to_lstm_state(x, dtype=torch.float32):
+    """[n_img, C, H, W] -> tile-transposed [tile][C][128] buffer (test helper, inverse of lstm_state_to_nchw)."""
+    lib = L.load()
+    n, Cc, H, W = x.shape
+    l = C.c_int()
+    lib.pvsr_choose_tile(H, W, C.byref(l))
+    tw, th = 1 << l.value, 128 >> l.value
+    tx, ty = (W + tw - 1) // tw, (H + th - 1) // th
+    pad = torch.zeros(n, Cc, ty * th, tx * tw, dtype=x.dtype, device=x.device)
+    pad[:, :, :H, :W] = x
+    s = pad.view(n, Cc, ty, th, tx, tw).permute(0, 2, 4, 1, 3, 5).contiguous()
+    return s.reshape(-1).to(dtype)
+
+
+def l1_multistage(out, target, weights, want_grad=True):
+    """out [lists, ...], target [...], weights [lists] -> (loss 0-dim, dout like out or None)."""
+    lib = L.load()
+    n_lists = out.shape[0]
+    n_per = target.numel()
+    loss = torch.zeros((), dtype=torch.float32, device=out.device)
+    dout = torch.empty_like(out) if want_grad else None
+    L.check(lib.pvsr_l1_multistage(L.ptr(out), L.ptr(target), L.ptr(weights), n_lists, n_per, L.ptr(loss), L.ptr(dout),
+                                   L.current_stream()), "l1_multistage")
+    return loss, dout
+
+
+def head_conv_last_bwd(x, w, dout):
+    """x bf16 [n,H,W,64], w (1,64,3,3), dout fp32 [n,H,W] -> (din bf16 [n,H,W,64], dw (1,64,3,3), db (1))."""
+    lib = L.load()
+    n, H, W, _ = x.shape
+    din = torch.empty_like(x)
+    dw = torch.zeros(1, 64, 3, 3, dtype=torch.float32, device=x.device)
+    db = torch.zeros(1, dtype=torch.float32, device=x.device)
+    L.check(lib.pvsr_head_conv_last_bwd_data(L.ptr(dout), L.ptr(w.contiguous()), L.ptr(din), n, H, W,
+                                             L.current_stream()), "head_conv_last_bwd_data")
+    L.check(lib.pvsr_head_conv_last_bwd_weight(L.ptr(x), L.ptr(dout), L.ptr(dw), L.ptr(db), n, H, W,
+                                               L.current_stream()), "head_conv_last_bwd_weight")
+    return din, dw, db
+
+
+def in_conv_prelu_bwd(x, w, b, slope, g):
+    """x fp32 [n,H,W], g fp32 [n,H,W,64] -> (dw (64,1,3,3), db (64), dslope (1))."""
+    lib = L.load()
+    n, H, W = x.shape
+    dw = torch.zeros(64, 1, 3, 3, dtype=torch.float32, device=x.device)
+    db = torch.zeros(64, dtype=torch.float32, device=x.device)
+    da = torch.zeros(1, dtype=torch.float32, device=x.device)
+    L.check(lib.pvsr_in_conv_prelu_bwd(L.ptr(x.contiguous()), L.ptr(w.contiguous()), L.ptr(b.contiguous()),
+                                       L.ptr(slope.contiguous()), L.ptr(g.contiguous()), L.ptr(dw), L.ptr(db),
+                                       L.ptr(da), n, H, W, L.current_stream()), "in_conv_prelu_bwd")
+    return dw, db, da
+
+
+def refine_posterm_bwd(g, pos, dw1, n_frames, frame0, window=5, feat=64):
+    """g bf16 [n_frames*B, H, W, ch]; pos fp32 [B, L]; dw1 (c_out, c_in, 3, 3) += on the pos channels."""
+    lib = L.load()
+    B, Lf = pos.shape
+    _, H, W, ch = g.shape
+    sums = torch.empty(n_frames * B, 16, ch, dtype=torch.float32, device=g.device)
+    L.check(lib.pvsr_refine_posterm_bwd(L.ptr(g), L.ptr(pos.contiguous()), L.ptr(sums), L.ptr(dw1), n_frames, B, Lf,
+                                        frame0, window, H, W, dw1.shape[0], dw1.shape[1], 2 * feat, ch,
+                                        L.current_stream()), "refine_posterm_bwd")
+    return sums
+
+
+def cast_f32_bf16(x):
+    lib = L.load()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    L.check(lib.pvsr_cast_f32_bf16(L.ptr(x.contiguous()), L.ptr(out), x.numel(), L.current_stream()), "cast_f32_bf16")
+    return out

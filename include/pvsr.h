@@ -60,6 +60,8 @@ typedef struct pvsr_pack_spec {
   int transpose_flip;
   int k_ps_r;   /* transpose_flip only: K channel ic of source s is parameter output channel ic*k_ps_r^2 + s
                    (sources = sub-pixels of a pixel-unshuffled gradient); 0 = src_ch_off[s] + ic */
+  int src_col_off[PVSR_MAX_SRC]; /* transpose_flip only: column n of source s is parameter input channel
+                   n + src_col_off[s] (window gather of the refine conv1 data gradient) */
 } pvsr_pack_spec;
 int64_t pvsr_pack_index_count(const pvsr_pack_spec* spec);
 int pvsr_pack_index_host(const pvsr_pack_spec* spec, int32_t* idx_host);
@@ -181,6 +183,37 @@ int pvsr_head_conv_last_fwd(const void* in_bf16, const float* w, const float* b,
 
 int pvsr_add_bf16(const void* a, const void* b, void* out, int64_t n_elems, void* stream);
 
+/* ---- backward / optimiser ops ---------------------------------------------------------------------------------- */
+/* Adjoint of the ConvLSTM gate math (refine_net.py:258-265) for one cell step over n_img images of H x W:
+ * dh fp32 NHWC [n_img][H][W][64]; gates bf16 / c, c_prev, dc fp32 tile-transposed (c_prev NULL = zeros; dc is
+ * in/out, dc_zero != 0 treats the incoming value as zero); dgates bf16 NHWC [n_img][H][W][256] (pre-activation). */
+int pvsr_lstm_cell_bwd_pointwise(const float* dh, const void* gates, const float* c, const float* c_prev, float* dc,
+                                 int dc_zero, void* dgates, int64_t n_img, int H, int W, void* stream);
+/* Trainer loss (acdc_vsr_refinenet_trainer.py:83-100 with nn.L1Loss): out fp32 [n_lists][n_per_list], target fp32
+ * [n_per_list], w fp32 [n_lists] (device) = per-list weight discount/(T*N*H*W).  *loss += sum_k w_k*sum|out_k - t|;
+ * dout (may be NULL) = w_k * sign(out_k - target).  n_per_list must be a multiple of 4. */
+int pvsr_l1_multistage(const float* out, const float* target, const float* w, int n_lists, int64_t n_per_list,
+                       float* loss, float* dout, void* stream);
+/* _OutBlock last conv backward: dout fp32 [n_img][H][W] -> din bf16 [n_img][H][W][64]; dw (1,64,3,3), db (1) +=. */
+int pvsr_head_conv_last_bwd_data(const float* dout, const float* w, void* din_bf16, int64_t n_img, int H, int W,
+                                 void* stream);
+int pvsr_head_conv_last_bwd_weight(const void* in_bf16, const float* dout, float* dw, float* db, int64_t n_img, int H,
+                                   int W, void* stream);
+/* _InBlock backward: x fp32 [n_img][H][W], g = dL/dy fp32 NHWC [n_img][H][W][64]; dw (64,1,3,3), db (64), dslope += */
+int pvsr_in_conv_prelu_bwd(const float* x, const float* w, const float* b, const float* slope, const float* g,
+                           float* dw, float* db, float* dslope, int64_t n_img, int H, int W, void* stream);
+/* Gradient of the positional-code channels of _RefineBlock conv1: g = dL/d(conv1 out) bf16 NHWC with `ch` channels
+ * for n_frames*B images (frame-major); the window of gradient frame f covers input frames frame0+f .. +window-1.
+ * sums: scratch fp32 [n_frames*B][16][ch]; dw1 (c_out, c_in, 3, 3) += on the pos channels only. */
+int pvsr_refine_posterm_bwd(const void* g_bf16, const float* pos, float* sums, float* dw1, int n_frames, int B, int L,
+                            int frame0, int window, int H, int W, int c_out, int c_in, int feat2, int ch,
+                            void* stream);
+int pvsr_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+/* torch.optim.Adam.step (amsgrad off) on flat fp32 buffers of n elements (n % 4 == 0); g is scaled by grad_scale
+ * first (1/world_size for averaged data-parallel gradients); state[0] (device float) is the step counter. */
+int pvsr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, float grad_scale, float* state, void* stream);
+
 /* ---- whole-network plan: RefineNet.forward (refine_net.py:61-135) --------------------------------------------- */
 typedef struct pvsr_net_config {
   int batch;              /* N: cine sequences processed together */
@@ -219,6 +252,31 @@ int pvsr_plan_pack(pvsr_plan* p, const pvsr_net_params* params, void* packed, vo
  * use_graph != 0 replays a CUDA graph captured on first use for this (workspace, packed, lr, pos, out) tuple. */
 int pvsr_plan_forward(pvsr_plan* p, const pvsr_net_params* params, const void* packed, const float* lr,
                       const float* pos, float* out, void* workspace, int use_graph, void* stream);
+
+/* ---- training: backward of the plan (cfg.save_for_backward = 1, cfg.all_heads = 1) ------------------------------
+ * Gradients are ACCUMULATED (+=) into fp32 buffers with the parameter layouts; NULL entries are skipped. */
+typedef struct pvsr_net_grads {
+  float* in_w; float* in_b; float* in_slope;
+  float* lstm_w[2][PVSR_MAX_LAYERS]; float* lstm_b[2][PVSR_MAX_LAYERS];
+  float* ref_w1; float* ref_b1; float* ref_w2; float* ref_b2;
+  float* head_w[PVSR_MAX_HEAD_CONVS]; float* head_b[PVSR_MAX_HEAD_CONVS];
+} pvsr_net_grads;
+/* dout: fp32 [lists][T][N][H*s][W*s] = dL/d(out) of the preceding pvsr_plan_forward on the same workspace (which
+ * must not have been overwritten since); lr / pos: the inputs of that forward.  Runs loss.backward()'s work:
+ * head / refine / ConvLSTM (truncated BPTT over the T gradient frames, refine_net.py:74-93,179-183) / in-block
+ * data and weight gradients (reference: autograd through refine_net.py:61-135). */
+int pvsr_plan_backward(pvsr_plan* p, const pvsr_net_params* params, const void* packed, const float* lr,
+                       const float* pos, const float* dout, const pvsr_net_grads* grads, void* workspace,
+                       int use_graph, void* stream);
+int64_t pvsr_plan_num_launches_bwd(const pvsr_plan* p);
+double pvsr_plan_flops_bwd(const pvsr_plan* p);
+/* Backward launch classes: 0 head last-conv adjoints, 1 head dgrad, 2 head wgrad, 3 refine dgrad, 4 refine wgrad,
+ * 5 ConvLSTM pointwise adjoint, 6 ConvLSTM dgrad, 7 ConvLSTM wgrad, 8 misc (memsets, casts, in-block, scatter). */
+#define PVSR_NUM_CLASSES_BWD 9
+int pvsr_plan_class_stats_bwd(const pvsr_plan* p, int64_t* launches, double* flops);
+int pvsr_plan_profile_bwd(pvsr_plan* p, const pvsr_net_params* params, const void* packed, const float* lr,
+                          const float* pos, const float* dout, const pvsr_net_grads* grads, void* workspace,
+                          double* ms_by_class, void* stream);
 
 /* Launch classes for accounting: 0 in_conv, 1 ConvLSTM cells, 2 refine conv1, 3 refine conv2, 4 head conv+shuffle,
  * 5 head last conv, 6 misc (adds, posterm).  Arrays must hold PVSR_NUM_CLASSES entries. */
