@@ -1,0 +1,27 @@
+"""`Dataloader` of the YAML registry (reference src/data/dataloader.py:6-53): torch's DataLoader whose workers
+re-seed numpy from the parent's numpy state, plus an optional `shard=(rank, world)` that gives every data-parallel
+rank its own slice of the dataset (the reference is single-GPU and has no equivalent)."""
+import numpy as np
+from torch.utils.data import DataLoader
+from torch.utils.data.distributed import DistributedSampler
+
+
+def _seed_worker(worker_id):
+    np.random.seed((np.random.get_state()[1][0] + worker_id) % (2 ** 32))
+
+
+class Dataloader(DataLoader):
+    def __init__(self, dataset, batch_size=1, shuffle=False, sampler=None, batch_sampler=None, num_workers=0,
+                 collate_fn=None, pin_memory=False, drop_last=False, timeout=0, worker_init_fn=None, shard=None):
+        if shard is not None and sampler is None and batch_sampler is None:
+            rank, world = shard
+            if world > 1:
+                sampler = DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=shuffle,
+                                             drop_last=drop_last)
+                shuffle = False
+        kwargs = dict(batch_size=batch_size, shuffle=shuffle, sampler=sampler, batch_sampler=batch_sampler,
+                      num_workers=num_workers, pin_memory=pin_memory, drop_last=drop_last, timeout=timeout,
+                      worker_init_fn=worker_init_fn or _seed_worker)
+        if collate_fn is not None:
+            kwargs['collate_fn'] = collate_fn
+        super().__init__(dataset, **kwargs)

@@ -1,0 +1,6 @@
+# Dataset registry: names resolved by `getattr(src.data.datasets, config.dataset.name)` (reference src/main.py:46).
+from .base_dataset import BaseDataset
+from .acdc_vsr_refinenet_dataset import AcdcVSRRefineNetDataset, Dsb15VSRRefineNetDataset
+from .synthetic_cine_dataset import SyntheticCineDataset
+
+__all__ = ['BaseDataset', 'AcdcVSRRefineNetDataset', 'Dsb15VSRRefineNetDataset', 'SyntheticCineDataset']

@@ -1,0 +1,116 @@
+"""The preprocessing / augmentation steps named by the RefineNet configs
+(configs/train/refine_net/exp1_x4.yaml:10-23): Normalize, ToTensor, RandomHorizontalFlip, RandomVerticalFlip,
+RandomCropPatch, resolved by name through `compose` (reference src/data/transforms.py:10-28).
+
+Every transform takes any number of numpy images (H, W, C) - the LR frames followed by the HR frames of one cine
+sequence - and returns the same number, applying ONE random decision to all of them.
+"""
+import importlib
+
+import numpy as np
+import torch
+
+
+def compose(transforms=None):
+    """Builds the chain described by a list of {name, kwargs} entries; None -> identity chain."""
+    if transforms is None:
+        return Compose([])
+    module = importlib.import_module(__name__)
+    steps = []
+    for t in transforms:
+        cls = getattr(module, t['name'] if isinstance(t, dict) else t.name)
+        kw = (t.get('kwargs') if isinstance(t, dict) else t.get('kwargs')) or {}
+        steps.append(cls(**kw))
+    return Compose(steps)
+
+
+class BaseTransform:
+    def __call__(self, *imgs, **kwargs):
+        raise NotImplementedError
+
+
+class Compose(BaseTransform):
+    def __init__(self, steps):
+        self.steps = steps
+
+    def __call__(self, *imgs, **kwargs):
+        for step in self.steps:
+            imgs = step(*imgs, **kwargs)
+            if not isinstance(imgs, tuple):
+                imgs = (imgs,)
+        return imgs[0] if len(imgs) == 1 else imgs
+
+
+class ToTensor(BaseTransform):
+    """numpy -> torch; `dtypes` optionally gives one torch dtype per image (default float32)."""
+
+    def __call__(self, *imgs, dtypes=None, **kwargs):
+        if dtypes is None:
+            dtypes = [torch.float32] * len(imgs)
+        return tuple(torch.as_tensor(np.ascontiguousarray(img)).to(dt) for img, dt in zip(imgs, dtypes))
+
+
+class Normalize(BaseTransform):
+    """(x - mean) / (std + 1e-10) per channel; without means/stds, per-image statistics.  `normalize_tags` selects
+    which images are touched (the positional code is passed with [False], acdc_vsr_refinenet_dataset.py:71)."""
+
+    def __init__(self, means=None, stds=None):
+        if (means is None) != (stds is None):
+            raise ValueError('means and stds should be both None or both given.')
+        self.means = None if means is None else np.asarray(means, dtype=np.float32)
+        self.stds = None if stds is None else np.asarray(stds, dtype=np.float32)
+
+    def __call__(self, *imgs, normalize_tags=None, **kwargs):
+        tags = normalize_tags if normalize_tags is not None else [True] * len(imgs)
+        out = []
+        for img, tag in zip(imgs, tags):
+            if tag:
+                img = np.asarray(img, dtype=np.float32)
+                if self.means is None:
+                    axes = tuple(range(img.ndim - 1))
+                    img = (img - img.mean(axis=axes)) / (img.std(axis=axes) + 1e-10)
+                else:
+                    img = (img - self.means) / (self.stds + 1e-10)
+            out.append(img)
+        return tuple(out)
+
+
+class _RandomFlip(BaseTransform):
+    axis = 0
+
+    def __init__(self, prob=0.5):
+        self.prob = prob
+
+    def __call__(self, *imgs, **kwargs):
+        if np.random.rand() < self.prob:
+            return tuple(np.flip(img, self.axis).copy() for img in imgs)
+        return imgs
+
+
+class RandomHorizontalFlip(_RandomFlip):
+    axis = 1
+
+
+class RandomVerticalFlip(_RandomFlip):
+    axis = 0
+
+
+class RandomCropPatch(BaseTransform):
+    """One random LR window of `size` and the aligned `ratio`x larger HR window: the first half of the images are
+    LR frames, the second half the HR frames of the same sequence."""
+
+    def __init__(self, size, ratio):
+        self.size, self.ratio = tuple(size), ratio
+
+    def __call__(self, *imgs, **kwargs):
+        half = len(imgs) // 2
+        h, w = imgs[0].shape[:2]
+        ph, pw = self.size
+        if ph > h or pw > w:
+            raise ValueError(f'The crop size {self.size} exceeds the LR image size {(h, w)}.')
+        y0 = np.random.randint(0, h - ph + 1)
+        x0 = np.random.randint(0, w - pw + 1)
+        r = self.ratio
+        lr = [img[y0:y0 + ph, x0:x0 + pw] for img in imgs[:half]]
+        hr = [img[y0 * r:(y0 + ph) * r, x0 * r:(x0 + pw) * r] for img in imgs[half:]]
+        return tuple(lr + hr)

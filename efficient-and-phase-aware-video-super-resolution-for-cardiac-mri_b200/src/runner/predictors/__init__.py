@@ -1,0 +1,5 @@
+# Predictor registry: names resolved by `getattr(src.runner.predictors, config.predictor.name)` (src/main.py:152).
+from .base_predictor import BasePredictor
+from .acdc_vsr_refinenet_predictor import AcdcVSRRefineNetPredictor, Dsb15VSRRefineNetPredictor
+
+__all__ = ['BasePredictor', 'AcdcVSRRefineNetPredictor', 'Dsb15VSRRefineNetPredictor']

@@ -1,0 +1,5 @@
+# Trainer registry: names resolved by `getattr(src.runner.trainers, config.trainer.name)` (reference src/main.py:102).
+from .base_trainer import BaseTrainer
+from .acdc_vsr_refinenet_trainer import AcdcVSRRefineNetTrainer, Dsb15VSRRefineNetTrainer
+
+__all__ = ['BaseTrainer', 'AcdcVSRRefineNetTrainer', 'Dsb15VSRRefineNetTrainer']

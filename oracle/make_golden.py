@@ -132,6 +132,29 @@ def known_answers(ref):
         json.dump(kat, f, indent=1)
 
 
+def metrics_golden():
+    """Known answers of the reference's own metrics.py / utils.py on seeded images (inputs are regenerated from the
+    seeds by the tests, only the expected values are stored)."""
+    metrics = importlib.import_module("src.model.metrics")
+    utils = importlib.import_module("src.utils")
+    out = []
+    for seed, (n, h, w) in enumerate([(1, 216, 252), (2, 40, 37), (1, 11, 11), (3, 64, 48)]):
+        g = torch.Generator().manual_seed(100 + seed)
+        a = torch.randn(n, 1, h, w, generator=g)
+        b = a + 0.1 * torch.randn(n, 1, h, w, generator=g)
+        rec = {"seed": 100 + seed, "shape": [n, 1, h, w]}
+        for ds in ("acdc", "dsb15"):
+            da, db = utils.denormalize(a, ds), utils.denormalize(b, ds)
+            rec[ds] = {"denorm_sum": float(da.double().sum()), "psnr": float(metrics.PSNR()(da, db)),
+                       "ssim": float(metrics.SSIM()(da, db)),
+                       "psnr_per_sample": [float(v) for v in metrics.PSNR(size_average=False)(da, db)],
+                       "ssim_per_sample": [float(v) for v in metrics.SSIM(size_average=False)(da, db)]}
+        out.append(rec)
+    with open(os.path.join(OUT, "metrics.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("metrics golden written")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -139,3 +162,4 @@ if __name__ == "__main__":
     for name, (kw, N, T, h, w) in CASES.items():
         make_case(ref, name, kw, N, T, h, w)
     known_answers(ref)
+    metrics_golden()
