@@ -139,6 +139,91 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+TRAIN_N, TRAIN_T, TRAIN_HW = 16, 7, 32     # configs/train/refine_net/exp1_x4.yaml:20-33: batch 16, 7 frames, 32x32 patches
+
+
+def bench_train(args, dev, rank, world, distributed, barrier):
+    """One RefineNet x4 training step (forward + multi-stage L1 + backward + gradient all-reduce + Adam) per step at
+    the reference's training shapes: N=16 per GPU, 7 target frames + 2x6 warm-up frames of 32x32 LR patches.
+    Returns a dict for the JSON line (rank 0) - SURVEY.md section 8 config 5."""
+    import torch.distributed as dist
+    from pvsr.optim import FusedAdam
+    from pvsr.parallel import DataParallelStep
+    from pvsr.synthetic import cine_batch
+    from src.model.nets import RefineNet
+    torch.manual_seed(0)
+    net = RefineNet(**NET_KW).to(dev).train()
+    opt = FusedAdam.for_net(net, lr=1e-4)
+    dp = DataParallelStep(net, opt)
+    eng = net.engine
+    eng.use_graph = not args.no_graph
+    inputs_h, pos_h, targets_h = cine_batch(TRAIN_N, T=TRAIN_T, U=U_FRAMES, h=TRAIN_HW, w=TRAIN_HW, scale=SCALE,
+                                            seed=4321 + rank, end_systole=3, with_targets=True)
+    inputs_h = [x.pin_memory() for x in inputs_h]
+    targets_h = [x.pin_memory() for x in targets_h]
+    pos_h = pos_h.pin_memory()
+    inputs_d, pos_d, targets_d = [x.to(dev) for x in inputs_h], pos_h.to(dev), [x.to(dev) for x in targets_h]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    loss_h = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def device_step():
+        flush.fill_(1)
+        loss, _ = eng.loss_and_grads(inputs_d, pos_d, targets_d)
+        dp.step()
+        return loss
+
+    def e2e_step():
+        flush.fill_(1)
+        xs = [x.to(dev, non_blocking=True) for x in inputs_h]
+        ts = [x.to(dev, non_blocking=True) for x in targets_h]
+        ps = pos_h.to(dev, non_blocking=True)
+        loss, _ = eng.loss_and_grads(xs, ps, ts)
+        dp.step()
+        loss_h.copy_(loss, non_blocking=True)
+        return loss
+
+    res = {}
+    for name, fn in (("device", device_step), ("e2e", e2e_step)):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = fn()
+        e1.record()
+        barrier()
+        res[name] = e0.elapsed_time(e1)
+    t = torch.tensor([res["device"], res["e2e"]], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    pl = eng.train_plan(inputs_d)
+    prof_f = eng.profile(pl)
+    prof_b = eng.profile_backward(pl)
+    flops = pl.flops + pl.flops_bwd
+    frames = world * TRAIN_N * TRAIN_T
+    h2d = sum(x.numel() * 4 for x in inputs_h + targets_h) + pos_h.numel() * 4
+    return {
+        "metric": "training target frames/s at x4", "value": frames * args.steps / (ms / 1e3), "unit": "frames/s",
+        "ms_per_step": ms / args.steps, "steps_per_s": args.steps / (ms / 1e3),
+        "config": {"workload": f"RefineNet x4 training step, N={TRAIN_N} per GPU, {TRAIN_T} target frames + 2x{U_FRAMES} "
+                               f"warm-up frames of {TRAIN_HW}x{TRAIN_HW} LR patches (HR 128x128), all 9 heads, L1 multi-stage "
+                               "loss, fused Adam", "global_batch": world * TRAIN_N,
+                   "parallelism": f"data-parallel x{world}, one NCCL all-reduce of the flat fp32 gradient per step"},
+        "e2e": {"value": frames * args.steps / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int((pl.launches + pl.launches_bwd + 3) * args.steps),
+        "algorithmic_tflop_per_step_per_gpu": flops / 1e12,
+        "whole_step_tflops_per_gpu": flops / (ms / args.steps / 1e3) / 1e12,
+        "loss": float(loss),
+        "kernel_ms_per_step": {**{k: round(v[0], 3) for k, v in prof_f.items()},
+                               **{k: round(v[0], 3) for k, v in prof_b.items()}},
+        "kernel_tflops": {k: round(v[2] / (v[0] / 1e3) / 1e12, 1) for k, v in {**prof_f, **prof_b}.items()
+                          if v[2] > 0 and v[0] > 0},
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -148,6 +233,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "both"],
+                    help="infer: BASELINE.json metric (default; adds a short train_step object at N=1); "
+                         "train: the training-step line; both: inference line with the train_step object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
@@ -173,6 +261,33 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.mode == "train":
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        tr = bench_train(args, dev, rank, world, distributed, barrier)
+        if rank == 0:
+            peaks = measured_peaks()
+            peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+            line = {"metric": tr["metric"], "value": tr["value"], "unit": tr["unit"], "n_gpus": world,
+                    "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": tr["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                    "data": "synthetic", "config": tr["config"], "e2e": tr["e2e"], "gpu_launches": tr["gpu_launches"],
+                    "clocks": sampler.stop(),
+                    "roofline": {"bound": "tensor", "kernel": "whole training step (all tcgen05 conv / dgrad / wgrad launches)",
+                                 "achieved": tr["whole_step_tflops_per_gpu"], "peak": peak, "unit": "TFLOP/s",
+                                 "frac": tr["whole_step_tflops_per_gpu"] / peak, "traffic": None,
+                                 "peak_source": peaks["_source"] + ", sustained bf16"},
+                    "kernel_ms_per_step": tr["kernel_ms_per_step"], "kernel_tflops": tr["kernel_tflops"],
+                    "loss": tr["loss"]}
+            print(json.dumps(line), flush=True)
+        if distributed:
+            dist.destroy_process_group()
+        return
+
     torch.manual_seed(0)
     net = RefineNet(**NET_KW).to(dev).eval()
     net.only_last_head = True
@@ -191,11 +306,6 @@ def main():
 
     eng = net.engine
     plan = eng.plan_for(B, len(inputs_d), LR_H, LR_W, False, dev)
-
-    def barrier():
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def device_step():
         flush.fill_(1)                      # L2 flush: 256 MiB write between steps
@@ -250,6 +360,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
+    # the training step of config 5 (short, same process) rides along on the single-GPU line
+    train_res = None
+    if args.mode == "both" or (args.mode == "infer" and world == 1):
+        targs = argparse.Namespace(**vars(args))
+        targs.steps = min(args.steps, 5)
+        train_res = bench_train(targs, dev, rank, world, distributed, barrier)
+
     if rank == 0:
         peaks = measured_peaks()
         frames_per_step = world * B * T_FRAMES
@@ -282,6 +399,11 @@ def main():
                          "whole_step_tflops": step_flops / (ms / args.steps / 1e3) / 1e12},
             "kernel_ms_per_step": {k: round(v[0], 3) for k, v in prof.items()},
         }
+        if train_res is not None:
+            line["train_step"] = {k: train_res[k] for k in ("metric", "value", "unit", "ms_per_step", "steps_per_s",
+                                                            "config", "e2e", "algorithmic_tflop_per_step_per_gpu",
+                                                            "whole_step_tflops_per_gpu", "kernel_ms_per_step",
+                                                            "kernel_tflops", "loss")}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             times = cpu_oracle_time(1, 1, cores)
