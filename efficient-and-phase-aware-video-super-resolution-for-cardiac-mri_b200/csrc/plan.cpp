@@ -1087,7 +1087,7 @@ int pvsr_plan_create(const pvsr_net_config* cfg, pvsr_plan** out) {
       p->off_dhead[q] = off;
       off = align_up(off + 3 * static_cast<size_t>(TB) * p->ps_h[q + 1] * p->ps_w[q + 1] * kFeat * 2, 1024);
     }
-    p->off_sums = off; off = align_up(off + static_cast<size_t>(TB) * 16 * 144 * 4, 1024);
+    p->off_sums = off; off = align_up(off + static_cast<size_t>(p->Wn) * 16 * 144 * 4, 1024);
 
     // ---- data-gradient operands: transposed, spatially flipped weights
     {

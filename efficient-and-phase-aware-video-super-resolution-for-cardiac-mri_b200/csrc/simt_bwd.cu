@@ -31,77 +31,97 @@ __device__ __forceinline__ float warp_sum(float v) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// lstm_bwd_pointwise.  One block per 128-pixel tile of one cell; thread = (tile row, half of the channels).
-// Tile-transposed tensors ([tile][ch][128]) are read coalesced along the row; dh / dgates are NHWC and each thread
-// touches whole 32/64-byte runs of its own pixel.
-__global__ void __launch_bounds__(256) lstm_bwd_pointwise_kernel(const __grid_constant__ LstmBwdParams p) {
+// lstm_bwd_pointwise.  One block per 128-pixel tile of one cell; thread = (4 consecutive tile rows, 8 channels).
+// Tile-transposed tensors ([tile][ch][128]) are read as 8/16-byte vectors over the 4 rows (7 vector loads per channel
+// instead of 28 scalar ones); dh / dgates are NHWC: the 8 channel-group threads of a pixel cover whole 128-byte lines.
+__global__ void __launch_bounds__(256, 2) lstm_bwd_pointwise_kernel(const __grid_constant__ LstmBwdParams p) {
   const LstmBwdProb& pr = p.prob[blockIdx.y];
   const int tile = blockIdx.x;
-  const int row = threadIdx.x & 127;
-  const int grp = threadIdx.x >> 7;
+  const int cg = threadIdx.x & 7;          // channels [8*cg, 8*cg + 8)
+  const int rq = threadIdx.x >> 3;         // tile rows [4*rq, 4*rq + 4)
   int t = tile;
   const int tx = t % p.tiles_x;
   t /= p.tiles_x;
   const int ty = t % p.tiles_y;
   const int img = t / p.tiles_y;
   const int TW = 1 << p.tw_log2;
-  const int y = ty * (128 >> p.tw_log2) + (row >> p.tw_log2), x = (tx << p.tw_log2) + (row & (TW - 1));
-  const bool valid = y < p.H && x < p.W;
-  const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
-  const __nv_bfloat16* gt = static_cast<const __nv_bfloat16*>(pr.gates) + static_cast<size_t>(tile) * 256 * 128 + row;
-  const float* ct = pr.c + static_cast<size_t>(tile) * 64 * 128 + row;
-  const float* cpt = pr.c_prev ? pr.c_prev + static_cast<size_t>(tile) * 64 * 128 + row : nullptr;
-  float* dct = pr.dc + static_cast<size_t>(tile) * 64 * 128 + row;
-#pragma unroll 1
-  for (int cc = 0; cc < 2; ++cc) {
-    const int ch0 = grp * 32 + cc * 16;
-    float dh[16];
-    if (valid) {
-      const float4* q = reinterpret_cast<const float4*>(pr.dh + pix * 64 + ch0);
+  size_t pix[4];
+  bool valid[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 v = q[j];
-        dh[4 * j] = v.x; dh[4 * j + 1] = v.y; dh[4 * j + 2] = v.z; dh[4 * j + 3] = v.w;
-      }
+  for (int r = 0; r < 4; ++r) {
+    const int row = rq * 4 + r;
+    const int y = ty * (128 >> p.tw_log2) + (row >> p.tw_log2), x = (tx << p.tw_log2) + (row & (TW - 1));
+    valid[r] = y < p.H && x < p.W;
+    pix[r] = (static_cast<size_t>(img) * p.H + y) * p.W + x;
+  }
+  const __nv_bfloat16* gt = static_cast<const __nv_bfloat16*>(pr.gates) + static_cast<size_t>(tile) * 256 * 128 + rq * 4;
+  const float* ct = pr.c + static_cast<size_t>(tile) * 64 * 128 + rq * 4;
+  const float* cpt = pr.c_prev ? pr.c_prev + static_cast<size_t>(tile) * 64 * 128 + rq * 4 : nullptr;
+  float* dct = pr.dc + static_cast<size_t>(tile) * 64 * 128 + rq * 4;
+
+  float dh[4][8];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (valid[r]) {
+      const float4* q = reinterpret_cast<const float4*>(pr.dh + pix[r] * 64 + cg * 8);
+      const float4 v0 = q[0], v1 = q[1];
+      dh[r][0] = v0.x; dh[r][1] = v0.y; dh[r][2] = v0.z; dh[r][3] = v0.w;
+      dh[r][4] = v1.x; dh[r][5] = v1.y; dh[r][6] = v1.z; dh[r][7] = v1.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) dh[j] = 0.f;
+      for (int j = 0; j < 8; ++j) dh[r][j] = 0.f;
     }
-    float ai[16], af[16], ao[16], ag[16];
+  }
+  uint32_t oi[4][4], of[4][4], oo[4][4], og[4][4];   // [row][channel pair] packed bf16
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int ch = ch0 + j;
-      const float gi = __bfloat162float(gt[ch * 128]);
-      const float gf = __bfloat162float(gt[(64 + ch) * 128]);
-      const float go = __bfloat162float(gt[(128 + ch) * 128]);
-      const float gg = __bfloat162float(gt[(192 + ch) * 128]);
-      const float cn = ct[ch * 128];
-      const float cp = cpt ? cpt[ch * 128] : 0.f;
-      const float dcin = pr.dc_zero ? 0.f : dct[ch * 128];
-      const float tc = tanhf(cn);
-      const float dcv = fmaf(dh[j] * go, 1.f - tc * tc, dcin);
-      ao[j] = dh[j] * tc * go * (1.f - go);
-      ai[j] = dcv * gg * gi * (1.f - gi);
-      af[j] = dcv * cp * gf * (1.f - gf);
-      ag[j] = dcv * gi * (1.f - gg * gg);
-      dct[ch * 128] = dcv * gf;
+  for (int j = 0; j < 8; ++j) {
+    const int ch = cg * 8 + j;
+    const uint2 ui = *reinterpret_cast<const uint2*>(gt + ch * 128);
+    const uint2 uf = *reinterpret_cast<const uint2*>(gt + (64 + ch) * 128);
+    const uint2 uo = *reinterpret_cast<const uint2*>(gt + (128 + ch) * 128);
+    const uint2 ug = *reinterpret_cast<const uint2*>(gt + (192 + ch) * 128);
+    const float4 cn4 = *reinterpret_cast<const float4*>(ct + ch * 128);
+    const float4 cp4 = cpt ? *reinterpret_cast<const float4*>(cpt + ch * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 dc4 = pr.dc_zero ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(dct + ch * 128);
+    const float gi[4] = {bf16lo(ui.x), bf16hi(ui.x), bf16lo(ui.y), bf16hi(ui.y)};
+    const float gf[4] = {bf16lo(uf.x), bf16hi(uf.x), bf16lo(uf.y), bf16hi(uf.y)};
+    const float go[4] = {bf16lo(uo.x), bf16hi(uo.x), bf16lo(uo.y), bf16hi(uo.y)};
+    const float gg[4] = {bf16lo(ug.x), bf16hi(ug.x), bf16lo(ug.y), bf16hi(ug.y)};
+    const float cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
+    const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
+    const float dcin[4] = {dc4.x, dc4.y, dc4.z, dc4.w};
+    float dco[4], ai[4], af[4], ao[4], ag[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float tc = tanhf(cn[r]);
+      const float dcv = fmaf(dh[r][j] * go[r], 1.f - tc * tc, dcin[r]);
+      ao[r] = dh[r][j] * tc * go[r] * (1.f - go[r]);
+      ai[r] = dcv * gg[r] * gi[r] * (1.f - gi[r]);
+      af[r] = dcv * cp[r] * gf[r] * (1.f - gf[r]);
+      ag[r] = dcv * gi[r] * (1.f - gg[r] * gg[r]);
+      dco[r] = dcv * gf[r];
     }
-    if (valid) {
-      __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(pr.dgates) + pix * 256 + ch0;
-      uint4* q;
-      q = reinterpret_cast<uint4*>(dst);
-      q[0] = make_uint4(pack2(ai[0], ai[1]), pack2(ai[2], ai[3]), pack2(ai[4], ai[5]), pack2(ai[6], ai[7]));
-      q[1] = make_uint4(pack2(ai[8], ai[9]), pack2(ai[10], ai[11]), pack2(ai[12], ai[13]), pack2(ai[14], ai[15]));
-      q = reinterpret_cast<uint4*>(dst + 64);
-      q[0] = make_uint4(pack2(af[0], af[1]), pack2(af[2], af[3]), pack2(af[4], af[5]), pack2(af[6], af[7]));
-      q[1] = make_uint4(pack2(af[8], af[9]), pack2(af[10], af[11]), pack2(af[12], af[13]), pack2(af[14], af[15]));
-      q = reinterpret_cast<uint4*>(dst + 128);
-      q[0] = make_uint4(pack2(ao[0], ao[1]), pack2(ao[2], ao[3]), pack2(ao[4], ao[5]), pack2(ao[6], ao[7]));
-      q[1] = make_uint4(pack2(ao[8], ao[9]), pack2(ao[10], ao[11]), pack2(ao[12], ao[13]), pack2(ao[14], ao[15]));
-      q = reinterpret_cast<uint4*>(dst + 192);
-      q[0] = make_uint4(pack2(ag[0], ag[1]), pack2(ag[2], ag[3]), pack2(ag[4], ag[5]), pack2(ag[6], ag[7]));
-      q[1] = make_uint4(pack2(ag[8], ag[9]), pack2(ag[10], ag[11]), pack2(ag[12], ag[13]), pack2(ag[14], ag[15]));
+    *reinterpret_cast<float4*>(dct + ch * 128) = make_float4(dco[0], dco[1], dco[2], dco[3]);
+    // pack channel pairs: even j fills the low half, odd j the high half
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if ((j & 1) == 0) {
+        oi[r][j >> 1] = pack2(ai[r], 0.f) & 0xFFFFu; of[r][j >> 1] = pack2(af[r], 0.f) & 0xFFFFu;
+        oo[r][j >> 1] = pack2(ao[r], 0.f) & 0xFFFFu; og[r][j >> 1] = pack2(ag[r], 0.f) & 0xFFFFu;
+      } else {
+        oi[r][j >> 1] |= pack2(0.f, ai[r]) & 0xFFFF0000u; of[r][j >> 1] |= pack2(0.f, af[r]) & 0xFFFF0000u;
+        oo[r][j >> 1] |= pack2(0.f, ao[r]) & 0xFFFF0000u; og[r][j >> 1] |= pack2(0.f, ag[r]) & 0xFFFF0000u;
+      }
     }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (!valid[r]) continue;
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(pr.dgates) + pix[r] * 256 + cg * 8;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(oi[r][0], oi[r][1], oi[r][2], oi[r][3]);
+    *reinterpret_cast<uint4*>(dst + 64) = make_uint4(of[r][0], of[r][1], of[r][2], of[r][3]);
+    *reinterpret_cast<uint4*>(dst + 128) = make_uint4(oo[r][0], oo[r][1], oo[r][2], oo[r][3]);
+    *reinterpret_cast<uint4*>(dst + 192) = make_uint4(og[r][0], og[r][1], og[r][2], og[r][3]);
   }
 }
 
@@ -166,107 +186,186 @@ int launch_l1_multistage(const float* out, const float* target, const float* w, 
 
 // ------------------------------------------------------------------------------------------------
 // head_last_bwd_data: dIn[y, x, c] = sum_tap dOut[y - dy, x - dx] * w[c, tap]   (zero outside the image)
-// 8 threads per pixel (8 channels each); a warp writes 4 pixels x 128 B contiguous.
-__global__ void __launch_bounds__(256) head_last_bwd_data_kernel(const float* __restrict__ dout,
-                                                                 const float* __restrict__ w,
-                                                                 __nv_bfloat16* __restrict__ din,
-                                                                 long long n_pix_total, int H, int W) {
-  __shared__ float sw[9][64];
-  for (int i = threadIdx.x; i < 576; i += blockDim.x) sw[i % 9][i / 9] = w[i];  // parameter layout (1, 64, 3, 3)
-  __syncthreads();
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long pix = gid >> 3;
-  const int cg = static_cast<int>(gid & 7) * 8;
-  if (pix >= n_pix_total) return;
-  const int xw = static_cast<int>(pix % W);
-  const int yh = static_cast<int>((pix / W) % H);
-  const float* img = dout + (pix - static_cast<long long>(yh) * W - xw);
-  float acc[8];
+// 8 threads per pixel (8 channels each; the 72 weights of a thread live in registers); a warp writes 4 pixels x 128 B
+// contiguous.  Grid-stride over pixels: no per-block weight staging, 9 L1-resident scalar loads per pixel.
+__global__ void __launch_bounds__(256, 2) head_last_bwd_data_kernel(const float* __restrict__ dout,
+                                                                    const float* __restrict__ w,
+                                                                    __nv_bfloat16* __restrict__ din,
+                                                                    long long n_pix_total, int H, int W) {
+  const int cg = (threadIdx.x & 7) * 8;
+  float wr[8][9];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 8; ++j)
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int yy = yh - (t / 3 - 1), xx = xw - (t % 3 - 1);
-    const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + static_cast<long long>(yy) * W + xx) : 0.f;
+    for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(w + (cg + j) * 9 + t);   // parameter layout (1, 64, 3, 3)
+  const long long stride = static_cast<long long>(gridDim.x) * 32;
+  for (long long pix = static_cast<long long>(blockIdx.x) * 32 + (threadIdx.x >> 3); pix < n_pix_total; pix += stride) {
+    const int xw = static_cast<int>(pix % W);
+    const int yh = static_cast<int>((pix / W) % H);
+    const float* img = dout + (pix - static_cast<long long>(yh) * W - xw);
+    float v[9];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, sw[t][cg + j], acc[j]);
+    for (int t = 0; t < 9; ++t) {
+      const int yy = yh - (t / 3 - 1), xx = xw - (t % 3 - 1);
+      v[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + static_cast<long long>(yy) * W + xx) : 0.f;
+    }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[j] = fmaf(v[t], wr[j][t], acc[j]);
+    }
+    *reinterpret_cast<uint4*>(din + pix * 64 + cg) =
+        make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
   }
-  *reinterpret_cast<uint4*>(din + pix * 64 + cg) =
-      make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
 }
 
 int launch_head_last_bwd_data(const float* dout, const float* w, void* din_bf16, long long n_img, int H, int W,
                               cudaStream_t s) {
   const long long n_pix = n_img * H * W;
   if (n_pix == 0) return 0;
-  const long long threads = n_pix * 8;
-  head_last_bwd_data_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(
+  long long blocks = (n_pix + 31) / 32;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  head_last_bwd_data_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
       dout, w, static_cast<__nv_bfloat16*>(din_bf16), n_pix, H, W);
   return static_cast<int>(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------------------------------------
 // head_last_bwd_weight: dW[c, tap] += sum_q in[q, c] * dOut[q - off(tap)],  db += sum dOut.
-// Thread = (pixel lane, 8-channel group); 72 fp32 accumulators; block-level reduction in shared memory, then one
-// atomic per (c, tap) per block.  Grid is persistent (a few blocks per SM).
-__global__ void __launch_bounds__(256) head_last_bwd_weight_kernel(const __nv_bfloat16* __restrict__ in,
-                                                                   const float* __restrict__ dout,
-                                                                   float* __restrict__ dw, float* __restrict__ db,
-                                                                   long long n_pix_total, int H, int W) {
+// A [16 taps x pixels] x [pixels x 64 channels] product on warp-level mma.sync (K = pixels).  Persistent blocks walk
+// 8x32-pixel tiles: the `in` tile is staged with cp.async (144-byte pixel pitch), the dOut halo (10x34 fp32) with
+// plain loads; warp w owns tile row w (two k16 steps).  The A operand D[tap][q] = dOut[q - off(tap)] is built in
+// registers from the halo and split into bf16 hi + lo (the loss gradient keeps ~16 mantissa bits); the B operand
+// in[q][c] comes from the tile via ldmatrix.trans.  The 16x64 fp32 accumulator (32 registers per thread) lives across
+// all tiles of the block; one shared-memory and one global atomic pass at the end.
+constexpr int kWTH = 8, kWTW = 32, kWPitch = 144, kWHaloW = 36;
+
+__global__ void __launch_bounds__(256, 2) head_last_bwd_weight_kernel(const __nv_bfloat16* __restrict__ in,
+                                                                      const float* __restrict__ dout,
+                                                                      float* __restrict__ dw, float* __restrict__ db,
+                                                                      int n_img, int H, int W, int tiles_x,
+                                                                      int tiles_y) {
+  __shared__ __align__(16) uint8_t tile[kWTH * kWTW * kWPitch];
+  __shared__ float halo[(kWTH + 2) * kWHaloW];
   __shared__ float sacc[577];
-  for (int i = threadIdx.x; i < 577; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  const int pl = threadIdx.x >> 3, cg = (threadIdx.x & 7) * 8;
-  float acc[8][9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+  float acc[8][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+  for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
   float bsum = 0.f;
-  for (long long q = static_cast<long long>(blockIdx.x) * 32 + pl; q < n_pix_total;
-       q += static_cast<long long>(gridDim.x) * 32) {
-    const int xw = static_cast<int>(q % W);
-    const int yh = static_cast<int>((q / W) % H);
-    const float* img = dout + (q - static_cast<long long>(yh) * W - xw);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + q * 64 + cg));
-    const float f[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y),
-                        bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+  const int total = n_img * tiles_y * tiles_x;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    int tt = t;
+    const int tx = tt % tiles_x;
+    tt /= tiles_x;
+    const int ty = tt % tiles_y;
+    const int img = tt / tiles_y;
+    const int y0 = ty * kWTH, x0 = tx * kWTW;
+    const __nv_bfloat16* src = in + static_cast<size_t>(img) * H * W * 64;
+    const float* dsrc = dout + static_cast<size_t>(img) * H * W;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int yy = yh - (t / 3 - 1), xx = xw - (t % 3 - 1);
-      const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + static_cast<long long>(yy) * W + xx) : 0.f;
+    for (int it = 0; it < kWTH * kWTW * 8 / 256; ++it) {
+      const int i = threadIdx.x + it * 256;
+      const int hp = i >> 3, ck = i & 7;
+      const int y = y0 + (hp >> 5), x = x0 + (hp & 31);
+      const bool ok = y < H && x < W;
+      const __nv_bfloat16* g = src + (static_cast<size_t>(ok ? y : 0) * W + (ok ? x : 0)) * 64 + ck * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_s + hp * kWPitch + ck * 16), "l"(g),
+                   "r"(ok ? 16 : 0)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = threadIdx.x; i < (kWTH + 2) * (kWTW + 2); i += 256) {
+      const int hy = i / (kWTW + 2), hx = i - hy * (kWTW + 2);
+      const int y = y0 + hy - 1, x = x0 + hx - 1;
+      const float v = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(dsrc + static_cast<size_t>(y) * W + x) : 0.f;
+      halo[hy * kWHaloW + hx] = v;
+      if (hy >= 1 && hy <= kWTH && hx >= 1 && hx <= kWTW) bsum += v;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int ly = warp;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j][t] = fmaf(f[j], v, acc[j][t]);
-      if (t == 4 && cg == 0) bsum += v;
+    for (int ks = 0; ks < 2; ++ks) {
+      const int lx0 = ks * 16;
+      // A fragments: rows = taps, columns = pixels of this k step
+      uint32_t ahi[4], alo[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int tap = (lane >> 2) + (f & 1) * 8;
+        const int k = (lane & 3) * 2 + (f >> 1) * 8;
+        float v0 = 0.f, v1 = 0.f;
+        if (tap < 9) {
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const float* hrow = halo + (ly - dy + 1) * kWHaloW + (lx0 + k - dx + 1);
+          v0 = hrow[0];
+          v1 = hrow[1];
+        }
+        const uint32_t hi = pack2(v0, v1);
+        ahi[f] = hi;
+        alo[f] = pack2(v0 - bf16lo(hi), v1 - bf16hi(hi));
+      }
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b0, b1, b2, b3;
+        const uint32_t addr = tile_s + (ly * kWTW + lx0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kWPitch +
+                              (16 * np + 8 * (lane >> 4)) * 2;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(addr));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t bb0 = h ? b2 : b0, bb1 = h ? b3 : b1;
+          float* c = acc[2 * np + h];
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+              "{%0, %1, %2, %3};"
+              : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+              : "r"(ahi[0]), "r"(ahi[1]), "r"(ahi[2]), "r"(ahi[3]), "r"(bb0), "r"(bb1));
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+              "{%0, %1, %2, %3};"
+              : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+              : "r"(alo[0]), "r"(alo[1]), "r"(alo[2]), "r"(alo[3]), "r"(bb0), "r"(bb1));
+        }
+      }
+    }
+    __syncthreads();   // the tile and the halo are overwritten by the next iteration
+  }
+  for (int i = threadIdx.x; i < 577; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int ch = nt * 8 + (lane & 3) * 2, tap = lane >> 2;
+    atomicAdd(&sacc[ch * 9 + tap], acc[nt][0]);
+    atomicAdd(&sacc[(ch + 1) * 9 + tap], acc[nt][1]);
+    if (tap == 0) {
+      atomicAdd(&sacc[ch * 9 + 8], acc[nt][2]);
+      atomicAdd(&sacc[(ch + 1) * 9 + 8], acc[nt][3]);
     }
   }
-  // reduce over the 4 pixel lanes that share a warp (lane bits 3,4), then shared-memory atomics across warps
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      float v = acc[j][t];
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if ((threadIdx.x & 31) < 8) atomicAdd(&sacc[(cg + j) * 9 + t], v);
-    }
-  bsum += __shfl_xor_sync(0xffffffffu, bsum, 8);
-  bsum += __shfl_xor_sync(0xffffffffu, bsum, 16);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[576], bsum);
+  bsum = warp_sum(bsum);
+  if (lane == 0) atomicAdd(&sacc[576], bsum);
   __syncthreads();
-  for (int i = threadIdx.x; i < 576; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
+  for (int i = threadIdx.x; i < 576; i += 256) atomicAdd(dw + i, sacc[i]);
   if (threadIdx.x == 0) atomicAdd(db, sacc[576]);
 }
 
 int launch_head_last_bwd_weight(const void* in_bf16, const float* dout, float* dw, float* db, long long n_img, int H,
                                 int W, int num_sms, cudaStream_t s) {
-  const long long n_pix = n_img * H * W;
-  if (n_pix == 0) return 0;
-  long long blocks = (n_pix + 31) / 32;
+  if (n_img * H * W == 0) return 0;
+  const int tiles_x = (W + kWTW - 1) / kWTW, tiles_y = (H + kWTH - 1) / kWTH;
+  long long blocks = n_img * tiles_x * tiles_y;
   const long long cap = 4LL * (num_sms > 0 ? num_sms : 148);
   if (blocks > cap) blocks = cap;
   head_last_bwd_weight_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(in_bf16), dout, dw, db, n_pix, H, W);
+      static_cast<const __nv_bfloat16*>(in_bf16), dout, dw, db, static_cast<int>(n_img), H, W, tiles_x, tiles_y);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -357,80 +456,81 @@ int launch_in_conv_prelu_bwd(const float* x, const float* w, const float* b, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// posterm_bwd, step 1: border-class sums of the conv1 output gradient.
-//   S[img][cls][o] = sum over pixels of class cls of G[img, pixel, o]        (G bf16 NHWC with `ch` channels)
-// One block per image, one thread per channel; per image row the (left, middle, right) sums are flushed to the
-// shared accumulator of the row's classes.
+// posterm_bwd: gradient of the positional-code input channels of conv1.  With S[img][cls][o] the sum of the conv1
+// output gradient G over the pixels of border class cls,
+//   dW1[o, (2F+1)*d + 2F, tap] += sum_{cls admitting tap} Q[d][cls][o],   Q[d][cls][o] = sum_img pos[b, f + d] * S.
+// Step 1: one block per (image, chunk of rows), one thread per channel; per row the (left, middle, right) sums go to
+// the row's classes, then the block adds pos-weighted sums into Q (only the few non-empty classes).  Step 2 folds Q
+// over the classes that admit each tap.  img = f * B + b; the window of gradient frame f covers input frames
+// frame0 + f + d.
+constexpr int kPosChunks = 8;
+
 __global__ void __launch_bounds__(192) posterm_bwd_sums_kernel(const __nv_bfloat16* __restrict__ g,
-                                                               float* __restrict__ sums, int H, int W, int ch) {
-  const int img = blockIdx.x;
+                                                               const float* __restrict__ pos, float* __restrict__ Q,
+                                                               int B, int L, int frame0, int window, int H, int W,
+                                                               int ch) {
+  const int img = blockIdx.x, chunk = blockIdx.y;
   const int o = threadIdx.x;
   if (o >= ch) return;
+  const int rows = (H + kPosChunks - 1) / kPosChunks;
+  const int ya = chunk * rows, yb = min(H, ya + rows);
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   const __nv_bfloat16* base = g + static_cast<size_t>(img) * H * W * ch + o;
-  for (int y = 0; y < H; ++y) {
+  for (int y = ya; y < yb; ++y) {
     const int rc = (y > 0 ? 1 : 0) | (y < H - 1 ? 2 : 0);
     const __nv_bfloat16* rowp = base + static_cast<size_t>(y) * W * ch;
-    float left = __bfloat162float(rowp[0]);
-    float right = W > 1 ? __bfloat162float(rowp[static_cast<size_t>(W - 1) * ch]) : 0.f;
+    const float left = __bfloat162float(rowp[0]);
+    const float right = W > 1 ? __bfloat162float(rowp[static_cast<size_t>(W - 1) * ch]) : 0.f;
     float mid = 0.f;
     for (int x = 1; x < W - 1; ++x) mid += __bfloat162float(rowp[static_cast<size_t>(x) * ch]);
     // classes: bit2 = x > 0, bit3 = x < W-1
-    const int cl = rc | (W > 1 ? 8 : 0);
-    const int cr = rc | 4;
-    const int cm = rc | 12;
-    // registers indexed by a runtime class: resolved with a short unrolled select to stay out of local memory
+    const int cl = rc | (W > 1 ? 8 : 0), cr = rc | 4, cm = rc | 12;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 16; ++i)
       acc[i] += (i == cl ? left : 0.f) + (i == cm ? mid : 0.f) + ((i == cr && W > 1) ? right : 0.f);
-    }
   }
+  const int f = img / B, b = img - f * B;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) sums[(static_cast<size_t>(img) * 16 + i) * ch + o] = acc[i];
+  for (int i = 0; i < 16; ++i) {
+    if (acc[i] == 0.f) continue;
+    for (int d = 0; d < window; ++d)
+      atomicAdd(Q + (static_cast<size_t>(d) * 16 + i) * ch + o, pos[static_cast<long long>(b) * L + frame0 + f + d] * acc[i]);
+  }
 }
 
-// step 2: dW1[o, (2F+1)*d + 2F, tap] += sum_img pos[b(img), f(img) + d] * sum_{cls admitting tap} S[img][cls][o]
-// img = f * B + b over the n_frames gradient frames; the window of gradient frame f covers input frames
-// frame0 + f + d, d = 0..window-1.
-__global__ void posterm_bwd_reduce_kernel(const float* __restrict__ sums, const float* __restrict__ pos,
-                                          float* __restrict__ dw1, int n_frames, int B, int L, int frame0, int window,
-                                          int c_out, int c_in, int feat2, int ch) {
+__global__ void posterm_bwd_reduce_kernel(const float* __restrict__ Q, float* __restrict__ dw1, int window, int c_out,
+                                          int c_in, int feat2, int ch) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = c_out * window * 9;
-  if (gid >= total) return;
+  if (gid >= c_out * window * 9) return;
   const int tap = gid % 9;
   const int d = (gid / 9) % window;
   const int o = gid / (9 * window);
   const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-  float acc = 0.f;
-  for (int f = 0; f < n_frames; ++f)
-    for (int b = 0; b < B; ++b) {
-      const float pc = pos[static_cast<long long>(b) * L + frame0 + f + d];
-      const float* S = sums + (static_cast<size_t>(f) * B + b) * 16 * ch + o;
-      float s = 0.f;
+  float s = 0.f;
 #pragma unroll
-      for (int cls = 0; cls < 16; ++cls) {
-        const bool ok = (dy >= 0 || (cls & 1)) && (dy <= 0 || (cls & 2)) && (dx >= 0 || (cls & 4)) &&
-                        (dx <= 0 || (cls & 8));
-        if (ok) s += S[static_cast<size_t>(cls) * ch];
-      }
-      acc = fmaf(pc, s, acc);
-    }
-  atomicAdd(dw1 + (static_cast<long long>(o) * c_in + (feat2 + 1) * d + feat2) * 9 + tap, acc);
+  for (int cls = 0; cls < 16; ++cls) {
+    const bool ok = (dy >= 0 || (cls & 1)) && (dy <= 0 || (cls & 2)) && (dx >= 0 || (cls & 4)) && (dx <= 0 || (cls & 8));
+    if (ok) s += Q[(static_cast<size_t>(d) * 16 + cls) * ch + o];
+  }
+  atomicAdd(dw1 + (static_cast<long long>(o) * c_in + (feat2 + 1) * d + feat2) * 9 + tap, s);
 }
 
 int launch_posterm_bwd(const void* g_bf16, const float* pos, float* sums, float* dw1, int n_frames, int B, int L,
                        int frame0, int window, int H, int W, int c_out, int c_in, int feat2, int ch, cudaStream_t s) {
   if (n_frames * B == 0) return 0;
   if (ch > 192) return static_cast<int>(cudaErrorInvalidValue);
-  posterm_bwd_sums_kernel<<<n_frames * B, 192, 0, s>>>(static_cast<const __nv_bfloat16*>(g_bf16), sums, H, W, ch);
-  int e = static_cast<int>(cudaGetLastError());
+  // Q [window][16][ch] is the scratch buffer
+  int e = static_cast<int>(cudaMemsetAsync(sums, 0, static_cast<size_t>(window) * 16 * ch * sizeof(float), s));
+  if (e) return e;
+  dim3 grid(n_frames * B, kPosChunks);
+  posterm_bwd_sums_kernel<<<grid, 192, 0, s>>>(static_cast<const __nv_bfloat16*>(g_bf16), pos, sums, B, L, frame0,
+                                               window, H, W, ch);
+  e = static_cast<int>(cudaGetLastError());
   if (e) return e;
   const int total = c_out * window * 9;
-  posterm_bwd_reduce_kernel<<<(total + 127) / 128, 128, 0, s>>>(sums, pos, dw1, n_frames, B, L, frame0, window, c_out,
-                                                                c_in, feat2, ch);
+  posterm_bwd_reduce_kernel<<<(total + 127) / 128, 128, 0, s>>>(sums, dw1, window, c_out, c_in, feat2, ch);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -75,73 +75,135 @@ int launch_in_conv_prelu(const float* x, const float* w, const float* b, const f
 
 // ------------------------------------------------------------------------------------------------
 // head_conv_last: in bf16 NHWC [n_img][H][W][64] -> out fp32 [n_img][H][W]; out = b + sum_{tap,c} in*w
-// Block = 8x32 output pixels; the (10 x 34) halo tile is staged in shared memory with a 144-byte pixel
-// pitch (conflict-free 16-byte reads across consecutive pixels); one thread per output pixel.
-constexpr int kLastTH = 8, kLastTW = 32, kLastPitch = 144;
-constexpr int kLastHaloPix = (kLastTH + 2) * (kLastTW + 2);
+//
+// HBM-bound (128 B in, 4 B out per pixel).  Every INPUT pixel q contributes to its 9 neighbours through
+//   P[q][tap] = sum_c in[q][c] * w[c][tap]            (a [pixels x 64] x [64 x 9] product),
+// and out[p] = b + sum_tap P[p + off(tap)][tap].  A block stages a 16x32 halo tile (512 pixels, 144-byte pixel
+// pitch: conflict-free ldmatrix rows) once, its 8 warps compute P for 64 pixels each with warp-level
+// mma.sync.m16n8k16 (bf16 operands, fp32 accumulate; the 64x9 weight matrix lives in 16 registers per thread as B
+// fragments), P goes to shared memory as [tap][pixel] and the 14x30 interior outputs gather 9 floats each.
+// Versus one thread per output pixel re-reading 9x128 B of inputs and all 576 weights from shared memory this cuts
+// shared-memory traffic ~7x and removes the FFMA bottleneck.
+constexpr int kLastHaloH = 16, kLastHaloW = 32, kLastPitch = 144;
+constexpr int kLastTH = kLastHaloH - 2, kLastTW = kLastHaloW - 2;
+constexpr int kLastHaloPix = kLastHaloH * kLastHaloW;   // 512
+constexpr int kLastPStride = 516;                       // [tap][516]: conflict-free fragment stores and row gathers
 
-__global__ void __launch_bounds__(256) head_conv_last_kernel(const __nv_bfloat16* __restrict__ in,
-                                                             const float* __restrict__ w,
-                                                             const float* __restrict__ b, float* __restrict__ out,
-                                                             const float* __restrict__ target,
-                                                             float* __restrict__ l1_partial, int H, int W,
-                                                             int tiles_x, int tiles_y) {
+__device__ __forceinline__ uint32_t f2_to_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256, 2) head_conv_last_kernel(const __nv_bfloat16* __restrict__ in,
+                                                                const float* __restrict__ w,
+                                                                const float* __restrict__ b, float* __restrict__ out,
+                                                                const float* __restrict__ target,
+                                                                float* __restrict__ l1_partial, int H, int W,
+                                                                int tiles_x, int tiles_y) {
   extern __shared__ __align__(16) uint8_t sm[];
-  uint8_t* tile = sm;                                                   // kLastHaloPix * 144 B
-  float* sw = reinterpret_cast<float*>(sm + kLastHaloPix * kLastPitch); // [9][64] fp32
+  uint8_t* tile = sm;                                                        // 512 * 144 B
+  float* P = reinterpret_cast<float*>(sm + kLastHaloPix * kLastPitch);      // [9][516] fp32
   int t = blockIdx.x;
   const int tx = t % tiles_x;
   t /= tiles_x;
   const int ty = t % tiles_y;
   const int img = t / tiles_y;
-  const int y0 = ty * kLastTH, x0 = tx * kLastTW;
-  for (int i = threadIdx.x; i < 576; i += blockDim.x) {
-    int c = i / 9, tap = i % 9;  // parameter layout (1, 64, 3, 3)
-    sw[tap * 64 + c] = w[i];
+  const int y0 = ty * kLastTH - 1, x0 = tx * kLastTW - 1;                    // image coordinates of halo pixel (0, 0)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // B fragments of the [64 x 16] weight matrix (taps 9..15 are zero): parameter layout (1, 64, 3, 3) -> w[c*9 + tap]
+  uint32_t bw[4][2][2];
+  {
+    const int n = lane >> 2, k0 = (lane & 3) * 2;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int tap = nt * 8 + n;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int c = ks * 16 + k0 + hh * 8;
+          const float lo = tap < 9 ? __ldg(w + c * 9 + tap) : 0.f;
+          const float hi = tap < 9 ? __ldg(w + (c + 1) * 9 + tap) : 0.f;
+          bw[ks][nt][hh] = f2_to_bf16x2(lo, hi);
+        }
+      }
   }
+
   const __nv_bfloat16* src = in + static_cast<size_t>(img) * H * W * 64;
-  // 8 x 16-byte chunks per halo pixel
-  for (int i = threadIdx.x; i < kLastHaloPix * 8; i += blockDim.x) {
+  // stage the halo tile with cp.async (16 x 16 B per thread, all in flight; src-size 0 zero-fills pixels outside
+  // the image = the conv padding)
+  const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+#pragma unroll
+  for (int it = 0; it < kLastHaloPix * 8 / 256; ++it) {
+    const int i = threadIdx.x + it * 256;
     const int hp = i >> 3, ck = i & 7;
-    const int hy = hp / (kLastTW + 2), hx = hp % (kLastTW + 2);
-    const int y = y0 + hy - 1, x = x0 + hx - 1;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (y >= 0 && y < H && x >= 0 && x < W)
-      v = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y) * W + x) * 64) + ck);
-    *reinterpret_cast<uint4*>(tile + hp * kLastPitch + ck * 16) = v;
+    const int y = y0 + (hp >> 5), x = x0 + (hp & 31);
+    const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+    const __nv_bfloat16* g = src + (static_cast<size_t>(ok ? y : 0) * W + (ok ? x : 0)) * 64 + ck * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_s + hp * kLastPitch + ck * 16), "l"(g),
+                 "r"(ok ? 16 : 0)
+                 : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const int ly = threadIdx.x / kLastTW, lx = threadIdx.x % kLastTW;
-  const int y = y0 + ly, x = x0 + lx;
-  float acc = b[0];
+
+  // P for this warp's 64 halo pixels: 4 m16 tiles x 4 k16 steps x 2 n8 tiles
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const uint8_t* prow = tile + ((ly + tap / 3) * (kLastTW + 2) + (lx + tap % 3)) * kLastPitch;
-    const float* wt = sw + tap * 64;
+  for (int mt = 0; mt < 4; ++mt) {
+    const int px0 = warp * 64 + mt * 16;
+    float acc[2][4];
 #pragma unroll
-    for (int ck = 0; ck < 8; ++ck) {
-      const uint4 u = *reinterpret_cast<const uint4*>(prow + ck * 16);
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-      const float4 w0 = *reinterpret_cast<const float4*>(wt + ck * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(wt + ck * 8 + 4);
-      float2 f;
-      f = __bfloat1622float2(h2[0]); acc = fmaf(f.x, w0.x, acc); acc = fmaf(f.y, w0.y, acc);
-      f = __bfloat1622float2(h2[1]); acc = fmaf(f.x, w0.z, acc); acc = fmaf(f.y, w0.w, acc);
-      f = __bfloat1622float2(h2[2]); acc = fmaf(f.x, w1.x, acc); acc = fmaf(f.y, w1.y, acc);
-      f = __bfloat1622float2(h2[3]); acc = fmaf(f.x, w1.z, acc); acc = fmaf(f.y, w1.w, acc);
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+    const uint32_t arow = tile_s + (px0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kLastPitch + 16 * (lane >> 4);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a0, a1, a2, a3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                   : "r"(arow + ks * 32));
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+            "{%0, %1, %2, %3};"
+            : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bw[ks][nt][0]), "r"(bw[ks][nt][1]));
+    }
+    const int r = px0 + (lane >> 2), c = (lane & 3) * 2;
+    P[c * kLastPStride + r] = acc[0][0];
+    P[(c + 1) * kLastPStride + r] = acc[0][1];
+    P[c * kLastPStride + r + 8] = acc[0][2];
+    P[(c + 1) * kLastPStride + r + 8] = acc[0][3];
+    if ((lane & 3) == 0) {
+      P[8 * kLastPStride + r] = acc[1][0];
+      P[8 * kLastPStride + r + 8] = acc[1][2];
     }
   }
+  __syncthreads();
+
+  const float bias = b[0];
   float l1 = 0.f;
-  if (y < H && x < W) {
-    const size_t o = (static_cast<size_t>(img) * H + y) * W + x;
-    out[o] = acc;
-    if (target) l1 = fabsf(acc - target[o]);
+  for (int i = threadIdx.x; i < kLastTH * kLastTW; i += 256) {
+    const int ly = i / kLastTW, lx = i - ly * kLastTW;
+    const int y = y0 + 1 + ly, x = x0 + 1 + lx;
+    float acc = bias;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) acc += P[tap * kLastPStride + (ly + tap / 3) * kLastHaloW + lx + tap % 3];
+    if (y < H && x < W) {
+      const size_t o = (static_cast<size_t>(img) * H + y) * W + x;
+      out[o] = acc;
+      if (target) l1 += fabsf(acc - target[o]);
+    }
   }
   if (l1_partial) {
     // |out - target| summed per image: warp shuffle, then one atomic per warp (nn.L1Loss numerator).
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, d);
-    if ((threadIdx.x & 31) == 0) atomicAdd(l1_partial + img, l1);
+    if (lane == 0) atomicAdd(l1_partial + img, l1);
   }
 }
 
@@ -149,7 +211,7 @@ int launch_head_conv_last(const void* in, const float* w, const float* b, float*
                           float* l1_partial, long long n_img, int H, int W, cudaStream_t s) {
   if (n_img == 0) return 0;
   const int tiles_x = (W + kLastTW - 1) / kLastTW, tiles_y = (H + kLastTH - 1) / kLastTH;
-  const size_t smem = kLastHaloPix * kLastPitch + 576 * sizeof(float);
+  const size_t smem = kLastHaloPix * kLastPitch + 9 * kLastPStride * sizeof(float);
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(head_conv_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

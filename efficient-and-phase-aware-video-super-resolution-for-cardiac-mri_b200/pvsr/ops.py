@@ -306,7 +306,7 @@ def refine_posterm_bwd(g, pos, dw1, n_frames, frame0, window=5, feat=64):
     lib = L.load()
     B, Lf = pos.shape
     _, H, W, ch = g.shape
-    sums = torch.empty(n_frames * B, 16, ch, dtype=torch.float32, device=g.device)
+    sums = torch.empty(window, 16, ch, dtype=torch.float32, device=g.device)
     L.check(lib.pvsr_refine_posterm_bwd(L.ptr(g), L.ptr(pos.contiguous()), L.ptr(sums), L.ptr(dw1), n_frames, B, Lf,
                                         frame0, window, H, W, dw1.shape[0], dw1.shape[1], 2 * feat, ch,
                                         L.current_stream()), "refine_posterm_bwd")

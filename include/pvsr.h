@@ -204,7 +204,7 @@ int pvsr_in_conv_prelu_bwd(const float* x, const float* w, const float* b, const
                            float* dw, float* db, float* dslope, int64_t n_img, int H, int W, void* stream);
 /* Gradient of the positional-code channels of _RefineBlock conv1: g = dL/d(conv1 out) bf16 NHWC with `ch` channels
  * for n_frames*B images (frame-major); the window of gradient frame f covers input frames frame0+f .. +window-1.
- * sums: scratch fp32 [n_frames*B][16][ch]; dw1 (c_out, c_in, 3, 3) += on the pos channels only. */
+ * sums: scratch fp32 [window][16][ch]; dw1 (c_out, c_in, 3, 3) += on the pos channels only. */
 int pvsr_refine_posterm_bwd(const void* g_bf16, const float* pos, float* sums, float* dw1, int n_frames, int B, int L,
                             int frame0, int window, int H, int W, int c_out, int c_in, int feat2, int ch,
                             void* stream);

@@ -228,8 +228,10 @@ def test_in_conv_prelu(pvsr_lib):
     assert rel_l2(nchw(out), ref) < 3e-3
 
 
-@pytest.mark.parametrize("H,W", [(216, 252), (24, 28), (9, 33)])
+@pytest.mark.parametrize("H,W", [(216, 252), (128, 128), (24, 28), (9, 33), (1, 1), (15, 31)])
 def test_head_conv_last_and_l1(pvsr_lib, H, W):
+    """64 -> 1 conv at HR.  Like every conv of the path it consumes bf16 operands (activations AND weights) and
+    accumulates in fp32: exact against a reference built from the bf16-rounded weights, 2^-9-level against fp32."""
     from pvsr import ops
     g = torch.Generator(device="cuda").manual_seed(8)
     n = 3
@@ -240,8 +242,10 @@ def test_head_conv_last_and_l1(pvsr_lib, H, W):
     part = torch.zeros(n, device="cuda")
     out = ops.head_conv_last(nhwc(x), w, b, target=tgt, l1_partial=part)
     torch.cuda.synchronize()
-    ref = F.conv2d(x, w, b, padding=1)[:, 0]
+    ref = F.conv2d(x, bf16r(w), b, padding=1)[:, 0]
     assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4), (out - ref).abs().max()
+    ref32 = F.conv2d(x, w, b, padding=1)[:, 0]
+    assert rel_l2(out, ref32) < 3e-3
     l1 = (ref - tgt).abs().sum(dim=(1, 2))
     assert torch.allclose(part, l1, rtol=1e-4)
 
