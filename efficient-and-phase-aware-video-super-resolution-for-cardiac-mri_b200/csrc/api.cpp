@@ -147,6 +147,12 @@ int pvsr_device_check(void) {
   return 0;
 }
 
+int pvsr_set_cta_pair(int enable) {
+  set_cta_pair(enable);
+  return 0;
+}
+int pvsr_get_cta_pair(void) { return get_cta_pair(); }
+
 int pvsr_choose_tile(int H, int W, int* tw_log2_out) {
   if (H <= 0 || W <= 0 || !tw_log2_out) return set_error(-2, "bad image size");
   choose_tile(H, W, tw_log2_out);

@@ -81,6 +81,11 @@ struct ConvMaps {
   CUtensorMap w;              // 2D (64, rows), box (64, BN)
 };
 
+// CTA pairs (tcgen05 cta_group::2) on/off; the weight tensor map box must be (64, bn / cta_pair_factor()).
+void set_cta_pair(int enable);
+int get_cta_pair();
+inline int cta_pair_factor() { return get_cta_pair() ? 2 : 1; }
+
 // Launches the tcgen05 kernel.  Returns a cudaError_t as int.
 int launch_conv3x3(int bn, int epi, const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream);
 

@@ -22,9 +22,11 @@ constexpr int kABytes = kTileM * kBlockK * 2;        // 16384
 constexpr int kAccStride = 256;                      // TMEM columns between the two accumulator stages
 constexpr int kTmemCols = 512;
 
-template <int BN>
+// CG = CTAs cooperating on one MMA: 1, or 2 = a CTA pair (tcgen05 cta_group::2): M = 256 pixels (128 per CTA), the
+// weight tile is split over the pair (each CTA stages BN/2 rows), halving its L2->SMEM traffic and stage footprint.
+template <int BN, int CG>
 struct Cfg {
-  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kBBytes = (BN / CG) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
@@ -69,27 +71,33 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
 
 struct TileCoord {
   int z, img, y0, x0, nt, tile_lin;
+  bool valid;   // false: padding tile of an odd pair (loaded and multiplied like its neighbour, never stored)
 };
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
+// Work item `it` (N tile fastest, then the group of CG consecutive M tiles, then the problem) -> the M tile of CTA
+// `rank` of the group.
+__device__ __forceinline__ TileCoord decode_item(const ConvParams& p, int it, int groups, int tiles_m, int cg, int rank) {
   TileCoord c;
-  c.nt = t % p.n_tiles_n;
-  t /= p.n_tiles_n;
-  int tx = t % p.tiles_x;
-  t /= p.tiles_x;
-  int ty = t % p.tiles_y;
-  t /= p.tiles_y;
-  c.img = t % p.n_img;
-  c.z = t / p.n_img;
+  c.nt = it % p.n_tiles_n;
+  it /= p.n_tiles_n;
+  const int grp = it % groups;
+  c.z = it / groups;
+  int m = grp * cg + rank;
+  c.valid = m < tiles_m;
+  if (!c.valid) m = tiles_m - 1;
+  const int tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  const int ty = m % p.tiles_y;
+  c.img = m / p.tiles_y;
   c.x0 = tx << p.tw_log2;
   c.y0 = ty * (kTileM >> p.tw_log2);
   c.tile_lin = (c.img * p.tiles_y + ty) * p.tiles_x + tx;
   return c;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   constexpr int S = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -105,7 +113,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.n_prob * p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
+  const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tiles_m = p.n_img * p.tiles_y * p.tiles_x;
+  const int groups = (tiles_m + CG - 1) / CG;
+  const int total_items = p.n_prob * groups * p.n_tiles_n;
+  const int item0 = blockIdx.x / CG, item_step = gridDim.x / CG;
 
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&maps.act[0]);
@@ -116,11 +128,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kNumEpiWarps * 32);
+      mbar_init(&tempty[i], CG * kNumEpiWarps * 32);   // pair: the epilogue warps of both CTAs release the leader
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_cg2<kTmemCols>(tmem_slot);
+    else tmem_alloc<kTmemCols>(tmem_slot);
+  }
   if constexpr (EPI == EPI_LSTM) {
     // Gate biases, pre-multiplied so that each gate costs one FFMA + ex2 + add + rcp:
     // i, f, o: -log2(e) * b (sigmoid);  g: 2 * log2(e) * b (tanh).
@@ -130,7 +145,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync();   // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -139,10 +155,10 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
+      for (int t = item0; t < total_items; t += item_step) {
+        const TileCoord tc = decode_item(p, t, groups, tiles_m, CG, rank);
         const ConvProblem& pr = p.prob[tc.z];
-        int wrow = pr.w_row_base + tc.nt * BN;
+        int wrow = pr.w_row_base + tc.nt * BN + rank * (BN / CG);
         for (int s = 0; s < pr.n_src; ++s) {
           const SrcView& sv = pr.src[s];
           const int img = sv.img_base + tc.img;
@@ -153,9 +169,17 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
             const int cy = sv.mul * (tc.y0 + tap / 3 - 1) + sv.off_y;
             for (int cb = 0; cb < p.kb_per_src; ++cb) {
               mbar_wait(&empty[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
-              tma_load_4d(smem_a + stage * kABytes, tm, &full[stage], sv.ch0 + cb * kBlockK, cx, cy, img);
-              tma_load_2d(smem_b + stage * C::kBBytes, &maps.w, &full[stage], 0, wrow);
+              if constexpr (CG == 2) {
+                // both CTAs' boxes are counted on the leader's barrier (its MMA warp consumes both halves)
+                if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::kStageBytes);
+                const uint32_t bar = mapa(smem_u32(&full[stage]), 0);
+                tma_load_4d_cg2(smem_a + stage * kABytes, tm, bar, sv.ch0 + cb * kBlockK, cx, cy, img);
+                tma_load_2d_cg2(smem_b + stage * C::kBBytes, &maps.w, bar, 0, wrow);
+              } else {
+                mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
+                tma_load_4d(smem_a + stage * kABytes, tm, &full[stage], sv.ch0 + cb * kBlockK, cx, cy, img);
+                tma_load_2d(smem_b + stage * C::kBBytes, &maps.w, &full[stage], 0, wrow);
+              }
               wrow += p.n_total;
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
@@ -164,18 +188,18 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(BN);
+    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
+    constexpr uint32_t idesc = make_idesc_bf16(BN, 128 * CG);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = item0; t < total_items && rank == 0; t += item_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * kAccStride;
-      const int kb_per_tile = p.prob[decode_tile(p, t).z].n_src * p.taps * p.kb_per_src;
+      const int kb_per_tile = p.prob[decode_item(p, t, groups, tiles_m, CG, 0).z].n_src * p.taps * p.kb_per_src;
       int cb = 0;
       for (int kb = 0; kb < kb_per_tile; ++kb) {
         mbar_wait(&full[stage], phase);
@@ -186,10 +210,16 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           const uint64_t bdesc = make_desc_k_sw128(smem_u32(smem_b + stage * C::kBBytes));
           for (int k = 0; k < nk16; ++k) {
             // +32 bytes per K=16 slice inside the 128-byte swizzle row (address field is in 16-byte units)
-            mma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CG == 2) mma_bf16_ss_cg2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else mma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          mma_commit(&empty[stage]);
-          if (kb == kb_per_tile - 1) mma_commit(&tfull[as]);
+          if constexpr (CG == 2) {
+            mma_commit_cg2(&empty[stage]);                       // frees the stage in both CTAs
+            if (kb == kb_per_tile - 1) mma_commit_cg2(&tfull[as]);
+          } else {
+            mma_commit(&empty[stage]);
+            if (kb == kb_per_tile - 1) mma_commit(&tfull[as]);
+          }
         }
         __syncwarp();
         if (++cb == p.kb_per_src) cb = 0;
@@ -205,13 +235,13 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     const int TW = 1 << p.tw_log2;
     const int ly = row >> p.tw_log2, lx = row & (TW - 1);
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = item0; t < total_items; t += item_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const TileCoord tc = decode_tile(p, t);
+      const TileCoord tc = decode_item(p, t, groups, tiles_m, CG, rank);
       const ConvProblem& pr = p.prob[tc.z];
       const int y = tc.y0 + ly, x = tc.x0 + lx;
-      const bool valid = (y < p.H) && (x < p.W);
+      const bool valid = tc.valid && (y < p.H) && (x < p.W);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * kAccStride + (static_cast<uint32_t>(quad * 32) << 16);
@@ -258,8 +288,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
               const float gg = tanh_from_scaled(fmaf(__uint_as_float(vg[j]), 2.f * kLog2e, bga[u]));
               const float cn = fmaf(gf, cprev[j], gi * gg);
               hn[u] = go * tanh_from_scaled(cn * (2.f * kLog2e));
-              cout[(ch0 + j) * kTileM] = cn;
-              if (gout) {
+              if (tc.valid) cout[(ch0 + j) * kTileM] = cn;   // padding tiles of an odd pair never store
+              if (gout && tc.valid) {
                 gout[(ch0 + j) * kTileM] = __float2bfloat16(gi);
                 gout[(64 + ch0 + j) * kTileM] = __float2bfloat16(gf);
                 gout[(128 + ch0 + j) * kTileM] = __float2bfloat16(go);
@@ -374,51 +404,86 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       }
       // All TMEM reads of this accumulator stage are complete (wait::ld above): hand it back to the MMA warp.
       tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      if constexpr (CG == 2) mbar_arrive_cluster(mapa(smem_u32(&tempty[as]), 0));
+      else mbar_arrive(&tempty[as]);
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+  if constexpr (CG == 2) {
+    cluster_sync();   // neither CTA may leave (or free TMEM) while its peer still reads its operands / barriers
+    if (warp == 1) tmem_dealloc_cg2<kTmemCols>(tmem_base);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+  }
 }
 
-template <int BN, int EPI>
+static int g_cta_pair = 1;   // 1: use CTA pairs (cta_group::2) whenever the grid allows it
+
+template <int BN, int EPI, int CG>
 static int launch_t(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
-  using C = Cfg<BN>;
-  auto kern = conv3x3_tc_kernel<BN, EPI>;
+  using C = Cfg<BN, CG>;
+  auto kern = conv3x3_tc_kernel<BN, EPI, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  const long long total = 1LL * p.n_prob * p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
-  if (total <= 0) return 0;
-  const int grid = static_cast<int>(total < num_sms ? total : num_sms);
-  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(maps, p);
-  return static_cast<int>(cudaGetLastError());
+  const long long tiles_m = 1LL * p.n_img * p.tiles_y * p.tiles_x;
+  const long long items = 1LL * p.n_prob * ((tiles_m + CG - 1) / CG) * p.n_tiles_n;
+  if (items <= 0) return 0;
+  const long long max_groups = num_sms / CG;
+  const int grid = static_cast<int>((items < max_groups ? items : max_groups) * CG);
+  if constexpr (CG == 1) {
+    kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(maps, p);
+    return static_cast<int>(cudaGetLastError());
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, maps, p));
+  }
 }
 
+template <int BN, int EPI>
+static int launch_cg(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
+  if (g_cta_pair && num_sms >= 2) return launch_t<BN, EPI, 2>(maps, p, num_sms, stream);
+  return launch_t<BN, EPI, 1>(maps, p, num_sms, stream);
+}
+
+void set_cta_pair(int enable) { g_cta_pair = enable ? 1 : 0; }
+int get_cta_pair() { return g_cta_pair; }
+
 int launch_conv3x3(int bn, int epi, const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
-  if (epi == EPI_LSTM && bn == 256) return launch_t<256, EPI_LSTM>(maps, p, num_sms, stream);
+  if (epi == EPI_LSTM && bn == 256) return launch_cg<256, EPI_LSTM>(maps, p, num_sms, stream);
   if (epi == EPI_STORE) {
     switch (bn) {
-      case 64: return launch_t<64, EPI_STORE>(maps, p, num_sms, stream);
-      case 144: return launch_t<144, EPI_STORE>(maps, p, num_sms, stream);
-      case 256: return launch_t<256, EPI_STORE>(maps, p, num_sms, stream);
+      case 64: return launch_cg<64, EPI_STORE>(maps, p, num_sms, stream);
+      case 144: return launch_cg<144, EPI_STORE>(maps, p, num_sms, stream);
+      case 256: return launch_cg<256, EPI_STORE>(maps, p, num_sms, stream);
     }
   }
   if (epi == EPI_PS) {
     switch (bn) {
-      case 192: return launch_t<192, EPI_PS>(maps, p, num_sms, stream);
-      case 256: return launch_t<256, EPI_PS>(maps, p, num_sms, stream);
+      case 192: return launch_cg<192, EPI_PS>(maps, p, num_sms, stream);
+      case 256: return launch_cg<256, EPI_PS>(maps, p, num_sms, stream);
     }
   }
   if (epi == EPI_GRAD) {
     switch (bn) {
-      case 64: return launch_t<64, EPI_GRAD>(maps, p, num_sms, stream);
-      case 128: return launch_t<128, EPI_GRAD>(maps, p, num_sms, stream);
+      case 64: return launch_cg<64, EPI_GRAD>(maps, p, num_sms, stream);
+      case 128: return launch_cg<128, EPI_GRAD>(maps, p, num_sms, stream);
     }
   }
   return static_cast<int>(cudaErrorInvalidValue);

@@ -143,6 +143,7 @@ struct pvsr_plan {
   int num_sms = 0;
   const void* maps_ws = nullptr;
   const void* maps_pk = nullptr;
+  int maps_cg = -1;      // CTA-pair setting the tensor maps (weight box height) were built for
   ConvMaps maps_lstm, maps_c1, maps_c2, maps_head[PVSR_MAX_HEAD_CONVS];   // act[0] + packed weights of each launch kind
   ConvMaps bm_lstm_dg, bm_lstm_wg, bm_c1_dg, bm_c1_wg, bm_c2_dg, bm_c2_wg, bm_head_dg[PVSR_MAX_HEAD_CONVS],
       bm_head_wg[PVSR_MAX_HEAD_CONVS];
@@ -754,7 +755,7 @@ void schedule_backward(Ctx& c) {
 }
 
 int build_maps(pvsr_plan* p, const void* ws, const void* pk) {
-  if (p->maps_ws == ws && p->maps_pk == pk) return 0;
+  if (p->maps_ws == ws && p->maps_pk == pk && p->maps_cg == get_cta_pair()) return 0;
   const uint8_t* w = static_cast<const uint8_t*>(ws);
   const uint8_t* k = static_cast<const uint8_t*>(pk);
   int rc = 0;
@@ -825,6 +826,7 @@ int build_maps(pvsr_plan* p, const void* ws, const void* pk) {
   if (rc) return set_error(-20, "tensor map encode failed");
   p->maps_ws = ws;
   p->maps_pk = pk;
+  p->maps_cg = get_cta_pair();
   for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
   p->graphs.clear();
   return 0;

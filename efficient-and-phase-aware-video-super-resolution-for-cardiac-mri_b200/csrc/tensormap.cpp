@@ -40,10 +40,11 @@ int make_act_tmap(CUtensorMap* out, const void* base, int channels, int W, int H
   return r == CUDA_SUCCESS ? 0 : -(1000 + (int)r);
 }
 
-// Packed weights: row-major [rows][64] bf16; box = (64, bn rows).
+// Packed weights: row-major [rows][64] bf16; box = (64, bn rows) - or half of them per CTA of a pair.
 int make_weight_tmap(CUtensorMap* out, const void* base, long long rows, int bn) {
   auto fn = get_encode_fn();
   if (!fn) return -100;
+  bn /= cta_pair_factor();
   cuuint64_t dims[2] = {64, (cuuint64_t)rows};
   cuuint64_t strides[1] = {128};
   cuuint32_t box[2] = {64, (cuuint32_t)bn};

@@ -35,6 +35,10 @@ int pvsr_version(void);
 const char* pvsr_last_error(void);
 /* 0 when the current CUDA device can run the kernels (compute capability 10.x); negative otherwise. */
 int pvsr_device_check(void);
+/* tcgen05 conv launches as CTA pairs (cta_group::2: two SMs share one weight tile, M = 256 pixels per MMA).
+ * Default on; 0 selects the single-CTA kernel (A/B measurements, debugging).  Process-wide. */
+int pvsr_set_cta_pair(int enable);
+int pvsr_get_cta_pair(void);
 
 /* ---- host-side packing logic (pure CPU; usable without a GPU) ------------------------------------------------ */
 /* Tile choice of the implicit GEMM: tile = (128 >> tw_log2) x (1 << tw_log2) output pixels. */
