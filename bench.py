@@ -31,6 +31,9 @@ for p in (PKG, ROOT):
 import torch  # noqa: E402
 
 T_FRAMES, U_FRAMES, LR_H, LR_W, SCALE = 30, 6, 54, 63, 4
+# BASELINE.json configs: [1] ACDC x4 (the headline workload), [2] the x2 / x3 scale variants, [3] DSB15SR-shaped x4
+WORKLOADS = {"acdc_x4": (54, 63, 4, "ACDCSR"), "acdc_x3": (72, 84, 3, "ACDCSR"), "acdc_x2": (108, 126, 2, "ACDCSR"),
+             "dsb15_x4": (63, 48, 4, "DSB15SR")}
 NET_KW = dict(in_channels=1, out_channels=1, num_features=[64, 64, 64], upscale_factor=SCALE, num_stages=3,
               update_memory=True, num_updated_frames=U_FRAMES, refine_window_size=5, positional_encoding=True)
 METRIC = "SR frames/s at x4"
@@ -127,12 +130,14 @@ def run_reference(args, rank):
     times = cpu_oracle_time(args.steps, args.warmup, cores)
     total = sum(times)
     value = T_FRAMES * len(times) / total
-    sample = f"{len(times)} step(s) x 1 ACDCSR x4 sequence (42 LR frames 54x63 -> 30 SR frames), all 9 heads, fp32"
+    sample = (f"{len(times)} step(s) x 1 {args.workload} sequence (42 LR frames {LR_H}x{LR_W} -> 30 SR frames), "
+              "all 9 heads, fp32")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "RefineNet x4 inference, synthetic ACDCSR-shaped cine sequences (LR 54x63, T=30, U=6), "
-                                   "1 sequence per step on the host CPU", "sequences_per_step": 1},
+            "config": {"workload": f"RefineNet x{SCALE} inference, synthetic cine sequences (LR {LR_H}x{LR_W}, T=30, U=6), "
+                                   "1 sequence per step on the host CPU", "name": args.workload,
+                       "sequences_per_step": 1},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -233,11 +238,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--workload", default="acdc_x4", choices=sorted(WORKLOADS),
+                    help="inference workload shape (default: the BASELINE.json headline config)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train", "both"],
                     help="infer: BASELINE.json metric (default; adds a short train_step object at N=1); "
                          "train: the training-step line; both: inference line with the train_step object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    global LR_H, LR_W, SCALE, METRIC
+    LR_H, LR_W, SCALE, shape_name = WORKLOADS[args.workload]
+    NET_KW["upscale_factor"] = SCALE
+    METRIC = f"SR frames/s at x{SCALE}"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -362,7 +373,7 @@ def main():
 
     # the training step of config 5 (short, same process) rides along on the single-GPU line
     train_res = None
-    if args.mode == "both" or (args.mode == "infer" and world == 1):
+    if args.mode == "both" or (args.mode == "infer" and world == 1 and args.workload == "acdc_x4"):
         targs = argparse.Namespace(**vars(args))
         targs.steps = min(args.steps, 5)
         train_res = bench_train(targs, dev, rank, world, distributed, barrier)
@@ -382,8 +393,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"RefineNet x4 inference, {B} synthetic ACDCSR-shaped cine sequences per GPU per step "
-                                   "(LR 54x63, T=30, U=6 -> 42 LR frames in, 30 SR frames 216x252 out), last output list only",
+            "config": {"workload": f"RefineNet x{SCALE} inference, {B} synthetic {shape_name}-shaped cine sequences per GPU per "
+                                   f"step (LR {LR_H}x{LR_W}, T=30, U=6 -> 42 LR frames in, 30 SR frames "
+                                   f"{LR_H * SCALE}x{LR_W * SCALE} out), last output list only",
+                       "name": args.workload,
                        "sequences_per_gpu": B, "frames_per_step": frames_per_step, "parallelism": f"sequence-sharded x{world}",
                        "l2": "256 MiB flush write between steps; per-step working set >> 126 MB L2",
                        "cuda_graph": not args.no_graph, "algorithmic_tflop_per_step_per_gpu": step_flops / 1e12},

@@ -152,6 +152,12 @@ int pvsr_set_cta_pair(int enable) {
   return 0;
 }
 int pvsr_get_cta_pair(void) { return get_cta_pair(); }
+int pvsr_set_halo_mode(int mode) {
+  if (mode < 0 || mode > 1) return set_error(-2, "halo mode must be 0 or 1");
+  set_halo_mode(mode);
+  return 0;
+}
+int pvsr_get_halo_mode(void) { return get_halo_mode(); }
 
 int pvsr_choose_tile(int H, int W, int* tw_log2_out) {
   if (H <= 0 || W <= 0 || !tw_log2_out) return set_error(-2, "bad image size");
@@ -232,10 +238,13 @@ int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream) {
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   const int tw = 1 << p.tw_log2, th = kTileM >> p.tw_log2;
+  int max_mul = 1;
+  for (int v = 0; v < d->n_views; ++v) max_mul = d->views[v].mul > max_mul ? d->views[v].mul : max_mul;
+  p.halo = halo_applicable(d->W, tw, p.tiles_x, d->taps, max_mul) ? get_halo_mode() : 0;
   for (int v = 0; v < d->n_views; ++v) {
     const pvsr_act_view& a = d->views[v];
     if (a.channels % 8 != 0) return set_error(-2, "view channels must be a multiple of 8");
-    rc = make_act_tmap(&maps.act[v], a.ptr, a.channels, a.W, a.H, a.images, tw, th, a.mul);
+    rc = make_act_tmap(&maps.act[v], a.ptr, a.channels, a.W, a.H, a.images, tw, p.halo ? th + 2 : th, a.mul);
     if (rc) return set_error(rc, "activation tensor map encode failed (%d)", rc);
   }
   rc = make_weight_tmap(&maps.w, d->w_packed, d->w_rows, d->bn);

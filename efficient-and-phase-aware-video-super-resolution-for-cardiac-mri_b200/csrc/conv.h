@@ -73,6 +73,7 @@ struct ConvParams {
   int out_ch;        // channels per pixel of the output tensor
   int ps_r;          // pixel-shuffle factor for EPI_PS
   int grad_split;    // EPI_GRAD column routing (see ConvProblem)
+  int halo;          // != 0: halo kernel (the activation maps carry (TH+2)-row boxes)
   ConvProblem prob[kMaxProb];
 };
 
@@ -85,6 +86,14 @@ struct ConvMaps {
 void set_cta_pair(int enable);
 int get_cta_pair();
 inline int cta_pair_factor() { return get_cta_pair() ? 2 : 1; }
+
+// Halo variant of the 3x3 launches (one activation slab per source instead of nine shifted boxes): 0 = off.
+void set_halo_mode(int mode);
+int get_halo_mode();
+// Applicable when a tile spans the image width with a spare zero column: 3x3 taps, plain views.
+inline bool halo_applicable(int W, int tw, int tiles_x, int taps, int max_mul) {
+  return get_halo_mode() != 0 && taps == 9 && max_mul == 1 && tiles_x == 1 && W + 1 <= tw;
+}
 
 // Launches the tcgen05 kernel.  Returns a cudaError_t as int.
 int launch_conv3x3(int bn, int epi, const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream);

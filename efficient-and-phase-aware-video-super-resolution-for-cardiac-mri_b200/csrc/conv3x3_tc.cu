@@ -94,6 +94,170 @@ __device__ __forceinline__ TileCoord decode_item(const ConvParams& p, int it, in
   return c;
 }
 
+// Epilogue of one accumulator tile for one epilogue thread (TMEM lane = tile row `row`, pixel (x, y)); `half`
+// selects which half of the column chunks this warp handles.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvProblem& pr, const TileCoord& tc,
+                                              uint32_t taddr, int row, int y, int x, bool valid, int half,
+                                              const float* bias_s) {
+  if constexpr (EPI == EPI_LSTM) {
+    // Columns: [i | f | o | g] x 64 channels (refine_net.py:258). This warp: channels [32*half, 32*half+32).
+    const float* cin = pr.c_in ? pr.c_in + (static_cast<size_t>(tc.tile_lin) * 64) * kTileM + row : nullptr;
+    float* cout = pr.c_out + (static_cast<size_t>(tc.tile_lin) * 64) * kTileM + row;
+    __nv_bfloat16* gout =
+        pr.gates_out ? pr.gates_out + (static_cast<size_t>(tc.tile_lin) * 256) * kTileM + row : nullptr;
+    __nv_bfloat16* hrow = pr.h_out + ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * 64;
+    const float4* bs4 = reinterpret_cast<const float4*>(bias_s + tc.z * 256);
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int ch0 = half * 32 + cc * 16;
+      uint32_t vi[16], vf[16], vo[16], vg[16];
+      tmem_ld16(taddr + ch0, vi);
+      tmem_ld16(taddr + 64 + ch0, vf);
+      tmem_ld16(taddr + 128 + ch0, vo);
+      tmem_ld16(taddr + 192 + ch0, vg);
+      float cprev[16];
+      if (cin) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cprev[j] = cin[(ch0 + j) * kTileM];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cprev[j] = 0.f;
+      }
+      tmem_ld_wait();
+      uint32_t hp[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 bi = bs4[(ch0 >> 2) + j4], bf = bs4[16 + (ch0 >> 2) + j4];
+        const float4 bo = bs4[32 + (ch0 >> 2) + j4], bg = bs4[48 + (ch0 >> 2) + j4];
+        const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, bfa[4] = {bf.x, bf.y, bf.z, bf.w};
+        const float boa[4] = {bo.x, bo.y, bo.z, bo.w}, bga[4] = {bg.x, bg.y, bg.z, bg.w};
+        float hn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j4 * 4 + u;
+          const float gi = sigmoid_from_scaled(fmaf(__uint_as_float(vi[j]), -kLog2e, bia[u]));
+          const float gf = sigmoid_from_scaled(fmaf(__uint_as_float(vf[j]), -kLog2e, bfa[u]));
+          const float go = sigmoid_from_scaled(fmaf(__uint_as_float(vo[j]), -kLog2e, boa[u]));
+          const float gg = tanh_from_scaled(fmaf(__uint_as_float(vg[j]), 2.f * kLog2e, bga[u]));
+          const float cn = fmaf(gf, cprev[j], gi * gg);
+          hn[u] = go * tanh_from_scaled(cn * (2.f * kLog2e));
+          if (tc.valid) cout[(ch0 + j) * kTileM] = cn;   // padding tiles of an odd pair never store
+          if (gout && tc.valid) {
+            gout[(ch0 + j) * kTileM] = __float2bfloat16(gi);
+            gout[(64 + ch0 + j) * kTileM] = __float2bfloat16(gf);
+            gout[(128 + ch0 + j) * kTileM] = __float2bfloat16(go);
+            gout[(192 + ch0 + j) * kTileM] = __float2bfloat16(gg);
+          }
+        }
+        hp[j4 * 2] = pack_bf16x2(hn[0], hn[1]);
+        hp[j4 * 2 + 1] = pack_bf16x2(hn[2], hn[3]);
+      }
+      if (valid) {
+        uint4* dst = reinterpret_cast<uint4*>(hrow + ch0);
+        dst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        dst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+      }
+    }
+  } else if constexpr (EPI == EPI_GRAD) {
+    // fp32 accumulation into NHWC 64-channel gradient tensors (data gradients of the convs).
+    const int nchunks = p.n_store >> 4;
+    const size_t pixoff = ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * 64;
+#pragma unroll 1
+    for (int ck = half; ck < nchunks; ck += 2) {
+      uint32_t v[16];
+      tmem_ld16(taddr + ck * 16, v);
+      tmem_ld_wait();
+      if (valid) {
+        float* d0 = p.grad_split ? ((ck < 4) ? pr.grad0 : pr.grad1) : pr.grad0;
+        float* d1 = p.grad_split ? nullptr : pr.grad1;
+        const int c0 = (ck & 3) * 16;
+        // Fire-and-forget vector reductions: several tiles of one launch (cells of a reverse wavefront) may add
+        // into the same gradient pixels, so a plain read-modify-write would race.
+        if (d0) {
+          float* q = d0 + pixoff + c0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            red_add_v4(q + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+        if (d1) {
+          float* q = d1 + pixoff + c0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            red_add_v4(q + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+  } else {
+    // EPI_STORE / EPI_PS: 16-column chunks, alternating between the two warp halves.
+    const int nchunks = p.n_store >> 4;
+    const int cls = (y > 0 ? 1 : 0) | (y < p.H - 1 ? 2 : 0) | (x > 0 ? 4 : 0) | (x < p.W - 1 ? 8 : 0);
+    const float* pterm =
+        pr.posterm ? pr.posterm + (static_cast<size_t>(tc.img) * 16 + cls) * p.n_total + tc.nt * BN : nullptr;
+    const float* bias = pr.bias ? pr.bias + tc.nt * BN : nullptr;
+#pragma unroll 1
+    for (int ck = half; ck < nchunks; ck += 2) {
+      uint32_t v[16];
+      tmem_ld16(taddr + ck * 16, v);
+      tmem_ld_wait();
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+      if (bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias + ck * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b = __ldg(b4 + j);
+          f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+        }
+      }
+      if (valid) {
+        if (pterm) {
+          const float4* t4 = reinterpret_cast<const float4*>(pterm + ck * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b = __ldg(t4 + j);
+            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+          }
+        }
+        size_t off;
+        if constexpr (EPI == EPI_PS) {
+          // column = q*64 + c with q = i*r + j  ->  HR pixel (y*r+i, x*r+j), channel c (PixelShuffle, :200,204)
+          const int col = tc.nt * BN + ck * 16;
+          const int q = col >> 6, c0 = col & 63;
+          const int r = p.ps_r;
+          const int qi = q / r, qj = q - qi * r;
+          off = ((static_cast<size_t>(tc.img) * p.H * r + (y * r + qi)) * (p.W * r) + (x * r + qj)) * 64 + c0;
+        } else {
+          off = ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * p.out_ch + tc.nt * BN + ck * 16;
+        }
+        if (pr.res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(pr.res + off);
+          float rf[16];
+          unpack_bf16x8(rp[0], rf);
+          unpack_bf16x8(rp[1], rf + 8);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] += rf[j];
+        }
+        if (pr.out_bf16) {
+          uint4* dst = reinterpret_cast<uint4*>(pr.out_bf16 + off);
+          dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                              pack_bf16x2(f[6], f[7]));
+          dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                              pack_bf16x2(f[14], f[15]));
+        }
+        if (pr.out_f32) {
+          float4* dst = reinterpret_cast<float4*>(pr.out_f32 + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
@@ -246,162 +410,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * kAccStride + (static_cast<uint32_t>(quad * 32) << 16);
 
-      if constexpr (EPI == EPI_LSTM) {
-        // Columns: [i | f | o | g] x 64 channels (refine_net.py:258). This warp: channels [32*half, 32*half+32).
-        const float* cin = pr.c_in ? pr.c_in + (static_cast<size_t>(tc.tile_lin) * 64) * kTileM + row : nullptr;
-        float* cout = pr.c_out + (static_cast<size_t>(tc.tile_lin) * 64) * kTileM + row;
-        __nv_bfloat16* gout =
-            pr.gates_out ? pr.gates_out + (static_cast<size_t>(tc.tile_lin) * 256) * kTileM + row : nullptr;
-        __nv_bfloat16* hrow = pr.h_out + ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * 64;
-        const float4* bs4 = reinterpret_cast<const float4*>(bias_s + tc.z * 256);
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int ch0 = half * 32 + cc * 16;
-          uint32_t vi[16], vf[16], vo[16], vg[16];
-          tmem_ld16(taddr + ch0, vi);
-          tmem_ld16(taddr + 64 + ch0, vf);
-          tmem_ld16(taddr + 128 + ch0, vo);
-          tmem_ld16(taddr + 192 + ch0, vg);
-          float cprev[16];
-          if (cin) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) cprev[j] = cin[(ch0 + j) * kTileM];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) cprev[j] = 0.f;
-          }
-          tmem_ld_wait();
-          uint32_t hp[8];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 bi = bs4[(ch0 >> 2) + j4], bf = bs4[16 + (ch0 >> 2) + j4];
-            const float4 bo = bs4[32 + (ch0 >> 2) + j4], bg = bs4[48 + (ch0 >> 2) + j4];
-            const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, bfa[4] = {bf.x, bf.y, bf.z, bf.w};
-            const float boa[4] = {bo.x, bo.y, bo.z, bo.w}, bga[4] = {bg.x, bg.y, bg.z, bg.w};
-            float hn[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int j = j4 * 4 + u;
-              const float gi = sigmoid_from_scaled(fmaf(__uint_as_float(vi[j]), -kLog2e, bia[u]));
-              const float gf = sigmoid_from_scaled(fmaf(__uint_as_float(vf[j]), -kLog2e, bfa[u]));
-              const float go = sigmoid_from_scaled(fmaf(__uint_as_float(vo[j]), -kLog2e, boa[u]));
-              const float gg = tanh_from_scaled(fmaf(__uint_as_float(vg[j]), 2.f * kLog2e, bga[u]));
-              const float cn = fmaf(gf, cprev[j], gi * gg);
-              hn[u] = go * tanh_from_scaled(cn * (2.f * kLog2e));
-              if (tc.valid) cout[(ch0 + j) * kTileM] = cn;   // padding tiles of an odd pair never store
-              if (gout && tc.valid) {
-                gout[(ch0 + j) * kTileM] = __float2bfloat16(gi);
-                gout[(64 + ch0 + j) * kTileM] = __float2bfloat16(gf);
-                gout[(128 + ch0 + j) * kTileM] = __float2bfloat16(go);
-                gout[(192 + ch0 + j) * kTileM] = __float2bfloat16(gg);
-              }
-            }
-            hp[j4 * 2] = pack_bf16x2(hn[0], hn[1]);
-            hp[j4 * 2 + 1] = pack_bf16x2(hn[2], hn[3]);
-          }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(hrow + ch0);
-            dst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-            dst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
-          }
-        }
-      } else if constexpr (EPI == EPI_GRAD) {
-        // fp32 accumulation into NHWC 64-channel gradient tensors (data gradients of the convs).
-        const int nchunks = p.n_store >> 4;
-        const size_t pixoff = ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * 64;
-#pragma unroll 1
-        for (int ck = half; ck < nchunks; ck += 2) {
-          uint32_t v[16];
-          tmem_ld16(taddr + ck * 16, v);
-          tmem_ld_wait();
-          if (valid) {
-            float* d0 = p.grad_split ? ((ck < 4) ? pr.grad0 : pr.grad1) : pr.grad0;
-            float* d1 = p.grad_split ? nullptr : pr.grad1;
-            const int c0 = (ck & 3) * 16;
-            // Fire-and-forget vector reductions: several tiles of one launch (cells of a reverse wavefront) may add
-            // into the same gradient pixels, so a plain read-modify-write would race.
-            if (d0) {
-              float* q = d0 + pixoff + c0;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                red_add_v4(q + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            }
-            if (d1) {
-              float* q = d1 + pixoff + c0;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                red_add_v4(q + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            }
-          }
-        }
-      } else {
-        // EPI_STORE / EPI_PS: 16-column chunks, alternating between the two warp halves.
-        const int nchunks = p.n_store >> 4;
-        const int cls = (y > 0 ? 1 : 0) | (y < p.H - 1 ? 2 : 0) | (x > 0 ? 4 : 0) | (x < p.W - 1 ? 8 : 0);
-        const float* pterm =
-            pr.posterm ? pr.posterm + (static_cast<size_t>(tc.img) * 16 + cls) * p.n_total + tc.nt * BN : nullptr;
-        const float* bias = pr.bias ? pr.bias + tc.nt * BN : nullptr;
-#pragma unroll 1
-        for (int ck = half; ck < nchunks; ck += 2) {
-          uint32_t v[16];
-          tmem_ld16(taddr + ck * 16, v);
-          tmem_ld_wait();
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          if (bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias + ck * 16);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b = __ldg(b4 + j);
-              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-            }
-          }
-          if (valid) {
-            if (pterm) {
-              const float4* t4 = reinterpret_cast<const float4*>(pterm + ck * 16);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 b = __ldg(t4 + j);
-                f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-              }
-            }
-            size_t off;
-            if constexpr (EPI == EPI_PS) {
-              // column = q*64 + c with q = i*r + j  ->  HR pixel (y*r+i, x*r+j), channel c (PixelShuffle, :200,204)
-              const int col = tc.nt * BN + ck * 16;
-              const int q = col >> 6, c0 = col & 63;
-              const int r = p.ps_r;
-              const int qi = q / r, qj = q - qi * r;
-              off = ((static_cast<size_t>(tc.img) * p.H * r + (y * r + qi)) * (p.W * r) + (x * r + qj)) * 64 + c0;
-            } else {
-              off = ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * p.out_ch + tc.nt * BN + ck * 16;
-            }
-            if (pr.res) {
-              const uint4* rp = reinterpret_cast<const uint4*>(pr.res + off);
-              float rf[16];
-              unpack_bf16x8(rp[0], rf);
-              unpack_bf16x8(rp[1], rf + 8);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] += rf[j];
-            }
-            if (pr.out_bf16) {
-              uint4* dst = reinterpret_cast<uint4*>(pr.out_bf16 + off);
-              dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                                  pack_bf16x2(f[6], f[7]));
-              dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                                  pack_bf16x2(f[14], f[15]));
-            }
-            if (pr.out_f32) {
-              float4* dst = reinterpret_cast<float4*>(pr.out_f32 + off);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            }
-          }
-        }
-      }
+      epilogue_tile<BN, EPI>(p, pr, tc, taddr, row, y, x, valid, half, bias_s);
       // All TMEM reads of this accumulator stage are complete (wait::ld above): hand it back to the MMA warp.
       tc_fence_before();
       if constexpr (CG == 2) mbar_arrive_cluster(mapa(smem_u32(&tempty[as]), 0));
@@ -419,15 +428,223 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
   }
 }
 
-static int g_cta_pair = 1;   // 1: use CTA pairs (cta_group::2) whenever the grid allows it
+// =====================================================================================================================
+// Halo variant.  When a tile spans the whole image width and at least one column of the tile is outside the image
+// (W < TW), the nine taps of a source are nine row-shifted views of ONE (TH+2) x TW pixel slab: the spare column is zero
+// (TMA fill) and serves as left and right padding of every row, rows above / below the image are zero-filled too.  The
+// slab is loaded once per (source, channel block) - 4.5x less activation traffic than nine shifted boxes - and the MMA
+// A descriptor simply starts (dy+1)*TW + dx rows into it (128 B per row; the 128B swizzle is a function of the absolute
+// shared-memory address, so shifted starts stay consistent with what TMA wrote - measured: the descriptor's
+// base-offset field must stay 0, setting it to the row phase gives wrong products).  One zeroed 1 KB guard before and
+// after every slab catches the -1 / +1 row of the corner taps.  Weights stream through their own ring, one box per tap.
+constexpr int kHaloMaxNA = 3;       // activation slabs in flight: 3 when the weight stages are small, else 2
+constexpr int kHaloGuard = 1024;
+constexpr int kHaloMaxNB = 8;       // weight stages in flight
+constexpr int kHaloBudget = 200 * 1024;
+
+__host__ __device__ inline int halo_slab_bytes(int tw) { return (kTileM + 2 * tw) * 128; }
+__host__ __device__ inline int halo_num_b(int tw, int b_bytes, int na) {
+  const int n = (kHaloBudget - na * (halo_slab_bytes(tw) + kHaloGuard) - kHaloGuard) / b_bytes;
+  return n > kHaloMaxNB ? kHaloMaxNB : n;
+}
+// three slabs if that still leaves >= 6 weight stages
+__host__ __device__ inline int halo_num_a(int tw, int b_bytes) { return halo_num_b(tw, b_bytes, 3) >= 6 ? 3 : 2; }
 
 template <int BN, int EPI, int CG>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
+  using C = Cfg<BN, CG>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int TW = 1 << p.tw_log2;
+  const int slab_bytes = halo_slab_bytes(TW);
+  const int NA = halo_num_a(TW, C::kBBytes);
+  const int NB = halo_num_b(TW, C::kBBytes, NA);
+  // [guard][slab 0][guard] .. [slab NA-1][guard][B stage 0 .. NB-1][barriers][LSTM biases]
+  uint8_t* slab0 = smem + kHaloGuard;
+  const int slab_pitch = slab_bytes + kHaloGuard;
+  uint8_t* smem_b = smem + kHaloGuard + NA * slab_pitch;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kHaloBudget);
+  uint64_t* afull = bars;                    // [3]
+  uint64_t* aempty = bars + 3;               // [3]
+  uint64_t* bfull = bars + 6;                // [8]
+  uint64_t* bempty = bars + 14;              // [8]
+  uint64_t* tfull = bars + 22;               // [2]
+  uint64_t* tempty = bars + 24;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  float* bias_s = reinterpret_cast<float*>(smem + kHaloBudget + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tiles_m = p.n_img * p.tiles_y * p.tiles_x;
+  const int groups = (tiles_m + CG - 1) / CG;
+  const int total_items = p.n_prob * groups * p.n_tiles_n;
+  const int item0 = blockIdx.x / CG, item_step = gridDim.x / CG;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&maps.act[0]);
+    prefetch_tmap(&maps.w);
+    for (int i = 0; i < kHaloMaxNA; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < kHaloMaxNB; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG * kNumEpiWarps * 32); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_cg2<kTmemCols>(tmem_slot);
+    else tmem_alloc<kTmemCols>(tmem_slot);
+  }
+  // zero guards (read by the MMA through the async proxy, never written by TMA)
+  for (int i = threadIdx.x; i < (NA + 1) * (kHaloGuard / 16); i += kNumThreads) {
+    const int g = i / (kHaloGuard / 16), o = i % (kHaloGuard / 16);
+    reinterpret_cast<uint4*>(smem + g * slab_pitch)[o] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  if constexpr (EPI == EPI_LSTM) {
+    for (int i = threadIdx.x; i < p.n_prob * 256; i += kNumThreads) {
+      const int z = i >> 8, n = i & 255;
+      bias_s[i] = p.prob[z].bias[n] * (n < 192 ? -kLog2e : 2.f * kLog2e);
+    }
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync();
+  else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int t = item0; t < total_items; t += item_step) {
+        const TileCoord tc = decode_item(p, t, groups, tiles_m, CG, rank);
+        const ConvProblem& pr = p.prob[tc.z];
+        const int wcol = pr.w_row_base + tc.nt * BN + rank * (BN / CG);
+        for (int s = 0; s < pr.n_src; ++s) {
+          const SrcView& sv = pr.src[s];
+          const CUtensorMap* tm = &maps.act[sv.map];
+          for (int cb = 0; cb < p.kb_per_src; ++cb) {
+            mbar_wait(&aempty[sa], pa ^ 1);
+            uint8_t* dst = slab0 + sa * slab_pitch;
+            if constexpr (CG == 2) {
+              if (rank == 0) mbar_arrive_expect_tx(&afull[sa], 2 * slab_bytes);
+              tma_load_4d_cg2(dst, tm, mapa(smem_u32(&afull[sa]), 0), sv.ch0 + cb * kBlockK, 0, tc.y0 - 1,
+                              sv.img_base + tc.img);
+            } else {
+              mbar_arrive_expect_tx(&afull[sa], slab_bytes);
+              tma_load_4d(dst, tm, &afull[sa], sv.ch0 + cb * kBlockK, 0, tc.y0 - 1, sv.img_base + tc.img);
+            }
+            if (++sa == NA) { sa = 0; pa ^= 1; }
+            for (int tap = 0; tap < 9; ++tap) {
+              const int wrow = wcol + ((s * 9 + tap) * p.kb_per_src + cb) * p.n_total;
+              mbar_wait(&bempty[sb], pb ^ 1);
+              if constexpr (CG == 2) {
+                if (rank == 0) mbar_arrive_expect_tx(&bfull[sb], 2 * C::kBBytes);
+                tma_load_2d_cg2(smem_b + sb * C::kBBytes, &maps.w, mapa(smem_u32(&bfull[sb]), 0), 0, wrow);
+              } else {
+                mbar_arrive_expect_tx(&bfull[sb], C::kBBytes);
+                tma_load_2d(smem_b + sb * C::kBBytes, &maps.w, &bfull[sb], 0, wrow);
+              }
+              if (++sb == NB) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
+    constexpr uint32_t idesc = make_idesc_bf16(BN, 128 * CG);
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it = 0;
+    for (int t = item0; t < total_items && rank == 0; t += item_step, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * kAccStride;
+      const int n_src = p.prob[decode_item(p, t, groups, tiles_m, CG, 0).z].n_src;
+      bool first = true;
+      for (int s = 0; s < n_src; ++s)
+        for (int cb = 0; cb < p.kb_per_src; ++cb) {
+          mbar_wait(&afull[sa], pa);
+          const uint32_t slab = smem_u32(slab0 + sa * slab_pitch);
+          const int nk16 = (cb == p.kb_per_src - 1) ? p.k16_last : 4;
+          const bool last_a = (s == n_src - 1) && (cb == p.kb_per_src - 1);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&bfull[sb], pb);
+            tc_fence_after();
+            if (elect_one()) {
+              const int shift = (tap / 3) * TW + (tap % 3) - 1;      // (dy + 1) * TW + dx rows of 128 B
+              const uint64_t adesc = make_desc_k_sw128(slab + shift * 128);
+              const uint64_t bdesc = make_desc_k_sw128(smem_u32(smem_b + sb * C::kBBytes));
+              for (int k = 0; k < nk16; ++k) {
+                if constexpr (CG == 2) mma_bf16_ss_cg2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, !(first && k == 0));
+                else mma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, !(first && k == 0));
+              }
+              if constexpr (CG == 2) {
+                mma_commit_cg2(&bempty[sb]);
+                if (tap == 8) mma_commit_cg2(&aempty[sa]);
+                if (tap == 8 && last_a) mma_commit_cg2(&tfull[as]);
+              } else {
+                mma_commit(&bempty[sb]);
+                if (tap == 8) mma_commit(&aempty[sa]);
+                if (tap == 8 && last_a) mma_commit(&tfull[as]);
+              }
+            }
+            __syncwarp();
+            first = false;
+            if (++sb == NB) { sb = 0; pb ^= 1; }
+          }
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (identical to the box kernel)
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    const int row = quad * 32 + lane;
+    const int ly = row >> p.tw_log2, lx = row & (TW - 1);
+    int it = 0;
+    for (int t = item0; t < total_items; t += item_step, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const TileCoord tc = decode_item(p, t, groups, tiles_m, CG, rank);
+      const ConvProblem& pr = p.prob[tc.z];
+      const int y = tc.y0 + ly, x = tc.x0 + lx;
+      const bool valid = tc.valid && (y < p.H) && (x < p.W);
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * kAccStride + (static_cast<uint32_t>(quad * 32) << 16);
+      epilogue_tile<BN, EPI>(p, pr, tc, taddr, row, y, x, valid, half, bias_s);
+      tc_fence_before();
+      if constexpr (CG == 2) mbar_arrive_cluster(mapa(smem_u32(&tempty[as]), 0));
+      else mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  if constexpr (CG == 2) {
+    cluster_sync();
+    if (warp == 1) tmem_dealloc_cg2<kTmemCols>(tmem_base);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+static int g_cta_pair = 1;   // 1: use CTA pairs (cta_group::2) whenever the grid allows it
+
+template <int BN, int EPI, int CG, bool HALO>
 static int launch_t(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<BN, CG>;
-  auto kern = conv3x3_tc_kernel<BN, EPI, CG>;
+  auto kern = HALO ? conv3x3_halo_kernel<BN, EPI, CG> : conv3x3_tc_kernel<BN, EPI, CG>;
+  constexpr int kSmem = HALO ? kHaloBudget + 1024 + 256 + kMaxProb * 256 * 4 : C::kSmemBytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
@@ -437,13 +654,13 @@ static int launch_t(const ConvMaps& maps, const ConvParams& p, int num_sms, cuda
   const long long max_groups = num_sms / CG;
   const int grid = static_cast<int>((items < max_groups ? items : max_groups) * CG);
   if constexpr (CG == 1) {
-    kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(maps, p);
+    kern<<<grid, kNumThreads, kSmem, stream>>>(maps, p);
     return static_cast<int>(cudaGetLastError());
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.dynamicSmemBytes = kSmem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -458,9 +675,17 @@ static int launch_t(const ConvMaps& maps, const ConvParams& p, int num_sms, cuda
 
 template <int BN, int EPI>
 static int launch_cg(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
-  if (g_cta_pair && num_sms >= 2) return launch_t<BN, EPI, 2>(maps, p, num_sms, stream);
-  return launch_t<BN, EPI, 1>(maps, p, num_sms, stream);
+  if (p.halo) {
+    if (g_cta_pair && num_sms >= 2) return launch_t<BN, EPI, 2, true>(maps, p, num_sms, stream);
+    return launch_t<BN, EPI, 1, true>(maps, p, num_sms, stream);
+  }
+  if (g_cta_pair && num_sms >= 2) return launch_t<BN, EPI, 2, false>(maps, p, num_sms, stream);
+  return launch_t<BN, EPI, 1, false>(maps, p, num_sms, stream);
 }
+
+static int g_halo = 1;   // 0: nine shifted TMA boxes per source, 1: one slab per source + shifted descriptors
+void set_halo_mode(int mode) { g_halo = mode; }
+int get_halo_mode() { return g_halo; }
 
 void set_cta_pair(int enable) { g_cta_pair = enable ? 1 : 0; }
 int get_cta_pair() { return g_cta_pair; }

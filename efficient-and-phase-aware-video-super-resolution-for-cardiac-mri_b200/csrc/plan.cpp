@@ -144,6 +144,9 @@ struct pvsr_plan {
   const void* maps_ws = nullptr;
   const void* maps_pk = nullptr;
   int maps_cg = -1;      // CTA-pair setting the tensor maps (weight box height) were built for
+  int maps_halo = -1;    // halo mode the activation maps (box rows) were built for
+  int halo_lr = 0;       // halo mode of the 3x3 launches at LR resolution (0 = nine shifted boxes)
+  int halo_ps[PVSR_MAX_HEAD_CONVS] = {0, 0, 0, 0};   // ... of head conv q (its input resolution)
   ConvMaps maps_lstm, maps_c1, maps_c2, maps_head[PVSR_MAX_HEAD_CONVS];   // act[0] + packed weights of each launch kind
   ConvMaps bm_lstm_dg, bm_lstm_wg, bm_c1_dg, bm_c1_wg, bm_c2_dg, bm_c2_wg, bm_head_dg[PVSR_MAX_HEAD_CONVS],
       bm_head_wg[PVSR_MAX_HEAD_CONVS];
@@ -395,6 +398,7 @@ void schedule(Ctx& c) {
           if (p->train && j >= U && j < L - U) pr.gates_out = gates_buf(c, s, dir, l, j - U);
         }
       cp.n_prob = np;
+      cp.halo = p->halo_lr;
       run_conv(c, CLS_LSTM, 256, EPI_LSTM, p->maps_lstm, cp, lstm_fl * px * B * np);
     }
 
@@ -417,6 +421,7 @@ void schedule(Ctx& c) {
         cp.n_total = 144; cp.n_store = 144; cp.out_ch = 144;
         pr.posterm = posterm;
         pr.out_bf16 = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_mid + slot * p->mid_stride);
+        cp.halo = p->halo_lr;
         run_conv(c, CLS_CONV1, 144, EPI_STORE, p->maps_c1, cp,
                  2.0 * 9 * (2 * kFeat + 1) * p->Wn * (2 * kFeat + 1) * px * cp.n_img);
         ConvParams c2;
@@ -431,6 +436,7 @@ void schedule(Ctx& c) {
         p2.bias = reinterpret_cast<const float*>(c.pk + p->pk_c2_b);
         p2.res = res;
         p2.out_bf16 = xnext;
+        c2.halo = p->halo_lr;
         run_conv(c, CLS_CONV2, 64, EPI_STORE, p->maps_c2, c2,
                  2.0 * 9 * (2 * kFeat + 1) * kFeat * px * c2.n_img);
       } else {
@@ -475,6 +481,7 @@ void schedule(Ctx& c) {
         pr.src[0] = view0(q == 0 ? in_img : static_cast<long long>(lslot) * n_head);
         pr.bias = reinterpret_cast<const float*>(c.pk + p->pk_head_b[q]);
         pr.out_bf16 = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_head[q] + lslot * p->head_stride[q]);
+        cp.halo = p->halo_ps[q];
         run_conv(c, CLS_HEAD_PS, p->ps_bn[q], EPI_PS, p->maps_head[q], cp,
                  2.0 * 9 * kFeat * (kFeat * p->ps_r[q] * p->ps_r[q]) * p->ps_h[q] * p->ps_w[q] * n_head);
       }
@@ -641,6 +648,7 @@ void schedule_backward(Ctx& c) {
         pr.n_src = 1;
         pr.src[0] = view0(static_cast<long long>(half) * B);
         pr.out_bf16 = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_gm) + static_cast<size_t>(half) * B * px * 144;
+        cp.halo = p->halo_lr;
         run_conv(c, BCLS_REFINE_DGRAD, 144, EPI_STORE, p->bm_c2_dg, cp, c2_fl);
       }
       if (c.dry || c.G->ref_w1)
@@ -663,6 +671,7 @@ void schedule_backward(Ctx& c) {
         for (int sd = 0; sd < Wn; ++sd) pr.src[sd] = view0(static_cast<long long>(sd) * B);
         pr.grad0 = grad_stack(c, dh_top_f, 0);
         pr.grad1 = grad_stack(c, dh_top_b, 0);
+        cp.halo = p->halo_lr;
         run_conv(c, BCLS_REFINE_DGRAD, 128, EPI_GRAD, p->bm_c1_dg, cp, c1_fl);
       }
     } else {
@@ -729,6 +738,7 @@ void schedule_backward(Ctx& c) {
         }
       lp.n_prob = np;
       cp.n_prob = np;
+      cp.halo = p->halo_lr;
       run_simt(c, BCLS_LSTM_POINT, "lstm_bwd_pointwise", [&] { return launch_lstm_bwd_pointwise(lp, c.stream); });
       run_conv(c, BCLS_LSTM_DGRAD, p->lstm_dg_bn, EPI_GRAD, p->bm_lstm_dg, cp, lstm_fl * px * B * np);
     }
@@ -755,22 +765,32 @@ void schedule_backward(Ctx& c) {
 }
 
 int build_maps(pvsr_plan* p, const void* ws, const void* pk) {
-  if (p->maps_ws == ws && p->maps_pk == pk && p->maps_cg == get_cta_pair()) return 0;
+  if (p->maps_ws == ws && p->maps_pk == pk && p->maps_cg == get_cta_pair() && p->maps_halo == get_halo_mode())
+    return 0;
   const uint8_t* w = static_cast<const uint8_t*>(ws);
   const uint8_t* k = static_cast<const uint8_t*>(pk);
   int rc = 0;
   const long long TB = static_cast<long long>(p->T) * p->B;
-  CUtensorMap tm_act;
+  // halo launches read (TH+2)-row slabs: their activation maps carry taller boxes
+  p->halo_lr = halo_applicable(p->w, p->lr.tw, p->lr.tiles_x, 9, 1) ? get_halo_mode() : 0;
+  for (int q = 0; q < p->n_ps; ++q) {
+    const Tiling& t = q == 0 ? p->lr : p->ps_tile[q];
+    p->halo_ps[q] = halo_applicable(p->ps_w[q], t.tw, t.tiles_x, 9, 1) ? get_halo_mode() : 0;
+  }
+  const int lr_rows = p->lr.th + (p->halo_lr ? 2 : 0);
+  CUtensorMap tm_act, tm_act_conv;
   rc |= make_act_tmap(&tm_act, w + p->off_act, kFeat, p->w, p->h, p->act_images, p->lr.tw, p->lr.th);
-  p->maps_lstm.act[0] = tm_act;
-  p->maps_c1.act[0] = tm_act;
-  p->maps_head[0].act[0] = tm_act;
+  rc |= make_act_tmap(&tm_act_conv, w + p->off_act, kFeat, p->w, p->h, p->act_images, p->lr.tw, lr_rows);
+  p->maps_lstm.act[0] = tm_act_conv;
+  p->maps_c1.act[0] = p->cfg.pos_enc ? tm_act_conv : tm_act;     // the 1x1 variant has a single tap
+  p->maps_head[0].act[0] = tm_act_conv;
   if (p->cfg.pos_enc)
     rc |= make_act_tmap(&p->maps_c2.act[0], w + p->off_mid, 144, p->w, p->h,
-                        static_cast<long long>(p->n_slots) * p->n_win * p->B, p->lr.tw, p->lr.th);
+                        static_cast<long long>(p->n_slots) * p->n_win * p->B, p->lr.tw, lr_rows);
   for (int q = 1; q < p->n_ps; ++q)
     rc |= make_act_tmap(&p->maps_head[q].act[0], w + p->off_head[q - 1], kFeat, p->ps_w[q], p->ps_h[q],
-                        static_cast<long long>(p->n_list_slots) * TB, p->ps_tile[q].tw, p->ps_tile[q].th);
+                        static_cast<long long>(p->n_list_slots) * TB, p->ps_tile[q].tw,
+                        p->ps_tile[q].th + (p->halo_ps[q] ? 2 : 0));
   rc |= make_weight_tmap(&p->maps_lstm.w, k + p->pk_lstm_w, static_cast<long long>(2 * p->NL) * p->lstm_rows_per_cell,
                          256);
   rc |= make_weight_tmap(&p->maps_c1.w, k + p->pk_c1_w, p->c1_rows, p->cfg.pos_enc ? 144 : 64);
@@ -780,25 +800,32 @@ int build_maps(pvsr_plan* p, const void* ws, const void* pk) {
 
   if (p->train) {
     const int n_pad = p->T + 2 * p->half;
-    CUtensorMap tm_dgates, tm_gr, tm_gm;
+    CUtensorMap tm_dgates, tm_gr, tm_gm, tm_dgates_conv, tm_gr_conv, tm_gm_conv;
     rc |= make_act_tmap(&tm_dgates, w + p->off_dgates, 256, p->w, p->h, 2LL * p->NL * TB, p->lr.tw, p->lr.th);
+    rc |= make_act_tmap(&tm_dgates_conv, w + p->off_dgates, 256, p->w, p->h, 2LL * p->NL * TB, p->lr.tw, lr_rows);
     rc |= make_act_tmap(&tm_gr, w + p->off_gr, kFeat, p->w, p->h, static_cast<long long>(n_pad) * p->B, p->lr.tw,
                         p->lr.th);
-    if (p->cfg.pos_enc)
+    rc |= make_act_tmap(&tm_gr_conv, w + p->off_gr, kFeat, p->w, p->h, static_cast<long long>(n_pad) * p->B, p->lr.tw,
+                        lr_rows);
+    if (p->cfg.pos_enc) {
       rc |= make_act_tmap(&tm_gm, w + p->off_gm, 144, p->w, p->h, static_cast<long long>(n_pad) * p->B, p->lr.tw,
                           p->lr.th);
+      rc |= make_act_tmap(&tm_gm_conv, w + p->off_gm, 144, p->w, p->h, static_cast<long long>(n_pad) * p->B, p->lr.tw,
+                          lr_rows);
+    }
     // ConvLSTM
-    p->bm_lstm_dg.act[0] = tm_dgates;
+    p->bm_lstm_dg.act[0] = tm_dgates_conv;
     rc |= make_weight_tmap(&p->bm_lstm_dg.w, k + p->pk_lstm_dg, 2LL * p->NL * p->lstm_dg_rows_per_cell, p->lstm_dg_bn);
     p->bm_lstm_wg.act[0] = tm_act;
     p->bm_lstm_wg.act[1] = tm_dgates;
     // refine
     if (p->cfg.pos_enc) {
-      p->bm_c2_dg.act[0] = tm_gr;
+      p->bm_c2_dg.act[0] = tm_gr_conv;
       rc |= make_weight_tmap(&p->bm_c2_dg.w, k + p->pk_c2_dg, p->c2_dg_rows, 144);
-      p->bm_c2_wg.act[0] = p->maps_c2.act[0];
+      rc |= make_act_tmap(&p->bm_c2_wg.act[0], w + p->off_mid, 144, p->w, p->h,
+                          static_cast<long long>(p->n_slots) * p->n_win * p->B, p->lr.tw, p->lr.th);
       p->bm_c2_wg.act[1] = tm_gr;
-      p->bm_c1_dg.act[0] = tm_gm;
+      p->bm_c1_dg.act[0] = tm_gm_conv;
       p->bm_c1_wg.act[0] = tm_act;
       p->bm_c1_wg.act[1] = tm_gm;
     } else {
@@ -827,6 +854,7 @@ int build_maps(pvsr_plan* p, const void* ws, const void* pk) {
   p->maps_ws = ws;
   p->maps_pk = pk;
   p->maps_cg = get_cta_pair();
+  p->maps_halo = get_halo_mode();
   for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
   p->graphs.clear();
   return 0;

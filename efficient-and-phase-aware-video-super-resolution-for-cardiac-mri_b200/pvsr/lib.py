@@ -84,6 +84,8 @@ SIGNATURES = {
     "pvsr_device_check": (c_int, []),
     "pvsr_set_cta_pair": (c_int, [c_int]),
     "pvsr_get_cta_pair": (c_int, []),
+    "pvsr_set_halo_mode": (c_int, [c_int]),
+    "pvsr_get_halo_mode": (c_int, []),
     "pvsr_choose_tile": (c_int, [c_int, c_int, C.POINTER(c_int)]),
     "pvsr_pack_index_count": (c_int64, [C.POINTER(PackSpec)]),
     "pvsr_pack_index_host": (c_int, [C.POINTER(PackSpec), c_void_p]),
@@ -157,6 +159,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("PVSR_HALO") is not None:           # A/B switch of the halo (slab) conv kernel
+        lib.pvsr_set_halo_mode(int(os.environ["PVSR_HALO"]))
     if os.environ.get("PVSR_CTA_PAIR") is not None:       # A/B switch of the cta_group::2 conv kernel
         lib.pvsr_set_cta_pair(int(os.environ["PVSR_CTA_PAIR"]))
     _lib = lib

@@ -39,6 +39,11 @@ int pvsr_device_check(void);
  * Default on; 0 selects the single-CTA kernel (A/B measurements, debugging).  Process-wide. */
 int pvsr_set_cta_pair(int enable);
 int pvsr_get_cta_pair(void);
+/* Halo variant of the 3x3 launches: when a tile spans the image width with a spare zero column (W < tile width) each
+ * source slab is loaded once and the nine taps are row-shifted shared-memory views of it.  0 = off (nine shifted TMA
+ * boxes), 1 = on (default).  Process-wide. */
+int pvsr_set_halo_mode(int mode);
+int pvsr_get_halo_mode(void);
 
 /* ---- host-side packing logic (pure CPU; usable without a GPU) ------------------------------------------------ */
 /* Tile choice of the implicit GEMM: tile = (128 >> tw_log2) x (1 << tw_log2) output pixels. */
