@@ -69,6 +69,17 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
   }
 }
 
+template <int CG>
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if constexpr (CG == 2) mma_bf16_ss_cg2(tmem_d, adesc, bdesc, idesc, acc);
+  else mma_bf16_ss(tmem_d, adesc, bdesc, idesc, acc);
+}
+template <int CG>
+__device__ __forceinline__ void mma_commit_t(uint64_t* bar) {
+  if constexpr (CG == 2) mma_commit_cg2(bar);
+  else mma_commit(bar);
+}
+
 struct TileCoord {
   int z, img, y0, x0, nt, tile_lin;
   bool valid;   // false: padding tile of an odd pair (loaded and multiplied like its neighbour, never stored)
@@ -99,7 +110,7 @@ __device__ __forceinline__ TileCoord decode_item(const ConvParams& p, int it, in
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvProblem& pr, const TileCoord& tc,
                                               uint32_t taddr, int row, int y, int x, bool valid, int half,
-                                              const float* bias_s) {
+                                              const float* bias_s, const uint4 (&res_pre)[4], bool has_pre) {
   if constexpr (EPI == EPI_LSTM) {
     // Columns: [i | f | o | g] x 64 channels (refine_net.py:258). This warp: channels [32*half, 32*half+32).
     const float* cin = pr.c_in ? pr.c_in + (static_cast<size_t>(tc.tile_lin) * 64) * kTileM + row : nullptr;
@@ -197,8 +208,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvPro
     const float* pterm =
         pr.posterm ? pr.posterm + (static_cast<size_t>(tc.img) * 16 + cls) * p.n_total + tc.nt * BN : nullptr;
     const float* bias = pr.bias ? pr.bias + tc.nt * BN : nullptr;
-#pragma unroll 1
-    for (int ck = half; ck < nchunks; ck += 2) {
+    auto chunk = [&](int ck, bool pre, const uint4& rpre0, const uint4& rpre1) {
       uint32_t v[16];
       tmem_ld16(taddr + ck * 16, v);
       tmem_ld_wait();
@@ -234,10 +244,15 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvPro
           off = ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * p.out_ch + tc.nt * BN + ck * 16;
         }
         if (pr.res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(pr.res + off);
           float rf[16];
-          unpack_bf16x8(rp[0], rf);
-          unpack_bf16x8(rp[1], rf + 8);
+          if (pre) {
+            unpack_bf16x8(rpre0, rf);
+            unpack_bf16x8(rpre1, rf + 8);
+          } else {
+            const uint4* rp = reinterpret_cast<const uint4*>(pr.res + off);
+            unpack_bf16x8(rp[0], rf);
+            unpack_bf16x8(rp[1], rf + 8);
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] += rf[j];
         }
@@ -254,7 +269,40 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvPro
           for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
       }
+    };
+    if constexpr (EPI == EPI_STORE && BN == 64) {
+      // Narrow tiles finish their MMAs in ~2.6k cycles: the residual was fetched BEFORE the accumulator wait
+      // (res_pre, see epilogue_prefetch) so that its global-load latency is not on the per-tile critical path.
+      if (half < nchunks) chunk(half, has_pre, res_pre[0], res_pre[1]);
+      if (half + 2 < nchunks) chunk(half + 2, has_pre, res_pre[2], res_pre[3]);
+    } else {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+      for (int ck = half; ck < nchunks; ck += 2) chunk(ck, false, z, z);
     }
+  }
+}
+
+// EPI_STORE, BN = 64: this thread's residual values (2 chunks x 16 bf16) loaded ahead of the accumulator wait.
+template <int BN, int EPI>
+__device__ __forceinline__ bool epilogue_prefetch(const ConvParams& p, const ConvProblem& pr, const TileCoord& tc, int y,
+                                                  int x, bool valid, int half, uint4 (&res_pre)[4]) {
+  if constexpr (EPI == EPI_STORE && BN == 64) {
+    if (pr.res == nullptr || !valid) return false;
+    const int nchunks = p.n_store >> 4;
+    const size_t off = ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * p.out_ch + tc.nt * BN;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int ck = half + 2 * i;
+      if (ck < nchunks) {
+        const uint4* rp = reinterpret_cast<const uint4*>(pr.res + off + ck * 16);
+        res_pre[2 * i] = rp[0];
+        res_pre[2 * i + 1] = rp[1];
+      }
+    }
+    return true;
+  } else {
+    return false;
   }
 }
 
@@ -352,44 +400,46 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
-    constexpr uint32_t idesc = make_idesc_bf16(BN, 128 * CG);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int t = item0; t < total_items && rank == 0; t += item_step, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tempty[as], aphase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + as * kAccStride;
-      const int kb_per_tile = p.prob[decode_item(p, t, groups, tiles_m, CG, 0).z].n_src * p.taps * p.kb_per_src;
-      int cb = 0;
-      for (int kb = 0; kb < kb_per_tile; ++kb) {
-        mbar_wait(&full[stage], phase);
+    // ------------------------------------------------------------------ MMA issuer: ONE thread of the leader CTA runs
+    // the whole loop (no per-K-block elect / warp sync: for N <= 144 the issue loop, not the tensor pipe, was the limit)
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BN, 128 * CG);
+      const uint64_t adesc0 = make_desc_k_sw128(smem_u32(smem_a));
+      const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(smem_b));
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = item0; t < total_items; t += item_step, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
-        const int nk16 = (cb == p.kb_per_src - 1) ? p.k16_last : 4;
-        if (elect_one()) {
-          const uint64_t adesc = make_desc_k_sw128(smem_u32(smem_a + stage * kABytes));
-          const uint64_t bdesc = make_desc_k_sw128(smem_u32(smem_b + stage * C::kBBytes));
-          for (int k = 0; k < nk16; ++k) {
-            // +32 bytes per K=16 slice inside the 128-byte swizzle row (address field is in 16-byte units)
-            if constexpr (CG == 2) mma_bf16_ss_cg2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            else mma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          }
-          if constexpr (CG == 2) {
-            mma_commit_cg2(&empty[stage]);                       // frees the stage in both CTAs
-            if (kb == kb_per_tile - 1) mma_commit_cg2(&tfull[as]);
+        const uint32_t tmem_d = tmem_base + as * kAccStride;
+        const int kb_per_tile = p.prob[decode_item(p, t, groups, tiles_m, CG, 0).z].n_src * p.taps * p.kb_per_src;
+        int cb = 0;
+        for (int kb = 0; kb < kb_per_tile; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          // +32 bytes per K=16 slice inside the 128-byte swizzle row (address field is in 16-byte units)
+          const uint64_t adesc = adesc0 + static_cast<uint32_t>(stage * (kABytes >> 4));
+          const uint64_t bdesc = bdesc0 + static_cast<uint32_t>(stage * (C::kBBytes >> 4));
+          const int nk16 = (cb == p.kb_per_src - 1) ? p.k16_last : 4;
+          mma_ss<CG>(tmem_d, adesc, bdesc, idesc, kb != 0);
+          if (nk16 == 4) {
+            mma_ss<CG>(tmem_d, adesc + 2, bdesc + 2, idesc, 1);
+            mma_ss<CG>(tmem_d, adesc + 4, bdesc + 4, idesc, 1);
+            mma_ss<CG>(tmem_d, adesc + 6, bdesc + 6, idesc, 1);
           } else {
-            mma_commit(&empty[stage]);
-            if (kb == kb_per_tile - 1) mma_commit(&tfull[as]);
+            for (int k = 1; k < nk16; ++k) mma_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
           }
+          mma_commit_t<CG>(&empty[stage]);                       // frees the stage (in both CTAs of a pair)
+          if (kb == kb_per_tile - 1) mma_commit_t<CG>(&tfull[as]);
+          if (++cb == p.kb_per_src) cb = 0;
+          if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++cb == p.kb_per_src) cb = 0;
-        if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue
     const int ew = warp - 2;
@@ -406,14 +456,16 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       const ConvProblem& pr = p.prob[tc.z];
       const int y = tc.y0 + ly, x = tc.x0 + lx;
       const bool valid = tc.valid && (y < p.H) && (x < p.W);
+      uint4 res_pre[4];
+      const bool has_pre = epilogue_prefetch<BN, EPI>(p, pr, tc, y, x, valid, half, res_pre);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * kAccStride + (static_cast<uint32_t>(quad * 32) << 16);
 
-      epilogue_tile<BN, EPI>(p, pr, tc, taddr, row, y, x, valid, half, bias_s);
+      epilogue_tile<BN, EPI>(p, pr, tc, taddr, row, y, x, valid, half, bias_s, res_pre, has_pre);
       // All TMEM reads of this accumulator stage are complete (wait::ld above): hand it back to the MMA warp.
       tc_fence_before();
-      if constexpr (CG == 2) mbar_arrive_cluster(mapa(smem_u32(&tempty[as]), 0));
+      if constexpr (CG == 2) mbar_arrive_cluster_relaxed(mapa(smem_u32(&tempty[as]), 0));
       else mbar_arrive(&tempty[as]);
     }
   }
@@ -442,12 +494,15 @@ constexpr int kHaloGuard = 1024;
 constexpr int kHaloMaxNB = 8;       // weight stages in flight
 constexpr int kHaloBudget = 200 * 1024;
 
+// Weight stage = G consecutive taps (one row of the 3x3 stencil when G = 3): narrow-N launches spend only 32-64 tensor
+// cycles per MMA, so one barrier round trip per tap would bound them; one wait + one commit per G taps does not.
+__host__ __device__ constexpr int halo_group(int b_bytes) { return b_bytes <= 8192 ? 3 : 1; }
 __host__ __device__ inline int halo_slab_bytes(int tw) { return (kTileM + 2 * tw) * 128; }
 __host__ __device__ inline int halo_num_b(int tw, int b_bytes, int na) {
   const int n = (kHaloBudget - na * (halo_slab_bytes(tw) + kHaloGuard) - kHaloGuard) / b_bytes;
   return n > kHaloMaxNB ? kHaloMaxNB : n;
 }
-// three slabs if that still leaves >= 6 weight stages
+// three slabs if that still leaves >= 6 (ungrouped) weight stages
 __host__ __device__ inline int halo_num_a(int tw, int b_bytes) { return halo_num_b(tw, b_bytes, 3) >= 6 ? 3 : 2; }
 
 template <int BN, int EPI, int CG>
@@ -458,8 +513,10 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int TW = 1 << p.tw_log2;
   const int slab_bytes = halo_slab_bytes(TW);
+  constexpr int G = halo_group(C::kBBytes);        // taps per weight stage
+  constexpr int kBStage = G * C::kBBytes;
   const int NA = halo_num_a(TW, C::kBBytes);
-  const int NB = halo_num_b(TW, C::kBBytes, NA);
+  const int NB = halo_num_b(TW, kBStage, NA);
   // [guard][slab 0][guard] .. [slab NA-1][guard][B stage 0 .. NB-1][barriers][LSTM biases]
   uint8_t* slab0 = smem + kHaloGuard;
   const int slab_pitch = slab_bytes + kHaloGuard;
@@ -536,15 +593,19 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
               tma_load_4d(dst, tm, &afull[sa], sv.ch0 + cb * kBlockK, 0, tc.y0 - 1, sv.img_base + tc.img);
             }
             if (++sa == NA) { sa = 0; pa ^= 1; }
-            for (int tap = 0; tap < 9; ++tap) {
-              const int wrow = wcol + ((s * 9 + tap) * p.kb_per_src + cb) * p.n_total;
+            for (int tg = 0; tg < 9 / G; ++tg) {
               mbar_wait(&bempty[sb], pb ^ 1);
               if constexpr (CG == 2) {
-                if (rank == 0) mbar_arrive_expect_tx(&bfull[sb], 2 * C::kBBytes);
-                tma_load_2d_cg2(smem_b + sb * C::kBBytes, &maps.w, mapa(smem_u32(&bfull[sb]), 0), 0, wrow);
+                if (rank == 0) mbar_arrive_expect_tx(&bfull[sb], 2 * kBStage);
               } else {
-                mbar_arrive_expect_tx(&bfull[sb], C::kBBytes);
-                tma_load_2d(smem_b + sb * C::kBBytes, &maps.w, &bfull[sb], 0, wrow);
+                mbar_arrive_expect_tx(&bfull[sb], kBStage);
+              }
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                const int wrow = wcol + ((s * 9 + tg * G + g) * p.kb_per_src + cb) * p.n_total;
+                uint8_t* bdst = smem_b + sb * kBStage + g * C::kBBytes;
+                if constexpr (CG == 2) tma_load_2d_cg2(bdst, &maps.w, mapa(smem_u32(&bfull[sb]), 0), 0, wrow);
+                else tma_load_2d(bdst, &maps.w, &bfull[sb], 0, wrow);
               }
               if (++sb == NB) { sb = 0; pb ^= 1; }
             }
@@ -553,53 +614,58 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
-    constexpr uint32_t idesc = make_idesc_bf16(BN, 128 * CG);
-    int sa = 0, sb = 0;
-    uint32_t pa = 0, pb = 0;
-    int it = 0;
-    for (int t = item0; t < total_items && rank == 0; t += item_step, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tempty[as], aphase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + as * kAccStride;
-      const int n_src = p.prob[decode_item(p, t, groups, tiles_m, CG, 0).z].n_src;
-      bool first = true;
-      for (int s = 0; s < n_src; ++s)
-        for (int cb = 0; cb < p.kb_per_src; ++cb) {
-          mbar_wait(&afull[sa], pa);
-          const uint32_t slab = smem_u32(slab0 + sa * slab_pitch);
-          const int nk16 = (cb == p.kb_per_src - 1) ? p.k16_last : 4;
-          const bool last_a = (s == n_src - 1) && (cb == p.kb_per_src - 1);
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&bfull[sb], pb);
-            tc_fence_after();
-            if (elect_one()) {
-              const int shift = (tap / 3) * TW + (tap % 3) - 1;      // (dy + 1) * TW + dx rows of 128 B
-              const uint64_t adesc = make_desc_k_sw128(slab + shift * 128);
-              const uint64_t bdesc = make_desc_k_sw128(smem_u32(smem_b + sb * C::kBBytes));
-              for (int k = 0; k < nk16; ++k) {
-                if constexpr (CG == 2) mma_bf16_ss_cg2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, !(first && k == 0));
-                else mma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, !(first && k == 0));
+    // ------------------------------------------------------------------ MMA issuer: one thread of the leader CTA
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BN, 128 * CG);
+      const uint32_t slab_base = smem_u32(slab0);
+      const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(smem_b));
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int t = item0; t < total_items; t += item_step, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kAccStride;
+        const int n_src = p.prob[decode_item(p, t, groups, tiles_m, CG, 0).z].n_src;
+        uint32_t acc = 0;   // the first MMA of the tile overwrites the accumulator
+        for (int s = 0; s < n_src; ++s)
+          for (int cb = 0; cb < p.kb_per_src; ++cb) {
+            mbar_wait(&afull[sa], pa);
+            // tap (dx, dy) starts (dy + 1) * TW + dx rows of 128 B into the slab (first row: the zero guard)
+            const uint32_t slab = slab_base + sa * slab_pitch - 128;
+            const int nk16 = (cb == p.kb_per_src - 1) ? p.k16_last : 4;
+            const bool last_a = (s == n_src - 1) && (cb == p.kb_per_src - 1);
+            for (int tg = 0; tg < 9 / G; ++tg) {
+              mbar_wait(&bfull[sb], pb);
+              tc_fence_after();
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                const int tap = tg * G + g;
+                const int dyp = G == 3 ? tg : tap / 3, dxp = G == 3 ? g : tap - 3 * dyp;
+                const uint64_t adesc = make_desc_k_sw128(slab + (dyp * TW + dxp) * 128);
+                const uint64_t bdesc = bdesc0 + static_cast<uint32_t>((sb * kBStage + g * C::kBBytes) >> 4);
+                mma_ss<CG>(tmem_d, adesc, bdesc, idesc, acc);
+                acc = 1;
+                if (nk16 == 4) {
+                  mma_ss<CG>(tmem_d, adesc + 2, bdesc + 2, idesc, 1);
+                  mma_ss<CG>(tmem_d, adesc + 4, bdesc + 4, idesc, 1);
+                  mma_ss<CG>(tmem_d, adesc + 6, bdesc + 6, idesc, 1);
+                } else {
+                  for (int k = 1; k < nk16; ++k) mma_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+                }
               }
-              if constexpr (CG == 2) {
-                mma_commit_cg2(&bempty[sb]);
-                if (tap == 8) mma_commit_cg2(&aempty[sa]);
-                if (tap == 8 && last_a) mma_commit_cg2(&tfull[as]);
-              } else {
-                mma_commit(&bempty[sb]);
-                if (tap == 8) mma_commit(&aempty[sa]);
-                if (tap == 8 && last_a) mma_commit(&tfull[as]);
-              }
+              mma_commit_t<CG>(&bempty[sb]);
+              if (++sb == NB) { sb = 0; pb ^= 1; }
             }
-            __syncwarp();
-            first = false;
-            if (++sb == NB) { sb = 0; pb ^= 1; }
+            mma_commit_t<CG>(&aempty[sa]);
+            if (last_a) mma_commit_t<CG>(&tfull[as]);
+            if (++sa == NA) { sa = 0; pa ^= 1; }
           }
-          if (++sa == NA) { sa = 0; pa ^= 1; }
-        }
+      }
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (identical to the box kernel)
     const int ew = warp - 2;
@@ -615,12 +681,14 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
       const ConvProblem& pr = p.prob[tc.z];
       const int y = tc.y0 + ly, x = tc.x0 + lx;
       const bool valid = tc.valid && (y < p.H) && (x < p.W);
+      uint4 res_pre[4];
+      const bool has_pre = epilogue_prefetch<BN, EPI>(p, pr, tc, y, x, valid, half, res_pre);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * kAccStride + (static_cast<uint32_t>(quad * 32) << 16);
-      epilogue_tile<BN, EPI>(p, pr, tc, taddr, row, y, x, valid, half, bias_s);
+      epilogue_tile<BN, EPI>(p, pr, tc, taddr, row, y, x, valid, half, bias_s, res_pre, has_pre);
       tc_fence_before();
-      if constexpr (CG == 2) mbar_arrive_cluster(mapa(smem_u32(&tempty[as]), 0));
+      if constexpr (CG == 2) mbar_arrive_cluster_relaxed(mapa(smem_u32(&tempty[as]), 0));
       else mbar_arrive(&tempty[as]);
     }
   }

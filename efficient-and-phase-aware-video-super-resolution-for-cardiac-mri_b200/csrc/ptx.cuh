@@ -161,6 +161,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Relaxed variant for "TMEM accumulator stage drained": the tcgen05.ld results are already in registers
+// (tcgen05.wait::ld) and ordered by tcgen05.fence::before_thread_sync; a release here would additionally wait for the
+// epilogue's outstanding global stores (MEMBAR + ERRBAR per tile), which nobody behind this barrier reads.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA loads of a CTA pair: data lands in THIS CTA's shared memory, completion bytes are counted on the mbarrier at
 // the shared::cluster address `bar_cluster` (the leader CTA's barrier).
 __device__ __forceinline__ void tma_load_2d_cg2(void* dst, const void* tmap, uint32_t bar_cluster, int c0, int c1) {
