@@ -53,6 +53,18 @@ def measured_peaks():
     return d
 
 
+def ncu_traffic(kernel_class):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json), or
+    None when the workload is not the captured one."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f).get(kernel_class)
+        return d["dram_read_bytes"] + d["dram_write_bytes"], d["source"]
+    except Exception:
+        return None, None
+
+
 def synthetic_sequences(batch, seed):
     """ACDCSR-shaped synthetic cine sequences: circular padding and positional code as the reference dataset
     builds them (acdc_vsr_refinenet_dataset.py:74-87, gen_positional_encoding.py:35-38)."""
@@ -387,6 +399,7 @@ def main():
         achieved = lstm_flops / (lstm_ms / 1e3) / 1e12
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         step_flops = sum(v[2] for v in prof.values())
+        traffic, traffic_src = ncu_traffic("convlstm_cell") if (args.workload == "acdc_x4" and B == 32) else (None, None)
         h2d = sum(x.numel() * 4 for x in inputs_h) + pos_h.numel() * 4
         d2h = out_h.numel() * 4
         line = {
@@ -406,7 +419,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel<256, EPI_LSTM> (ConvLSTM cell wavefront)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peaks["_source"] + ", sustained bf16",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peaks["_source"] + ", sustained bf16",
                          "launches_per_step": lstm_launches, "avg_launch_ms": lstm_ms / max(lstm_launches, 1),
                          "share_of_step": lstm_ms / sum(v[0] for v in prof.values()),
                          "whole_step_tflops": step_flops / (ms / args.steps / 1e3) / 1e12},

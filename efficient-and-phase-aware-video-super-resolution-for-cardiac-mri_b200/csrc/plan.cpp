@@ -369,7 +369,12 @@ void schedule(Ctx& c) {
   for (int s = 0; s < S && !c.rc; ++s) {
     const int slot = p->train ? s : 0;
     // ---------------------------------------------------------------- bidirectional ConvLSTM wavefront
-    for (int d = 0; d < L + NL - 1; ++d) {
+    // Last stage: nothing reads the hidden maps of the trailing U - half steps of either direction (no next-stage
+    // feature update; the heads and the refine windows of the T output frames stop `half` frames past them), so the
+    // recurrence stops there - same results, (U - half) / L less ConvLSTM work in that stage.
+    const int dead = (s == S - 1 && U > half) ? U - half : 0;
+    const int Lrun = L - dead;
+    for (int d = 0; d < Lrun + NL - 1; ++d) {
       ConvParams cp;
       base_params(p->lr, p->h, p->w, &cp);
       cp.n_img = B;
@@ -378,7 +383,7 @@ void schedule(Ctx& c) {
       for (int dir = 0; dir < 2; ++dir)
         for (int l = 0; l < NL; ++l) {
           const int t = d - l;
-          if (t < 0 || t >= L) continue;
+          if (t < 0 || t >= Lrun) continue;
           const int j = dir == 0 ? t : L - 1 - t;
           const int jp = dir == 0 ? j - 1 : j + 1;
           ConvProblem& pr = cp.prob[np++];
@@ -405,34 +410,39 @@ void schedule(Ctx& c) {
     // ---------------------------------------------------------------- refine block -> next-stage features
     const long long hf_top = p->img_h[slot][0][NL - 1], hb_top = p->img_h[slot][1][NL - 1];
     {
+      // windows computed: all n_win of them, except in the last stage where only the T output frames are read
+      const int w0 = dead;                                  // first window (frame half + w0)
+      const int n_run = p->n_win - 2 * dead;
+      const long long wimg = static_cast<long long>(w0) * B;
       ConvParams cp;
       base_params(p->lr, p->h, p->w, &cp);
-      cp.n_img = p->n_win * B;
+      cp.n_img = n_run * B;
       ConvProblem& pr = cp.prob[0];
       cp.n_prob = 1;
       pr.n_src = 2 * p->Wn;
       for (int jw = 0; jw < p->Wn; ++jw) {
-        pr.src[2 * jw] = view0(hf_top + static_cast<long long>(jw) * B);
-        pr.src[2 * jw + 1] = view0(hb_top + static_cast<long long>(jw) * B);
+        pr.src[2 * jw] = view0(hf_top + static_cast<long long>(jw) * B + wimg);
+        pr.src[2 * jw + 1] = view0(hb_top + static_cast<long long>(jw) * B + wimg);
       }
-      const __nv_bfloat16* res = act_img(c, p->img_x[s] + static_cast<long long>(half) * B);
-      __nv_bfloat16* xnext = act_img(c, p->img_x[s + 1] + static_cast<long long>(half) * B);
+      const __nv_bfloat16* res = act_img(c, p->img_x[s] + static_cast<long long>(half) * B + wimg);
+      __nv_bfloat16* xnext = act_img(c, p->img_x[s + 1] + static_cast<long long>(half) * B + wimg);
       if (p->cfg.pos_enc) {
         cp.n_total = 144; cp.n_store = 144; cp.out_ch = 144;
-        pr.posterm = posterm;
-        pr.out_bf16 = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_mid + slot * p->mid_stride);
+        pr.posterm = posterm + static_cast<size_t>(wimg) * 16 * 144;
+        pr.out_bf16 = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_mid + slot * p->mid_stride) +
+                      static_cast<size_t>(wimg) * px * 144;
         cp.halo = p->halo_lr;
         run_conv(c, CLS_CONV1, 144, EPI_STORE, p->maps_c1, cp,
                  2.0 * 9 * (2 * kFeat + 1) * p->Wn * (2 * kFeat + 1) * px * cp.n_img);
         ConvParams c2;
         base_params(p->lr, p->h, p->w, &c2);
-        c2.n_img = p->n_win * B;
+        c2.n_img = n_run * B;
         c2.n_prob = 1;
         c2.kb_per_src = 3; c2.k16_last = 1;
         c2.n_total = 64; c2.n_store = 64; c2.out_ch = 64;
         ConvProblem& p2 = c2.prob[0];
         p2.n_src = 1;
-        p2.src[0] = view0(static_cast<long long>(slot) * p->n_win * B);
+        p2.src[0] = view0(static_cast<long long>(slot) * p->n_win * B + wimg);
         p2.bias = reinterpret_cast<const float*>(c.pk + p->pk_c2_b);
         p2.res = res;
         p2.out_bf16 = xnext;

@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "simt.h"
+#include "stencil.cuh"
 
 namespace pvsr {
 
@@ -186,49 +187,29 @@ int launch_l1_multistage(const float* out, const float* target, const float* w, 
 
 // ------------------------------------------------------------------------------------------------
 // head_last_bwd_data: dIn[y, x, c] = sum_tap dOut[y - dy, x - dx] * w[c, tap]   (zero outside the image)
-// 8 threads per pixel (8 channels each; the 72 weights of a thread live in registers); a warp writes 4 pixels x 128 B
-// contiguous.  Grid-stride over pixels: no per-block weight staging, 9 L1-resident scalar loads per pixel.
-__global__ void __launch_bounds__(256, 2) head_last_bwd_data_kernel(const float* __restrict__ dout,
+// 8 threads per pixel run (8 channels each; the 72 weights of a thread live in registers); see stencil.cuh.
+__global__ void __launch_bounds__(kStencilThreads, 3) head_last_bwd_data_kernel(const float* __restrict__ dout,
                                                                     const float* __restrict__ w,
-                                                                    __nv_bfloat16* __restrict__ din,
-                                                                    long long n_pix_total, int H, int W) {
+                                                                    __nv_bfloat16* __restrict__ din, unsigned n_rows,
+                                                                    int H, int W) {
   const int cg = (threadIdx.x & 7) * 8;
-  float wr[8][9];
+  float wr[8][9], br[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+  for (int j = 0; j < 8; ++j) {
+    br[j] = 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(w + (cg + j) * 9 + t);   // parameter layout (1, 64, 3, 3)
-  const long long stride = static_cast<long long>(gridDim.x) * 32;
-  for (long long pix = static_cast<long long>(blockIdx.x) * 32 + (threadIdx.x >> 3); pix < n_pix_total; pix += stride) {
-    const int xw = static_cast<int>(pix % W);
-    const int yh = static_cast<int>((pix / W) % H);
-    const float* img = dout + (pix - static_cast<long long>(yh) * W - xw);
-    float v[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int yy = yh - (t / 3 - 1), xx = xw - (t % 3 - 1);
-      v[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + static_cast<long long>(yy) * W + xx) : 0.f;
-    }
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[j] = 0.f;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) acc[j] = fmaf(v[t], wr[j][t], acc[j]);
-    }
-    *reinterpret_cast<uint4*>(din + pix * 64 + cg) =
-        make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
   }
+  stencil_1to64_runs<true, false>(dout, wr, br, 0.f, din, n_rows, H, W, cg);
 }
 
 int launch_head_last_bwd_data(const float* dout, const float* w, void* din_bf16, long long n_img, int H, int W,
                               cudaStream_t s) {
-  const long long n_pix = n_img * H * W;
-  if (n_pix == 0) return 0;
-  long long blocks = (n_pix + 31) / 32;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  head_last_bwd_data_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
-      dout, w, static_cast<__nv_bfloat16*>(din_bf16), n_pix, H, W);
+  const long long n_rows = n_img * H;
+  if (n_rows == 0) return 0;
+  if (n_rows * ((W + 7) / 8) >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
+  head_last_bwd_data_kernel<<<stencil_blocks(n_rows, W, 148 * 24), kStencilThreads, 0, s>>>(
+      dout, w, static_cast<__nv_bfloat16*>(din_bf16), static_cast<unsigned>(n_rows), H, W);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -11,17 +11,17 @@
 #include <stdint.h>
 
 #include "simt.h"
+#include "stencil.cuh"
 
 namespace pvsr {
 
 // ------------------------------------------------------------------------------------------------
 // in_conv_prelu: x fp32 [n_img][H][W] -> out bf16 NHWC [n_img][H][W][64]
-// 8 threads per pixel, 8 channels each (their 72 weights + 8 biases live in registers); a warp writes 4 pixels x 128 B
-// contiguous.  Grid-stride over pixels: no per-block weight staging, 9 L1-resident scalar loads per pixel.
-__global__ void __launch_bounds__(256, 2) in_conv_prelu_kernel(const float* __restrict__ x, const float* __restrict__ w,
+// 8 threads per pixel run, 8 channels each (their 72 weights + 8 biases live in registers); see stencil.cuh.
+__global__ void __launch_bounds__(kStencilThreads, 3) in_conv_prelu_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ b,
                                                                const float* __restrict__ slope,
-                                                               __nv_bfloat16* __restrict__ out, long long n_pix_total,
+                                                               __nv_bfloat16* __restrict__ out, unsigned n_rows,
                                                                int H, int W) {
   const int cg = static_cast<int>(threadIdx.x & 7) * 8;
   float wr[8][9], br[8];
@@ -31,44 +31,16 @@ __global__ void __launch_bounds__(256, 2) in_conv_prelu_kernel(const float* __re
 #pragma unroll
     for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(w + (cg + j) * 9 + t);   // parameter layout (64, 1, 3, 3)
   }
-  const float a = slope[0];
-  const long long stride = static_cast<long long>(gridDim.x) * 32;
-  for (long long pix = static_cast<long long>(blockIdx.x) * 32 + (threadIdx.x >> 3); pix < n_pix_total; pix += stride) {
-    const int xw = static_cast<int>(pix % W);
-    const int yh = static_cast<int>((pix / W) % H);
-    const float* img = x + (pix - static_cast<long long>(yh) * W - xw);
-    float v[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
-      v[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + static_cast<long long>(yy) * W + xx) : 0.f;
-    }
-    uint32_t pk[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float f0 = br[2 * j], f1 = br[2 * j + 1];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        f0 = fmaf(v[t], wr[2 * j][t], f0);
-        f1 = fmaf(v[t], wr[2 * j + 1][t], f1);
-      }
-      f0 = f0 >= 0.f ? f0 : a * f0;
-      f1 = f1 >= 0.f ? f1 : a * f1;
-      __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-      pk[j] = *reinterpret_cast<uint32_t*>(&h);
-    }
-    *reinterpret_cast<uint4*>(out + pix * 64 + cg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  }
+  stencil_1to64_runs<false, true>(x, wr, br, slope[0], out, n_rows, H, W, cg);
 }
 
 int launch_in_conv_prelu(const float* x, const float* w, const float* b, const float* slope, void* out,
                          long long n_img, int H, int W, cudaStream_t s) {
-  const long long n_pix = n_img * H * W;
-  if (n_pix == 0) return 0;
-  long long blocks = (n_pix + 31) / 32;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  in_conv_prelu_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, w, b, slope, static_cast<__nv_bfloat16*>(out),
-                                                                    n_pix, H, W);
+  const long long n_rows = n_img * H;
+  if (n_rows == 0) return 0;
+  if (n_rows * ((W + 7) / 8) >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
+  in_conv_prelu_kernel<<<stencil_blocks(n_rows, W, 148 * 24), kStencilThreads, 0, s>>>(
+      x, w, b, slope, static_cast<__nv_bfloat16*>(out), static_cast<unsigned>(n_rows), H, W);
   return static_cast<int>(cudaGetLastError());
 }
 
