@@ -124,10 +124,19 @@ void build_wgrad_jobs(const std::vector<WgSource>& srcs, int kb_per_src, int tap
 }
 
 int auto_wgrad_splits(int n_jobs, long long total_tiles, int num_sms) {
-  long long s = (2LL * num_sms + n_jobs - 1) / n_jobs;
-  if (s < 1) s = 1;
-  if (s > total_tiles) s = total_tiles;
-  return static_cast<int>(s);
+  // One CTA per SM is resident (193 KB of shared memory), so the launch runs in ceil(n_jobs * s / num_sms) waves of
+  // (total_tiles / s) tiles each: pick the split count minimising waves / s (ties: fewer splits = fewer epilogues).
+  // The former "about two waves" rule produced grids such as 300 or 322 CTAs on 148 SMs: a third wave for 2-9 % of
+  // the work.
+  long long best_s = 1;
+  double best = 1e30;
+  const long long max_s = total_tiles < 24 ? total_tiles : 24;
+  for (long long s = 1; s <= max_s; ++s) {
+    const long long waves = (static_cast<long long>(n_jobs) * s + num_sms - 1) / num_sms;
+    const double t = static_cast<double>(waves) * static_cast<double>((total_tiles + s - 1) / s);
+    if (t < best * 0.999) { best = t; best_s = s; }
+  }
+  return static_cast<int>(best_s);
 }
 
 }  // namespace pvsr
@@ -158,6 +167,11 @@ int pvsr_set_halo_mode(int mode) {
   return 0;
 }
 int pvsr_get_halo_mode(void) { return get_halo_mode(); }
+int pvsr_set_pdl(int enable) {
+  set_pdl(enable);
+  return 0;
+}
+int pvsr_get_pdl(void) { return get_pdl(); }
 
 int pvsr_choose_tile(int H, int W, int* tw_log2_out) {
   if (H <= 0 || W <= 0 || !tw_log2_out) return set_error(-2, "bad image size");
@@ -240,11 +254,21 @@ int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream) {
   const int tw = 1 << p.tw_log2, th = kTileM >> p.tw_log2;
   int max_mul = 1;
   for (int v = 0; v < d->n_views; ++v) max_mul = d->views[v].mul > max_mul ? d->views[v].mul : max_mul;
-  p.halo = halo_applicable(d->W, tw, p.tiles_x, d->taps, max_mul) ? get_halo_mode() : 0;
+  // slab (padded-raster) kernel whenever the geometry allows it; ConvLSTM launches only in the classic whole-row case
+  // because their state tensors are laid out by the box kernel's tile -> pixel map (pvsr_lstm_state_elems)
+  PrGeom g{0, 0, 0};
+  const bool slab = get_halo_mode() != 0 && d->taps == 9 &&
+                    (d->epi == EPI_LSTM ? (max_mul == 1 && classic_halo(d->H, d->W, tw, p.tiles_x, &g))
+                                        : choose_pr(d->H, d->W, max_mul, &g));
+  int bw = tw, bh = th;
+  if (slab) {
+    p.halo = 1; p.pr_wp = g.wp; p.pr_rows = g.rows; p.tiles_x = 1; p.tiles_y = g.tiles;
+    bw = g.wp; bh = g.rows;
+  }
   for (int v = 0; v < d->n_views; ++v) {
     const pvsr_act_view& a = d->views[v];
     if (a.channels % 8 != 0) return set_error(-2, "view channels must be a multiple of 8");
-    rc = make_act_tmap(&maps.act[v], a.ptr, a.channels, a.W, a.H, a.images, tw, p.halo ? th + 2 : th, a.mul);
+    rc = make_act_tmap(&maps.act[v], a.ptr, a.channels, a.W, a.H, a.images, bw, bh, a.mul);
     if (rc) return set_error(rc, "activation tensor map encode failed (%d)", rc);
   }
   rc = make_weight_tmap(&maps.w, d->w_packed, d->w_rows, d->bn);

@@ -73,7 +73,9 @@ struct ConvParams {
   int out_ch;        // channels per pixel of the output tensor
   int ps_r;          // pixel-shuffle factor for EPI_PS
   int grad_split;    // EPI_GRAD column routing (see ConvProblem)
-  int halo;          // != 0: halo kernel (the activation maps carry (TH+2)-row boxes)
+  int halo;          // != 0: padded-raster slab kernel (below); tiles_x = 1, tiles_y = pr_tiles
+  int pr_wp;         // padded row pitch Wp >= W + 1: output position p = y * Wp + x, tile t covers [128 t, 128 t + 128)
+  int pr_rows;       // rows of the activation box = rows a tile can span + 2 (the maps carry (64, Wp, pr_rows, 1) boxes)
   ConvProblem prob[kMaxProb];
 };
 
@@ -87,12 +89,64 @@ void set_cta_pair(int enable);
 int get_cta_pair();
 inline int cta_pair_factor() { return get_cta_pair() ? 2 : 1; }
 
-// Halo variant of the 3x3 launches (one activation slab per source instead of nine shifted boxes): 0 = off.
+// Programmatic dependent launch (griddepcontrol) on the tcgen05 launches and the LSTM gate-adjoint kernel: 0 = off.
+void set_pdl(int enable);
+int get_pdl();
+
+// Slab ("halo") variant of the 3x3 launches: one activation slab per source instead of nine shifted boxes. 0 = off.
 void set_halo_mode(int mode);
 int get_halo_mode();
-// Applicable when a tile spans the image width with a spare zero column: 3x3 taps, plain views.
-inline bool halo_applicable(int W, int tw, int tiles_x, int taps, int max_mul) {
-  return get_halo_mode() != 0 && taps == 9 && max_mul == 1 && tiles_x == 1 && W + 1 <= tw;
+
+// Padded-raster geometry of a slab launch.  Output pixels are numbered p = y * Wp + x with a row pitch Wp > W, so
+// that every row ends in at least one column the TMA box zero-fills (x >= W): the left / right neighbour of a border
+// pixel is then a zero of the previous / same row and all nine taps of a source are row-shifted views of ONE slab of
+// `rows` image rows (the rows a 128-position tile touches, plus one above and one below).  Wp = 64 for W = 63 is the
+// special case "tile = whole rows"; any W works (Wp = 33 for 32-pixel training patches: 9 tiles instead of 8 per
+// image, but 4.9x less activation traffic than nine 16 KB boxes).
+struct PrGeom {
+  int wp, rows, tiles;   // pitch, box rows, tiles per image
+};
+constexpr int kPrMaxSlabBytes = 56 * 1024;
+inline int pr_rows_for(int H, int W, int wp) {
+  (void)W;
+  const int tiles = (H * wp + kTileM - 1) / kTileM;
+  int rmax = 1;
+  for (int t = 0; t < tiles; ++t) {
+    const int o = (t * kTileM) % wp;
+    const int r = (o + kTileM - 1) / wp + 1;
+    rmax = r > rmax ? r : rmax;
+  }
+  return rmax + 2;
+}
+// Picks Wp minimising (tiles per image, slab positions); false if no pitch satisfies the TMA box / smem limits.
+inline bool choose_pr(int H, int W, int max_mul, PrGeom* g) {
+  long long best_tiles = -1, best_pos = -1;
+  int cand[10], nc = 0;
+  for (int i = 1; i <= 8; ++i) cand[nc++] = W + i;
+  int p2 = 8;
+  while (p2 < W + 1) p2 <<= 1;
+  cand[nc++] = p2;
+  for (int i = 0; i < nc; ++i) {
+    const int wp = cand[i];
+    const int rows = pr_rows_for(H, W, wp);
+    if (wp * max_mul > 256 || rows * max_mul > 256) continue;
+    const long long pos = static_cast<long long>(rows) * wp;
+    if (pos * 128 > kPrMaxSlabBytes) continue;
+    const long long tiles = (static_cast<long long>(H) * wp + kTileM - 1) / kTileM;
+    if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && pos < best_pos)) {
+      best_tiles = tiles; best_pos = pos;
+      g->wp = wp; g->rows = rows; g->tiles = static_cast<int>(tiles);
+    }
+  }
+  return best_tiles > 0;
+}
+// The classic whole-row special case (power-of-two pitch = tile width): keeps the tile -> pixel map of the box kernel,
+// which the tile-transposed ConvLSTM state / gate tensors are laid out by.
+inline bool classic_halo(int H, int W, int tw, int tiles_x, PrGeom* g) {
+  if (tiles_x != 1 || W + 1 > tw) return false;
+  const int th = kTileM / tw;
+  g->wp = tw; g->rows = th + 2; g->tiles = (H + th - 1) / th;
+  return true;
 }
 
 // Launches the tcgen05 kernel.  Returns a cudaError_t as int.
@@ -100,7 +154,7 @@ int launch_conv3x3(int bn, int epi, const ConvMaps& maps, const ConvParams& p, i
 
 // Host helpers (tensormap.cpp)
 int make_act_tmap(CUtensorMap* out, const void* base, int channels, int W, int H, long long images, int tw, int th,
-                  int mul = 1);
+                  int mul = 1);   // box (64, tw * mul, th * mul, 1); tw / th need not be powers of two
 int make_weight_tmap(CUtensorMap* out, const void* base, long long rows, int bn);
 
 inline void choose_tile(int H, int W, int* tw_log2_out, int max_tw = 128) {

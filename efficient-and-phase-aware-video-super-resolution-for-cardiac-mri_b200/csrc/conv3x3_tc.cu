@@ -81,23 +81,37 @@ __device__ __forceinline__ void mma_commit_t(uint64_t* bar) {
 }
 
 struct TileCoord {
-  int z, img, y0, x0, nt, tile_lin;
+  int z, img, y0, x0, nt, tile_lin, ty;
   bool valid;   // false: padding tile of an odd pair (loaded and multiplied like its neighbour, never stored)
 };
-// Work item `it` (N tile fastest, then the group of CG consecutive M tiles, then the problem) -> the M tile of CTA
-// `rank` of the group.
+// Work item `it` (N tile fastest, then the group of CG M tiles, then the problem) -> the M tile of CTA `rank` of the
+// group.  Box kernel: a group = CG consecutive tiles of the (image, ty, tx) raster.  Slab kernel (p.halo): a group =
+// the SAME tile of CG consecutive images, so that both CTAs of a pair share the tile's row phase inside the slab (one
+// MMA descriptor offset serves both).
 __device__ __forceinline__ TileCoord decode_item(const ConvParams& p, int it, int groups, int tiles_m, int cg, int rank) {
   TileCoord c;
   c.nt = it % p.n_tiles_n;
   it /= p.n_tiles_n;
   const int grp = it % groups;
   c.z = it / groups;
+  if (p.halo) {
+    c.ty = grp % p.tiles_y;
+    int img = (grp / p.tiles_y) * cg + rank;
+    c.valid = img < p.n_img;
+    if (!c.valid) img = p.n_img - 1;
+    c.img = img;
+    c.x0 = 0;
+    c.y0 = 0;
+    c.tile_lin = img * p.tiles_y + c.ty;
+    return c;
+  }
   int m = grp * cg + rank;
   c.valid = m < tiles_m;
   if (!c.valid) m = tiles_m - 1;
   const int tx = m % p.tiles_x;
   m /= p.tiles_x;
   const int ty = m % p.tiles_y;
+  c.ty = ty;
   c.img = m / p.tiles_y;
   c.x0 = tx << p.tw_log2;
   c.y0 = ty * (kTileM >> p.tw_log2);
@@ -348,6 +362,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     if constexpr (CG == 2) tmem_alloc_cg2<kTmemCols>(tmem_slot);
     else tmem_alloc<kTmemCols>(tmem_slot);
   }
+  // PDL: everything above touches no global memory; the next launch may start its own prologue as our CTAs retire.
+  pdl_launch_dependents();
+  pdl_wait();
   if constexpr (EPI == EPI_LSTM) {
     // Gate biases, pre-multiplied so that each gate costs one FFMA + ex2 + add + rcp:
     // i, f, o: -log2(e) * b (sigmoid);  g: 2 * log2(e) * b (tanh).
@@ -481,14 +498,16 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
 }
 
 // =====================================================================================================================
-// Halo variant.  When a tile spans the whole image width and at least one column of the tile is outside the image
-// (W < TW), the nine taps of a source are nine row-shifted views of ONE (TH+2) x TW pixel slab: the spare column is zero
-// (TMA fill) and serves as left and right padding of every row, rows above / below the image are zero-filled too.  The
-// slab is loaded once per (source, channel block) - 4.5x less activation traffic than nine shifted boxes - and the MMA
-// A descriptor simply starts (dy+1)*TW + dx rows into it (128 B per row; the 128B swizzle is a function of the absolute
-// shared-memory address, so shifted starts stay consistent with what TMA wrote - measured: the descriptor's
-// base-offset field must stay 0, setting it to the row phase gives wrong products).  One zeroed 1 KB guard before and
-// after every slab catches the -1 / +1 row of the corner taps.  Weights stream through their own ring, one box per tap.
+// Slab ("halo") variant on the padded raster (conv.h: PrGeom).  Output positions p = y * Wp + x with Wp > W: a tile is
+// 128 consecutive positions, and the nine taps of a source are nine row-shifted views of ONE slab holding the image
+// rows the tile touches plus one above and one below (TMA box (64 ch, Wp, rows): the columns x >= W and the rows
+// outside the image arrive as zeros and serve as left / right / top / bottom padding of every row).  The slab is
+// loaded once per (source, channel block) - ~4.5x less activation traffic than nine shifted boxes - and the MMA A
+// descriptor simply starts o + (dy+1)*Wp + dx rows into it (o = the tile's offset inside its first row; 128 B per
+// row; the 128B swizzle is a function of the absolute shared-memory address, so shifted starts stay consistent with
+// what TMA wrote - measured: the descriptor's base-offset field must stay 0, setting it to the row phase gives wrong
+// products).  One zeroed 1 KB guard before and after every slab catches the -1 / +1 row of the corner taps.  Weights
+// stream through their own ring.  Positions with x >= W or y >= H are computed and never stored.
 constexpr int kHaloMaxNA = 3;       // activation slabs in flight: 3 when the weight stages are small, else 2
 constexpr int kHaloGuard = 1024;
 constexpr int kHaloMaxNB = 8;       // weight stages in flight
@@ -497,13 +516,15 @@ constexpr int kHaloBudget = 200 * 1024;
 // Weight stage = G consecutive taps (one row of the 3x3 stencil when G = 3): narrow-N launches spend only 32-64 tensor
 // cycles per MMA, so one barrier round trip per tap would bound them; one wait + one commit per G taps does not.
 __host__ __device__ constexpr int halo_group(int b_bytes) { return b_bytes <= 8192 ? 3 : 1; }
-__host__ __device__ inline int halo_slab_bytes(int tw) { return (kTileM + 2 * tw) * 128; }
-__host__ __device__ inline int halo_num_b(int tw, int b_bytes, int na) {
-  const int n = (kHaloBudget - na * (halo_slab_bytes(tw) + kHaloGuard) - kHaloGuard) / b_bytes;
+__host__ __device__ inline int halo_slab_bytes(int positions) { return (positions * 128 + 1023) & ~1023; }
+__host__ __device__ inline int halo_num_b(int slab_bytes, int b_bytes, int na) {
+  const int n = (kHaloBudget - na * (slab_bytes + kHaloGuard) - kHaloGuard) / b_bytes;
   return n > kHaloMaxNB ? kHaloMaxNB : n;
 }
 // three slabs if that still leaves >= 6 (ungrouped) weight stages
-__host__ __device__ inline int halo_num_a(int tw, int b_bytes) { return halo_num_b(tw, b_bytes, 3) >= 6 ? 3 : 2; }
+__host__ __device__ inline int halo_num_a(int slab_bytes, int b_bytes) {
+  return halo_num_b(slab_bytes, b_bytes, 3) >= 6 ? 3 : 2;
+}
 
 template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -511,12 +532,13 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
   using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int TW = 1 << p.tw_log2;
-  const int slab_bytes = halo_slab_bytes(TW);
+  const int Wp = p.pr_wp;                          // padded-raster pitch (conv.h: PrGeom)
+  const int box_bytes = p.pr_rows * Wp * 128;      // what one TMA box delivers
+  const int slab_bytes = halo_slab_bytes(p.pr_rows * Wp);
   constexpr int G = halo_group(C::kBBytes);        // taps per weight stage
   constexpr int kBStage = G * C::kBBytes;
-  const int NA = halo_num_a(TW, C::kBBytes);
-  const int NB = halo_num_b(TW, kBStage, NA);
+  const int NA = halo_num_a(slab_bytes, C::kBBytes);
+  const int NB = halo_num_b(slab_bytes, kBStage, NA);
   // [guard][slab 0][guard] .. [slab NA-1][guard][B stage 0 .. NB-1][barriers][LSTM biases]
   uint8_t* slab0 = smem + kHaloGuard;
   const int slab_pitch = slab_bytes + kHaloGuard;
@@ -535,7 +557,7 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   const int tiles_m = p.n_img * p.tiles_y * p.tiles_x;
-  const int groups = (tiles_m + CG - 1) / CG;
+  const int groups = ((p.n_img + CG - 1) / CG) * p.tiles_y;   // pairs are formed across images (decode_item)
   const int total_items = p.n_prob * groups * p.n_tiles_n;
   const int item0 = blockIdx.x / CG, item_step = gridDim.x / CG;
 
@@ -551,12 +573,20 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
     if constexpr (CG == 2) tmem_alloc_cg2<kTmemCols>(tmem_slot);
     else tmem_alloc<kTmemCols>(tmem_slot);
   }
-  // zero guards (read by the MMA through the async proxy, never written by TMA)
-  for (int i = threadIdx.x; i < (NA + 1) * (kHaloGuard / 16); i += kNumThreads) {
-    const int g = i / (kHaloGuard / 16), o = i % (kHaloGuard / 16);
-    reinterpret_cast<uint4*>(smem + g * slab_pitch)[o] = make_uint4(0, 0, 0, 0);
+  // zero guards (read by the MMA through the async proxy, never written by TMA): 1 KB in front of the first slab, and
+  // behind every slab the bytes from the end of the TMA box to the next slab (round-up slack + 1 KB)
+  for (int i = threadIdx.x; i < kHaloGuard / 16; i += kNumThreads)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  {
+    const int tail16 = (slab_pitch - box_bytes) / 16;
+    for (int i = threadIdx.x; i < NA * tail16; i += kNumThreads) {
+      const int g = i / tail16, o = i - g * tail16;
+      reinterpret_cast<uint4*>(slab0 + g * slab_pitch + box_bytes)[o] = make_uint4(0, 0, 0, 0);
+    }
   }
   fence_proxy_async();
+  pdl_launch_dependents();
+  pdl_wait();
   if constexpr (EPI == EPI_LSTM) {
     for (int i = threadIdx.x; i < p.n_prob * 256; i += kNumThreads) {
       const int z = i >> 8, n = i & 255;
@@ -578,19 +608,21 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
         const TileCoord tc = decode_item(p, t, groups, tiles_m, CG, rank);
         const ConvProblem& pr = p.prob[tc.z];
         const int wcol = pr.w_row_base + tc.nt * BN + rank * (BN / CG);
+        const int row0 = (tc.ty * kTileM) / Wp;    // first image row the tile touches
         for (int s = 0; s < pr.n_src; ++s) {
           const SrcView& sv = pr.src[s];
           const CUtensorMap* tm = &maps.act[sv.map];
           for (int cb = 0; cb < p.kb_per_src; ++cb) {
             mbar_wait(&aempty[sa], pa ^ 1);
             uint8_t* dst = slab0 + sa * slab_pitch;
+            const int cx = sv.off_x, cy = sv.mul * (row0 - 1) + sv.off_y;   // image rows row0 - 1 .. row0 + pr_rows - 2
             if constexpr (CG == 2) {
-              if (rank == 0) mbar_arrive_expect_tx(&afull[sa], 2 * slab_bytes);
-              tma_load_4d_cg2(dst, tm, mapa(smem_u32(&afull[sa]), 0), sv.ch0 + cb * kBlockK, 0, tc.y0 - 1,
+              if (rank == 0) mbar_arrive_expect_tx(&afull[sa], 2 * box_bytes);
+              tma_load_4d_cg2(dst, tm, mapa(smem_u32(&afull[sa]), 0), sv.ch0 + cb * kBlockK, cx, cy,
                               sv.img_base + tc.img);
             } else {
-              mbar_arrive_expect_tx(&afull[sa], slab_bytes);
-              tma_load_4d(dst, tm, &afull[sa], sv.ch0 + cb * kBlockK, 0, tc.y0 - 1, sv.img_base + tc.img);
+              mbar_arrive_expect_tx(&afull[sa], box_bytes);
+              tma_load_4d(dst, tm, &afull[sa], sv.ch0 + cb * kBlockK, cx, cy, sv.img_base + tc.img);
             }
             if (++sa == NA) { sa = 0; pa ^= 1; }
             for (int tg = 0; tg < 9 / G; ++tg) {
@@ -628,13 +660,16 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * kAccStride;
-        const int n_src = p.prob[decode_item(p, t, groups, tiles_m, CG, 0).z].n_src;
+        const TileCoord tc0 = decode_item(p, t, groups, tiles_m, CG, 0);   // both CTAs of a pair: same row phase
+        const int n_src = p.prob[tc0.z].n_src;
+        // Both CTAs of a pair work on the same tile index of two images: one descriptor offset serves both.
+        const int o0 = tc0.ty * kTileM - ((tc0.ty * kTileM) / Wp) * Wp;
         uint32_t acc = 0;   // the first MMA of the tile overwrites the accumulator
         for (int s = 0; s < n_src; ++s)
           for (int cb = 0; cb < p.kb_per_src; ++cb) {
             mbar_wait(&afull[sa], pa);
-            // tap (dx, dy) starts (dy + 1) * TW + dx rows of 128 B into the slab (first row: the zero guard)
-            const uint32_t slab = slab_base + sa * slab_pitch - 128;
+            // tap (dx, dy) of output position m reads slab row o0 + m + (dy + 1) * Wp + dx (row -1: the zero guard)
+            const uint32_t slab = slab_base + sa * slab_pitch + (o0 - 1) * 128;
             const int nk16 = (cb == p.kb_per_src - 1) ? p.k16_last : 4;
             const bool last_a = (s == n_src - 1) && (cb == p.kb_per_src - 1);
             for (int tg = 0; tg < 9 / G; ++tg) {
@@ -644,7 +679,7 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
               for (int g = 0; g < G; ++g) {
                 const int tap = tg * G + g;
                 const int dyp = G == 3 ? tg : tap / 3, dxp = G == 3 ? g : tap - 3 * dyp;
-                const uint64_t adesc = make_desc_k_sw128(slab + (dyp * TW + dxp) * 128);
+                const uint64_t adesc = make_desc_k_sw128(slab + (dyp * Wp + dxp) * 128);
                 const uint64_t bdesc = bdesc0 + static_cast<uint32_t>((sb * kBStage + g * C::kBBytes) >> 4);
                 mma_ss<CG>(tmem_d, adesc, bdesc, idesc, acc);
                 acc = 1;
@@ -672,14 +707,14 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
     const int quad = warp & 3;
     const int half = ew >> 2;
     const int row = quad * 32 + lane;
-    const int ly = row >> p.tw_log2, lx = row & (TW - 1);
     int it = 0;
     for (int t = item0; t < total_items; t += item_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const TileCoord tc = decode_item(p, t, groups, tiles_m, CG, rank);
       const ConvProblem& pr = p.prob[tc.z];
-      const int y = tc.y0 + ly, x = tc.x0 + lx;
+      const int pos = tc.ty * kTileM + row;        // padded-raster position of this thread's output pixel
+      const int y = pos / Wp, x = pos - y * Wp;
       const bool valid = tc.valid && (y < p.H) && (x < p.W);
       uint4 res_pre[4];
       const bool has_pre = epilogue_prefetch<BN, EPI>(p, pr, tc, y, x, valid, half, res_pre);
@@ -717,28 +752,33 @@ static int launch_t(const ConvMaps& maps, const ConvParams& p, int num_sms, cuda
     attr_set = true;
   }
   const long long tiles_m = 1LL * p.n_img * p.tiles_y * p.tiles_x;
-  const long long items = 1LL * p.n_prob * ((tiles_m + CG - 1) / CG) * p.n_tiles_n;
+  const long long groups = HALO ? 1LL * ((p.n_img + CG - 1) / CG) * p.tiles_y : (tiles_m + CG - 1) / CG;
+  const long long items = 1LL * p.n_prob * groups * p.n_tiles_n;
   if (items <= 0) return 0;
   const long long max_groups = num_sms / CG;
   const int grid = static_cast<int>((items < max_groups ? items : max_groups) * CG);
-  if constexpr (CG == 1) {
-    kern<<<grid, kNumThreads, kSmem, stream>>>(maps, p);
-    return static_cast<int>(cudaGetLastError());
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = kSmem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, maps, p));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = kSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CG;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (get_pdl()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, maps, p));
 }
 
 template <int BN, int EPI>
@@ -754,6 +794,10 @@ static int launch_cg(const ConvMaps& maps, const ConvParams& p, int num_sms, cud
 static int g_halo = 1;   // 0: nine shifted TMA boxes per source, 1: one slab per source + shifted descriptors
 void set_halo_mode(int mode) { g_halo = mode; }
 int get_halo_mode() { return g_halo; }
+
+static int g_pdl = 1;   // programmatic dependent launch between consecutive kernels of the schedule
+void set_pdl(int enable) { g_pdl = enable ? 1 : 0; }
+int get_pdl() { return g_pdl; }
 
 void set_cta_pair(int enable) { g_cta_pair = enable ? 1 : 0; }
 int get_cta_pair() { return g_cta_pair; }

@@ -145,8 +145,12 @@ struct pvsr_plan {
   const void* maps_pk = nullptr;
   int maps_cg = -1;      // CTA-pair setting the tensor maps (weight box height) were built for
   int maps_halo = -1;    // halo mode the activation maps (box rows) were built for
-  int halo_lr = 0;       // halo mode of the 3x3 launches at LR resolution (0 = nine shifted boxes)
-  int halo_ps[PVSR_MAX_HEAD_CONVS] = {0, 0, 0, 0};   // ... of head conv q (its input resolution)
+  // Slab (padded-raster) geometry per launch kind; on = false: nine shifted boxes (conv.h: PrGeom)
+  struct Geo { bool on = false; PrGeom g{0, 0, 0}; };
+  Geo geo_lstm;                           // ConvLSTM cells: classic whole-row case only (state tensors are tile-laid-out)
+  Geo geo_lr;                             // other 3x3 launches at LR resolution (refine convs, their data gradients, ...)
+  Geo geo_ps[PVSR_MAX_HEAD_CONVS];        // head conv q (its input resolution)
+  Geo geo_hdg[PVSR_MAX_HEAD_CONVS];       // data gradient of head conv q (sources: pixel-unshuffled views, mul = r)
   ConvMaps maps_lstm, maps_c1, maps_c2, maps_head[PVSR_MAX_HEAD_CONVS];   // act[0] + packed weights of each launch kind
   ConvMaps bm_lstm_dg, bm_lstm_wg, bm_c1_dg, bm_c1_wg, bm_c2_dg, bm_c2_wg, bm_head_dg[PVSR_MAX_HEAD_CONVS],
       bm_head_wg[PVSR_MAX_HEAD_CONVS];
@@ -316,6 +320,15 @@ void base_params(const Tiling& t, int H, int W, ConvParams* cp) {
   cp->taps = 9; cp->kb_per_src = 1; cp->k16_last = 4; cp->n_tiles_n = 1;
 }
 
+void set_slab(ConvParams* cp, const pvsr_plan::Geo& g) {
+  if (!g.on) return;
+  cp->halo = 1;
+  cp->pr_wp = g.g.wp;
+  cp->pr_rows = g.g.rows;
+  cp->tiles_x = 1;
+  cp->tiles_y = g.g.tiles;
+}
+
 inline SrcView view0(long long img_base) { return SrcView{0, static_cast<int>(img_base), 0, 1, 0, 0}; }
 
 void run_conv(Ctx& c, int cls, int bn, int epi, const ConvMaps& maps, const ConvParams& cp, double fl) {
@@ -403,7 +416,7 @@ void schedule(Ctx& c) {
           if (p->train && j >= U && j < L - U) pr.gates_out = gates_buf(c, s, dir, l, j - U);
         }
       cp.n_prob = np;
-      cp.halo = p->halo_lr;
+      set_slab(&cp, p->geo_lstm);
       run_conv(c, CLS_LSTM, 256, EPI_LSTM, p->maps_lstm, cp, lstm_fl * px * B * np);
     }
 
@@ -431,7 +444,7 @@ void schedule(Ctx& c) {
         pr.posterm = posterm + static_cast<size_t>(wimg) * 16 * 144;
         pr.out_bf16 = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_mid + slot * p->mid_stride) +
                       static_cast<size_t>(wimg) * px * 144;
-        cp.halo = p->halo_lr;
+        set_slab(&cp, p->geo_lr);
         run_conv(c, CLS_CONV1, 144, EPI_STORE, p->maps_c1, cp,
                  2.0 * 9 * (2 * kFeat + 1) * p->Wn * (2 * kFeat + 1) * px * cp.n_img);
         ConvParams c2;
@@ -446,7 +459,7 @@ void schedule(Ctx& c) {
         p2.bias = reinterpret_cast<const float*>(c.pk + p->pk_c2_b);
         p2.res = res;
         p2.out_bf16 = xnext;
-        c2.halo = p->halo_lr;
+        set_slab(&c2, p->geo_lr);
         run_conv(c, CLS_CONV2, 64, EPI_STORE, p->maps_c2, c2,
                  2.0 * 9 * (2 * kFeat + 1) * kFeat * px * c2.n_img);
       } else {
@@ -491,7 +504,7 @@ void schedule(Ctx& c) {
         pr.src[0] = view0(q == 0 ? in_img : static_cast<long long>(lslot) * n_head);
         pr.bias = reinterpret_cast<const float*>(c.pk + p->pk_head_b[q]);
         pr.out_bf16 = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_head[q] + lslot * p->head_stride[q]);
-        cp.halo = p->halo_ps[q];
+        set_slab(&cp, p->geo_ps[q]);
         run_conv(c, CLS_HEAD_PS, p->ps_bn[q], EPI_PS, p->maps_head[q], cp,
                  2.0 * 9 * kFeat * (kFeat * p->ps_r[q] * p->ps_r[q]) * p->ps_h[q] * p->ps_w[q] * n_head);
       }
@@ -604,6 +617,7 @@ void schedule_backward(Ctx& c) {
       run_wgrad(c, BCLS_HEAD_WGRAD, p->bm_head_wg[q], p->wl_head[s][q], p->ps_h[q], p->ps_w[q], conv_fl);
       ConvParams cp;
       base_params(p->bw_tile[q], p->ps_h[q], p->ps_w[q], &cp);
+      set_slab(&cp, p->geo_hdg[q]);
       cp.n_total = 64; cp.n_store = 64; cp.out_ch = 64;
       if (q > 0) {
         cp.n_img = static_cast<int>(3 * TB);
@@ -658,7 +672,7 @@ void schedule_backward(Ctx& c) {
         pr.n_src = 1;
         pr.src[0] = view0(static_cast<long long>(half) * B);
         pr.out_bf16 = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_gm) + static_cast<size_t>(half) * B * px * 144;
-        cp.halo = p->halo_lr;
+        set_slab(&cp, p->geo_lr);
         run_conv(c, BCLS_REFINE_DGRAD, 144, EPI_STORE, p->bm_c2_dg, cp, c2_fl);
       }
       if (c.dry || c.G->ref_w1)
@@ -681,7 +695,7 @@ void schedule_backward(Ctx& c) {
         for (int sd = 0; sd < Wn; ++sd) pr.src[sd] = view0(static_cast<long long>(sd) * B);
         pr.grad0 = grad_stack(c, dh_top_f, 0);
         pr.grad1 = grad_stack(c, dh_top_b, 0);
-        cp.halo = p->halo_lr;
+        set_slab(&cp, p->geo_lr);
         run_conv(c, BCLS_REFINE_DGRAD, 128, EPI_GRAD, p->bm_c1_dg, cp, c1_fl);
       }
     } else {
@@ -748,7 +762,7 @@ void schedule_backward(Ctx& c) {
         }
       lp.n_prob = np;
       cp.n_prob = np;
-      cp.halo = p->halo_lr;
+      set_slab(&cp, p->geo_lr);
       run_simt(c, BCLS_LSTM_POINT, "lstm_bwd_pointwise", [&] { return launch_lstm_bwd_pointwise(lp, c.stream); });
       run_conv(c, BCLS_LSTM_DGRAD, p->lstm_dg_bn, EPI_GRAD, p->bm_lstm_dg, cp, lstm_fl * px * B * np);
     }
@@ -781,26 +795,35 @@ int build_maps(pvsr_plan* p, const void* ws, const void* pk) {
   const uint8_t* k = static_cast<const uint8_t*>(pk);
   int rc = 0;
   const long long TB = static_cast<long long>(p->T) * p->B;
-  // halo launches read (TH+2)-row slabs: their activation maps carry taller boxes
-  p->halo_lr = halo_applicable(p->w, p->lr.tw, p->lr.tiles_x, 9, 1) ? get_halo_mode() : 0;
+  // Slab launches read (rows x Wp)-position boxes (conv.h: PrGeom); box launches read TH x TW tiles.
+  const bool slab = get_halo_mode() != 0;
+  p->geo_lstm.on = slab && classic_halo(p->h, p->w, p->lr.tw, p->lr.tiles_x, &p->geo_lstm.g);
+  p->geo_lr.on = slab && choose_pr(p->h, p->w, 1, &p->geo_lr.g);
+  if (p->geo_lstm.on && p->geo_lr.on && p->geo_lr.g.tiles >= p->geo_lstm.g.tiles) p->geo_lr = p->geo_lstm;
   for (int q = 0; q < p->n_ps; ++q) {
-    const Tiling& t = q == 0 ? p->lr : p->ps_tile[q];
-    p->halo_ps[q] = halo_applicable(p->ps_w[q], t.tw, t.tiles_x, 9, 1) ? get_halo_mode() : 0;
+    if (q == 0) p->geo_ps[q] = p->geo_lr;
+    else p->geo_ps[q].on = slab && choose_pr(p->ps_h[q], p->ps_w[q], 1, &p->geo_ps[q].g);
+    p->geo_hdg[q].on = slab && p->train && choose_pr(p->ps_h[q], p->ps_w[q], p->ps_r[q], &p->geo_hdg[q].g);
   }
-  const int lr_rows = p->lr.th + (p->halo_lr ? 2 : 0);
-  CUtensorMap tm_act, tm_act_conv;
+  auto box_w = [](const pvsr_plan::Geo& g, const Tiling& t) { return g.on ? g.g.wp : t.tw; };
+  auto box_h = [](const pvsr_plan::Geo& g, const Tiling& t) { return g.on ? g.g.rows : t.th; };
+  CUtensorMap tm_act, tm_act_conv, tm_act_lstm;
   rc |= make_act_tmap(&tm_act, w + p->off_act, kFeat, p->w, p->h, p->act_images, p->lr.tw, p->lr.th);
-  rc |= make_act_tmap(&tm_act_conv, w + p->off_act, kFeat, p->w, p->h, p->act_images, p->lr.tw, lr_rows);
-  p->maps_lstm.act[0] = tm_act_conv;
+  rc |= make_act_tmap(&tm_act_conv, w + p->off_act, kFeat, p->w, p->h, p->act_images, box_w(p->geo_lr, p->lr),
+                      box_h(p->geo_lr, p->lr));
+  rc |= make_act_tmap(&tm_act_lstm, w + p->off_act, kFeat, p->w, p->h, p->act_images, box_w(p->geo_lstm, p->lr),
+                      box_h(p->geo_lstm, p->lr));
+  p->maps_lstm.act[0] = tm_act_lstm;
   p->maps_c1.act[0] = p->cfg.pos_enc ? tm_act_conv : tm_act;     // the 1x1 variant has a single tap
   p->maps_head[0].act[0] = tm_act_conv;
   if (p->cfg.pos_enc)
     rc |= make_act_tmap(&p->maps_c2.act[0], w + p->off_mid, 144, p->w, p->h,
-                        static_cast<long long>(p->n_slots) * p->n_win * p->B, p->lr.tw, lr_rows);
+                        static_cast<long long>(p->n_slots) * p->n_win * p->B, box_w(p->geo_lr, p->lr),
+                        box_h(p->geo_lr, p->lr));
   for (int q = 1; q < p->n_ps; ++q)
     rc |= make_act_tmap(&p->maps_head[q].act[0], w + p->off_head[q - 1], kFeat, p->ps_w[q], p->ps_h[q],
-                        static_cast<long long>(p->n_list_slots) * TB, p->ps_tile[q].tw,
-                        p->ps_tile[q].th + (p->halo_ps[q] ? 2 : 0));
+                        static_cast<long long>(p->n_list_slots) * TB, box_w(p->geo_ps[q], p->ps_tile[q]),
+                        box_h(p->geo_ps[q], p->ps_tile[q]));
   rc |= make_weight_tmap(&p->maps_lstm.w, k + p->pk_lstm_w, static_cast<long long>(2 * p->NL) * p->lstm_rows_per_cell,
                          256);
   rc |= make_weight_tmap(&p->maps_c1.w, k + p->pk_c1_w, p->c1_rows, p->cfg.pos_enc ? 144 : 64);
@@ -812,16 +835,17 @@ int build_maps(pvsr_plan* p, const void* ws, const void* pk) {
     const int n_pad = p->T + 2 * p->half;
     CUtensorMap tm_dgates, tm_gr, tm_gm, tm_dgates_conv, tm_gr_conv, tm_gm_conv;
     rc |= make_act_tmap(&tm_dgates, w + p->off_dgates, 256, p->w, p->h, 2LL * p->NL * TB, p->lr.tw, p->lr.th);
-    rc |= make_act_tmap(&tm_dgates_conv, w + p->off_dgates, 256, p->w, p->h, 2LL * p->NL * TB, p->lr.tw, lr_rows);
+    const int lr_bw = box_w(p->geo_lr, p->lr), lr_bh = box_h(p->geo_lr, p->lr);
+    rc |= make_act_tmap(&tm_dgates_conv, w + p->off_dgates, 256, p->w, p->h, 2LL * p->NL * TB, lr_bw, lr_bh);
     rc |= make_act_tmap(&tm_gr, w + p->off_gr, kFeat, p->w, p->h, static_cast<long long>(n_pad) * p->B, p->lr.tw,
                         p->lr.th);
-    rc |= make_act_tmap(&tm_gr_conv, w + p->off_gr, kFeat, p->w, p->h, static_cast<long long>(n_pad) * p->B, p->lr.tw,
-                        lr_rows);
+    rc |= make_act_tmap(&tm_gr_conv, w + p->off_gr, kFeat, p->w, p->h, static_cast<long long>(n_pad) * p->B, lr_bw,
+                        lr_bh);
     if (p->cfg.pos_enc) {
       rc |= make_act_tmap(&tm_gm, w + p->off_gm, 144, p->w, p->h, static_cast<long long>(n_pad) * p->B, p->lr.tw,
                           p->lr.th);
-      rc |= make_act_tmap(&tm_gm_conv, w + p->off_gm, 144, p->w, p->h, static_cast<long long>(n_pad) * p->B, p->lr.tw,
-                          lr_rows);
+      rc |= make_act_tmap(&tm_gm_conv, w + p->off_gm, 144, p->w, p->h, static_cast<long long>(n_pad) * p->B, lr_bw,
+                          lr_bh);
     }
     // ConvLSTM
     p->bm_lstm_dg.act[0] = tm_dgates_conv;
@@ -846,10 +870,12 @@ int build_maps(pvsr_plan* p, const void* ws, const void* pk) {
     rc |= make_weight_tmap(&p->bm_c1_dg.w, k + p->pk_c1_dg, p->c1_dg_rows, 128);
     // heads: gradient wrt the output of conv q lives at resolution q+1 and is read pixel-unshuffled (mul = r)
     for (int q = 0; q < p->n_ps; ++q) {
-      CUtensorMap tm_dy;
+      CUtensorMap tm_dy, tm_dy_dg;
       rc |= make_act_tmap(&tm_dy, w + p->off_dhead[q], kFeat, p->ps_w[q + 1], p->ps_h[q + 1], 3 * TB, p->bw_tile[q].tw,
                           p->bw_tile[q].th, p->ps_r[q]);
-      p->bm_head_dg[q].act[0] = tm_dy;
+      rc |= make_act_tmap(&tm_dy_dg, w + p->off_dhead[q], kFeat, p->ps_w[q + 1], p->ps_h[q + 1], 3 * TB,
+                          box_w(p->geo_hdg[q], p->bw_tile[q]), box_h(p->geo_hdg[q], p->bw_tile[q]), p->ps_r[q]);
+      p->bm_head_dg[q].act[0] = tm_dy_dg;
       rc |= make_weight_tmap(&p->bm_head_dg[q].w, k + p->pk_head_dg[q], p->head_dg_rows[q], 64);
       if (q == 0)
         rc |= make_act_tmap(&p->bm_head_wg[q].act[0], w + p->off_act, kFeat, p->w, p->h, p->act_images,

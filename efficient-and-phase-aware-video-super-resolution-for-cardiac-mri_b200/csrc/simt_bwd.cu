@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "conv.h"
 #include "simt.h"
 #include "stencil.cuh"
 
@@ -36,6 +37,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Tile-transposed tensors ([tile][ch][128]) are read as 8/16-byte vectors over the 4 rows (7 vector loads per channel
 // instead of 28 scalar ones); dh / dgates are NHWC: the 8 channel-group threads of a pixel cover whole 128-byte lines.
 __global__ void __launch_bounds__(256, 2) lstm_bwd_pointwise_kernel(const __grid_constant__ LstmBwdParams p) {
+  // PDL: this kernel alternates with the tcgen05 data-gradient launches of the reverse wavefront
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const LstmBwdProb& pr = p.prob[blockIdx.y];
   const int tile = blockIdx.x;
   const int cg = threadIdx.x & 7;          // channels [8*cg, 8*cg + 8)
@@ -129,8 +133,16 @@ __global__ void __launch_bounds__(256, 2) lstm_bwd_pointwise_kernel(const __grid
 int launch_lstm_bwd_pointwise(const LstmBwdParams& p, cudaStream_t s) {
   if (p.n_prob <= 0 || p.n_img <= 0) return 0;
   dim3 grid(static_cast<unsigned>(p.n_img * p.tiles_x * p.tiles_y), static_cast<unsigned>(p.n_prob));
-  lstm_bwd_pointwise_kernel<<<grid, 256, 0, s>>>(p);
-  return static_cast<int>(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(256);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = get_pdl() ? 1 : 0;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, lstm_bwd_pointwise_kernel, p));
 }
 
 // ------------------------------------------------------------------------------------------------

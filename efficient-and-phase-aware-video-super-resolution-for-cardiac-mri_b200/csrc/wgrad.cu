@@ -75,6 +75,8 @@ wgrad_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ W
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -172,8 +174,17 @@ int launch_wgrad(const ConvMaps& maps, const WgParams& p, cudaStream_t stream) {
     attr = true;
   }
   if (p.n_jobs <= 0 || p.n_splits <= 0) return 0;
-  wgrad_tc_kernel<<<p.n_jobs * p.n_splits, kWgThreads, kWgSmem, stream>>>(maps, p);
-  return static_cast<int>(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.n_jobs * p.n_splits);
+  cfg.blockDim = dim3(kWgThreads);
+  cfg.dynamicSmemBytes = kWgSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  la[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = la;
+  cfg.numAttrs = get_pdl() ? 1 : 0;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel, maps, p));
 }
 
 // param_grad[idx[e]] += packed[e]  (idx < 0: padding).  The packing index is injective on real entries.

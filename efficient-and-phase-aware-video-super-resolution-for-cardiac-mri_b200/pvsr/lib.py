@@ -86,6 +86,8 @@ SIGNATURES = {
     "pvsr_get_cta_pair": (c_int, []),
     "pvsr_set_halo_mode": (c_int, [c_int]),
     "pvsr_get_halo_mode": (c_int, []),
+    "pvsr_set_pdl": (c_int, [c_int]),
+    "pvsr_get_pdl": (c_int, []),
     "pvsr_choose_tile": (c_int, [c_int, c_int, C.POINTER(c_int)]),
     "pvsr_pack_index_count": (c_int64, [C.POINTER(PackSpec)]),
     "pvsr_pack_index_host": (c_int, [C.POINTER(PackSpec), c_void_p]),
@@ -161,6 +163,8 @@ def load():
         fn.argtypes = args
     if os.environ.get("PVSR_HALO") is not None:           # A/B switch of the halo (slab) conv kernel
         lib.pvsr_set_halo_mode(int(os.environ["PVSR_HALO"]))
+    if os.environ.get("PVSR_PDL") is not None:            # A/B switch of programmatic dependent launch
+        lib.pvsr_set_pdl(int(os.environ["PVSR_PDL"]))
     if os.environ.get("PVSR_CTA_PAIR") is not None:       # A/B switch of the cta_group::2 conv kernel
         lib.pvsr_set_cta_pair(int(os.environ["PVSR_CTA_PAIR"]))
     _lib = lib

@@ -44,6 +44,11 @@ int pvsr_get_cta_pair(void);
  * boxes), 1 = on (default).  Process-wide. */
 int pvsr_set_halo_mode(int mode);
 int pvsr_get_halo_mode(void);
+/* Programmatic dependent launch (griddepcontrol) between consecutive launches of a schedule: the next kernel's prologue
+ * (barrier init, TMEM allocation) overlaps the tail of the previous one.  Default on; set BEFORE the first run of a
+ * plan (captured CUDA graphs keep the setting they were captured with).  Process-wide. */
+int pvsr_set_pdl(int enable);
+int pvsr_get_pdl(void);
 
 /* ---- host-side packing logic (pure CPU; usable without a GPU) ------------------------------------------------ */
 /* Tile choice of the implicit GEMM: tile = (128 >> tw_log2) x (1 << tw_log2) output pixels. */
