@@ -221,7 +221,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvPro
     const int cls = (y > 0 ? 1 : 0) | (y < p.H - 1 ? 2 : 0) | (x > 0 ? 4 : 0) | (x < p.W - 1 ? 8 : 0);
     const float* pterm =
         pr.posterm ? pr.posterm + (static_cast<size_t>(tc.img) * 16 + cls) * p.n_total + tc.nt * BN : nullptr;
-    const float* bias = pr.bias ? pr.bias + tc.nt * BN : nullptr;
+    // bias_s: this launch's biases staged in shared memory by the prologue ([problem][n_total]); a dependent global
+    // load per 16-column chunk was the top stall of the short-K head launches (ncu: 29 % of samples)
+    const float* bias = pr.bias ? bias_s + tc.z * p.n_total + tc.nt * BN : nullptr;
     auto chunk = [&](int ck, bool pre, const uint4& rpre0, const uint4& rpre1) {
       uint32_t v[16];
       tmem_ld16(taddr + ck * 16, v);
@@ -233,7 +235,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvPro
         const float4* b4 = reinterpret_cast<const float4*>(bias + ck * 16);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 b = __ldg(b4 + j);
+          const float4 b = b4[j];
           f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
         }
       }
@@ -294,6 +296,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvPro
 #pragma unroll 1
       for (int ck = half; ck < nchunks; ck += 2) chunk(ck, false, z, z);
     }
+  }
+}
+
+// EPI_STORE / EPI_PS: biases of every problem of the launch -> shared memory [problem][n_total] (fits: launch_conv3x3).
+__device__ __forceinline__ void stage_bias(const ConvParams& p, float* bias_s) {
+  for (int i = threadIdx.x; i < p.n_prob * p.n_total; i += kNumThreads) {
+    const int z = i / p.n_total, n = i - z * p.n_total;
+    bias_s[i] = p.prob[z].bias ? p.prob[z].bias[n] : 0.f;
   }
 }
 
@@ -372,6 +382,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       const int z = i >> 8, n = i & 255;
       bias_s[i] = p.prob[z].bias[n] * (n < 192 ? -kLog2e : 2.f * kLog2e);
     }
+  } else if constexpr (EPI == EPI_STORE || EPI == EPI_PS) {
+    stage_bias(p, bias_s);
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync();   // the peer's barriers must be initialised before anything signals them
@@ -592,6 +604,8 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
       const int z = i >> 8, n = i & 255;
       bias_s[i] = p.prob[z].bias[n] * (n < 192 ? -kLog2e : 2.f * kLog2e);
     }
+  } else if constexpr (EPI == EPI_STORE || EPI == EPI_PS) {
+    stage_bias(p, bias_s);
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync();
@@ -803,6 +817,8 @@ void set_cta_pair(int enable) { g_cta_pair = enable ? 1 : 0; }
 int get_cta_pair() { return g_cta_pair; }
 
 int launch_conv3x3(int bn, int epi, const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
+  if ((epi == EPI_STORE || epi == EPI_PS) && p.n_prob * p.n_total > kMaxProb * 256)   // bias staging area
+    return static_cast<int>(cudaErrorInvalidValue);
   if (epi == EPI_LSTM && bn == 256) return launch_cg<256, EPI_LSTM>(maps, p, num_sms, stream);
   if (epi == EPI_STORE) {
     switch (bn) {
