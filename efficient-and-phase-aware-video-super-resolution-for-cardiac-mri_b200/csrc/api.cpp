@@ -87,7 +87,8 @@ int fill_conv_params(const pvsr_conv_desc* d, ConvParams* p) {
 }
 
 void build_wgrad_jobs(const std::vector<WgSource>& srcs, int kb_per_src, int taps, const std::vector<WgChunk>& chunks,
-                      int n_total, bool with_bias, long long dw_off, long long db_off, std::vector<WgJob>* out) {
+                      int n_total, bool with_bias, long long dw_off, long long db_off, std::vector<WgJob>* out,
+                      int contig_cols) {
   std::vector<WgUnit> units;
   int kb = 0;
   for (size_t s = 0; s < srcs.size(); ++s)
@@ -109,34 +110,69 @@ void build_wgrad_jobs(const std::vector<WgSource>& srcs, int kb_per_src, int tap
     u.kind = 1;
     units.push_back(u);
   }
-  for (size_t u0 = 0; u0 < units.size(); u0 += kWgUnits)
-    for (size_t c0 = 0; c0 < chunks.size(); c0 += kWgChunks) {
+  // Column groups: what the two CTAs of a pair stage of dY.  contig_cols > 0: chunks[0] is the first 64-channel view of
+  // ONE tensor with contig_cols consecutive gradient channels - it is cut into two equal halves (any multiple of 8
+  // columns each, e.g. 72 + 72 for the 144-channel refine conv1), so no MMA column is wasted.  Otherwise the chunks
+  // are independent 64-column views (pixel-unshuffled phases of a head gradient), two per CTA.
+  struct ColGroup { int n_half; int n_slots[2]; SrcView dy[2][kWgSlots]; int col0[2][kWgSlots], ncols[2][kWgSlots]; };
+  std::vector<ColGroup> groups;
+  if (contig_cols > 0) {
+    for (int c0 = 0; c0 < contig_cols; c0 += 256) {
+      const int cols = std::min(256, contig_cols - c0);
+      ColGroup g{};
+      g.n_half = ((cols + 15) / 16) * 8;
+      for (int r = 0; r < 2; ++r) {
+        const int first = c0 + r * g.n_half, last = std::min(c0 + cols, first + g.n_half);
+        g.n_slots[r] = 0;
+        for (int c = first; c < last; c += 64) {
+          const int sl = g.n_slots[r]++;
+          g.dy[r][sl] = chunks[0].view;
+          g.dy[r][sl].ch0 += c;
+          g.col0[r][sl] = chunks[0].col0 + c;
+          g.ncols[r][sl] = std::min(64, last - c);
+        }
+      }
+      groups.push_back(g);
+    }
+  } else {
+    for (size_t c0 = 0; c0 < chunks.size(); c0 += 2 * kWgSlots) {
+      const int n = static_cast<int>(std::min<size_t>(2 * kWgSlots, chunks.size() - c0));
+      ColGroup g{};
+      const int per = (n + 1) / 2;
+      g.n_half = 64 * per;
+      for (int r = 0; r < 2; ++r) {
+        g.n_slots[r] = 0;
+        for (int i = r * per; i < std::min(n, (r + 1) * per); ++i) {
+          const int sl = g.n_slots[r]++;
+          g.dy[r][sl] = chunks[c0 + i].view;
+          g.col0[r][sl] = chunks[c0 + i].col0;
+          g.ncols[r][sl] = 64;
+        }
+      }
+      groups.push_back(g);
+    }
+  }
+  // Unit groups of up to 2 * kWgUnits, split evenly over the pair (the leader gets the odd one).
+  for (size_t u0 = 0; u0 < units.size(); u0 += 2 * kWgUnits) {
+    const int n = static_cast<int>(std::min<size_t>(2 * kWgUnits, units.size() - u0));
+    const int n0 = (n + 1) / 2;
+    for (const ColGroup& g : groups) {
       WgJob j{};
-      j.n_units = static_cast<int>(std::min<size_t>(kWgUnits, units.size() - u0));
-      j.n_chunks = static_cast<int>(std::min<size_t>(kWgChunks, chunks.size() - c0));
-      for (int i = 0; i < j.n_units; ++i) j.unit[i] = units[u0 + i];
-      for (int i = 0; i < j.n_chunks; ++i) { j.dy[i] = chunks[c0 + i].view; j.col0[i] = chunks[c0 + i].col0; }
+      j.n_units[0] = n0;
+      j.n_units[1] = n - n0;
+      for (int i = 0; i < n0; ++i) j.unit[0][i] = units[u0 + i];
+      for (int i = n0; i < n; ++i) j.unit[1][i - n0] = units[u0 + i];
+      j.n_half = g.n_half;
+      for (int r = 0; r < 2; ++r) {
+        j.n_slots[r] = g.n_slots[r];
+        for (int c = 0; c < kWgSlots; ++c) { j.dy[r][c] = g.dy[r][c]; j.col0[r][c] = g.col0[r][c]; j.ncols[r][c] = g.ncols[r][c]; }
+      }
       j.n_total = n_total;
       j.dw_off = dw_off;
       j.db_off = db_off;
       out->push_back(j);
     }
-}
-
-int auto_wgrad_splits(int n_jobs, long long total_tiles, int num_sms) {
-  // One CTA per SM is resident (193 KB of shared memory), so the launch runs in ceil(n_jobs * s / num_sms) waves of
-  // (total_tiles / s) tiles each: pick the split count minimising waves / s (ties: fewer splits = fewer epilogues).
-  // The former "about two waves" rule produced grids such as 300 or 322 CTAs on 148 SMs: a third wave for 2-9 % of
-  // the work.
-  long long best_s = 1;
-  double best = 1e30;
-  const long long max_s = total_tiles < 24 ? total_tiles : 24;
-  for (long long s = 1; s <= max_s; ++s) {
-    const long long waves = (static_cast<long long>(n_jobs) * s + num_sms - 1) / num_sms;
-    const double t = static_cast<double>(waves) * static_cast<double>((total_tiles + s - 1) / s);
-    if (t < best * 0.999) { best = t; best_s = s; }
   }
-  return static_cast<int>(best_s);
 }
 
 }  // namespace pvsr
@@ -313,14 +349,18 @@ int pvsr_conv3x3_wgrad(const pvsr_wgrad_desc* d, void* stream) {
   build_wgrad_jobs(srcs, d->kb_per_src, d->taps, chunks, d->n_total, d->with_bias != 0, 0,
                    d->with_bias ? static_cast<long long>(d->db_packed - d->dw_packed) : 0, &jobs);
   if (jobs.size() > 256) return set_error(-2, "too many wgrad jobs");
+  p.n_heavy = sort_wgrad_jobs(jobs.data(), static_cast<int>(jobs.size()));
   int e = cudaMemcpyAsync(d->job_scratch, jobs.data(), jobs.size() * sizeof(WgJob), cudaMemcpyHostToDevice, s);
   if (e) return check_cuda(e, "job upload");
   e = cudaStreamSynchronize(s);   // the host vector dies at return (test/tool entry point; the plan pre-uploads)
   if (e) return check_cuda(e, "job upload sync");
   p.n_jobs = static_cast<int>(jobs.size());
   const long long total_tiles = static_cast<long long>(p.n_img) * p.tiles_x * p.tiles_y;
-  p.n_splits = d->n_splits > 0 ? d->n_splits : auto_wgrad_splits(p.n_jobs, total_tiles, device_num_sms());
-  if (p.n_splits > total_tiles) p.n_splits = static_cast<int>(total_tiles);
+  if (d->n_splits > 0) {
+    p.n_splits = p.n_splits_light = static_cast<int>(d->n_splits > total_tiles ? total_tiles : d->n_splits);
+  } else {
+    choose_wgrad_splits(p.n_heavy, p.n_jobs - p.n_heavy, total_tiles, device_num_sms(), &p.n_splits, &p.n_splits_light);
+  }
   p.jobs = static_cast<const WgJob*>(d->job_scratch);
   p.grad = d->dw_packed;
   return check_cuda(launch_wgrad(maps, p, s), "wgrad");

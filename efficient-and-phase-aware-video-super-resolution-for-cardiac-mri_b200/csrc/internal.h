@@ -15,8 +15,9 @@ int fill_conv_params(const pvsr_conv_desc* d, ConvParams* p);
 // One X source of a weight-gradient problem (its taps / channel blocks become units) and one dY chunk.
 struct WgSource { SrcView view; };
 struct WgChunk { SrcView view; int col0; };
-// Splits (units x chunks) into CTA jobs; the optional bias ("ones") unit rides in the last unit group.
+// Splits (units x chunks) into CTA-pair jobs; the optional bias ("ones") unit rides in the last unit group.
+// contig_cols > 0: chunks[0] is the first view of one tensor with that many consecutive gradient channels.
 void build_wgrad_jobs(const std::vector<WgSource>& srcs, int kb_per_src, int taps, const std::vector<WgChunk>& chunks,
-                      int n_total, bool with_bias, long long dw_off, long long db_off, std::vector<WgJob>* out);
-int auto_wgrad_splits(int n_jobs, long long total_tiles, int num_sms);
+                      int n_total, bool with_bias, long long dw_off, long long db_off, std::vector<WgJob>* out,
+                      int contig_cols = 0);
 }  // namespace pvsr

@@ -134,7 +134,7 @@ struct pvsr_plan {
   struct ScatterJob { int kind, a, b; long long n, src; size_t idx, idx2; bool has2, is_bias; };
   std::vector<ScatterJob> sc_jobs;
   // weight-gradient launches: job lists pre-built at creation, uploaded on the first backward
-  struct WgLaunch { int job_begin, n_jobs, n_img; Tiling tile; };
+  struct WgLaunch { int job_begin, n_jobs, n_heavy, n_img; Tiling tile; };
   std::vector<WgJob> wg_jobs;
   WgLaunch wl_lstm[kMaxStages], wl_c1[kMaxStages], wl_c2[kMaxStages], wl_head[kMaxStages][PVSR_MAX_HEAD_CONVS];
   const void* jobs_uploaded_for = nullptr;
@@ -539,7 +539,8 @@ void run_wgrad(Ctx& c, int cls, const ConvMaps& maps, const pvsr_plan::WgLaunch&
     wp.n_img = wl.n_img;
     wp.n_jobs = wl.n_jobs;
     const long long total_tiles = static_cast<long long>(wl.n_img) * wl.tile.tiles_x * wl.tile.tiles_y;
-    wp.n_splits = auto_wgrad_splits(wl.n_jobs, total_tiles, c.p->num_sms);
+    wp.n_heavy = wl.n_heavy;
+    choose_wgrad_splits(wl.n_heavy, wl.n_jobs - wl.n_heavy, total_tiles, c.p->num_sms, &wp.n_splits, &wp.n_splits_light);
     wp.jobs = reinterpret_cast<const WgJob*>(c.ws + c.p->off_jobs) + wl.job_begin;
     wp.grad = reinterpret_cast<float*>(c.ws + c.p->off_wg);
     int e = launch_wgrad(maps, wp, c.stream);
@@ -901,7 +902,9 @@ void push_wg_launch(pvsr_plan* p, pvsr_plan::WgLaunch* wl, const std::vector<WgJ
   wl->n_jobs = static_cast<int>(jobs.size());
   wl->n_img = n_img;
   wl->tile = t;
-  p->wg_jobs.insert(p->wg_jobs.end(), jobs.begin(), jobs.end());
+  std::vector<WgJob> sorted(jobs);
+  wl->n_heavy = sort_wgrad_jobs(sorted.data(), static_cast<int>(sorted.size()));   // heavy-first (launch_wgrad)
+  p->wg_jobs.insert(p->wg_jobs.end(), sorted.begin(), sorted.end());
 }
 
 // Weight-gradient job lists of every stage (image bases are fixed by the workspace layout).
@@ -922,9 +925,8 @@ void build_wg_jobs(pvsr_plan* p) {
           srcs.push_back(WgSource{SrcView{0, static_cast<int>(hp), 0, 1, 0, 0}});
         }
         std::vector<WgChunk> chunks;
-        for (int cidx = 0; cidx < 4; ++cidx)
-          chunks.push_back(WgChunk{SrcView{1, ci * TB, 64 * cidx, 1, 0, 0}, 64 * cidx});
-        build_wgrad_jobs(srcs, 1, 9, chunks, 256, true, p->wg_lstm_w[ci], p->wg_lstm_b[ci], &jobs);
+        chunks.push_back(WgChunk{SrcView{1, ci * TB, 0, 1, 0, 0}, 0});
+        build_wgrad_jobs(srcs, 1, 9, chunks, 256, true, p->wg_lstm_w[ci], p->wg_lstm_b[ci], &jobs, 256);
       }
     push_wg_launch(p, &p->wl_lstm[s], jobs, TB, p->lr);
 
@@ -939,12 +941,11 @@ void build_wg_jobs(pvsr_plan* p) {
         }
       std::vector<WgChunk> chunks;
       if (p->cfg.pos_enc) {
-        for (int cidx = 0; cidx < 3; ++cidx)
-          chunks.push_back(WgChunk{SrcView{1, half * B, 64 * cidx, 1, 0, 0}, 64 * cidx});
-        build_wgrad_jobs(srcs, 1, 9, chunks, p->c1_wg_ntotal, true, p->wg_c1_w, p->wg_c1_b, &jobs);
+        chunks.push_back(WgChunk{SrcView{1, half * B, 0, 1, 0, 0}, 0});
+        build_wgrad_jobs(srcs, 1, 9, chunks, p->c1_wg_ntotal, true, p->wg_c1_w, p->wg_c1_b, &jobs, 144);
       } else {
         chunks.push_back(WgChunk{SrcView{1, half * B, 0, 1, 0, 0}, 0});
-        build_wgrad_jobs(srcs, 1, 1, chunks, p->c1_wg_ntotal, true, p->wg_c1_w, p->wg_c1_b, &jobs);
+        build_wgrad_jobs(srcs, 1, 1, chunks, p->c1_wg_ntotal, true, p->wg_c1_w, p->wg_c1_b, &jobs, 64);
       }
     }
     push_wg_launch(p, &p->wl_c1[s], jobs, TB, p->lr);
@@ -956,7 +957,7 @@ void build_wg_jobs(pvsr_plan* p) {
       srcs.push_back(WgSource{SrcView{0, (s * p->n_win + (U - half)) * B, 0, 1, 0, 0}});
       std::vector<WgChunk> chunks;
       chunks.push_back(WgChunk{SrcView{1, half * B, 0, 1, 0, 0}, 0});
-      build_wgrad_jobs(srcs, 3, 9, chunks, 64, true, p->wg_c2_w, p->wg_c2_b, &jobs);
+      build_wgrad_jobs(srcs, 3, 9, chunks, 64, true, p->wg_c2_w, p->wg_c2_b, &jobs, 64);
     }
     push_wg_launch(p, &p->wl_c2[s], jobs, TB, p->lr);
 
