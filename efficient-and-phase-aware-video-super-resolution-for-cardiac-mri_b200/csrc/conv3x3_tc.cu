@@ -809,7 +809,7 @@ static int g_halo = 1;   // 0: nine shifted TMA boxes per source, 1: one slab pe
 void set_halo_mode(int mode) { g_halo = mode; }
 int get_halo_mode() { return g_halo; }
 
-static int g_pdl = 1;   // programmatic dependent launch between consecutive kernels of the schedule
+static int g_pdl = 0;   // programmatic dependent launch between consecutive kernels (measured: no gain; off)
 void set_pdl(int enable) { g_pdl = enable ? 1 : 0; }
 int get_pdl() { return g_pdl; }
 

@@ -45,7 +45,8 @@ int pvsr_get_cta_pair(void);
 int pvsr_set_halo_mode(int mode);
 int pvsr_get_halo_mode(void);
 /* Programmatic dependent launch (griddepcontrol) between consecutive launches of a schedule: the next kernel's prologue
- * (barrier init, TMEM allocation) overlaps the tail of the previous one.  Default on; set BEFORE the first run of a
+ * (barrier init, TMEM allocation) overlaps the tail of the previous one.  Default off (no measurable gain under CUDA-graph
+ * replay on B200: profiles/r01); set BEFORE the first run of a
  * plan (captured CUDA graphs keep the setting they were captured with).  Process-wide. */
 int pvsr_set_pdl(int enable);
 int pvsr_get_pdl(void);
