@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
 #include "simt.h"
 #include "stencil.cuh"
 
@@ -65,22 +67,45 @@ __device__ __forceinline__ uint32_t f2_to_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(256, 2) head_conv_last_kernel(const __nv_bfloat16* __restrict__ in,
-                                                                const float* __restrict__ w,
-                                                                const float* __restrict__ b, float* __restrict__ out,
-                                                                const float* __restrict__ target,
-                                                                float* __restrict__ l1_partial, int H, int W,
-                                                                int tiles_x, int tiles_y) {
-  extern __shared__ __align__(16) uint8_t sm[];
-  uint8_t* tile = sm;                                                        // 512 * 144 B
-  float* P = reinterpret_cast<float*>(sm + kLastHaloPix * kLastPitch);      // [9][516] fp32
-  int t = blockIdx.x;
+// Persistent, double-buffered: a block walks tiles grid-stride and issues the cp.async loads of tile i+1 into the other
+// halo buffer before computing tile i, so every SM always has one 64 KB tile in flight.  Measured stand-alone
+// (profiles/membound_bench.py): 4.05 TB/s = 0.64 of the copy bandwidth of the same box - exactly what the former
+// single-stage form (one tile per block, two blocks per SM) reached, i.e. load/compute overlap is NOT what limits it;
+// ~19 MB are in flight at that rate, so the bound is on the memory side of the access pattern (open).
+__device__ __forceinline__ void head_last_issue_tile(const __nv_bfloat16* __restrict__ in, uint32_t tile_s, int t,
+                                                     int H, int W, int tiles_x, int tiles_y) {
   const int tx = t % tiles_x;
   t /= tiles_x;
   const int ty = t % tiles_y;
   const int img = t / tiles_y;
-  const int y0 = ty * kLastTH - 1, x0 = tx * kLastTW - 1;                    // image coordinates of halo pixel (0, 0)
+  const int y0 = ty * kLastTH - 1, x0 = tx * kLastTW - 1;
+  const __nv_bfloat16* src = in + static_cast<size_t>(img) * H * W * 64;
+  // 16 x 16 B per thread, all in flight; src-size 0 zero-fills pixels outside the image = the conv padding
+#pragma unroll
+  for (int it = 0; it < kLastHaloPix * 8 / 256; ++it) {
+    const int i = threadIdx.x + it * 256;
+    const int hp = i >> 3, ck = i & 7;
+    const int y = y0 + (hp >> 5), x = x0 + (hp & 31);
+    const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+    const __nv_bfloat16* g = src + (static_cast<size_t>(ok ? y : 0) * W + (ok ? x : 0)) * 64 + ck * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_s + hp * kLastPitch + ck * 16), "l"(g),
+                 "r"(ok ? 16 : 0)
+                 : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(256, 1) head_conv_last_kernel(const __nv_bfloat16* __restrict__ in,
+                                                                const float* __restrict__ w,
+                                                                const float* __restrict__ b, float* __restrict__ out,
+                                                                const float* __restrict__ target,
+                                                                float* __restrict__ l1_partial, int H, int W,
+                                                                int tiles_x, int tiles_y, int n_tiles) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  constexpr int kTileBytes = kLastHaloPix * kLastPitch;                      // 512 * 144 B
+  float* P = reinterpret_cast<float*>(sm + 2 * kTileBytes);                  // [9][516] fp32
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t sm_s = static_cast<uint32_t>(__cvta_generic_to_shared(sm));
 
   // B fragments of the [64 x 16] weight matrix (taps 9..15 are zero): parameter layout (1, 64, 3, 3) -> w[c*9 + tap]
   uint32_t bw[4][2][2];
@@ -100,81 +125,83 @@ __global__ void __launch_bounds__(256, 2) head_conv_last_kernel(const __nv_bfloa
         }
       }
   }
+  const float bias = b[0];
 
-  const __nv_bfloat16* src = in + static_cast<size_t>(img) * H * W * 64;
-  // stage the halo tile with cp.async (16 x 16 B per thread, all in flight; src-size 0 zero-fills pixels outside
-  // the image = the conv padding)
-  const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
-#pragma unroll
-  for (int it = 0; it < kLastHaloPix * 8 / 256; ++it) {
-    const int i = threadIdx.x + it * 256;
-    const int hp = i >> 3, ck = i & 7;
-    const int y = y0 + (hp >> 5), x = x0 + (hp & 31);
-    const bool ok = y >= 0 && y < H && x >= 0 && x < W;
-    const __nv_bfloat16* g = src + (static_cast<size_t>(ok ? y : 0) * W + (ok ? x : 0)) * 64 + ck * 8;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_s + hp * kLastPitch + ck * 16), "l"(g),
-                 "r"(ok ? 16 : 0)
-                 : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
+  int t = blockIdx.x;
+  if (t < n_tiles) head_last_issue_tile(in, sm_s, t, H, W, tiles_x, tiles_y);
+  for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int tn = t + gridDim.x;
+    if (tn < n_tiles) {
+      head_last_issue_tile(in, sm_s + (buf ^ 1) * kTileBytes, tn, H, W, tiles_x, tiles_y);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();                     // tile `t` landed for every thread; P of the previous tile fully consumed
+    const uint32_t tile_s = sm_s + buf * kTileBytes;
+    int q = t;
+    const int tx = q % tiles_x;
+    q /= tiles_x;
+    const int ty = q % tiles_y;
+    const int img = q / tiles_y;
+    const int y0 = ty * kLastTH - 1, x0 = tx * kLastTW - 1;                  // image coordinates of halo pixel (0, 0)
 
-  // P for this warp's 64 halo pixels: 4 m16 tiles x 4 k16 steps x 2 n8 tiles
+    // P for this warp's 64 halo pixels: 4 m16 tiles x 4 k16 steps x 2 n8 tiles
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) {
-    const int px0 = warp * 64 + mt * 16;
-    float acc[2][4];
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
-    const uint32_t arow = tile_s + (px0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kLastPitch + 16 * (lane >> 4);
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      uint32_t a0, a1, a2, a3;
-      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
-                   : "r"(arow + ks * 32));
+    for (int mt = 0; mt < 4; ++mt) {
+      const int px0 = warp * 64 + mt * 16;
+      float acc[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
-        asm volatile(
-            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-            "{%0, %1, %2, %3};"
-            : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
-            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bw[ks][nt][0]), "r"(bw[ks][nt][1]));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+      const uint32_t arow = tile_s + (px0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kLastPitch + 16 * (lane >> 4);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                     : "r"(arow + ks * 32));
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+              "{%0, %1, %2, %3};"
+              : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+              : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bw[ks][nt][0]), "r"(bw[ks][nt][1]));
+      }
+      const int r = px0 + (lane >> 2), c = (lane & 3) * 2;
+      P[c * kLastPStride + r] = acc[0][0];
+      P[(c + 1) * kLastPStride + r] = acc[0][1];
+      P[c * kLastPStride + r + 8] = acc[0][2];
+      P[(c + 1) * kLastPStride + r + 8] = acc[0][3];
+      if ((lane & 3) == 0) {
+        P[8 * kLastPStride + r] = acc[1][0];
+        P[8 * kLastPStride + r + 8] = acc[1][2];
+      }
     }
-    const int r = px0 + (lane >> 2), c = (lane & 3) * 2;
-    P[c * kLastPStride + r] = acc[0][0];
-    P[(c + 1) * kLastPStride + r] = acc[0][1];
-    P[c * kLastPStride + r + 8] = acc[0][2];
-    P[(c + 1) * kLastPStride + r + 8] = acc[0][3];
-    if ((lane & 3) == 0) {
-      P[8 * kLastPStride + r] = acc[1][0];
-      P[8 * kLastPStride + r + 8] = acc[1][2];
-    }
-  }
-  __syncthreads();
+    __syncthreads();                     // P complete; halo buffer `buf` free for the loads issued next iteration
 
-  const float bias = b[0];
-  float l1 = 0.f;
-  for (int i = threadIdx.x; i < kLastTH * kLastTW; i += 256) {
-    const int ly = i / kLastTW, lx = i - ly * kLastTW;
-    const int y = y0 + 1 + ly, x = x0 + 1 + lx;
-    float acc = bias;
+    float l1 = 0.f;
+    for (int i = threadIdx.x; i < kLastTH * kLastTW; i += 256) {
+      const int ly = i / kLastTW, lx = i - ly * kLastTW;
+      const int y = y0 + 1 + ly, x = x0 + 1 + lx;
+      float acc = bias;
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) acc += P[tap * kLastPStride + (ly + tap / 3) * kLastHaloW + lx + tap % 3];
-    if (y < H && x < W) {
-      const size_t o = (static_cast<size_t>(img) * H + y) * W + x;
-      out[o] = acc;
-      if (target) l1 += fabsf(acc - target[o]);
+      for (int tap = 0; tap < 9; ++tap) acc += P[tap * kLastPStride + (ly + tap / 3) * kLastHaloW + lx + tap % 3];
+      if (y < H && x < W) {
+        const size_t o = (static_cast<size_t>(img) * H + y) * W + x;
+        out[o] = acc;
+        if (target) l1 += fabsf(acc - target[o]);
+      }
     }
-  }
-  if (l1_partial) {
-    // |out - target| summed per image: warp shuffle, then one atomic per warp (nn.L1Loss numerator).
+    if (l1_partial) {
+      // |out - target| summed per image: warp shuffle, then one atomic per warp (nn.L1Loss numerator).
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, d);
-    if (lane == 0) atomicAdd(l1_partial + img, l1);
+      for (int d = 16; d > 0; d >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, d);
+      if (lane == 0) atomicAdd(l1_partial + img, l1);
+    }
   }
 }
 
@@ -182,17 +209,23 @@ int launch_head_conv_last(const void* in, const float* w, const float* b, float*
                           float* l1_partial, long long n_img, int H, int W, cudaStream_t s) {
   if (n_img == 0) return 0;
   const int tiles_x = (W + kLastTW - 1) / kLastTW, tiles_y = (H + kLastTH - 1) / kLastTH;
-  const size_t smem = kLastHaloPix * kLastPitch + 9 * kLastPStride * sizeof(float);
+  const size_t smem = 2 * kLastHaloPix * kLastPitch + 9 * kLastPStride * sizeof(float);
   static bool attr = false;
+  static int num_sms = 0;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(head_conv_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     attr = true;
   }
   const long long blocks = n_img * tiles_x * tiles_y;
-  head_conv_last_kernel<<<static_cast<unsigned>(blocks), 256, smem, s>>>(
-      static_cast<const __nv_bfloat16*>(in), w, b, out, target, l1_partial, H, W, tiles_x, tiles_y);
+  if (blocks >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
+  const unsigned grid = static_cast<unsigned>(blocks < num_sms ? blocks : num_sms);
+  head_conv_last_kernel<<<grid, 256, smem, s>>>(static_cast<const __nv_bfloat16*>(in), w, b, out, target, l1_partial,
+                                               H, W, tiles_x, tiles_y, static_cast<int>(blocks));
   return static_cast<int>(cudaGetLastError());
 }
 

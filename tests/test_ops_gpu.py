@@ -213,10 +213,11 @@ def test_convlstm_cell(pvsr_lib, n, H, W):
     assert torch.allclose(h2, h2r, atol=5e-3, rtol=8e-3), (h2 - h2r).abs().max()
 
 
-def test_in_conv_prelu(pvsr_lib):
+@pytest.mark.parametrize("n,H,W", [(5, 54, 63), (2, 32, 32), (3, 7, 1), (1, 1, 9), (2, 5, 130)])
+def test_in_conv_prelu(pvsr_lib, n, H, W):
+    """Run-based stencil (csrc/stencil.cuh): full / partial / single-pixel runs of 8, single rows and columns."""
     from pvsr import ops
     g = torch.Generator(device="cuda").manual_seed(7)
-    n, H, W = 5, 54, 63
     x = torch.randn(n, H, W, generator=g, device="cuda")
     w = torch.randn(64, 1, 3, 3, generator=g, device="cuda") * 0.3
     b = torch.randn(64, generator=g, device="cuda") * 0.1

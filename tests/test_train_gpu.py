@@ -104,7 +104,7 @@ def test_l1_multistage(pvsr_lib):
     assert abs(float(O.trainer_loss(lists, tl)) - loss.item()) <= 1e-5 * abs(loss.item())
 
 
-@pytest.mark.parametrize("n,H,W", [(3, 24, 28), (2, 128, 128), (1, 9, 33)])
+@pytest.mark.parametrize("n,H,W", [(3, 24, 28), (2, 128, 128), (1, 9, 33), (2, 3, 1), (1, 1, 13)])
 def test_head_conv_last_bwd(pvsr_lib, n, H, W):
     from pvsr import ops
     g = torch.Generator(device="cuda").manual_seed(33)
