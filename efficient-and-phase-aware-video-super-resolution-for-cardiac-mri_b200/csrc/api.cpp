@@ -290,12 +290,11 @@ int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream) {
   const int tw = 1 << p.tw_log2, th = kTileM >> p.tw_log2;
   int max_mul = 1;
   for (int v = 0; v < d->n_views; ++v) max_mul = d->views[v].mul > max_mul ? d->views[v].mul : max_mul;
-  // slab (padded-raster) kernel whenever the geometry allows it; ConvLSTM launches only in the classic whole-row case
-  // because their state tensors are laid out by the box kernel's tile -> pixel map (pvsr_lstm_state_elems)
+  // slab (padded-raster) kernel whenever the geometry allows it (ConvLSTM state tensors follow the same tile map:
+  // conv.h lstm_tile_geometry)
   PrGeom g{0, 0, 0};
-  const bool slab = get_halo_mode() != 0 && d->taps == 9 &&
-                    (d->epi == EPI_LSTM ? (max_mul == 1 && classic_halo(d->H, d->W, tw, p.tiles_x, &g))
-                                        : choose_pr(d->H, d->W, max_mul, &g));
+  const bool slab = get_halo_mode() != 0 && d->taps == 9 && choose_pr(d->H, d->W, max_mul, &g);
+  if (d->epi == EPI_LSTM && max_mul != 1) return set_error(-2, "ConvLSTM sources must be plain views");
   int bw = tw, bh = th;
   if (slab) {
     p.halo = 1; p.pr_wp = g.wp; p.pr_rows = g.rows; p.tiles_x = 1; p.tiles_y = g.tiles;
@@ -373,10 +372,20 @@ int pvsr_scatter_add(float* param_grad, const int32_t* idx, const int32_t* idx2,
 }
 
 int64_t pvsr_lstm_state_elems(int64_t n_img, int H, int W) {
+  // large enough for either tile map (the A/B switch pvsr_set_halo_mode may change between plan creation and run)
   int l;
   choose_tile(H, W, &l);
   const int tw = 1 << l, th = kTileM >> l;
-  return n_img * ((W + tw - 1) / tw) * ((H + th - 1) / th) * 64 * kTileM;
+  long long tiles = static_cast<long long>((W + tw - 1) / tw) * ((H + th - 1) / th);
+  PrGeom g{0, 0, 0};
+  if (choose_pr(H, W, 1, &g) && g.tiles > tiles) tiles = g.tiles;
+  return n_img * tiles * 64 * kTileM;
+}
+
+int pvsr_lstm_tile_geometry(int H, int W, int* wp, int* tiles_per_img) {
+  if (H <= 0 || W <= 0 || !wp || !tiles_per_img) return set_error(-2, "bad image size");
+  lstm_tile_geometry(H, W, wp, tiles_per_img);
+  return 0;
 }
 
 int pvsr_refine_posterm(const float* w1, const float* b1, const float* pos, float* table, int n_frames_out, int B,
@@ -405,6 +414,7 @@ int pvsr_lstm_cell_bwd_pointwise(const float* dh, const void* gates, const float
   const int tw = 1 << p.tw_log2, th = kTileM >> p.tw_log2;
   p.tiles_x = (W + tw - 1) / tw;
   p.tiles_y = (H + th - 1) / th;
+  lstm_tile_geometry(H, W, &p.wp, &p.tiles_per_img);
   p.n_img = static_cast<int>(n_img);
   p.n_prob = 1;
   p.prob[0] = LstmBwdProb{dh, gates, c, c_prev, dc, dc_zero, dgates};

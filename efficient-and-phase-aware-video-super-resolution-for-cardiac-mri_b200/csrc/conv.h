@@ -140,15 +140,6 @@ inline bool choose_pr(int H, int W, int max_mul, PrGeom* g) {
   }
   return best_tiles > 0;
 }
-// The classic whole-row special case (power-of-two pitch = tile width): keeps the tile -> pixel map of the box kernel,
-// which the tile-transposed ConvLSTM state / gate tensors are laid out by.
-inline bool classic_halo(int H, int W, int tw, int tiles_x, PrGeom* g) {
-  if (tiles_x != 1 || W + 1 > tw) return false;
-  const int th = kTileM / tw;
-  g->wp = tw; g->rows = th + 2; g->tiles = (H + th - 1) / th;
-  return true;
-}
-
 // Launches the tcgen05 kernel.  Returns a cudaError_t as int.
 int launch_conv3x3(int bn, int epi, const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream);
 
@@ -168,6 +159,24 @@ inline void choose_tile(int H, int W, int* tw_log2_out, int max_tw = 128) {
     if (best < 0 || tiles < best) { best = tiles; best_l = l; }
   }
   *tw_log2_out = best_l;
+}
+
+// Tile -> pixel map of the tile-transposed ConvLSTM state / gate tensors ([tile][channel][128 rows]): the padded raster
+// (row r of tile t of an image = position 128 t + r = y * wp + x) whenever the slab kernel runs the cells, else
+// (wp = 0) the box kernel's TH x TW rectangles of choose_tile.  One definition for the forward epilogue, the gate
+// adjoint kernel, the workspace sizing and the test helpers (pvsr_lstm_tile_geometry).
+inline void lstm_tile_geometry(int H, int W, int* wp, int* tiles_per_img) {
+  PrGeom g{0, 0, 0};
+  if (get_halo_mode() != 0 && choose_pr(H, W, 1, &g)) {
+    *wp = g.wp;
+    *tiles_per_img = g.tiles;
+    return;
+  }
+  int l;
+  choose_tile(H, W, &l);
+  const int tw = 1 << l, th = kTileM >> l;
+  *wp = 0;
+  *tiles_per_img = ((W + tw - 1) / tw) * ((H + th - 1) / th);
 }
 
 }  // namespace pvsr

@@ -124,7 +124,8 @@ __device__ __forceinline__ TileCoord decode_item(const ConvParams& p, int it, in
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvProblem& pr, const TileCoord& tc,
                                               uint32_t taddr, int row, int y, int x, bool valid, int half,
-                                              const float* bias_s, const uint4 (&res_pre)[4], bool has_pre) {
+                                              const float* bias_s, const uint4 (&res_pre)[4], bool has_pre,
+                                              const float (&c_pre)[16]) {
   if constexpr (EPI == EPI_LSTM) {
     // Columns: [i | f | o | g] x 64 channels (refine_net.py:258). This warp: channels [32*half, 32*half+32).
     const float* cin = pr.c_in ? pr.c_in + (static_cast<size_t>(tc.tile_lin) * 64) * kTileM + row : nullptr;
@@ -133,6 +134,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvPro
         pr.gates_out ? pr.gates_out + (static_cast<size_t>(tc.tile_lin) * 256) * kTileM + row : nullptr;
     __nv_bfloat16* hrow = pr.h_out + ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * 64;
     const float4* bs4 = reinterpret_cast<const float4*>(bias_s + tc.z * 256);
+    // c_{t-1} of the first 16 channels was fetched before the accumulator wait (c_pre, epilogue_prefetch); the second
+    // 16 are requested while the first chunk is processed - the state loads are off the per-tile critical path.
+    float cnext[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cnext[j] = c_pre[j];
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       const int ch0 = half * 32 + cc * 16;
@@ -142,12 +148,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvPro
       tmem_ld16(taddr + 128 + ch0, vo);
       tmem_ld16(taddr + 192 + ch0, vg);
       float cprev[16];
-      if (cin) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) cprev[j] = cin[(ch0 + j) * kTileM];
-      } else {
+      for (int j = 0; j < 16; ++j) cprev[j] = cnext[j];
+      if (cc == 0 && cin) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) cprev[j] = 0.f;
+        for (int j = 0; j < 16; ++j) cnext[j] = cin[(ch0 + 16 + j) * kTileM];
       }
       tmem_ld_wait();
       uint32_t hp[8];
@@ -299,19 +304,53 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvPro
   }
 }
 
-// EPI_STORE / EPI_PS: biases of every problem of the launch -> shared memory [problem][n_total] (fits: launch_conv3x3).
+// Biases of every problem of the launch -> shared memory [problem][n_total], by the 256 epilogue threads only (the
+// TMA and MMA warps start right after the barrier setup; the first accumulator is ~5 us away).  All (<= 6) global loads
+// of a thread are issued before the first store: the former one-load-per-iteration loop in the CTA prologue cost 5
+// dependent global-latency round trips per launch.  EPI_LSTM: gate biases pre-multiplied so that each gate costs one
+// FFMA + ex2 + add + rcp: i, f, o: -log2(e) * b (sigmoid); g: 2 * log2(e) * b (tanh).
+template <int EPI>
 __device__ __forceinline__ void stage_bias(const ConvParams& p, float* bias_s) {
-  for (int i = threadIdx.x; i < p.n_prob * p.n_total; i += kNumThreads) {
-    const int z = i / p.n_total, n = i - z * p.n_total;
-    bias_s[i] = p.prob[z].bias ? p.prob[z].bias[n] : 0.f;
+  if constexpr (EPI == EPI_GRAD) return;
+  const int e = static_cast<int>(threadIdx.x) - 64;          // 0..255
+  const int n_tot = EPI == EPI_LSTM ? 256 : p.n_total;
+  const int count = p.n_prob * n_tot;                        // <= kMaxProb * 256 (launch_conv3x3)
+  float v[kMaxProb];
+#pragma unroll
+  for (int k = 0; k < kMaxProb; ++k) {
+    const int i = e + k * 256;
+    v[k] = 0.f;
+    if (i < count) {
+      const int z = i / n_tot, n = i - z * n_tot;
+      const float* b = p.prob[z].bias;
+      if (b) v[k] = EPI == EPI_LSTM ? b[n] * (n < 192 ? -kLog2e : 2.f * kLog2e) : b[n];
+    }
   }
+#pragma unroll
+  for (int k = 0; k < kMaxProb; ++k) {
+    const int i = e + k * 256;
+    if (i < count) bias_s[i] = v[k];
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");             // epilogue warps only
 }
 
 // EPI_STORE, BN = 64: this thread's residual values (2 chunks x 16 bf16) loaded ahead of the accumulator wait.
 template <int BN, int EPI>
 __device__ __forceinline__ bool epilogue_prefetch(const ConvParams& p, const ConvProblem& pr, const TileCoord& tc, int y,
-                                                  int x, bool valid, int half, uint4 (&res_pre)[4]) {
-  if constexpr (EPI == EPI_STORE && BN == 64) {
+                                                  int x, bool valid, int half, uint4 (&res_pre)[4], float (&c_pre)[16],
+                                                  int row) {
+  if constexpr (EPI == EPI_LSTM) {
+    // first 16 channels of this thread's half of c_{t-1} (tile-transposed: [tile][channel][128 rows])
+    if (pr.c_in) {
+      const float* cin = pr.c_in + (static_cast<size_t>(tc.tile_lin) * 64 + half * 32) * kTileM + row;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) c_pre[j] = cin[j * kTileM];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) c_pre[j] = 0.f;
+    }
+    return false;
+  } else if constexpr (EPI == EPI_STORE && BN == 64) {
     if (pr.res == nullptr || !valid) return false;
     const int nchunks = p.n_store >> 4;
     const size_t off = ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * p.out_ch + tc.nt * BN;
@@ -375,16 +414,6 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
   // PDL: everything above touches no global memory; the next launch may start its own prologue as our CTAs retire.
   pdl_launch_dependents();
   pdl_wait();
-  if constexpr (EPI == EPI_LSTM) {
-    // Gate biases, pre-multiplied so that each gate costs one FFMA + ex2 + add + rcp:
-    // i, f, o: -log2(e) * b (sigmoid);  g: 2 * log2(e) * b (tanh).
-    for (int i = threadIdx.x; i < p.n_prob * 256; i += kNumThreads) {
-      const int z = i >> 8, n = i & 255;
-      bias_s[i] = p.prob[z].bias[n] * (n < 192 ? -kLog2e : 2.f * kLog2e);
-    }
-  } else if constexpr (EPI == EPI_STORE || EPI == EPI_PS) {
-    stage_bias(p, bias_s);
-  }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync();   // the peer's barriers must be initialised before anything signals them
   else __syncthreads();
@@ -477,6 +506,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     const int row = quad * 32 + lane;
     const int TW = 1 << p.tw_log2;
     const int ly = row >> p.tw_log2, lx = row & (TW - 1);
+    stage_bias<EPI>(p, bias_s);
     int it = 0;
     for (int t = item0; t < total_items; t += item_step, ++it) {
       const int as = it & 1;
@@ -486,12 +516,13 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       const int y = tc.y0 + ly, x = tc.x0 + lx;
       const bool valid = tc.valid && (y < p.H) && (x < p.W);
       uint4 res_pre[4];
-      const bool has_pre = epilogue_prefetch<BN, EPI>(p, pr, tc, y, x, valid, half, res_pre);
+      float c_pre[16];
+      const bool has_pre = epilogue_prefetch<BN, EPI>(p, pr, tc, y, x, valid, half, res_pre, c_pre, row);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * kAccStride + (static_cast<uint32_t>(quad * 32) << 16);
 
-      epilogue_tile<BN, EPI>(p, pr, tc, taddr, row, y, x, valid, half, bias_s, res_pre, has_pre);
+      epilogue_tile<BN, EPI>(p, pr, tc, taddr, row, y, x, valid, half, bias_s, res_pre, has_pre, c_pre);
       // All TMEM reads of this accumulator stage are complete (wait::ld above): hand it back to the MMA warp.
       tc_fence_before();
       if constexpr (CG == 2) mbar_arrive_cluster_relaxed(mapa(smem_u32(&tempty[as]), 0));
@@ -599,14 +630,6 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
   fence_proxy_async();
   pdl_launch_dependents();
   pdl_wait();
-  if constexpr (EPI == EPI_LSTM) {
-    for (int i = threadIdx.x; i < p.n_prob * 256; i += kNumThreads) {
-      const int z = i >> 8, n = i & 255;
-      bias_s[i] = p.prob[z].bias[n] * (n < 192 ? -kLog2e : 2.f * kLog2e);
-    }
-  } else if constexpr (EPI == EPI_STORE || EPI == EPI_PS) {
-    stage_bias(p, bias_s);
-  }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync();
   else __syncthreads();
@@ -721,6 +744,7 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
     const int quad = warp & 3;
     const int half = ew >> 2;
     const int row = quad * 32 + lane;
+    stage_bias<EPI>(p, bias_s);
     int it = 0;
     for (int t = item0; t < total_items; t += item_step, ++it) {
       const int as = it & 1;
@@ -731,11 +755,12 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
       const int y = pos / Wp, x = pos - y * Wp;
       const bool valid = tc.valid && (y < p.H) && (x < p.W);
       uint4 res_pre[4];
-      const bool has_pre = epilogue_prefetch<BN, EPI>(p, pr, tc, y, x, valid, half, res_pre);
+      float c_pre[16];
+      const bool has_pre = epilogue_prefetch<BN, EPI>(p, pr, tc, y, x, valid, half, res_pre, c_pre, row);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * kAccStride + (static_cast<uint32_t>(quad * 32) << 16);
-      epilogue_tile<BN, EPI>(p, pr, tc, taddr, row, y, x, valid, half, bias_s, res_pre, has_pre);
+      epilogue_tile<BN, EPI>(p, pr, tc, taddr, row, y, x, valid, half, bias_s, res_pre, has_pre, c_pre);
       tc_fence_before();
       if constexpr (CG == 2) mbar_arrive_cluster_relaxed(mapa(smem_u32(&tempty[as]), 0));
       else mbar_arrive(&tempty[as]);

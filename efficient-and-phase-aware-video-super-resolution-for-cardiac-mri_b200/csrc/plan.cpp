@@ -147,7 +147,7 @@ struct pvsr_plan {
   int maps_halo = -1;    // halo mode the activation maps (box rows) were built for
   // Slab (padded-raster) geometry per launch kind; on = false: nine shifted boxes (conv.h: PrGeom)
   struct Geo { bool on = false; PrGeom g{0, 0, 0}; };
-  Geo geo_lstm;                           // ConvLSTM cells: classic whole-row case only (state tensors are tile-laid-out)
+  Geo geo_lstm;                           // ConvLSTM cells (= geo_lr; their state tensors are laid out by this tile map)
   Geo geo_lr;                             // other 3x3 launches at LR resolution (refine convs, their data gradients, ...)
   Geo geo_ps[PVSR_MAX_HEAD_CONVS];        // head conv q (its input resolution)
   Geo geo_hdg[PVSR_MAX_HEAD_CONVS];       // data gradient of head conv q (sources: pixel-unshuffled views, mul = r)
@@ -723,6 +723,8 @@ void schedule_backward(Ctx& c) {
       LstmBwdParams lp{};
       lp.H = p->h; lp.W = p->w;
       lp.tw_log2 = p->lr.tw_log2; lp.tiles_x = p->lr.tiles_x; lp.tiles_y = p->lr.tiles_y;
+      lp.wp = p->geo_lstm.on ? p->geo_lstm.g.wp : 0;
+      lp.tiles_per_img = p->geo_lstm.on ? p->geo_lstm.g.tiles : p->lr.tiles_x * p->lr.tiles_y;
       lp.n_img = B;
       ConvParams cp;
       base_params(p->lr, p->h, p->w, &cp);
@@ -798,9 +800,8 @@ int build_maps(pvsr_plan* p, const void* ws, const void* pk) {
   const long long TB = static_cast<long long>(p->T) * p->B;
   // Slab launches read (rows x Wp)-position boxes (conv.h: PrGeom); box launches read TH x TW tiles.
   const bool slab = get_halo_mode() != 0;
-  p->geo_lstm.on = slab && classic_halo(p->h, p->w, p->lr.tw, p->lr.tiles_x, &p->geo_lstm.g);
   p->geo_lr.on = slab && choose_pr(p->h, p->w, 1, &p->geo_lr.g);
-  if (p->geo_lstm.on && p->geo_lr.on && p->geo_lr.g.tiles >= p->geo_lstm.g.tiles) p->geo_lr = p->geo_lstm;
+  p->geo_lstm = p->geo_lr;   // the state tensors follow the same tile -> pixel map (conv.h: lstm_tile_geometry)
   for (int q = 0; q < p->n_ps; ++q) {
     if (q == 0) p->geo_ps[q] = p->geo_lr;
     else p->geo_ps[q].on = slab && choose_pr(p->ps_h[q], p->ps_w[q], 1, &p->geo_ps[q].g);

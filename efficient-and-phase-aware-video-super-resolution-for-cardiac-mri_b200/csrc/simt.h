@@ -27,6 +27,7 @@ struct LstmBwdProb {
 };
 struct LstmBwdParams {
   int H, W, tw_log2, tiles_x, tiles_y, n_img, n_prob;
+  int wp, tiles_per_img;    // tile -> pixel map of the tile-transposed tensors (conv.h lstm_tile_geometry; wp = 0: box tiles)
   LstmBwdProb prob[6];
 };
 int launch_lstm_bwd_pointwise(const LstmBwdParams& p, cudaStream_t s);

@@ -44,20 +44,32 @@ __global__ void __launch_bounds__(256, 2) lstm_bwd_pointwise_kernel(const __grid
   const int tile = blockIdx.x;
   const int cg = threadIdx.x & 7;          // channels [8*cg, 8*cg + 8)
   const int rq = threadIdx.x >> 3;         // tile rows [4*rq, 4*rq + 4)
-  int t = tile;
-  const int tx = t % p.tiles_x;
-  t /= p.tiles_x;
-  const int ty = t % p.tiles_y;
-  const int img = t / p.tiles_y;
-  const int TW = 1 << p.tw_log2;
   size_t pix[4];
   bool valid[4];
+  if (p.wp > 0) {
+    // padded raster: row r of tile t of an image is position 128 t + r = y * wp + x
+    const int img = tile / p.tiles_per_img;
+    const int pos0 = (tile - img * p.tiles_per_img) * 128 + rq * 4;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int row = rq * 4 + r;
-    const int y = ty * (128 >> p.tw_log2) + (row >> p.tw_log2), x = (tx << p.tw_log2) + (row & (TW - 1));
-    valid[r] = y < p.H && x < p.W;
-    pix[r] = (static_cast<size_t>(img) * p.H + y) * p.W + x;
+    for (int r = 0; r < 4; ++r) {
+      const int y = (pos0 + r) / p.wp, x = (pos0 + r) - y * p.wp;
+      valid[r] = y < p.H && x < p.W;
+      pix[r] = (static_cast<size_t>(img) * p.H + y) * p.W + x;
+    }
+  } else {
+    int t = tile;
+    const int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int img = t / p.tiles_y;
+    const int TW = 1 << p.tw_log2;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = rq * 4 + r;
+      const int y = ty * (128 >> p.tw_log2) + (row >> p.tw_log2), x = (tx << p.tw_log2) + (row & (TW - 1));
+      valid[r] = y < p.H && x < p.W;
+      pix[r] = (static_cast<size_t>(img) * p.H + y) * p.W + x;
+    }
   }
   const __nv_bfloat16* gt = static_cast<const __nv_bfloat16*>(pr.gates) + static_cast<size_t>(tile) * 256 * 128 + rq * 4;
   const float* ct = pr.c + static_cast<size_t>(tile) * 64 * 128 + rq * 4;
@@ -132,7 +144,8 @@ __global__ void __launch_bounds__(256, 2) lstm_bwd_pointwise_kernel(const __grid
 
 int launch_lstm_bwd_pointwise(const LstmBwdParams& p, cudaStream_t s) {
   if (p.n_prob <= 0 || p.n_img <= 0) return 0;
-  dim3 grid(static_cast<unsigned>(p.n_img * p.tiles_x * p.tiles_y), static_cast<unsigned>(p.n_prob));
+  const int tiles = p.wp > 0 ? p.tiles_per_img : p.tiles_x * p.tiles_y;
+  dim3 grid(static_cast<unsigned>(p.n_img * tiles), static_cast<unsigned>(p.n_prob));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(256);

@@ -98,6 +98,7 @@ SIGNATURES = {
                                        c_void_p]),
     "pvsr_conv3x3_fwd": (c_int, [C.POINTER(ConvDesc), c_void_p]),
     "pvsr_lstm_state_elems": (c_int64, [c_int64, c_int, c_int]),
+    "pvsr_lstm_tile_geometry": (c_int, [c_int, c_int, C.POINTER(c_int), C.POINTER(c_int)]),
     "pvsr_wgrad_scratch_bytes": (c_int64, []),
     "pvsr_conv3x3_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
     "pvsr_scatter_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

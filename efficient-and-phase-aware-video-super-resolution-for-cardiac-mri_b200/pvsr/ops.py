@@ -151,15 +151,31 @@ def lstm_state(n_img, H, W, device):
     return torch.zeros(n, dtype=torch.float32, device=device)
 
 
-def lstm_state_to_nchw(state, n_img, H, W):
-    """Tile-transposed cell state -> [n_img, 64, H, W] fp32 (test helper)."""
+def _lstm_tile_index(H, W, device):
+    """(wp, tiles_per_img, flat index [H*W] of pixel (y, x) inside an image's [tiles][128] row space or None)."""
     lib = L.load()
+    wp, tiles = C.c_int(), C.c_int()
+    L.check(lib.pvsr_lstm_tile_geometry(H, W, C.byref(wp), C.byref(tiles)), "lstm_tile_geometry")
+    if wp.value == 0:
+        return 0, tiles.value, None
+    y = torch.arange(H, device=device).view(H, 1)
+    x = torch.arange(W, device=device).view(1, W)
+    return wp.value, tiles.value, (y * wp.value + x).reshape(-1)
+
+
+def lstm_state_to_nchw(state, n_img, H, W):
+    """Tile-transposed cell state -> [n_img, 64, H, W] fp32 (test helper; layout: pvsr_lstm_tile_geometry)."""
+    lib = L.load()
+    wp, tiles, pos = _lstm_tile_index(H, W, state.device)
+    if wp:
+        s = state[:n_img * tiles * 64 * 128].view(n_img, tiles, 64, 128).permute(0, 2, 1, 3).reshape(n_img, 64, tiles * 128)
+        return s[:, :, pos].reshape(n_img, 64, H, W).contiguous()
     l = C.c_int()
     lib.pvsr_choose_tile(H, W, C.byref(l))
     tw, th = 1 << l.value, 128 >> l.value
     tx, ty = (W + tw - 1) // tw, (H + th - 1) // th
-    s = state.view(n_img, ty, tx, 64, th, tw).permute(0, 3, 1, 4, 2, 5).reshape(n_img, 64, ty * th, tx * tw)
-    return s[:, :, :H, :W].contiguous()
+    s = state[:n_img * ty * tx * 64 * 128].view(n_img, ty, tx, 64, th, tw).permute(0, 3, 1, 4, 2, 5)
+    return s.reshape(n_img, 64, ty * th, tx * tw)[:, :, :H, :W].contiguous()
 
 
 def refine_posterm(w1, b1, pos, n_frames_out, window=5, feat=64, n_total=144):
@@ -252,6 +268,11 @@ def nchw_to_lstm_state(x, dtype=torch.float32):
     """[n_img, C, H, W] -> tile-transposed [tile][C][128] buffer (test helper, inverse of lstm_state_to_nchw)."""
     lib = L.load()
     n, Cc, H, W = x.shape
+    wp, tiles, pos = _lstm_tile_index(H, W, x.device)
+    if wp:
+        flat = torch.zeros(n, Cc, tiles * 128, dtype=x.dtype, device=x.device)
+        flat[:, :, pos] = x.reshape(n, Cc, H * W)
+        return flat.view(n, Cc, tiles, 128).permute(0, 2, 1, 3).contiguous().reshape(-1).to(dtype)
     l = C.c_int()
     lib.pvsr_choose_tile(H, W, C.byref(l))
     tw, th = 1 << l.value, 128 >> l.value

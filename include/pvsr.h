@@ -186,6 +186,10 @@ int pvsr_scatter_add(float* param_grad, const int32_t* idx, const int32_t* idx2,
 
 /* Number of fp32 elements of a tile-transposed ConvLSTM cell-state buffer for n_img images of H x W. */
 int64_t pvsr_lstm_state_elems(int64_t n_img, int H, int W);
+/* Tile -> pixel map of the tile-transposed ConvLSTM tensors ([tile][channel][128 rows]) under the current kernel
+ * selection: *wp > 0: row r of tile t of an image is the padded-raster position 128 t + r = y * wp + x (positions with
+ * x >= W or y >= H are unused); *wp == 0: the TH x TW rectangles of pvsr_choose_tile.  *tiles_per_img tiles per image. */
+int pvsr_lstm_tile_geometry(int H, int W, int* wp, int* tiles_per_img);
 
 /* _RefineBlock positional-code term (refine_net.py:168-172) as a border-class table, bias included. */
 int pvsr_refine_posterm(const float* w1, const float* b1, const float* pos, float* table, int n_frames_out, int B,
