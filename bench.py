@@ -325,7 +325,6 @@ def main():
     inputs_d = [x.to(dev) for x in inputs_h]
     pos_d = pos_h.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    out_h = torch.empty(T_FRAMES, B, 1, LR_H * SCALE, LR_W * SCALE, dtype=torch.float32).pin_memory()
 
     eng = net.engine
     plan = eng.plan_for(B, len(inputs_d), LR_H, LR_W, False, dev)
@@ -334,14 +333,17 @@ def main():
         flush.fill_(1)                      # L2 flush: 256 MiB write between steps
         eng.run(plan)                       # inputs already staged in HBM
 
+    from pvsr.hostio import HostFrameRing
+    ring = HostFrameRing(dev, slots=2)      # pinned host slots + copy stream: the D2H of step i overlaps step i+1
+
     def e2e_step():
         flush.fill_(1)
+        ring.before_launch()                                             # output buffer reuse vs copies in flight
         xs = [x.to(dev, non_blocking=True) for x in inputs_h]           # H2D from pinned host memory
         ps = pos_h.to(dev, non_blocking=True)
         with torch.no_grad():
             frames = net(xs, ps)[-1]                                     # the public module call
-        for t, f in enumerate(frames):
-            out_h[t].copy_(f, non_blocking=True)                        # D2H read of the SR frames
+        ring.submit(frames)                                              # D2H read of all SR frames of the step
         return frames
 
     with torch.no_grad():
@@ -369,11 +371,13 @@ def main():
         # end-to-end leg through the public API with host buffers
         for _ in range(2):
             e2e_step()
+        ring.drain()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for _ in range(args.steps):
             e2e_step()
+        ring.drain()                        # the timed region ends when the last step's frames are in host memory
         f1.record()
         barrier()
         ms_e2e = f0.elapsed_time(f1)
@@ -401,7 +405,7 @@ def main():
         step_flops = sum(v[2] for v in prof.values())
         traffic, traffic_src = ncu_traffic("convlstm_cell") if (args.workload == "acdc_x4" and B == 32) else (None, None)
         h2d = sum(x.numel() * 4 for x in inputs_h) + pos_h.numel() * 4
-        d2h = out_h.numel() * 4
+        d2h = ring.bytes_per_step
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -146,3 +146,34 @@ def test_batched_sequences_are_independent(pvsr_lib):
     for n in range(N):
         one = _stack(_run(net, [x[n:n + 1] for x in inputs], pos[n:n + 1]))[0]
         assert torch.allclose(one[:, 0], full[:, n], atol=1e-6), n
+
+
+def test_host_frame_ring_overlapped_readback(pvsr_lib):
+    """pvsr.hostio.HostFrameRing: frames of consecutive steps (engine output buffer reused) arrive intact."""
+    from pvsr.hostio import HostFrameRing
+    from src.model.nets import RefineNet
+    torch.manual_seed(0)
+    kw = dict(in_channels=1, out_channels=1, num_features=[64, 64, 64], num_stages=2, update_memory=True,
+              num_updated_frames=3, refine_window_size=5, upscale_factor=2, positional_encoding=True)
+    net = RefineNet(**kw).to("cuda").eval()
+    net.only_last_head = True
+    net.reuse_output_buffers = True
+    ring = HostFrameRing("cuda", slots=2)
+    g = torch.Generator().manual_seed(5)
+    batches = [([torch.randn(2, 1, 9, 11, generator=g) for _ in range(8)], torch.randn(2, 8, 1, generator=g))
+               for _ in range(4)]
+    want, slots = [], []
+    with torch.no_grad():
+        for xs, ps in batches:                       # reference results, one step at a time
+            want.append(torch.stack([f.clone() for f in net([x.cuda() for x in xs], ps.cuda())[-1]]).cpu())
+        got = []
+        for i, (xs, ps) in enumerate(batches):       # pipelined: submit, keep going, read two steps later
+            ring.before_launch()
+            frames = net([x.cuda() for x in xs], ps.cuda())[-1]
+            slots.append(ring.submit(frames))
+            if i >= 1:
+                got.append(ring.result(slots[i - 1]).clone())
+        got.append(ring.result(slots[-1]).clone())
+        ring.drain()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
