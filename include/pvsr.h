@@ -39,9 +39,11 @@ int pvsr_device_check(void);
  * Default on; 0 selects the single-CTA kernel (A/B measurements, debugging).  Process-wide. */
 int pvsr_set_cta_pair(int enable);
 int pvsr_get_cta_pair(void);
-/* Halo variant of the 3x3 launches: when a tile spans the image width with a spare zero column (W < tile width) each
- * source slab is loaded once and the nine taps are row-shifted shared-memory views of it.  0 = off (nine shifted TMA
- * boxes), 1 = on (default).  Process-wide. */
+/* Slab ("halo") variant of the 3x3 launches on the padded raster: output pixels are numbered p = y * Wp + x with a pitch
+ * Wp > W, a tile is 128 consecutive positions, each source slab (the rows a tile touches + one above and below) is loaded
+ * once and the nine taps are row-shifted shared-memory views of it; works for any image width.  0 = off (nine shifted TMA
+ * boxes per source), 1 = on (default).  Also selects the tile -> pixel map of the ConvLSTM state tensors
+ * (pvsr_lstm_tile_geometry): set it BEFORE the first forward of a model.  Process-wide. */
 int pvsr_set_halo_mode(int mode);
 int pvsr_get_halo_mode(void);
 /* Programmatic dependent launch (griddepcontrol) between consecutive launches of a schedule: the next kernel's prologue
