@@ -1,0 +1,64 @@
+// Input-pipeline kernel: batches are cut out of cine volumes that stay RESIDENT in HBM.
+//   cine_gather : what AcdcVSRRefineNetDataset.__getitem__ + the transform chain do per item on the host
+//                 (reference src/data/datasets/acdc_vsr_refinenet_dataset.py:65-87: circular padding of the cardiac
+//                 cycle, frame window; src/data/transforms.py:100-168 Normalize, :321-426 flips and RandomCropPatch),
+//                 for a whole batch in one launch.  The random decisions are drawn on the host (same numpy stream as
+//                 the host path) and arrive as one descriptor per sample; the kernel is a pure gather:
+//                     out[f][n][y][x] = (float(vol_n[(t_first_n + f) mod T_n][ay*y + by][ax*x + bx]) - mean) / std
+//                 HBM-bound: 2-4 B read + 4 B written per output pixel, rows contiguous (reversed rows under a
+//                 horizontal flip still cover whole 128 B lines per warp).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pvsr.h"
+#include "simt.h"
+
+namespace pvsr {
+
+template <typename T>
+__global__ void __launch_bounds__(256) cine_gather_kernel(const T* __restrict__ vols,
+                                                          const pvsr_cine_sample* __restrict__ samples, int n_samples,
+                                                          int n_frames, int h, int w, float mean, float stdv,
+                                                          float* __restrict__ out, const float* __restrict__ pos_codes,
+                                                          float* __restrict__ pos_out) {
+  // blockIdx.y = frame * n_samples + sample; blockIdx.x strides over the pixels of that image
+  const int img = blockIdx.y;
+  const int f = img / n_samples, n = img - f * n_samples;
+  const pvsr_cine_sample s = samples[n];
+  int t = (s.t_first + f) % s.T;
+  if (t < 0) t += s.T;
+  const T* __restrict__ src = vols + s.vol_off + static_cast<int64_t>(t) * s.Hs * s.Ws;
+  float* __restrict__ dst = out + static_cast<int64_t>(img) * h * w;
+  const int n_pix = h * w;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += gridDim.x * blockDim.x) {
+    const int y = p / w, x = p - y * w;
+    const float v = static_cast<float>(src[static_cast<int64_t>(s.ay * y + s.by) * s.Ws + (s.ax * x + s.bx)]);
+    dst[p] = __fdiv_rn(__fsub_rn(v, mean), stdv);
+  }
+  if (pos_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+    pos_out[static_cast<int64_t>(n) * n_frames + f] = s.pos_off >= 0 ? pos_codes[s.pos_off + t] : 0.f;
+}
+
+int launch_cine_gather(const void* vols, int dtype, const pvsr_cine_sample* samples, int n_samples, int n_frames, int h,
+                       int w, float mean, float stdv, float* out, const float* pos_codes, float* pos_out,
+                       cudaStream_t st) {
+  if (n_samples <= 0 || n_frames <= 0 || h <= 0 || w <= 0) return 0;
+  const long long imgs = static_cast<long long>(n_samples) * n_frames;
+  if (imgs > 65535) return static_cast<int>(cudaErrorInvalidValue);
+  const int bx = (h * w + 256 * 4 - 1) / (256 * 4);   // ~4 pixels per thread
+  dim3 grid(bx < 1 ? 1 : bx, static_cast<unsigned>(imgs));
+#define PVSR_GATHER(T) \
+  cine_gather_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(vols), samples, n_samples, n_frames, h, w, mean, \
+                                             stdv, out, pos_codes, pos_out)
+  switch (dtype) {
+    case PVSR_DT_F32: PVSR_GATHER(float); break;
+    case PVSR_DT_I16: PVSR_GATHER(int16_t); break;
+    case PVSR_DT_U16: PVSR_GATHER(uint16_t); break;
+    case PVSR_DT_U8: PVSR_GATHER(uint8_t); break;
+    default: return static_cast<int>(cudaErrorInvalidValue);
+  }
+#undef PVSR_GATHER
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace pvsr

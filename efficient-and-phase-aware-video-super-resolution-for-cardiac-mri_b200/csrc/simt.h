@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+struct pvsr_cine_sample;
+
 namespace pvsr {
 
 int launch_in_conv_prelu(const float* x, const float* w, const float* b, const float* slope, void* out_bf16_nhwc,
@@ -12,6 +14,9 @@ int launch_posterm(const float* w1, const float* b1, const float* pos, float* ta
                    int window, int c_out, int c_in, int feat2, int n_total, cudaStream_t s);
 int launch_pack_weights(const float* w, const int* idx, const int* idx2, void* out_bf16, long long n, cudaStream_t s);
 int launch_gather_f32(const float* src, const int* idx, float* out, long long n, cudaStream_t s);
+int launch_cine_gather(const void* vols, int dtype, const struct pvsr_cine_sample* samples, int n_samples, int n_frames,
+                       int h, int w, float mean, float stdv, float* out, const float* pos_codes, float* pos_out,
+                       cudaStream_t s);
 int launch_add_bf16(const void* a, const void* b, void* out, long long n_elems, cudaStream_t s);
 
 

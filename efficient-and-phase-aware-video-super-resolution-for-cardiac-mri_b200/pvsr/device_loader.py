@@ -1,0 +1,189 @@
+"""HBM-resident cine loader.
+
+The reference feeds the net through a numpy pipeline - per item it re-opens two NIfTI volumes and the position-code
+pickle, normalises every frame of the cycle, flips and crops on the host, and 8 DataLoader workers collate the result
+(src/data/datasets/acdc_vsr_refinenet_dataset.py:49-89, src/data/transforms.py:100-168,321-426,
+src/data/dataloader.py:6-53).  At ~15 k SR frames/s per GPU that pipeline cannot keep one B200 busy, let alone eight.
+Here the decoded volumes are uploaded ONCE in their stored dtype (the whole preprocessed ACDC set is a few GB; a B200
+has 180 GB), and a batch is one `pvsr_cine_gather` launch per resolution: the host only draws the random decisions -
+from the SAME numpy stream, in the same order as the host transform chain, so a seeded run produces bit-identical
+batches on either path - and ships one 48-byte descriptor per sample.
+
+The loader yields the dataset's batch contract: {'lr_imgs': list of L x (N,1,h,w), 'hr_imgs': list of T x (N,1,sh,sw),
+'pos_code': (N,L,1), 'index': (N,)} with all tensors on the device.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+from torch.utils.data import BatchSampler, RandomSampler, SequentialSampler
+from torch.utils.data.distributed import DistributedSampler
+
+from . import lib as L
+
+_DT = {np.dtype(np.float32): L.DT_F32, np.dtype(np.int16): L.DT_I16, np.dtype(np.uint16): L.DT_U16,
+       np.dtype(np.uint8): L.DT_U8}
+_TORCH_DT = {L.DT_F32: torch.float32, L.DT_I16: torch.int16, L.DT_U16: torch.int16, L.DT_U8: torch.uint8}   # u16 bits kept in an int16 tensor
+
+
+class Affine:
+    """Composite of flips and crops on one image axis pair: source (row, col) = (ay*y + by, ax*x + bx)."""
+
+    def __init__(self, h, w):
+        self.ay, self.by, self.ax, self.bx, self.h, self.w = 1, 0, 1, 0, h, w
+
+    def flip(self, axis):
+        if axis == 0:
+            self.ay, self.by = -self.ay, self.ay * (self.h - 1) + self.by
+        else:
+            self.ax, self.bx = -self.ax, self.ax * (self.w - 1) + self.bx
+
+    def crop(self, y0, x0, h, w):
+        if y0 < 0 or x0 < 0 or y0 + h > self.h or x0 + w > self.w:
+            raise ValueError(f'crop ({y0},{x0},{h},{w}) leaves the {self.h}x{self.w} image')
+        self.by += self.ay * y0
+        self.bx += self.ax * x0
+        self.h, self.w = h, w
+
+
+class _Store:
+    """All sequences of one resolution in one device buffer, each as [T][H][W]."""
+
+    def __init__(self, volumes, device):
+        kinds = {v.dtype for v in volumes}
+        self.dtype = _DT[next(iter(kinds))] if len(kinds) == 1 and next(iter(kinds)) in _DT else L.DT_F32
+        tdt = _TORCH_DT[self.dtype]
+        self.offsets, total = [], 0
+        for v in volumes:
+            self.offsets.append(total)
+            total += v.size
+        self.buf = torch.empty(total, dtype=tdt, device=device)
+        self.shapes = []
+        for v, off in zip(volumes, self.offsets):
+            if v.ndim != 4 or v.shape[2] != 1:
+                raise ValueError(f'expected single-channel volumes (H, W, 1, T), got {v.shape}')
+            frames = np.ascontiguousarray(np.transpose(v[:, :, 0, :], (2, 0, 1)))       # [T][H][W]
+            if self.dtype == L.DT_F32:
+                frames = frames.astype(np.float32, copy=False)
+            t = torch.from_numpy(frames.view(np.int16) if self.dtype == L.DT_U16 else frames).reshape(-1)
+            self.buf[off:off + v.size].copy_(t)
+            self.shapes.append(frames.shape)
+
+
+class DeviceDataloader:
+    """Drop-in for `Dataloader` (same constructor keywords; `num_workers`, `pin_memory`, `collate_fn`, `timeout` and
+    `worker_init_fn` have nothing to do here and are ignored).  The dataset must expose `sequence_table()`,
+    `transform_plan()` and `window(index)` (AcdcVSRRefineNetDataset / SyntheticCineDataset do)."""
+
+    def __init__(self, dataset, batch_size=1, shuffle=False, sampler=None, batch_sampler=None, drop_last=False,
+                 shard=None, device=None, **_ignored):
+        for need in ('sequence_table', 'transform_plan', 'window'):
+            if not hasattr(dataset, need):
+                raise TypeError(f'{type(dataset).__name__} has no {need}(): it cannot be served from device memory')
+        if not torch.cuda.is_available():
+            raise L.PvsrError('DeviceDataloader needs a CUDA device (the volumes live in HBM); use Dataloader on CPU')
+        self.dataset, self.batch_size, self.drop_last = dataset, batch_size, drop_last
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.collate_fn = None
+        if batch_sampler is None:
+            if sampler is None:
+                rank, world = shard if shard is not None else (0, 1)
+                if world > 1:
+                    sampler = DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=shuffle,
+                                                 drop_last=drop_last)
+                else:
+                    sampler = RandomSampler(dataset) if shuffle else SequentialSampler(dataset)
+            batch_sampler = BatchSampler(sampler, batch_size, drop_last)
+        self.sampler, self.batch_sampler = sampler, batch_sampler
+        self._lr = self._hr = self._pos = None
+        self.mean, self.std, self.augments = dataset.transform_plan()
+        self.scale = dataset.downscale_factor
+
+    def __len__(self):
+        return len(self.batch_sampler)
+
+    # ------------------------------------------------------------------ residency
+    def _upload(self):
+        if self._lr is not None:
+            return
+        seqs = self.dataset.sequence_table()
+        with torch.cuda.device(self.device):
+            self._lr = _Store([s[0] for s in seqs], self.device)
+            self._hr = _Store([s[1] for s in seqs], self.device)
+            codes = [np.asarray(s[2], dtype=np.float32).reshape(-1) for s in seqs]
+            self._pos_off = np.concatenate([[0], np.cumsum([c.size for c in codes])]).astype(np.int64)
+            self._pos = torch.from_numpy(np.concatenate(codes)).to(self.device)
+
+    def resident_bytes(self):
+        self._upload()
+        return sum(t.numel() * t.element_size() for t in (self._lr.buf, self._hr.buf, self._pos))
+
+    # ------------------------------------------------------------------ batches
+    def decide(self, index):
+        """Draws the augmentation decisions of one item (numpy global RNG, same order as the host transform chain)
+        and returns (seq, lr_first, n_lr, hr_first, n_hr, lr Affine, hr Affine)."""
+        seq, a, b, c, d = self.dataset.window(index)
+        T, H, W = self._lr.shapes[seq]
+        _, Hh, Wh = self._hr.shapes[seq]
+        lr, hr = Affine(H, W), Affine(Hh, Wh)
+        if self.dataset.type == 'train':
+            for aug in self.augments:
+                step = aug.decide(lr.h, lr.w)
+                if step is None:
+                    continue
+                if step[0] == 'flip':
+                    lr.flip(step[1])
+                    hr.flip(step[1])
+                else:
+                    _, y0, x0, ph, pw, r = step
+                    lr.crop(y0, x0, ph, pw)
+                    hr.crop(y0 * r, x0 * r, ph * r, pw * r)
+        return seq, a, b - a, c, d - c, lr, hr
+
+    def _descriptors(self, store, rows):
+        arr = (L.CineSample * len(rows))()
+        for i, (seq, first, aff, with_pos) in enumerate(rows):
+            T, Hs, Ws = store.shapes[seq]
+            arr[i] = L.CineSample(store.offsets[seq], int(self._pos_off[seq]) if with_pos else -1, T, first % T, Hs, Ws,
+                                  aff.ay, aff.by, aff.ax, aff.bx)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+        return host.to(self.device, non_blocking=True), host
+
+    def fetch(self, indices):
+        """One batch for the given dataset indices (all items must agree on frame counts and output sizes)."""
+        self._upload()
+        items = [self.decide(int(i)) for i in indices]
+        _, _, n_lr, _, n_hr, lr0, hr0 = items[0]
+        for it in items[1:]:
+            if (it[2], it[4], it[5].h, it[5].w, it[6].h, it[6].w) != (n_lr, n_hr, lr0.h, lr0.w, hr0.h, hr0.w):
+                raise ValueError('the items of a batch differ in frame count or size; crop to a common patch size '
+                                 '(RandomCropPatch) or use batch_size 1')
+        n = len(items)
+        lib = L.load()
+        with torch.cuda.device(self.device):
+            lr = torch.empty(n_lr, n, 1, lr0.h, lr0.w, dtype=torch.float32, device=self.device)
+            hr = torch.empty(n_hr, n, 1, hr0.h, hr0.w, dtype=torch.float32, device=self.device)
+            pos = torch.empty(n, n_lr, 1, dtype=torch.float32, device=self.device)
+            d_lr, keep1 = self._descriptors(self._lr, [(it[0], it[1], it[5], True) for it in items])
+            d_hr, keep2 = self._descriptors(self._hr, [(it[0], it[3], it[6], False) for it in items])
+            st = L.current_stream()
+            L.check(lib.pvsr_cine_gather(L.ptr(self._lr.buf), self._lr.dtype, L.ptr(d_lr), n, n_lr, lr0.h, lr0.w,
+                                         self.mean, self.std, L.ptr(lr), L.ptr(self._pos), L.ptr(pos), st),
+                    'pvsr_cine_gather(LR)')
+            L.check(lib.pvsr_cine_gather(L.ptr(self._hr.buf), self._hr.dtype, L.ptr(d_hr), n, n_hr, hr0.h, hr0.w,
+                                         self.mean, self.std, L.ptr(hr), None, None, st), 'pvsr_cine_gather(HR)')
+            d_lr.record_stream(torch.cuda.current_stream())
+            d_hr.record_stream(torch.cuda.current_stream())
+        self._keep = (keep1, keep2)      # pinned staging stays alive until the next batch replaces it
+        return {'lr_imgs': list(lr.unbind(0)), 'hr_imgs': list(hr.unbind(0)), 'pos_code': pos,
+                'index': torch.as_tensor([int(i) for i in indices])}
+
+    def item_key(self, index):
+        """Hashable shape key of a test item (frame count, LR size): items with equal keys can share a launch."""
+        self._upload()
+        seq, a, b, _, _ = self.dataset.window(int(index))
+        return (b - a,) + tuple(self._lr.shapes[seq][1:])
+
+    def __iter__(self):
+        for indices in self.batch_sampler:
+            yield self.fetch(indices)

@@ -75,6 +75,13 @@ class NetGrads(C.Structure):
     _fields_ = NetParams._fields_
 
 
+class CineSample(C.Structure):
+    _fields_ = [("vol_off", c_int64), ("pos_off", c_int64), ("T", C.c_int32), ("t_first", C.c_int32),
+                ("Hs", C.c_int32), ("Ws", C.c_int32), ("ay", C.c_int32), ("by", C.c_int32), ("ax", C.c_int32),
+                ("bx", C.c_int32)]
+
+
+DT_F32, DT_I16, DT_U16, DT_U8 = 0, 1, 2, 3
 NUM_CLASSES, NUM_CLASSES_BWD = 7, 9
 
 # name -> (restype, argtypes); every symbol declared in include/pvsr.h
@@ -106,6 +113,8 @@ SIGNATURES = {
                                     c_int, c_int, c_int, c_void_p]),
     "pvsr_head_conv_last_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                         c_int, c_void_p]),
+    "pvsr_cine_gather": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, C.c_float, C.c_float, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
     "pvsr_add_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "pvsr_lstm_cell_bwd_pointwise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64,
                                              c_int, c_int, c_void_p]),

@@ -1,9 +1,14 @@
 """`Dataloader` of the YAML registry (reference src/data/dataloader.py:6-53): torch's DataLoader whose workers
 re-seed numpy from the parent's numpy state, plus an optional `shard=(rank, world)` that gives every data-parallel
-rank its own slice of the dataset (the reference is single-GPU and has no equivalent)."""
+rank its own slice of the dataset (the reference is single-GPU and has no equivalent).
+
+`DeviceDataloader` (pvsr/device_loader.py) takes the same keywords and serves the same batches from volumes resident
+in HBM: one gather kernel per batch instead of numpy workers."""
 import numpy as np
 from torch.utils.data import DataLoader
 from torch.utils.data.distributed import DistributedSampler
+
+from pvsr.device_loader import DeviceDataloader  # noqa: F401  (registry name: `dataloader: {name: DeviceDataloader}`)
 
 
 def _seed_worker(worker_id):

@@ -19,11 +19,12 @@ from .base_dataset import BaseDataset
 
 
 def _load_nifti(path):
+    """(H, W, C, T) array of a preprocessed 2d+1d volume; nibabel when installed, else the built-in NIfTI-1 reader."""
     try:
         import nibabel as nib
-    except ImportError as e:
-        raise ImportError('nibabel is required to read the ACDC / DSB15 NIfTI volumes; '
-                          'use SyntheticCineDataset when the datasets are unavailable') from e
+    except ImportError:
+        from pvsr import nifti
+        return nifti.read(path)
     return np.asarray(nib.load(str(path)).dataobj)
 
 
@@ -35,6 +36,22 @@ def window_slices(T, t, num_frames, num_updated_frames, train):
         start = end - num_frames
         return start - U, end + U, start, end
     return T - U, 2 * T + U, 0, T
+
+
+def device_transform_plan(transforms, augments):
+    from ..transforms import Normalize, ToTensor
+    mean, std = np.float32(0), np.float32(1)
+    for step in transforms.steps:
+        if isinstance(step, Normalize):
+            if step.means is None or step.means.size != 1:
+                raise TypeError('per-image statistics / multi-channel Normalize cannot be served from device memory')
+            mean, std = step.means.reshape(-1)[0], (step.stds + 1e-10).astype(np.float32).reshape(-1)[0]
+        elif not isinstance(step, ToTensor):
+            raise TypeError(f'transform {type(step).__name__} cannot be served from device memory')
+    for step in augments.steps:
+        if not hasattr(step, 'decide'):
+            raise TypeError(f'augment {type(step).__name__} cannot be served from device memory')
+    return float(mean), float(std), list(augments.steps)
 
 
 class AcdcVSRRefineNetDataset(BaseDataset):
@@ -76,6 +93,35 @@ class AcdcVSRRefineNetDataset(BaseDataset):
 
     def __len__(self):
         return len(self.data)
+
+    # ---- device-resident serving (pvsr.device_loader.DeviceDataloader) -------------------------------------------
+    def _sequences(self):
+        if not hasattr(self, '_seq_paths'):
+            self._seq_paths, self._seq_of = [], {}
+            for entry in self.data:
+                if entry[0] not in self._seq_of:
+                    self._seq_of[entry[0]] = len(self._seq_paths)
+                    self._seq_paths.append((entry[0], entry[1]))
+        return self._seq_paths
+
+    def sequence_table(self):
+        """[(lr volume (H,W,1,T), hr volume, positional code (T,))] of every distinct cine sequence."""
+        return [(self._volume(lr), self._volume(hr), np.asarray(self._pos_code(lr), dtype=np.float32))
+                for lr, hr in self._sequences()]
+
+    def transform_plan(self):
+        """(mean, std, augment steps) of the configured chains, or TypeError when they cannot run as one gather."""
+        return device_transform_plan(self.transforms, self.augments)
+
+    def window(self, index):
+        """(sequence number, lr_start, lr_end, hr_start, hr_end): the frame window of item `index` in cycle indices
+        (taken modulo T by the consumer) - the same slices __getitem__ cuts out of the tiled lists."""
+        entry = self.data[index]
+        self._sequences()
+        T = self._volume(entry[0]).shape[-1]
+        train = self.type == 'train'
+        return (self._seq_of[entry[0]],) + window_slices(T, entry[2] if train else 0, self.num_frames,
+                                                         self.num_updated_frames, train)
 
     def __getitem__(self, index):
         entry = self.data[index]

@@ -23,14 +23,39 @@ class SyntheticCineDataset(BaseDataset):
     def __len__(self):
         return len(self.data)
 
+    def _frames(self, seq):
+        g = torch.Generator().manual_seed(self.seed + seq)
+        T, (h, w), s = self.num_phases, self.lr_size, self.downscale_factor
+        lr = [torch.randn(1, h, w, generator=g) for _ in range(T)]
+        hr = [torch.randn(1, h * s, w * s, generator=g) for _ in range(T)]
+        return lr, hr
+
+    # ---- device-resident serving (pvsr.device_loader.DeviceDataloader) -------------------------------------------
+    def sequence_table(self):
+        from pvsr.synthetic import positional_code
+        code = positional_code(self.num_phases, self.end_systole)
+        table = []
+        for seq in sorted({int(e[0][9:12]) for e in self.data}):
+            lr, hr = self._frames(seq)
+            table.append((torch.stack(lr, dim=-1).permute(1, 2, 0, 3).numpy(),      # (H, W, 1, T)
+                          torch.stack(hr, dim=-1).permute(1, 2, 0, 3).numpy(), code))
+        return table
+
+    def transform_plan(self):
+        return 0.0, 1.0, []
+
+    def window(self, index):
+        entry = self.data[index]
+        train = self.type == 'train'
+        return (int(entry[0][9:12]),) + window_slices(self.num_phases, entry[2] if train else 0, self.num_frames,
+                                                      self.num_updated_frames, train)
+
     def __getitem__(self, index):
         from pvsr.synthetic import positional_code
         entry = self.data[index]
         seq = int(entry[0][9:12])
-        g = torch.Generator().manual_seed(self.seed + seq)
-        T, (h, w), s = self.num_phases, self.lr_size, self.downscale_factor
-        lr = [torch.randn(1, h, w, generator=g) for _ in range(T)] * 3
-        hr = [torch.randn(1, h * s, w * s, generator=g) for _ in range(T)] * 3
+        T = self.num_phases
+        lr, hr = (frames * 3 for frames in self._frames(seq))
         code = torch.from_numpy(positional_code(T, self.end_systole)).repeat(3).unsqueeze(1)
         a, b, c, d = window_slices(T, entry[2] if self.type == 'train' else 0, self.num_frames,
                                    self.num_updated_frames, self.type == 'train')

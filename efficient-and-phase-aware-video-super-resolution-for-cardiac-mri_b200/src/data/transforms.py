@@ -81,8 +81,12 @@ class _RandomFlip(BaseTransform):
     def __init__(self, prob=0.5):
         self.prob = prob
 
+    def decide(self, h, w):
+        """Draws this step's decision for an (h, w) LR image: ('flip', axis) or None (pvsr.device_loader)."""
+        return ('flip', self.axis) if np.random.rand() < self.prob else None
+
     def __call__(self, *imgs, **kwargs):
-        if np.random.rand() < self.prob:
+        if self.decide(*imgs[0].shape[:2]) is not None:
             return tuple(np.flip(img, self.axis).copy() for img in imgs)
         return imgs
 
@@ -102,15 +106,18 @@ class RandomCropPatch(BaseTransform):
     def __init__(self, size, ratio):
         self.size, self.ratio = tuple(size), ratio
 
-    def __call__(self, *imgs, **kwargs):
-        half = len(imgs) // 2
-        h, w = imgs[0].shape[:2]
+    def decide(self, h, w):
+        """('crop', y0, x0, ph, pw, ratio) for an (h, w) LR image."""
         ph, pw = self.size
         if ph > h or pw > w:
             raise ValueError(f'The crop size {self.size} exceeds the LR image size {(h, w)}.')
         y0 = np.random.randint(0, h - ph + 1)
         x0 = np.random.randint(0, w - pw + 1)
-        r = self.ratio
+        return ('crop', y0, x0, ph, pw, self.ratio)
+
+    def __call__(self, *imgs, **kwargs):
+        half = len(imgs) // 2
+        _, y0, x0, ph, pw, r = self.decide(*imgs[0].shape[:2])
         lr = [img[y0:y0 + ph, x0:x0 + pw] for img in imgs[:half]]
         hr = [img[y0 * r:(y0 + ph) * r, x0 * r:(x0 + pw) * r] for img in imgs[half:]]
         return tuple(lr + hr)

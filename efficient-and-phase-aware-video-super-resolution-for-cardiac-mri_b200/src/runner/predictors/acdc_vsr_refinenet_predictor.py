@@ -65,11 +65,14 @@ class AcdcVSRRefineNetPredictor(BasePredictor):
         rows = []
         log, count = self._init_log(), 0
 
+        # a DeviceDataloader cuts batches out of HBM-resident volumes itself (pvsr/device_loader.py)
+        device_side = hasattr(self.test_dataloader, 'fetch')
         pending = {}    # shape -> list of (index, item)
         def flush(items):
             nonlocal count
             idx = [i for i, _ in items]
-            batch = self._allocate_data(collate([it for _, it in items]))
+            batch = (self.test_dataloader.fetch(idx) if device_side
+                     else self._allocate_data(collate([it for _, it in items])))
             inputs, targets, pos_codes, _ = self._get_inputs_targets(batch)
             with torch.no_grad():
                 outputs = self.net(inputs, pos_codes)[-1]           # T x (n, 1, H, W)
@@ -83,8 +86,11 @@ class AcdcVSRRefineNetPredictor(BasePredictor):
                     rows.extend(self._export(index, losses, metrics, sr))
 
         for index in mine:
-            item = dataset[index]
-            key = (len(item['lr_imgs']),) + tuple(item['lr_imgs'][0].shape)
+            if device_side:
+                item, key = None, self.test_dataloader.item_key(index)
+            else:
+                item = dataset[index]
+                key = (len(item['lr_imgs']),) + tuple(item['lr_imgs'][0].shape)
             pending.setdefault(key, []).append((index, item))
             if len(pending[key]) == self.sequences_per_launch:
                 flush(pending.pop(key))

@@ -186,6 +186,31 @@ int pvsr_conv3x3_wgrad(const pvsr_wgrad_desc* d, void* stream);
 int pvsr_scatter_add(float* param_grad, const int32_t* idx, const int32_t* idx2, const float* packed, int64_t n,
                      void* stream);
 
+/* ---- input pipeline: batches cut out of HBM-resident cine volumes --------------------------------
+ * Replaces, per batch, AcdcVSRRefineNetDataset.__getitem__ (src/data/datasets/acdc_vsr_refinenet_dataset.py:49-89:
+ * frame window of the circularly padded cycle, positional code slice) and the transform chain applied to it
+ * (src/data/transforms.py:100-168 Normalize, :321-426 RandomHorizontalFlip / RandomVerticalFlip / RandomCropPatch).
+ * `volumes`: every sequence stored as [T][Hs][Ws] (one channel) in one device buffer of element type `vol_dtype`.
+ * One descriptor per sample of the batch (device memory); out fp32 [n_frames][n_samples][h][w],
+ *     out[f][n][y][x] = (float(vol_n[(t_first + f) mod T][ay*y + by][ax*x + bx]) - mean) / std      (IEEE fp32)
+ * pos_out (optional) fp32 [n_samples][n_frames] = pos_codes[pos_off + (t_first + f) mod T]. */
+#define PVSR_DT_F32 0
+#define PVSR_DT_I16 1
+#define PVSR_DT_U16 2
+#define PVSR_DT_U8 3
+typedef struct pvsr_cine_sample {
+  int64_t vol_off;         /* element offset of frame 0 of the sequence inside `volumes` */
+  int64_t pos_off;         /* element offset of the sequence's code [T] inside `pos_codes`, or -1 */
+  int32_t T;               /* phases of the cardiac cycle */
+  int32_t t_first;         /* cycle index of output frame 0 (may be negative; wraps modulo T) */
+  int32_t Hs, Ws;          /* frame size of the stored volume */
+  int32_t ay, by;          /* source row = ay * y + by (ay = -1 under a vertical flip) */
+  int32_t ax, bx;          /* source column = ax * x + bx */
+} pvsr_cine_sample;
+int pvsr_cine_gather(const void* volumes, int vol_dtype, const pvsr_cine_sample* samples, int n_samples, int n_frames,
+                     int h, int w, float mean, float std, float* out, const float* pos_codes, float* pos_out,
+                     void* stream);
+
 /* Number of fp32 elements of a tile-transposed ConvLSTM cell-state buffer for n_img images of H x W. */
 int64_t pvsr_lstm_state_elems(int64_t n_img, int H, int W);
 /* Tile -> pixel map of the tile-transposed ConvLSTM tensors ([tile][channel][128 rows]) under the current kernel
