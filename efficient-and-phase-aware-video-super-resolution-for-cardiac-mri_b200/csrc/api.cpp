@@ -64,6 +64,9 @@ int fill_conv_params(const pvsr_conv_desc* d, ConvParams* p) {
   p->out_ch = d->out_ch;
   p->ps_r = d->ps_r;
   p->grad_split = d->grad_split;
+  p->relu = d->relu;
+  p->out_scale = d->out_scale;
+  if (d->ps_r > 0) p->ps_ch = p->n_total / (d->ps_r * d->ps_r);
   ConvProblem& pr = p->prob[0];
   pr.n_src = d->n_src;
   for (int i = 0; i < d->n_src; ++i) {
@@ -77,6 +80,7 @@ int fill_conv_params(const pvsr_conv_desc* d, ConvParams* p) {
   pr.out_f32 = d->out_f32;
   pr.res = static_cast<const __nv_bfloat16*>(d->res);
   pr.posterm = d->posterm;
+  pr.mask = static_cast<const __nv_bfloat16*>(d->mask);
   pr.grad0 = d->grad0;
   pr.grad1 = d->grad1;
   pr.c_in = d->c_in;
@@ -222,7 +226,8 @@ int64_t pvsr_pack_index_count(const pvsr_pack_spec* s) {
 static int spec_out_channel(const pvsr_pack_spec* s, int n) {
   if (s->ps_r == 0) return n;
   const int r2 = s->ps_r * s->ps_r;
-  const int q = n / 64, c = n % 64;
+  const int pc = s->ps_ch > 0 ? s->ps_ch : 64;
+  const int q = n / pc, c = n % pc;
   if (q >= r2) return -1;
   return c * r2 + q;
 }
@@ -315,6 +320,19 @@ int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream) {
 int64_t pvsr_wgrad_scratch_bytes(void) { return 256 * static_cast<int64_t>(sizeof(WgJob)); }
 
 int pvsr_conv3x3_wgrad(const pvsr_wgrad_desc* d, void* stream) {
+  int rc = pvsr_conv3x3_wgrad_staged(d, 1, stream);
+  return rc ? rc : pvsr_conv3x3_wgrad_staged(d, 0, stream);
+}
+
+int pvsr_pad_channel_bf16(const float* x, void* out, int64_t n, void* stream) {
+  return check_cuda(launch_pad_channel_bf16(x, out, n, static_cast<cudaStream_t>(stream)), "pad_channel_bf16");
+}
+int pvsr_take_channel0_f32(const float* in, int stride, float* out, int64_t n, void* stream) {
+  if (stride < 1) return set_error(-2, "stride must be positive");
+  return check_cuda(launch_take_channel0(in, stride, out, n, static_cast<cudaStream_t>(stream)), "take_channel0");
+}
+
+int pvsr_conv3x3_wgrad_staged(const pvsr_wgrad_desc* d, int upload, void* stream) {
   if (d->n_views < 1 || d->n_views > kMaxMaps) return set_error(-2, "n_views out of range");
   if (d->n_src < 1 || d->n_src > kMaxSrc || d->n_dy < 1 || d->n_dy > PVSR_MAX_DY) return set_error(-2, "bad source count");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -349,10 +367,12 @@ int pvsr_conv3x3_wgrad(const pvsr_wgrad_desc* d, void* stream) {
                    d->with_bias ? static_cast<long long>(d->db_packed - d->dw_packed) : 0, &jobs);
   if (jobs.size() > 256) return set_error(-2, "too many wgrad jobs");
   p.n_heavy = sort_wgrad_jobs(jobs.data(), static_cast<int>(jobs.size()));
-  int e = cudaMemcpyAsync(d->job_scratch, jobs.data(), jobs.size() * sizeof(WgJob), cudaMemcpyHostToDevice, s);
-  if (e) return check_cuda(e, "job upload");
-  e = cudaStreamSynchronize(s);   // the host vector dies at return (test/tool entry point; the plan pre-uploads)
-  if (e) return check_cuda(e, "job upload sync");
+  if (upload) {
+    int e = cudaMemcpyAsync(d->job_scratch, jobs.data(), jobs.size() * sizeof(WgJob), cudaMemcpyHostToDevice, s);
+    if (e) return check_cuda(e, "job upload");
+    e = cudaStreamSynchronize(s);   // the host vector dies at return (the RefineNet plan pre-uploads its own jobs)
+    return check_cuda(e, "job upload sync");
+  }
   p.n_jobs = static_cast<int>(jobs.size());
   const long long total_tiles = static_cast<long long>(p.n_img) * p.tiles_x * p.tiles_y;
   if (d->n_splits > 0) {
@@ -369,6 +389,12 @@ int pvsr_scatter_add(float* param_grad, const int32_t* idx, const int32_t* idx2,
                      void* stream) {
   return check_cuda(launch_scatter_add(param_grad, idx, idx2, packed, n, static_cast<cudaStream_t>(stream)),
                     "scatter_add");
+}
+
+int pvsr_scatter_add_scaled(float* param_grad, const int32_t* idx, const float* packed, int64_t n, float scale,
+                            void* stream) {
+  return check_cuda(launch_scatter_add(param_grad, idx, nullptr, packed, n, static_cast<cudaStream_t>(stream), scale),
+                    "scatter_add_scaled");
 }
 
 int64_t pvsr_lstm_state_elems(int64_t n_img, int H, int W) {

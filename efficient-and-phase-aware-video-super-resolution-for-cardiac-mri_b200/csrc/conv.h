@@ -19,6 +19,7 @@ constexpr int kMaxProb = 6;   // one ConvLSTM wavefront: up to 3 layers x 2 dire
 constexpr int kMaxMaps = 4;   // distinct activation tensors (TMA descriptors) one launch may read
 constexpr int kTileM = 128;   // output pixels per tile (UMMA M)
 constexpr int kBlockK = 64;   // bf16 channels per K block (one 128-byte swizzle row)
+constexpr int kBiasStage = 2304;   // fp32 biases of one launch staged in shared memory (>= kMaxProb * 256; 9 * 256)
 
 enum EpiKind : int {
   EPI_STORE = 0,  // bias (+ border-class term) (+ residual) -> NHWC bf16 and/or fp32
@@ -48,6 +49,7 @@ struct ConvProblem {
   float* out_f32;             // NHWC fp32 (nullptr = skip)
   const __nv_bfloat16* res;   // optional residual, same shape as out_bf16
   const float* posterm;       // optional [n_img][16][n_total] border-class additive term
+  const __nv_bfloat16* mask;  // optional, shape of out_bf16: the value is zeroed where mask <= 0 (ReLU adjoint, EDSR)
   // EPI_GRAD: fp32 [n_img][H][W][64]; split: cols [0,64) -> grad0, [64,128) -> grad1; else cols [0,64) -> both
   float* grad0;
   float* grad1;
@@ -73,6 +75,9 @@ struct ConvParams {
   int out_ch;        // channels per pixel of the output tensor
   int ps_r;          // pixel-shuffle factor for EPI_PS
   int grad_split;    // EPI_GRAD column routing (see ConvProblem)
+  int relu;          // EPI_STORE: max(x, 0) after the bias, before mask / residual (edsr_net.py:50 relu1)
+  float out_scale;   // EPI_STORE: (acc + bias) * out_scale before mask / residual; 0 = 1 (edsr_net.py:56 res_scale)
+  int ps_ch;         // EPI_PS: channels per shuffled pixel (0 = 64): column q * ps_ch + c -> sub-pixel q, channel c
   int halo;          // != 0: padded-raster slab kernel (below); tiles_x = 1, tiles_y = pr_tiles
   int pr_wp;         // padded row pitch Wp >= W + 1: output position p = y * Wp + x, tile t covers [128 t, 128 t + 128)
   int pr_rows;       // rows of the activation box = rows a tile can span + 2 (the maps carry (64, Wp, pr_rows, 1) boxes)

@@ -30,7 +30,7 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
-                                    kMaxProb * 256 * 4 /*pre-scaled LSTM biases*/;
+                                    kBiasStage * 4 /*biases of the launch (LSTM: pre-scaled)*/;
   static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment for the 128B swizzle");
   static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint for M=128");
 };
@@ -257,12 +257,29 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvPro
         if constexpr (EPI == EPI_PS) {
           // column = q*64 + c with q = i*r + j  ->  HR pixel (y*r+i, x*r+j), channel c (PixelShuffle, :200,204)
           const int col = tc.nt * BN + ck * 16;
-          const int q = col >> 6, c0 = col & 63;
+          const int pc = p.ps_ch ? p.ps_ch : 64;
+          const int q = col / pc, c0 = col - q * pc;
           const int r = p.ps_r;
           const int qi = q / r, qj = q - qi * r;
-          off = ((static_cast<size_t>(tc.img) * p.H * r + (y * r + qi)) * (p.W * r) + (x * r + qj)) * 64 + c0;
+          off = ((static_cast<size_t>(tc.img) * p.H * r + (y * r + qi)) * (p.W * r) + (x * r + qj)) * pc + c0;
         } else {
           off = ((static_cast<size_t>(tc.img) * p.H + y) * p.W + x) * p.out_ch + tc.nt * BN + ck * 16;
+        }
+        if (p.out_scale != 0.f) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] *= p.out_scale;
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (pr.mask) {
+          float mf[16];
+          const uint4* mp = reinterpret_cast<const uint4*>(pr.mask + off);
+          unpack_bf16x8(mp[0], mf);
+          unpack_bf16x8(mp[1], mf + 8);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = mf[j] > 0.f ? f[j] : 0.f;
         }
         if (pr.res) {
           float rf[16];
@@ -314,10 +331,11 @@ __device__ __forceinline__ void stage_bias(const ConvParams& p, float* bias_s) {
   if constexpr (EPI == EPI_GRAD) return;
   const int e = static_cast<int>(threadIdx.x) - 64;          // 0..255
   const int n_tot = EPI == EPI_LSTM ? 256 : p.n_total;
-  const int count = p.n_prob * n_tot;                        // <= kMaxProb * 256 (launch_conv3x3)
-  float v[kMaxProb];
+  const int count = p.n_prob * n_tot;                        // <= kBiasStage (launch_conv3x3)
+  constexpr int kIters = kBiasStage / 256;
+  float v[kIters];
 #pragma unroll
-  for (int k = 0; k < kMaxProb; ++k) {
+  for (int k = 0; k < kIters; ++k) {
     const int i = e + k * 256;
     v[k] = 0.f;
     if (i < count) {
@@ -327,7 +345,7 @@ __device__ __forceinline__ void stage_bias(const ConvParams& p, float* bias_s) {
     }
   }
 #pragma unroll
-  for (int k = 0; k < kMaxProb; ++k) {
+  for (int k = 0; k < kIters; ++k) {
     const int i = e + k * 256;
     if (i < count) bias_s[i] = v[k];
   }
@@ -783,7 +801,7 @@ template <int BN, int EPI, int CG, bool HALO>
 static int launch_t(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<BN, CG>;
   auto kern = HALO ? conv3x3_halo_kernel<BN, EPI, CG> : conv3x3_tc_kernel<BN, EPI, CG>;
-  constexpr int kSmem = HALO ? kHaloBudget + 1024 + 256 + kMaxProb * 256 * 4 : C::kSmemBytes;
+  constexpr int kSmem = HALO ? kHaloBudget + 1024 + 256 + kBiasStage * 4 : C::kSmemBytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
@@ -842,7 +860,7 @@ void set_cta_pair(int enable) { g_cta_pair = enable ? 1 : 0; }
 int get_cta_pair() { return g_cta_pair; }
 
 int launch_conv3x3(int bn, int epi, const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
-  if ((epi == EPI_STORE || epi == EPI_PS) && p.n_prob * p.n_total > kMaxProb * 256)   // bias staging area
+  if ((epi == EPI_STORE || epi == EPI_PS) && p.n_prob * p.n_total > kBiasStage)   // bias staging area
     return static_cast<int>(cudaErrorInvalidValue);
   if (epi == EPI_LSTM && bn == 256) return launch_cg<256, EPI_LSTM>(maps, p, num_sms, stream);
   if (epi == EPI_STORE) {

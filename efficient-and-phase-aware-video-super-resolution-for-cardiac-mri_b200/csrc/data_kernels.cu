@@ -7,6 +7,7 @@
 //                     out[f][n][y][x] = (float(vol_n[(t_first_n + f) mod T_n][ay*y + by][ax*x + bx]) - mean) / std
 //                 HBM-bound: 2-4 B read + 4 B written per output pixel, rows contiguous (reversed rows under a
 //                 horizontal flip still cover whole 128 B lines per warp).
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -58,6 +59,41 @@ int launch_cine_gather(const void* vols, int dtype, const pvsr_cine_sample* samp
     default: return static_cast<int>(cudaErrorInvalidValue);
   }
 #undef PVSR_GATHER
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Single-channel ends of a net whose features are tensor-core operands (EDSR, edsr_net.py:29,33): the image (or the
+// gradient of the output) becomes channel 0 of a zero-padded 64-channel bf16 K block; the 1-channel result of the tail
+// conv is column 0 of its 16-column fp32 output.
+__global__ void __launch_bounds__(256) pad_channel_bf16_kernel(const float* __restrict__ x, uint4* __restrict__ out,
+                                                               long long n) {
+  // 8 threads per pixel, one 16-byte store each: the pixel's 128-byte row is written by one quarter-warp
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long pix = i >> 3;
+  if (pix >= n) return;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if ((i & 7) == 0) {
+    __nv_bfloat16 h = __float2bfloat16(x[pix]);
+    v.x = *reinterpret_cast<unsigned short*>(&h);
+  }
+  out[i] = v;
+}
+int launch_pad_channel_bf16(const float* x, void* out, long long n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const long long threads = n * 8;
+  pad_channel_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(x, static_cast<uint4*>(out), n);
+  return static_cast<int>(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) take_channel0_kernel(const float* __restrict__ in, int stride,
+                                                            float* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i * stride];
+}
+int launch_take_channel0(const float* in, int stride, float* out, long long n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  take_channel0_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(in, stride, out, n);
   return static_cast<int>(cudaGetLastError());
 }
 

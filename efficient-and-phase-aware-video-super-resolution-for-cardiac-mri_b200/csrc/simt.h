@@ -17,6 +17,8 @@ int launch_gather_f32(const float* src, const int* idx, float* out, long long n,
 int launch_cine_gather(const void* vols, int dtype, const struct pvsr_cine_sample* samples, int n_samples, int n_frames,
                        int h, int w, float mean, float stdv, float* out, const float* pos_codes, float* pos_out,
                        cudaStream_t s);
+int launch_pad_channel_bf16(const float* x, void* out_bf16, long long n, cudaStream_t s);
+int launch_take_channel0(const float* in, int stride, float* out, long long n, cudaStream_t s);
 int launch_add_bf16(const void* a, const void* b, void* out, long long n_elems, cudaStream_t s);
 
 

@@ -254,10 +254,11 @@ void choose_wgrad_splits(int n_heavy, int n_light, long long total_tiles, int nu
 
 // param_grad[idx[e]] += packed[e]  (idx < 0: padding).  The packing index is injective on real entries.
 __global__ void scatter_add_kernel(float* __restrict__ param_grad, const int* __restrict__ idx,
-                                   const int* __restrict__ idx2, const float* __restrict__ packed, long long n) {
+                                   const int* __restrict__ idx2, const float* __restrict__ packed, long long n,
+                                   float scale) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float v = packed[i];
+  const float v = packed[i] * scale;
   const int a = idx[i];
   if (a >= 0) atomicAdd(param_grad + a, v);
   if (idx2) {
@@ -267,9 +268,10 @@ __global__ void scatter_add_kernel(float* __restrict__ param_grad, const int* __
 }
 
 int launch_scatter_add(float* param_grad, const int* idx, const int* idx2, const float* packed, long long n,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, float scale) {
   if (n == 0) return 0;
-  scatter_add_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(param_grad, idx, idx2, packed, n);
+  scatter_add_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(param_grad, idx, idx2, packed, n,
+                                                                                 scale);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -58,6 +58,6 @@ int sort_wgrad_jobs(WgJob* jobs, int n);
 // Picks the split counts (heavy / light) minimising waves x tiles-per-split on num_sms / 2 cluster slots.
 void choose_wgrad_splits(int n_heavy, int n_light, long long total_tiles, int num_sms, int* s_heavy, int* s_light);
 int launch_scatter_add(float* param_grad, const int* idx, const int* idx2, const float* packed, long long n,
-                       cudaStream_t stream);
+                       cudaStream_t stream, float scale = 1.f);
 
 }  // namespace pvsr

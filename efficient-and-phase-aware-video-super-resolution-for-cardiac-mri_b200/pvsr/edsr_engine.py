@@ -1,0 +1,449 @@
+"""Host-side runtime of EDSRNet (reference src/model/nets/edsr_net.py:8-71) on the RefineNet
+conv core: every convolution of the net - head 1 -> F, 2R + 1 body convs F -> F, the up-sampler convs F -> r*r*F with
+PixelShuffle as epilogue addressing, tail F -> 1 - and every data / weight gradient is a launch of the tcgen05
+implicit-GEMM kernels behind `pvsr_conv3x3_fwd` / `pvsr_conv3x3_wgrad_staged` (include/pvsr.h):
+
+    head        x (fp32, 1 ch)  -> channel 0 of a zero-padded 64-channel bf16 K block (pvsr_pad_channel_bf16), K = 16
+    resblock i  t_i = relu(conv1(x_i))                      EPI_STORE, relu = 1
+                x_{i+1} = res_scale * conv2(t_i) + x_i      EPI_STORE, out_scale = res_scale, res = x_i
+    body.conv   u_0 = conv(x_R) + head                      EPI_STORE, res = head
+    up-sampler  u_{k+1} = PixelShuffle_r(conv(u_k))         EPI_PS (columns grouped per sub-pixel)
+    tail        out = conv(u_last)                          EPI_STORE, N = 64 tile of which 16 fp32 columns are stored,
+                                                            column 0 is the image (pvsr_take_channel0_f32)
+Backward mirrors it with transposed / tap-flipped packs of the same parameters (pack spec `transpose_flip`), the
+ReLU adjoint as a mask on the stored t_i (`mask`), the residual adjoint as `res`, PixelShuffle's adjoint as
+pixel-unshuffled TMA views, and one pixel-reduction wgrad launch per conv whose packed result is scattered into the
+fp32 parameter-layout gradient (`pvsr_scatter_add[_scaled]`).  torch carries device memory, streams and (optionally)
+replays the launch sequence as a CUDA graph; there is no CPU / PyTorch fallback.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import lib as L
+from . import ops
+
+
+def up_factors(upscale_factor):
+    if (math.log(upscale_factor, 2) % 1) == 0:
+        return [2] * int(math.log(upscale_factor, 2))
+    if upscale_factor == 3:
+        return [3]
+    raise NotImplementedError(f'upscale factor {upscale_factor}')
+
+
+def _spec(c_out, c_in, n_src, src_ch, kb, n_total, ps_r=0, ps_ch=0, transpose_flip=0, k_ps_r=0):
+    s = L.PackSpec()
+    s.c_out, s.c_in, s.kh, s.kw, s.n_src = c_out, c_in, 3, 3, n_src
+    s.src_ch, s.kb_per_src, s.taps, s.n_total = src_ch, kb, 9, n_total
+    s.ps_r, s.ps_ch, s.transpose_flip, s.k_ps_r = ps_r, ps_ch, transpose_flip, k_ps_r
+    return s
+
+
+def _tile(n):
+    """(bn, n_tiles_n) of an EPI_STORE launch with n output columns."""
+    return (256, n // 256) if n % 256 == 0 else (64, n // 64)
+
+
+class _Layer:
+    """One Conv2d of the net: parameter names, pack specs / device indices, packed operands."""
+
+    def __init__(self, eng, name, c_in, c_out, kind, r=0):
+        self.name, self.c_in, self.c_out, self.kind, self.r = name, c_in, c_out, kind, r
+        F = eng.F
+        kb = max(1, c_in // 64)
+        if kind == 'head':          # 1 -> F
+            self.fwd = _spec(F, 1, 1, 1, 1, F)
+            self.bwd = None         # no data gradient wrt the input image
+        elif kind == 'body':        # F -> F
+            self.fwd = _spec(F, F, 1, F, kb, F)
+            self.bwd = _spec(F, F, 1, F, kb, F, transpose_flip=1)
+        elif kind == 'up':          # F -> r*r*F, columns in pixel-shuffle order
+            self.fwd = _spec(F * r * r, F, 1, F, kb, F * r * r, ps_r=r, ps_ch=F)
+            self.bwd = _spec(F * r * r, F, r * r, F, kb, F, transpose_flip=1, k_ps_r=r)
+        else:                       # tail F -> 1 (one real column of a 64-column tile)
+            self.fwd = _spec(1, F, 1, F, kb, 64)
+            self.bwd = _spec(1, F, 1, 1, 1, F, transpose_flip=1)
+        self.n_kb = self.fwd.n_src * 9 * self.fwd.kb_per_src
+        self.n_total = self.fwd.n_total
+        self.idx_w = eng.index(self.fwd, False)
+        self.idx_b = eng.index(self.fwd, True)
+        self.idx_wt = eng.index(self.bwd, False) if self.bwd is not None else None
+        dev = eng.device
+        self.w = torch.empty(self.idx_w.numel() // 64, 64, dtype=torch.bfloat16, device=dev)
+        self.b = torch.empty(self.n_total, dtype=torch.float32, device=dev)
+        self.wt = (torch.empty(self.idx_wt.numel() // 64, 64, dtype=torch.bfloat16, device=dev)
+                   if self.idx_wt is not None else None)
+
+
+class _Geometry:
+    """Buffers and wgrad job scratch of one (N, h, w, train) input geometry."""
+
+    def __init__(self, eng, n, h, w, train):
+        self.n, self.h, self.w, self.train = n, h, w, train
+        F, dev = eng.F, eng.device
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        self.x32 = torch.empty(n, h, w, dtype=torch.float32, device=dev)
+        self.x64 = torch.empty(n, h, w, 64, **bf)
+        n_feat = (2 * eng.R + 2) if train else 3            # head, (t_i, x_{i+1}) per block, u_0 | ping-pong
+        self.feat = [torch.empty(n, h, w, F, **bf) for _ in range(n_feat)]
+        self.sizes = [(h, w)]
+        for r in eng.factors:
+            self.sizes.append((self.sizes[-1][0] * r, self.sizes[-1][1] * r))
+        self.up = [torch.empty(n, hh, ww, F, **bf) for hh, ww in self.sizes[1:]]
+        H, W = self.sizes[-1]
+        self.out16 = torch.empty(n, H, W, 16, dtype=torch.float32, device=dev)
+        self.out = torch.empty(n, 1, H, W, dtype=torch.float32, device=dev)
+        self.graph_fwd = self.graph_bwd = None
+        if train:
+            self.dout = torch.zeros(n, 1, H, W, dtype=torch.float32, device=dev)
+            self.target = torch.empty(n, 1, H, W, dtype=torch.float32, device=dev)
+            self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+            self.g64 = torch.empty(n, H, W, 64, **bf)
+            self.dup = [torch.empty_like(u) for u in self.up]          # gradients wrt u_1 .. u_last
+            self.dfeat = [torch.empty(n, h, w, F, **bf) for _ in range(4)]
+            big = max(l.n_kb * l.n_total * 64 + l.n_total for l in eng.layers)
+            self.dw = torch.zeros(big, dtype=torch.float32, device=dev)
+            sb = L.load().pvsr_wgrad_scratch_bytes()
+            self.jobs = {l.name: torch.empty(sb, dtype=torch.uint8, device=dev) for l in eng.layers}
+            self.jobs_ready = False
+
+
+class EDSREngine:
+    def __init__(self, net):
+        self.net = net
+        self.F, self.R = net.num_features, net.num_resblocks
+        self.factors = up_factors(net.upscale_factor)
+        self.res_scale = float(net.res_scale)
+        self.use_graph = True
+        self.device = None
+        self.layers = None
+        self.geoms = {}
+        self._idx = {}
+        self._packed_version = None
+        self._flat = None
+
+    # ------------------------------------------------------------------------------------------ parameters
+    def index(self, spec, bias):
+        key = (bytes(spec), bias)
+        t = self._idx.get(key)
+        if t is None:
+            t = torch.from_numpy(ops.pack_bias_index(spec) if bias else ops.pack_index(spec)).to(self.device)
+            self._idx[key] = t
+        return t
+
+    def _build_layers(self, device):
+        if self.layers is not None and self.device == device:
+            return
+        self.device = device
+        self._idx, self.geoms, self._packed_version = {}, {}, None
+        F = self.F
+        self.layers = [_Layer(self, 'head.0', 1, F, 'head')]
+        for i in range(self.R):
+            self.layers.append(_Layer(self, f'body.{i}.body.conv1', F, F, 'body'))
+            self.layers.append(_Layer(self, f'body.{i}.body.conv2', F, F, 'body'))
+        self.layers.append(_Layer(self, 'body.conv', F, F, 'body'))
+        for k, r in enumerate(self.factors):
+            self.layers.append(_Layer(self, f'tail.0.conv{k + 1}', F, F * r * r, 'up', r))
+        self.layers.append(_Layer(self, 'tail.conv', F, 1, 'tail'))
+        self.by_name = {l.name: l for l in self.layers}
+
+    def _named(self):
+        return dict(self.net.named_parameters())
+
+    def _param_version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.net.parameters())
+
+    def params_changed(self):
+        self._packed_version = None
+
+    def flatten_parameters(self):
+        """One flat fp32 parameter buffer + one flat gradient buffer (single all-reduce / single Adam kernel), as
+        RefineNetEngine.flatten_parameters."""
+        if self._flat is not None:
+            return self._flat
+        params = list(self.net.parameters())
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                n = p.numel()
+                flat_p[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = flat_p[o:o + n].view(p.shape)
+                p.grad = flat_g[o:o + n].view(p.shape)
+        self._flat = (flat_p, flat_g)
+        self.params_changed()
+        return self._flat
+
+    def _ensure_packed(self):
+        ver = self._param_version()
+        if self._packed_version == ver:
+            return
+        lib, st, P = L.load(), L.current_stream(), self._named()
+        for l in self.layers:
+            w, b = P[l.name + '.weight'], P[l.name + '.bias']
+            if w.dtype != torch.float32 or not w.is_contiguous():
+                raise L.PvsrError(f'{l.name}.weight must be contiguous fp32')
+            L.check(lib.pvsr_pack_weights(L.ptr(w), L.ptr(l.idx_w), None, L.ptr(l.w), l.idx_w.numel(), st), 'pack')
+            L.check(lib.pvsr_gather_f32(L.ptr(b), L.ptr(l.idx_b), L.ptr(l.b), l.idx_b.numel(), st), 'pack bias')
+            if l.wt is not None:
+                L.check(lib.pvsr_pack_weights(L.ptr(w), L.ptr(l.idx_wt), None, L.ptr(l.wt), l.idx_wt.numel(), st),
+                        'pack^T')
+        self._packed_version = ver
+
+    # ------------------------------------------------------------------------------------------ geometry
+    def geometry(self, x, train):
+        if not x.is_cuda:
+            raise L.PvsrError('EDSRNet (B200) runs on CUDA only; there is no CPU fallback - move inputs to cuda')
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise ValueError(f'expected an input of shape (N, 1, h, w), got {tuple(x.shape)}')
+        self._build_layers(x.device)
+        n, _, h, w = x.shape
+        key = (n, h, w, bool(train))
+        g = self.geoms.get(key)
+        if g is None:
+            g = _Geometry(self, n, h, w, train)
+            self.geoms[key] = g
+        return g
+
+    # ------------------------------------------------------------------------------------------ launches
+    def _conv(self, src, layer, out, relu=0, res=None, scale=0.0):
+        bn, nt = _tile(self.F)
+        ops.conv3x3(src, [0], src.shape[0], layer.w, bn, epi=L.EPI_STORE, kb_per_src=layer.fwd.kb_per_src,
+                    k16_last=1 if layer.kind == 'head' else 4, bias=layer.b, n_tiles_n=nt, out_bf16=out, res=res,
+                    relu=relu, out_scale=scale)
+
+    def _forward_launches(self, g):
+        lib, st = L.load(), L.current_stream()
+        F, R, by = self.F, self.R, self.by_name
+        n_px = g.n * g.h * g.w
+        L.check(lib.pvsr_pad_channel_bf16(L.ptr(g.x32), L.ptr(g.x64), n_px, st), 'pad_channel')
+        feat = g.feat
+        self._conv(g.x64, by['head.0'], feat[0])
+        # training keeps every activation (x_0 = head = feat[0], t_i = feat[1 + 2i], x_{i+1} = feat[2 + 2i], u_0 last);
+        # inference needs three buffers: head (read again by body.conv's residual), x and t.  x_{i+1} overwrites x_i
+        # in place for i >= 1: conv2 reads t, and x_i only enters as the residual of the very pixel a thread stores.
+        cur = 0                                              # index of x_i in feat
+        for i in range(R):
+            t = feat[1 + 2 * i] if g.train else feat[2]
+            nxt = feat[2 + 2 * i] if g.train else feat[1]
+            self._conv(feat[cur], by[f'body.{i}.body.conv1'], t, relu=1)
+            self._conv(t, by[f'body.{i}.body.conv2'], nxt, res=feat[cur], scale=self.res_scale)
+            cur = 2 + 2 * i if g.train else 1
+        u0 = feat[2 * R + 1] if g.train else feat[2]
+        self._conv(feat[cur], by['body.conv'], u0, res=feat[0])
+        g.u0 = u0
+        src = u0
+        for k, r in enumerate(self.factors):
+            l = by[f'tail.0.conv{k + 1}']
+            bn = 256 if r == 2 else 192
+            ops.conv3x3(src, [0], g.n, l.w, bn, epi=L.EPI_PS, kb_per_src=l.fwd.kb_per_src, bias=l.b,
+                        n_tiles_n=l.n_total // bn, out_bf16=g.up[k], ps_r=r)
+            src = g.up[k]
+        l = by['tail.conv']
+        ops.conv3x3(src, [0], g.n, l.w, 64, epi=L.EPI_STORE, kb_per_src=l.fwd.kb_per_src, bias=l.b, n_tiles_n=1,
+                    out_f32=g.out16, out_ch=16, n_store=16)
+        H, W = g.sizes[-1]
+        L.check(lib.pvsr_take_channel0_f32(L.ptr(g.out16), 16, L.ptr(g.out), g.n * H * W, st), 'take_channel0')
+
+    def _wgrad(self, g, layer, x_view, dy_views, out_hw, grads, scale=1.0):
+        """Weight + bias gradient of `layer`: X = x_view (tensor), dY chunks over `dy_views` [(tensor, mul)] given as
+        (view, img_base, ch0, off_x, off_y) tuples in packed-column order; accumulated into grads[name]."""
+        lib, st = L.load(), L.current_stream()
+        views = [(x_view, 1)] + dy_views[0]
+        d = L.WgradDesc()
+        d.H, d.W = out_hw
+        d.n_img = g.n
+        d.n_views = len(views)
+        for i, (t, mul) in enumerate(views):
+            d.views[i].ptr = t.data_ptr()
+            d.views[i].channels = t.shape[3]
+            d.views[i].H, d.views[i].W = t.shape[1], t.shape[2]
+            d.views[i].images = t.shape[0]
+            d.views[i].mul = mul
+        d.n_src = 1
+        d.src_view[0] = 0
+        d.n_dy = len(dy_views[1])
+        for i, (v, base, ch0, ox, oy) in enumerate(dy_views[1]):
+            d.dy_view[i], d.dy_img_base[i], d.dy_ch0[i], d.dy_off_x[i], d.dy_off_y[i] = v, base, ch0, ox, oy
+        d.kb_per_src, d.taps, d.n_total, d.with_bias, d.n_splits = layer.fwd.kb_per_src, 9, layer.n_total, 1, 0
+        n_w = layer.n_kb * layer.n_total * 64
+        dw, db = g.dw[:n_w], g.dw[n_w:n_w + layer.n_total]
+        d.dw_packed, d.db_packed = dw.data_ptr(), db.data_ptr()
+        d.job_scratch = g.jobs[layer.name].data_ptr()
+        if not g.jobs_ready:
+            L.check(lib.pvsr_conv3x3_wgrad_staged(C.byref(d), 1, st), 'wgrad job upload')
+            return
+        g.dw[:n_w + layer.n_total].zero_()
+        L.check(lib.pvsr_conv3x3_wgrad_staged(C.byref(d), 0, st), 'wgrad')
+        gw, gb = grads[layer.name + '.weight'], grads[layer.name + '.bias']
+        L.check(lib.pvsr_scatter_add_scaled(L.ptr(gw), L.ptr(layer.idx_w), L.ptr(dw), n_w, scale, st), 'scatter w')
+        L.check(lib.pvsr_scatter_add_scaled(L.ptr(gb), L.ptr(layer.idx_b), L.ptr(db), layer.n_total, scale, st),
+                'scatter b')
+
+    def _dgrad(self, src, layer, out, mask=None, res=None, scale=0.0, views=None, srcs=None, kb=None, k16_last=4):
+        bn, nt = _tile(self.F)
+        ops.conv3x3(views if views is not None else src, srcs if srcs is not None else [0], out.shape[0], layer.wt, bn,
+                    epi=L.EPI_STORE, kb_per_src=kb if kb is not None else layer.bwd.kb_per_src, k16_last=k16_last,
+                    n_tiles_n=nt, out_bf16=out, res=res, mask=mask, out_scale=scale,
+                    out_hw=(out.shape[1], out.shape[2]))
+
+    def _chunks(self, view, r=1):
+        """dY chunk list of an F-channel gradient tensor: plain (r = 1) or per sub-pixel of a pixel-unshuffled view."""
+        cb = self.F // 64
+        if r == 1:
+            return [(view, 0, c * 64, 0, 0) for c in range(cb)]
+        return [(view, 0, c * 64, q % r, q // r) for q in range(r * r) for c in range(cb)]
+
+    def _backward_launches(self, g, grads):
+        """Gradients of everything wrt g.dout, accumulated into `grads` ({name: fp32 tensor}).  Called once with
+        g.jobs_ready = False to stage the wgrad job lists (no launches), then for real."""
+        lib, st = L.load(), L.current_stream()
+        R, by, s = self.R, self.by_name, self.res_scale
+        H, W = g.sizes[-1]
+        stage_only = not g.jobs_ready
+        if not stage_only:
+            L.check(lib.pvsr_pad_channel_bf16(L.ptr(g.dout), L.ptr(g.g64), g.n * H * W, st), 'pad_channel(dout)')
+        # tail conv
+        l = by['tail.conv']
+        self._wgrad(g, l, g.up[-1], ([(g.g64, 1)], [(1, 0, 0, 0, 0)]), (H, W), grads)
+        if not stage_only:
+            self._dgrad(g.g64, l, g.dup[-1], kb=1, k16_last=1)
+        # up-sampler, last to first
+        for k in reversed(range(len(self.factors))):
+            r = self.factors[k]
+            l = by[f'tail.0.conv{k + 1}']
+            x_in = g.up[k - 1] if k > 0 else g.u0
+            self._wgrad(g, l, x_in, ([(g.dup[k], r)], self._chunks(1, r)), g.sizes[k], grads)
+            if not stage_only:
+                d_in = g.dup[k - 1] if k > 0 else g.dfeat[3]
+                self._dgrad(None, l, d_in, views=[(g.dup[k], r)],
+                            srcs=[(0, 0, 0, q % r, q // r) for q in range(r * r)])
+        du0 = g.dfeat[3]
+        # body.conv: u_0 = conv(x_R) + head
+        l = by['body.conv']
+        self._wgrad(g, l, g.feat[2 * R], ([(du0, 1)], self._chunks(1)), (g.h, g.w), grads)
+        a, b, t = g.dfeat[0], g.dfeat[1], g.dfeat[2]
+        if not stage_only:
+            self._dgrad(du0, l, a)
+        for i in reversed(range(R)):
+            x_i, t_i = g.feat[2 * i], g.feat[1 + 2 * i]
+            l2, l1 = by[f'body.{i}.body.conv2'], by[f'body.{i}.body.conv1']
+            # x_{i+1} = s * conv2(t_i) + x_i;  t_i = relu(conv1(x_i))
+            self._wgrad(g, l2, t_i, ([(a, 1)], self._chunks(1)), (g.h, g.w), grads, scale=s)
+            if not stage_only:
+                self._dgrad(a, l2, t, mask=t_i, scale=s)
+            self._wgrad(g, l1, x_i, ([(t, 1)], self._chunks(1)), (g.h, g.w), grads)
+            if not stage_only:
+                self._dgrad(t, l1, b, res=a)
+            a, b = b, a
+        # head: its output feeds block 0 (gradient in `a`) and body.conv's residual (du0)
+        if not stage_only:
+            L.check(lib.pvsr_add_bf16(L.ptr(a), L.ptr(du0), L.ptr(t), a.numel(), st), 'add_bf16')
+        # the dY buffer of the head wgrad is `t` whatever the parity of R (a/b swap only between dfeat[0] and [1])
+        self._wgrad(g, by['head.0'], g.x64, ([(t, 1)], self._chunks(1)), (g.h, g.w), grads)
+
+    # ------------------------------------------------------------------------------------------ public
+    def _replay(self, g, which, fn):
+        """Runs `fn` eagerly the first two times (warm-up: lazy attribute setup inside the library must not happen
+        under capture), then captures it into a CUDA graph and replays."""
+        attr = 'graph_' + which
+        state = getattr(g, attr)
+        if not self.use_graph:
+            fn()
+            return
+        if state is None:
+            fn()
+            setattr(g, attr, 1)
+        elif state == 1:
+            fn()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fn()
+            setattr(g, attr, graph)
+        else:
+            state.replay()
+
+    def forward(self, x, train=False, clone=True):
+        g = self.geometry(x, train)
+        self._ensure_packed()
+        g.x32.copy_(x.reshape(g.n, g.h, g.w))
+        self._replay(g, 'fwd', lambda: self._forward_launches(g))
+        return (g.out.clone() if clone else g.out), g
+
+    def backward(self, g, grads):
+        """Backward of the last forward(train=True) of geometry `g`; g.dout holds dL/d(out)."""
+        if not g.jobs_ready:
+            self._backward_launches(g, grads)           # stages the wgrad job lists only
+            g.jobs_ready = True
+        key = tuple(t.data_ptr() for t in grads.values())
+        if getattr(g, 'bwd_key', None) != key:          # a captured graph writes to the buffers it was captured with
+            g.bwd_key, g.graph_bwd = key, None
+        self._replay(g, 'bwd', lambda: self._backward_launches(g, grads))
+
+    def grad_buffers(self):
+        if getattr(self, '_grad_buf', None) is None:
+            self._grad_buf = {k: torch.zeros_like(p) for k, p in self._named().items()}
+        return self._grad_buf
+
+    def loss_and_grads(self, x, target, zero_grads=True):
+        """Fused training-step body: forward, nn.L1Loss(output, target) (acdc_sisr_trainer.py:27-37 with the L1Loss
+        of configs/train/edsr_net/exp1_x4.yaml:44-46) and backward into `p.grad`.  Returns (loss, output)."""
+        out, g = self.forward(x, train=True, clone=False)
+        g.target.copy_(target.reshape(g.target.shape))
+        n = g.out.numel()
+        key = ('lw', n)
+        w = getattr(self, '_lw', {}).get(key)
+        if w is None:
+            self._lw = getattr(self, '_lw', {})
+            w = self._lw[key] = torch.tensor([1.0 / n], dtype=torch.float32, device=self.device)
+        g.loss.zero_()
+        L.check(L.load().pvsr_l1_multistage(L.ptr(g.out), L.ptr(g.target), L.ptr(w), 1, n, L.ptr(g.loss),
+                                            L.ptr(g.dout), L.current_stream()), 'pvsr_l1_multistage')
+        grads = {}
+        for k, p in self._named().items():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            grads[k] = p.grad
+        if zero_grads:
+            if self._flat is not None:
+                self._flat[1].zero_()
+            else:
+                for t in grads.values():
+                    t.zero_()
+        self.backward(g, grads)
+        return g.loss.clone(), out
+
+
+class _EDSRFunction(torch.autograd.Function):
+    """Autograd bridge: `net(input)` in training mode is differentiable wrt the parameters, so the reference's SISR
+    trainer sequence (acdc_sisr_trainer.py / base_trainer.py: any torch loss, loss.backward(), any torch optimiser)
+    works unchanged; the input image receives no gradient (the reference never asks for one)."""
+
+    @staticmethod
+    def forward(ctx, engine, x, names, *params):
+        out, g = engine.forward(x, train=True, clone=True)
+        ctx.engine, ctx.g, ctx.names = engine, g, names
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        engine, g = ctx.engine, ctx.g
+        g.dout.copy_(grad_out.reshape(g.dout.shape))
+        bufs = engine.grad_buffers()
+        for b in bufs.values():
+            b.zero_()
+        engine.backward(g, bufs)
+        return (None, None, None) + tuple(bufs[k].clone() for k in ctx.names)
+
+
+def edsr_train_forward(net, x):
+    named = list(net.named_parameters())
+    return _EDSRFunction.apply(net.engine, x.detach(), tuple(k for k, _ in named), *[p for _, p in named])

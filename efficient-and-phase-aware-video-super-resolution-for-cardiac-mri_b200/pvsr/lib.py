@@ -23,7 +23,7 @@ class PackSpec(C.Structure):
     _fields_ = [("c_out", c_int), ("c_in", c_int), ("kh", c_int), ("kw", c_int), ("n_src", c_int),
                 ("src_ch_off", c_int * MAX_SRC), ("src_ch", c_int), ("kb_per_src", c_int), ("taps", c_int),
                 ("n_total", c_int), ("ps_r", c_int), ("transpose_flip", c_int), ("k_ps_r", c_int),
-                ("src_col_off", c_int * MAX_SRC)]
+                ("src_col_off", c_int * MAX_SRC), ("ps_ch", c_int)]
 
 
 class ActView(C.Structure):
@@ -41,10 +41,11 @@ class ConvDesc(C.Structure):
                 ("bias", c_void_p), ("out_bf16", c_void_p), ("out_f32", c_void_p), ("res", c_void_p),
                 ("posterm", c_void_p), ("out_ch", c_int), ("n_store", c_int), ("ps_r", c_int),
                 ("grad0", c_void_p), ("grad1", c_void_p), ("grad_split", c_int),
-                ("c_in", c_void_p), ("c_out", c_void_p), ("h_out", c_void_p), ("gates_out", c_void_p)]
+                ("c_in", c_void_p), ("c_out", c_void_p), ("h_out", c_void_p), ("gates_out", c_void_p),
+                ("relu", c_int), ("mask", c_void_p), ("out_scale", C.c_float)]
 
 
-MAX_DY = 9
+MAX_DY = 36
 
 
 class WgradDesc(C.Structure):
@@ -104,10 +105,14 @@ SIGNATURES = {
     "pvsr_in_conv_prelu_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                        c_void_p]),
     "pvsr_conv3x3_fwd": (c_int, [C.POINTER(ConvDesc), c_void_p]),
+    "pvsr_scatter_add_scaled": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.c_float, c_void_p]),
     "pvsr_lstm_state_elems": (c_int64, [c_int64, c_int, c_int]),
     "pvsr_lstm_tile_geometry": (c_int, [c_int, c_int, C.POINTER(c_int), C.POINTER(c_int)]),
     "pvsr_wgrad_scratch_bytes": (c_int64, []),
     "pvsr_conv3x3_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
+    "pvsr_conv3x3_wgrad_staged": (c_int, [C.POINTER(WgradDesc), c_int, c_void_p]),
+    "pvsr_pad_channel_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "pvsr_take_channel0_f32": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "pvsr_scatter_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "pvsr_refine_posterm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_int, c_void_p]),

@@ -79,6 +79,7 @@ typedef struct pvsr_pack_spec {
                    (sources = sub-pixels of a pixel-unshuffled gradient); 0 = src_ch_off[s] + ic */
   int src_col_off[PVSR_MAX_SRC]; /* transpose_flip only: column n of source s is parameter input channel
                    n + src_col_off[s] (window gather of the refine conv1 data gradient) */
+  int ps_ch;    /* ps_r > 0: channels per shuffled pixel (0 = 64): column q*ps_ch + c is channel c*r*r + q */
 } pvsr_pack_spec;
 int64_t pvsr_pack_index_count(const pvsr_pack_spec* spec);
 int pvsr_pack_index_host(const pvsr_pack_spec* spec, int32_t* idx_host);
@@ -147,13 +148,17 @@ typedef struct pvsr_conv_desc {
   float* c_out;
   void* h_out;             /* bf16 [n_img][H][W][64] */
   void* gates_out;         /* optional bf16 [tiles][256][128] */
+  /* PVSR_EPI_STORE extras (EDSR residual blocks, edsr_net.py:44-58) */
+  int relu;                /* 1: max(x, 0) after the bias (conv1 + relu1) */
+  const void* mask;        /* bf16, shape of out_bf16: result zeroed where mask <= 0 (adjoint of relu1), or NULL */
+  float out_scale;         /* (acc + bias) * out_scale before relu / mask / residual; 0 = 1 (res_scale, :56) */
 } pvsr_conv_desc;
 int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream);
 /* Weight (+ bias) gradient of a conv described like pvsr_conv_desc: X sources (source, tap, channel block) against
  * the output gradient dY given as `n_dy` 64-column chunks (views; pixel-unshuffled views for conv+PixelShuffle).
  * Result: fp32, ACCUMULATED, in the layout of the forward packed operand [n_src*taps*kb_per_src][n_total][64]
  * (scatter to the parameter with the packing index: pvsr_scatter_add) and [n_total] for the bias. */
-#define PVSR_MAX_DY 9
+#define PVSR_MAX_DY 36
 typedef struct pvsr_wgrad_desc {
   int H, W;
   int64_t n_img;
@@ -182,9 +187,21 @@ typedef struct pvsr_wgrad_desc {
 } pvsr_wgrad_desc;
 int64_t pvsr_wgrad_scratch_bytes(void);
 int pvsr_conv3x3_wgrad(const pvsr_wgrad_desc* d, void* stream);
+/* Two-phase form for CUDA-graph capture: upload = 1 builds the job list and copies it to d->job_scratch
+ * (synchronises the stream; call once, outside capture); upload = 0 launches against the jobs already resident in
+ * d->job_scratch (no host<->device traffic, capturable).  The descriptor must be identical in both calls. */
+int pvsr_conv3x3_wgrad_staged(const pvsr_wgrad_desc* d, int upload, void* stream);
+/* x fp32 [n] -> out bf16 [n][64] with channel 0 = x and channels 1..63 = 0: single-channel images / gradients as a
+ * 64-channel K block of the tensor-core conv (EDSR head conv edsr_net.py:29 and the adjoint of its tail conv :33). */
+int pvsr_pad_channel_bf16(const float* x, void* out_bf16, int64_t n, void* stream);
+/* in fp32 [n][stride] -> out fp32 [n] = in[:, 0]  (channel 0 of a 16-column conv output). */
+int pvsr_take_channel0_f32(const float* in, int stride, float* out, int64_t n, void* stream);
 /* param_grad[idx[e]] += packed[e] for idx[e] >= 0 (idx2 optional second target). */
 int pvsr_scatter_add(float* param_grad, const int32_t* idx, const int32_t* idx2, const float* packed, int64_t n,
                      void* stream);
+/* param_grad[idx[e]] += scale * packed[e]  (gradient of a conv whose output is multiplied by res_scale). */
+int pvsr_scatter_add_scaled(float* param_grad, const int32_t* idx, const float* packed, int64_t n, float scale,
+                            void* stream);
 
 /* ---- input pipeline: batches cut out of HBM-resident cine volumes --------------------------------
  * Replaces, per batch, AcdcVSRRefineNetDataset.__getitem__ (src/data/datasets/acdc_vsr_refinenet_dataset.py:49-89:
