@@ -1,4 +1,6 @@
 from .base_logger import BaseLogger
 from .acdc_vsr_logger import AcdcVSRLogger
 
-__all__ = ['BaseLogger', 'AcdcVSRLogger']
+from .acdc_sisr_logger import AcdcSISRLogger, Dsb15SISRLogger
+
+__all__ = ['BaseLogger', 'AcdcVSRLogger', 'AcdcSISRLogger', 'Dsb15SISRLogger']

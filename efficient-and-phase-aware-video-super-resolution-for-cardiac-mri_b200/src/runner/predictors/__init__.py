@@ -2,4 +2,7 @@
 from .base_predictor import BasePredictor
 from .acdc_vsr_refinenet_predictor import AcdcVSRRefineNetPredictor, Dsb15VSRRefineNetPredictor
 
-__all__ = ['BasePredictor', 'AcdcVSRRefineNetPredictor', 'Dsb15VSRRefineNetPredictor']
+from .acdc_sisr_predictor import AcdcSISRPredictor, Dsb15SISRPredictor
+
+__all__ = ['BasePredictor', 'AcdcVSRRefineNetPredictor', 'Dsb15VSRRefineNetPredictor', 'AcdcSISRPredictor',
+           'Dsb15SISRPredictor']

@@ -1,0 +1,107 @@
+"""Test loop of the single-image nets (reference src/runner/predictors/acdc_sisr_predictor.py:14-170).
+
+Per frame: SR = net(lr), the configured losses, PSNR / SSIM (/ Cardiac*) on the de-normalised images; optional export
+of a per-frame CSV, one PNG per frame and one GIF per slice.  B200 differences (results identical): frames of equal
+shape are batched into one launch (`frames_per_launch`; the reference runs one frame per iteration), frames are
+sharded over the ranks under torch.distributed, and the scalars of a launch cross PCIe once.
+"""
+import csv
+import functools
+import logging
+from pathlib import Path
+
+import torch
+
+from pvsr import parallel
+from src.utils import denormalize
+from .acdc_vsr_refinenet_predictor import AcdcVSRRefineNetPredictor, _write_png
+from .base_predictor import BasePredictor
+
+
+class AcdcSISRPredictor(BasePredictor):
+    dataset_name = 'acdc'
+
+    def __init__(self, saved_dir=None, exported=False, frames_per_launch=32, **kwargs):
+        super().__init__(**kwargs)
+        if self.test_dataloader.batch_size != 1:
+            raise ValueError(f'The testing batch size should be 1. Got {self.test_dataloader.batch_size}.')
+        self.exported = exported
+        if exported:
+            self.saved_dir = Path(saved_dir)
+        self.frames_per_launch = max(1, int(frames_per_launch))
+        self._denormalize = functools.partial(denormalize, dataset=self.dataset_name)
+
+    def _name(self, index):
+        filename = Path(self.test_dataloader.dataset.data[index][0]).parts[-1].split('.')[0]
+        patient, _, sid, fid = filename.split('_')
+        return filename, patient, sid, fid
+
+    def predict(self):
+        self.net.eval()
+        dataset = self.test_dataloader.dataset
+        mine = parallel.shard_indices(len(dataset), self.rank, self.world)
+        names = [fn.__class__.__name__ for fn in self.metric_fns + self.loss_fns]
+        log, count, rows, frames = self._init_log(), 0, [], {}
+
+        def flush(items):
+            nonlocal count
+            lr = torch.stack([it['lr_img'] for _, it in items]).to(self.device, non_blocking=True)
+            hr = torch.stack([it['hr_img'] for _, it in items]).to(self.device, non_blocking=True)
+            with torch.no_grad():
+                sr = self.net(lr)
+                srd, hrd = self._denormalize(sr), self._denormalize(hr)
+                vals = []
+                for n, (index, _) in enumerate(items):
+                    patient = self._name(index)[1]
+                    a, b = srd[n:n + 1], hrd[n:n + 1]
+                    for fn in self.metric_fns:
+                        vals.append(fn(a, b, patient) if 'Cardiac' in fn.__class__.__name__ else fn(a, b))
+                    vals.extend(fn(sr[n:n + 1], hr[n:n + 1]) for fn in self.loss_fns)
+                flat = torch.stack([v.float() for v in vals]).cpu().view(len(items), -1)
+                imgs = srd[:, 0].to(torch.uint8).cpu().numpy() if self.exported else None
+            nm = len(self.metric_fns)
+            for n, (index, _) in enumerate(items):
+                metrics, losses = flat[n, :nm], flat[n, nm:]
+                log['Loss'] += float((losses * self.loss_weights.cpu()).sum())
+                for fn, v in zip(self.loss_fns, losses.tolist()):
+                    log[fn.__class__.__name__] += v
+                for fn, v in zip(self.metric_fns, metrics.tolist()):
+                    log[fn.__class__.__name__] += v
+                count += 1
+                if self.exported:
+                    filename, patient, sid, fid = self._name(index)
+                    rows.append([filename, *metrics.tolist(), *losses.tolist()])
+                    idir = self.saved_dir / 'imgs' / patient
+                    idir.mkdir(parents=True, exist_ok=True)
+                    _write_png(idir / f'{sid}_{fid}.png', imgs[n])
+                    frames.setdefault((patient, sid), []).append((fid, imgs[n]))
+
+        pending = {}
+        for index in mine:
+            item = dataset[index]
+            key = tuple(item['lr_img'].shape)
+            pending.setdefault(key, []).append((index, item))
+            if len(pending[key]) == self.frames_per_launch:
+                flush(pending.pop(key))
+        for items in pending.values():
+            flush(items)
+
+        log, count = parallel.reduce_log(log, count, self.device)
+        if self.exported:
+            for (patient, sid), fs in frames.items():          # one GIF per slice (reference :70-77)
+                vdir = self.saved_dir / 'videos' / patient
+                vdir.mkdir(parents=True, exist_ok=True)
+                AcdcVSRRefineNetPredictor._dump_video(self, vdir / (sid.replace('slice', 'sequence') + '.gif'),
+                                                      [img for _, img in sorted(fs, key=lambda f: f[0])])
+            rows = AcdcVSRRefineNetPredictor._gather_rows(self, rows)
+            if self.rank == 0:
+                self.saved_dir.mkdir(parents=True, exist_ok=True)
+                with open(self.saved_dir / 'results.csv', 'w', newline='') as f:
+                    csv.writer(f).writerows([['name'] + names] + sorted(rows, key=lambda r: r[0]))
+        log = {k: v / max(count, 1) for k, v in log.items()}
+        logging.info(f'Test log: {log}.')
+        return log
+
+
+class Dsb15SISRPredictor(AcdcSISRPredictor):
+    dataset_name = 'dsb15'

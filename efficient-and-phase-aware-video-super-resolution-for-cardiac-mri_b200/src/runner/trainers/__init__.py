@@ -2,4 +2,6 @@
 from .base_trainer import BaseTrainer
 from .acdc_vsr_refinenet_trainer import AcdcVSRRefineNetTrainer, Dsb15VSRRefineNetTrainer
 
-__all__ = ['BaseTrainer', 'AcdcVSRRefineNetTrainer', 'Dsb15VSRRefineNetTrainer']
+from .acdc_sisr_trainer import AcdcSISRTrainer, Dsb15SISRTrainer
+
+__all__ = ['BaseTrainer', 'AcdcVSRRefineNetTrainer', 'Dsb15VSRRefineNetTrainer', 'AcdcSISRTrainer', 'Dsb15SISRTrainer']
