@@ -317,7 +317,8 @@ int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream) {
                     "conv3x3");
 }
 
-int64_t pvsr_wgrad_scratch_bytes(void) { return 256 * static_cast<int64_t>(sizeof(WgJob)); }
+constexpr int kMaxWgJobs = 1024;
+int64_t pvsr_wgrad_scratch_bytes(void) { return kMaxWgJobs * static_cast<int64_t>(sizeof(WgJob)); }
 
 int pvsr_conv3x3_wgrad(const pvsr_wgrad_desc* d, void* stream) {
   int rc = pvsr_conv3x3_wgrad_staged(d, 1, stream);
@@ -333,8 +334,13 @@ int pvsr_take_channel0_f32(const float* in, int stride, float* out, int64_t n, v
 }
 
 int pvsr_conv3x3_wgrad_staged(const pvsr_wgrad_desc* d, int upload, void* stream) {
+  return pvsr_conv3x3_wgrad_multi(d, 1, upload, stream);
+}
+
+int pvsr_conv3x3_wgrad_multi(const pvsr_wgrad_desc* descs, int n_desc, int upload, void* stream) {
+  if (n_desc < 1) return set_error(-2, "no wgrad descriptors");
+  const pvsr_wgrad_desc* d = &descs[0];
   if (d->n_views < 1 || d->n_views > kMaxMaps) return set_error(-2, "n_views out of range");
-  if (d->n_src < 1 || d->n_src > kMaxSrc || d->n_dy < 1 || d->n_dy > PVSR_MAX_DY) return set_error(-2, "bad source count");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   WgParams p{};
   p.H = d->H; p.W = d->W;
@@ -352,20 +358,33 @@ int pvsr_conv3x3_wgrad_staged(const pvsr_wgrad_desc* d, int upload, void* stream
     int rc = make_act_tmap(&maps.act[v], a.ptr, a.channels, a.W, a.H, a.images, tw, th, a.mul);
     if (rc) return set_error(rc, "tensor map encode failed (%d)", rc);
   }
-  std::vector<WgSource> srcs;
-  for (int i = 0; i < d->n_src; ++i) {
-    const int v = d->src_view[i];
-    srcs.push_back(WgSource{SrcView{v, d->src_img_base[i], d->src_ch0[i], d->views[v].mul, d->src_off_x[i], d->src_off_y[i]}});
-  }
-  std::vector<WgChunk> chunks;
-  for (int i = 0; i < d->n_dy; ++i) {
-    const int v = d->dy_view[i];
-    chunks.push_back(WgChunk{SrcView{v, d->dy_img_base[i], d->dy_ch0[i], d->views[v].mul, d->dy_off_x[i], d->dy_off_y[i]}, 64 * i});
-  }
+  // every descriptor = one conv; all share descs[0]'s views / geometry, results are addressed relative to
+  // descs[0].dw_packed (one launch reduces the weight gradients of many layers: few jobs per layer would otherwise
+  // force many pixel splits, each paying a full red.add of its accumulator tile)
   std::vector<WgJob> jobs;
-  build_wgrad_jobs(srcs, d->kb_per_src, d->taps, chunks, d->n_total, d->with_bias != 0, 0,
-                   d->with_bias ? static_cast<long long>(d->db_packed - d->dw_packed) : 0, &jobs);
-  if (jobs.size() > 256) return set_error(-2, "too many wgrad jobs");
+  for (int k = 0; k < n_desc; ++k) {
+    const pvsr_wgrad_desc* e = &descs[k];
+    if (e->n_src < 1 || e->n_src > kMaxSrc || e->n_dy < 1 || e->n_dy > PVSR_MAX_DY)
+      return set_error(-2, "bad source count in wgrad descriptor %d", k);
+    if (e->H != d->H || e->W != d->W || e->n_img != d->n_img)
+      return set_error(-2, "wgrad descriptor %d differs in geometry from descriptor 0", k);
+    std::vector<WgSource> srcs;
+    for (int i = 0; i < e->n_src; ++i) {
+      const int v = e->src_view[i];
+      if (v < 0 || v >= d->n_views) return set_error(-2, "src_view out of range");
+      srcs.push_back(WgSource{SrcView{v, e->src_img_base[i], e->src_ch0[i], d->views[v].mul, e->src_off_x[i], e->src_off_y[i]}});
+    }
+    std::vector<WgChunk> chunks;
+    for (int i = 0; i < e->n_dy; ++i) {
+      const int v = e->dy_view[i];
+      if (v < 0 || v >= d->n_views) return set_error(-2, "dy_view out of range");
+      chunks.push_back(WgChunk{SrcView{v, e->dy_img_base[i], e->dy_ch0[i], d->views[v].mul, e->dy_off_x[i], e->dy_off_y[i]}, 64 * i});
+    }
+    build_wgrad_jobs(srcs, e->kb_per_src, e->taps, chunks, e->n_total, e->with_bias != 0,
+                     static_cast<long long>(e->dw_packed - d->dw_packed),
+                     e->with_bias ? static_cast<long long>(e->db_packed - d->dw_packed) : 0, &jobs);
+  }
+  if (jobs.size() > static_cast<size_t>(kMaxWgJobs)) return set_error(-2, "too many wgrad jobs (%d)", static_cast<int>(jobs.size()));
   p.n_heavy = sort_wgrad_jobs(jobs.data(), static_cast<int>(jobs.size()));
   if (upload) {
     int e = cudaMemcpyAsync(d->job_scratch, jobs.data(), jobs.size() * sizeof(WgJob), cudaMemcpyHostToDevice, s);
@@ -383,6 +402,11 @@ int pvsr_conv3x3_wgrad_staged(const pvsr_wgrad_desc* d, int upload, void* stream
   p.jobs = static_cast<const WgJob*>(d->job_scratch);
   p.grad = d->dw_packed;
   return check_cuda(launch_wgrad(maps, p, s), "wgrad");
+}
+
+int pvsr_run_table(const pvsr_table_job* jobs_dev, int n_jobs, int64_t max_n, void* stream) {
+  if (n_jobs < 0 || n_jobs > 65535) return set_error(-2, "table job count out of range");
+  return check_cuda(launch_table(jobs_dev, n_jobs, max_n, static_cast<cudaStream_t>(stream)), "run_table");
 }
 
 int pvsr_scatter_add(float* param_grad, const int32_t* idx, const int32_t* idx2, const float* packed, int64_t n,

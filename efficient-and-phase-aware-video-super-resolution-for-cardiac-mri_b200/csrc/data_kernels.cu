@@ -97,4 +97,44 @@ int launch_take_channel0(const float* in, int stride, float* out, long long n, c
   return static_cast<int>(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Table-driven pack / gather / scatter (include/pvsr.h: pvsr_table_job): blockIdx.y = job, blockIdx.x grid-strides over
+// the job's elements.  One launch per training step replaces one pack + one bias gather + one transposed pack per
+// layer (EDSR: 207 launches) resp. two scatters per layer.
+__global__ void __launch_bounds__(256) table_kernel(const pvsr_table_job* __restrict__ jobs) {
+  const pvsr_table_job j = jobs[blockIdx.y];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int* __restrict__ idx = j.idx;
+  const float* __restrict__ src = static_cast<const float*>(j.src);
+  if (j.kind == PVSR_TJ_PACK) {
+    // 2 consecutive elements per thread -> one 4-byte bf16x2 store (n is a multiple of 64)
+    __nv_bfloat162* __restrict__ dst = static_cast<__nv_bfloat162*>(j.dst);
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; 2 * e < j.n; e += stride) {
+      const int2 i2 = reinterpret_cast<const int2*>(idx)[e];
+      const float a = i2.x >= 0 ? __ldg(src + i2.x) : 0.f;
+      const float b = i2.y >= 0 ? __ldg(src + i2.y) : 0.f;
+      dst[e] = __floats2bfloat162_rn(a, b);
+    }
+  } else if (j.kind == PVSR_TJ_GATHER) {
+    float* __restrict__ dst = static_cast<float*>(j.dst);
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < j.n; e += stride) {
+      const int i = idx[e];
+      dst[e] = i >= 0 ? __ldg(src + i) : 0.f;
+    }
+  } else {
+    float* __restrict__ dst = static_cast<float*>(j.dst);
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < j.n; e += stride) {
+      const int i = idx[e];
+      if (i >= 0) atomicAdd(dst + i, j.scale * src[e]);
+    }
+  }
+}
+int launch_table(const pvsr_table_job* jobs, int n_jobs, long long max_n, cudaStream_t s) {
+  if (n_jobs <= 0 || max_n <= 0) return 0;
+  long long bx = (max_n + 256 * 8 - 1) / (256 * 8);      // ~8 elements per thread of the largest job
+  if (bx > 1024) bx = 1024;
+  table_kernel<<<dim3(static_cast<unsigned>(bx), static_cast<unsigned>(n_jobs)), 256, 0, s>>>(jobs);
+  return static_cast<int>(cudaGetLastError());
+}
+
 }  // namespace pvsr

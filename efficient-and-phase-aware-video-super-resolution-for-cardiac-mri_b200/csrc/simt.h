@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 struct pvsr_cine_sample;
+struct pvsr_table_job;
 
 namespace pvsr {
 
@@ -19,6 +20,7 @@ int launch_cine_gather(const void* vols, int dtype, const struct pvsr_cine_sampl
                        cudaStream_t s);
 int launch_pad_channel_bf16(const float* x, void* out_bf16, long long n, cudaStream_t s);
 int launch_take_channel0(const float* in, int stride, float* out, long long n, cudaStream_t s);
+int launch_table(const struct pvsr_table_job* jobs, int n_jobs, long long max_n, cudaStream_t s);
 int launch_add_bf16(const void* a, const void* b, void* out, long long n_elems, cudaStream_t s);
 
 

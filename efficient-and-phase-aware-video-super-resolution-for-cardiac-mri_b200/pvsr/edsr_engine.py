@@ -87,7 +87,11 @@ class _Geometry:
         self.x32 = torch.empty(n, h, w, dtype=torch.float32, device=dev)
         self.x64 = torch.empty(n, h, w, 64, **bf)
         n_feat = (2 * eng.R + 2) if train else 3            # head, (t_i, x_{i+1}) per block, u_0 | ping-pong
-        self.feat = [torch.empty(n, h, w, F, **bf) for _ in range(n_feat)]
+        # ONE image-stacked tensor (slot-major, like the frame-major stacks of the RefineNet plan): in training, body
+        # layer l reads slot l and writes slot l + 1, so a single TMA descriptor serves the weight gradients of all
+        # body layers in one launch
+        self.acts = torch.empty(n_feat * n, h, w, F, **bf)
+        self.feat = [self.acts[i * n:(i + 1) * n] for i in range(n_feat)]
         self.sizes = [(h, w)]
         for r in eng.factors:
             self.sizes.append((self.sizes[-1][0] * r, self.sizes[-1][1] * r))
@@ -102,11 +106,17 @@ class _Geometry:
             self.loss = torch.zeros((), dtype=torch.float32, device=dev)
             self.g64 = torch.empty(n, H, W, 64, **bf)
             self.dup = [torch.empty_like(u) for u in self.up]          # gradients wrt u_1 .. u_last
-            self.dfeat = [torch.empty(n, h, w, F, **bf) for _ in range(4)]
-            big = max(l.n_kb * l.n_total * 64 + l.n_total for l in eng.layers)
-            self.dw = torch.zeros(big, dtype=torch.float32, device=dev)
-            sb = L.load().pvsr_wgrad_scratch_bytes()
-            self.jobs = {l.name: torch.empty(sb, dtype=torch.uint8, device=dev) for l in eng.layers}
+            # gradient stack, same slots as `acts`: slot j = dL/d(what acts slot j holds; pre-ReLU for the t_i slots)
+            self.gacts = torch.empty(n_feat * n, h, w, F, **bf)
+            self.gfeat = [self.gacts[i * n:(i + 1) * n] for i in range(n_feat)]
+            # packed fp32 weight / bias gradients of every layer, side by side (zeroed once per step, scattered once)
+            self.dw_off, total = {}, 0
+            for l in eng.layers:
+                self.dw_off[l.name] = total
+                total += l.n_kb * l.n_total * 64 + l.n_total
+            self.dw = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.wg_launches = None          # [(ctypes desc array, n_desc, job scratch tensor)]
+            self.scatter_table = None
             self.jobs_ready = False
 
 
@@ -181,20 +191,35 @@ class EDSREngine:
         self.params_changed()
         return self._flat
 
+    def _upload_table(self, jobs):
+        arr = (L.TableJob * len(jobs))(*jobs)
+        t = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+        return t, max(j.n for j in jobs)
+
     def _ensure_packed(self):
+        """fp32 master parameters -> bf16 forward / transposed operands + packed biases of every layer: ONE
+        table-driven launch (pvsr_run_table) per optimiser step."""
         ver = self._param_version()
         if self._packed_version == ver:
             return
-        lib, st, P = L.load(), L.current_stream(), self._named()
-        for l in self.layers:
-            w, b = P[l.name + '.weight'], P[l.name + '.bias']
-            if w.dtype != torch.float32 or not w.is_contiguous():
-                raise L.PvsrError(f'{l.name}.weight must be contiguous fp32')
-            L.check(lib.pvsr_pack_weights(L.ptr(w), L.ptr(l.idx_w), None, L.ptr(l.w), l.idx_w.numel(), st), 'pack')
-            L.check(lib.pvsr_gather_f32(L.ptr(b), L.ptr(l.idx_b), L.ptr(l.b), l.idx_b.numel(), st), 'pack bias')
-            if l.wt is not None:
-                L.check(lib.pvsr_pack_weights(L.ptr(w), L.ptr(l.idx_wt), None, L.ptr(l.wt), l.idx_wt.numel(), st),
-                        'pack^T')
+        P = self._named()
+        key = tuple(p.data_ptr() for p in P.values())
+        if getattr(self, '_pack_key', None) != key:
+            jobs = []
+            for l in self.layers:
+                w, b = P[l.name + '.weight'], P[l.name + '.bias']
+                if w.dtype != torch.float32 or not w.is_contiguous() or b.dtype != torch.float32:
+                    raise L.PvsrError(f'{l.name}: parameters must be contiguous fp32')
+                jobs.append(L.TableJob(w.data_ptr(), l.idx_w.data_ptr(), l.w.data_ptr(), l.idx_w.numel(), 1.0, L.TJ_PACK))
+                jobs.append(L.TableJob(b.data_ptr(), l.idx_b.data_ptr(), l.b.data_ptr(), l.idx_b.numel(), 1.0,
+                                       L.TJ_GATHER))
+                if l.wt is not None:
+                    jobs.append(L.TableJob(w.data_ptr(), l.idx_wt.data_ptr(), l.wt.data_ptr(), l.idx_wt.numel(), 1.0,
+                                           L.TJ_PACK))
+            self._pack_table, self._pack_max = self._upload_table(jobs)
+            self._pack_jobs, self._pack_key = len(jobs), key
+        L.check(L.load().pvsr_run_table(L.ptr(self._pack_table), self._pack_jobs, self._pack_max, L.current_stream()),
+                'pack table')
         self._packed_version = ver
 
     # ------------------------------------------------------------------------------------------ geometry
@@ -252,12 +277,9 @@ class EDSREngine:
         H, W = g.sizes[-1]
         L.check(lib.pvsr_take_channel0_f32(L.ptr(g.out16), 16, L.ptr(g.out), g.n * H * W, st), 'take_channel0')
 
-    def _wgrad(self, g, layer, x_view, dy_views, out_hw, grads, scale=1.0):
-        """Weight + bias gradient of `layer`: X = x_view (tensor), dY chunks over `dy_views` [(tensor, mul)] given as
-        (view, img_base, ch0, off_x, off_y) tuples in packed-column order; accumulated into grads[name]."""
-        lib, st = L.load(), L.current_stream()
-        views = [(x_view, 1)] + dy_views[0]
-        d = L.WgradDesc()
+    def _wgrad_desc(self, g, d, layer, views, src_img_base, dys, out_hw):
+        """Fills one pvsr_wgrad_desc: X = view 0 at image offset src_img_base, dY chunks `dys` (view, img_base, ch0,
+        off_x, off_y) in packed-column order; result slab of `layer` inside g.dw."""
         d.H, d.W = out_hw
         d.n_img = g.n
         d.n_views = len(views)
@@ -268,24 +290,68 @@ class EDSREngine:
             d.views[i].images = t.shape[0]
             d.views[i].mul = mul
         d.n_src = 1
-        d.src_view[0] = 0
-        d.n_dy = len(dy_views[1])
-        for i, (v, base, ch0, ox, oy) in enumerate(dy_views[1]):
+        d.src_view[0], d.src_img_base[0] = 0, src_img_base
+        d.n_dy = len(dys)
+        for i, (v, base, ch0, ox, oy) in enumerate(dys):
             d.dy_view[i], d.dy_img_base[i], d.dy_ch0[i], d.dy_off_x[i], d.dy_off_y[i] = v, base, ch0, ox, oy
         d.kb_per_src, d.taps, d.n_total, d.with_bias, d.n_splits = layer.fwd.kb_per_src, 9, layer.n_total, 1, 0
+        off = g.dw_off[layer.name]
         n_w = layer.n_kb * layer.n_total * 64
-        dw, db = g.dw[:n_w], g.dw[n_w:n_w + layer.n_total]
-        d.dw_packed, d.db_packed = dw.data_ptr(), db.data_ptr()
-        d.job_scratch = g.jobs[layer.name].data_ptr()
-        if not g.jobs_ready:
-            L.check(lib.pvsr_conv3x3_wgrad_staged(C.byref(d), 1, st), 'wgrad job upload')
-            return
-        g.dw[:n_w + layer.n_total].zero_()
-        L.check(lib.pvsr_conv3x3_wgrad_staged(C.byref(d), 0, st), 'wgrad')
-        gw, gb = grads[layer.name + '.weight'], grads[layer.name + '.bias']
-        L.check(lib.pvsr_scatter_add_scaled(L.ptr(gw), L.ptr(layer.idx_w), L.ptr(dw), n_w, scale, st), 'scatter w')
-        L.check(lib.pvsr_scatter_add_scaled(L.ptr(gb), L.ptr(layer.idx_b), L.ptr(db), layer.n_total, scale, st),
-                'scatter b')
+        d.dw_packed = g.dw.data_ptr() + 4 * off
+        d.db_packed = g.dw.data_ptr() + 4 * (off + n_w)
+
+    def _build_wgrad_launches(self, g):
+        """Weight-gradient launches of a training geometry: tail, every up-sampler conv, ALL body convs in one launch
+        (layer l: X = acts slot l, dY = gacts slot l + 1), head.  Job lists are staged on the device once."""
+        lib, st, by, n = L.load(), L.current_stream(), self.by_name, g.n
+        sb = lib.pvsr_wgrad_scratch_bytes()
+        launches = []
+
+        def add(descs):
+            arr = (L.WgradDesc * len(descs))(*descs)
+            scratch = torch.empty(sb, dtype=torch.uint8, device=self.device)
+            arr[0].job_scratch = scratch.data_ptr()
+            L.check(lib.pvsr_conv3x3_wgrad_multi(C.cast(arr, C.c_void_p), len(descs), 1, st), 'wgrad job upload')
+            launches.append((arr, len(descs), scratch))
+
+        H, W = g.sizes[-1]
+        d = L.WgradDesc()
+        self._wgrad_desc(g, d, by['tail.conv'], [(g.up[-1], 1), (g.g64, 1)], 0, [(1, 0, 0, 0, 0)], (H, W))
+        add([d])
+        for k, r in enumerate(self.factors):
+            x_in = g.up[k - 1] if k > 0 else g.feat[2 * self.R + 1]
+            d = L.WgradDesc()
+            self._wgrad_desc(g, d, by[f'tail.0.conv{k + 1}'], [(x_in, 1), (g.dup[k], r)], 0, self._chunks(1, r),
+                             g.sizes[k])
+            add([d])
+        body = [l for l in self.layers if l.kind == 'body']          # conv1_0, conv2_0, ..., body.conv: slot l -> l + 1
+        views = [(g.acts, 1), (g.gacts, 1)]
+        for c0 in range(0, len(body), 128):
+            descs = []
+            for li in range(c0, min(c0 + 128, len(body))):
+                d = L.WgradDesc()
+                self._wgrad_desc(g, d, body[li], views, li * n,
+                                 [(1, (li + 1) * n, c * 64, 0, 0) for c in range(self.F // 64)], (g.h, g.w))
+                descs.append(d)
+            add(descs)
+        d = L.WgradDesc()
+        self._wgrad_desc(g, d, by['head.0'], [(g.x64, 1), (g.gfeat[0], 1)], 0, self._chunks(1), (g.h, g.w))
+        add([d])
+        g.wg_launches = launches
+
+    def _build_scatter_table(self, g, grads):
+        jobs = []
+        for l in self.layers:
+            off = g.dw_off[l.name]
+            n_w = l.n_kb * l.n_total * 64
+            s = self.res_scale if l.name.endswith('.body.conv2') else 1.0      # x_{i+1} = s * conv2(t_i) + x_i
+            base = g.dw.data_ptr()
+            jobs.append(L.TableJob(base + 4 * off, l.idx_w.data_ptr(), grads[l.name + '.weight'].data_ptr(), n_w, s,
+                                   L.TJ_SCATTER))
+            jobs.append(L.TableJob(base + 4 * (off + n_w), l.idx_b.data_ptr(), grads[l.name + '.bias'].data_ptr(),
+                                   l.n_total, s, L.TJ_SCATTER))
+        g.scatter_table, g.scatter_max = self._upload_table(jobs)
+        g.scatter_jobs = len(jobs)
 
     def _dgrad(self, src, layer, out, mask=None, res=None, scale=0.0, views=None, srcs=None, kb=None, k16_last=4):
         bn, nt = _tile(self.F)
@@ -301,53 +367,32 @@ class EDSREngine:
             return [(view, 0, c * 64, 0, 0) for c in range(cb)]
         return [(view, 0, c * 64, q % r, q // r) for q in range(r * r) for c in range(cb)]
 
-    def _backward_launches(self, g, grads):
-        """Gradients of everything wrt g.dout, accumulated into `grads` ({name: fp32 tensor}).  Called once with
-        g.jobs_ready = False to stage the wgrad job lists (no launches), then for real."""
+    def _backward_launches(self, g):
+        """Gradients of everything wrt g.dout -> packed weight gradients in g.dw -> the scatter table's targets."""
         lib, st = L.load(), L.current_stream()
         R, by, s = self.R, self.by_name, self.res_scale
         H, W = g.sizes[-1]
-        stage_only = not g.jobs_ready
-        if not stage_only:
-            L.check(lib.pvsr_pad_channel_bf16(L.ptr(g.dout), L.ptr(g.g64), g.n * H * W, st), 'pad_channel(dout)')
-        # tail conv
-        l = by['tail.conv']
-        self._wgrad(g, l, g.up[-1], ([(g.g64, 1)], [(1, 0, 0, 0, 0)]), (H, W), grads)
-        if not stage_only:
-            self._dgrad(g.g64, l, g.dup[-1], kb=1, k16_last=1)
-        # up-sampler, last to first
+        gf = g.gfeat
+        g.dw.zero_()
+        L.check(lib.pvsr_pad_channel_bf16(L.ptr(g.dout), L.ptr(g.g64), g.n * H * W, st), 'pad_channel(dout)')
+        # ---- data gradients, output to input
+        self._dgrad(g.g64, by['tail.conv'], g.dup[-1], kb=1, k16_last=1)
         for k in reversed(range(len(self.factors))):
             r = self.factors[k]
-            l = by[f'tail.0.conv{k + 1}']
-            x_in = g.up[k - 1] if k > 0 else g.u0
-            self._wgrad(g, l, x_in, ([(g.dup[k], r)], self._chunks(1, r)), g.sizes[k], grads)
-            if not stage_only:
-                d_in = g.dup[k - 1] if k > 0 else g.dfeat[3]
-                self._dgrad(None, l, d_in, views=[(g.dup[k], r)],
-                            srcs=[(0, 0, 0, q % r, q // r) for q in range(r * r)])
-        du0 = g.dfeat[3]
-        # body.conv: u_0 = conv(x_R) + head
-        l = by['body.conv']
-        self._wgrad(g, l, g.feat[2 * R], ([(du0, 1)], self._chunks(1)), (g.h, g.w), grads)
-        a, b, t = g.dfeat[0], g.dfeat[1], g.dfeat[2]
-        if not stage_only:
-            self._dgrad(du0, l, a)
+            d_in = g.dup[k - 1] if k > 0 else gf[2 * R + 1]
+            self._dgrad(None, by[f'tail.0.conv{k + 1}'], d_in, views=[(g.dup[k], r)],
+                        srcs=[(0, 0, 0, q % r, q // r) for q in range(r * r)])
+        self._dgrad(gf[2 * R + 1], by['body.conv'], gf[2 * R])                 # u_0 = conv(x_R) + head
         for i in reversed(range(R)):
-            x_i, t_i = g.feat[2 * i], g.feat[1 + 2 * i]
-            l2, l1 = by[f'body.{i}.body.conv2'], by[f'body.{i}.body.conv1']
             # x_{i+1} = s * conv2(t_i) + x_i;  t_i = relu(conv1(x_i))
-            self._wgrad(g, l2, t_i, ([(a, 1)], self._chunks(1)), (g.h, g.w), grads, scale=s)
-            if not stage_only:
-                self._dgrad(a, l2, t, mask=t_i, scale=s)
-            self._wgrad(g, l1, x_i, ([(t, 1)], self._chunks(1)), (g.h, g.w), grads)
-            if not stage_only:
-                self._dgrad(t, l1, b, res=a)
-            a, b = b, a
-        # head: its output feeds block 0 (gradient in `a`) and body.conv's residual (du0)
-        if not stage_only:
-            L.check(lib.pvsr_add_bf16(L.ptr(a), L.ptr(du0), L.ptr(t), a.numel(), st), 'add_bf16')
-        # the dY buffer of the head wgrad is `t` whatever the parity of R (a/b swap only between dfeat[0] and [1])
-        self._wgrad(g, by['head.0'], g.x64, ([(t, 1)], self._chunks(1)), (g.h, g.w), grads)
+            self._dgrad(gf[2 + 2 * i], by[f'body.{i}.body.conv2'], gf[1 + 2 * i], mask=g.feat[1 + 2 * i], scale=s)
+            self._dgrad(gf[1 + 2 * i], by[f'body.{i}.body.conv1'], gf[2 * i], res=gf[2 + 2 * i])
+        # the head output feeds block 0 (gradient now in slot 0) and body.conv's residual (slot 2R + 1)
+        L.check(lib.pvsr_add_bf16(L.ptr(gf[0]), L.ptr(gf[2 * R + 1]), L.ptr(gf[0]), gf[0].numel(), st), 'add_bf16')
+        # ---- weight gradients
+        for arr, n_desc, _ in g.wg_launches:
+            L.check(lib.pvsr_conv3x3_wgrad_multi(C.cast(arr, C.c_void_p), n_desc, 0, st), 'wgrad')
+        L.check(lib.pvsr_run_table(L.ptr(g.scatter_table), g.scatter_jobs, g.scatter_max, st), 'scatter table')
 
     # ------------------------------------------------------------------------------------------ public
     def _replay(self, g, which, fn):
@@ -381,12 +426,13 @@ class EDSREngine:
     def backward(self, g, grads):
         """Backward of the last forward(train=True) of geometry `g`; g.dout holds dL/d(out)."""
         if not g.jobs_ready:
-            self._backward_launches(g, grads)           # stages the wgrad job lists only
+            self._build_wgrad_launches(g)               # stages the wgrad job lists on the device
             g.jobs_ready = True
-        key = tuple(t.data_ptr() for t in grads.values())
+        key = tuple(grads[k].data_ptr() for k in sorted(grads))
         if getattr(g, 'bwd_key', None) != key:          # a captured graph writes to the buffers it was captured with
+            self._build_scatter_table(g, grads)
             g.bwd_key, g.graph_bwd = key, None
-        self._replay(g, 'bwd', lambda: self._backward_launches(g, grads))
+        self._replay(g, 'bwd', lambda: self._backward_launches(g))
 
     def grad_buffers(self):
         if getattr(self, '_grad_buf', None) is None:

@@ -82,6 +82,12 @@ class CineSample(C.Structure):
                 ("bx", C.c_int32)]
 
 
+class TableJob(C.Structure):
+    _fields_ = [("src", c_void_p), ("idx", c_void_p), ("dst", c_void_p), ("n", c_int64), ("scale", C.c_float),
+                ("kind", c_int)]
+
+
+TJ_PACK, TJ_GATHER, TJ_SCATTER = 0, 1, 2
 DT_F32, DT_I16, DT_U16, DT_U8 = 0, 1, 2, 3
 NUM_CLASSES, NUM_CLASSES_BWD = 7, 9
 
@@ -111,6 +117,8 @@ SIGNATURES = {
     "pvsr_wgrad_scratch_bytes": (c_int64, []),
     "pvsr_conv3x3_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
     "pvsr_conv3x3_wgrad_staged": (c_int, [C.POINTER(WgradDesc), c_int, c_void_p]),
+    "pvsr_conv3x3_wgrad_multi": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "pvsr_run_table": (c_int, [c_void_p, c_int, c_int64, c_void_p]),
     "pvsr_pad_channel_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "pvsr_take_channel0_f32": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "pvsr_scatter_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

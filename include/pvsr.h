@@ -191,6 +191,27 @@ int pvsr_conv3x3_wgrad(const pvsr_wgrad_desc* d, void* stream);
  * (synchronises the stream; call once, outside capture); upload = 0 launches against the jobs already resident in
  * d->job_scratch (no host<->device traffic, capturable).  The descriptor must be identical in both calls. */
 int pvsr_conv3x3_wgrad_staged(const pvsr_wgrad_desc* d, int upload, void* stream);
+/* Weight gradients of n_desc convs in ONE launch.  All descriptors share descs[0]'s views, image size, image count
+ * and job_scratch; descs[k].dw_packed / db_packed must lie in the same fp32 allocation as descs[0].dw_packed (results
+ * are addressed relative to it).  Same two-phase protocol as pvsr_conv3x3_wgrad_staged; at most 1024 jobs. */
+int pvsr_conv3x3_wgrad_multi(const pvsr_wgrad_desc* descs, int n_desc, int upload, void* stream);
+/* Table-driven parameter traffic: one launch runs n_jobs independent element-wise jobs (device-resident table):
+ *   PVSR_TJ_PACK   : dst bf16[e] = bf16(src f32[idx[e]])  (0 when idx[e] < 0)   - pvsr_pack_weights for many layers
+ *   PVSR_TJ_GATHER : dst f32[e]  = src f32[idx[e]]        (0 when idx[e] < 0)   - pvsr_gather_f32
+ *   PVSR_TJ_SCATTER: dst f32[idx[e]] += scale * src f32[e] for idx[e] >= 0      - pvsr_scatter_add_scaled
+ * max_n = the largest n of the table (sizes the grid). */
+#define PVSR_TJ_PACK 0
+#define PVSR_TJ_GATHER 1
+#define PVSR_TJ_SCATTER 2
+typedef struct pvsr_table_job {
+  const void* src;
+  const int32_t* idx;
+  void* dst;
+  int64_t n;
+  float scale;
+  int kind;
+} pvsr_table_job;
+int pvsr_run_table(const pvsr_table_job* jobs_dev, int n_jobs, int64_t max_n, void* stream);
 /* x fp32 [n] -> out bf16 [n][64] with channel 0 = x and channels 1..63 = 0: single-channel images / gradients as a
  * 64-channel K block of the tensor-core conv (EDSR head conv edsr_net.py:29 and the adjoint of its tail conv :33). */
 int pvsr_pad_channel_bf16(const float* x, void* out_bf16, int64_t n, void* stream);

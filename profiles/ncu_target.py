@@ -1,6 +1,6 @@
 """Profiling target: exactly two eager (no CUDA graph) passes of the bench workload, so that an ncu launch list of
 this command shows every kernel of a step by name and `profiles/ncu_capture.sh` can pick representative launches
-for the `--set full` captures.  python profiles/ncu_target.py infer|train [batch]"""
+for the `--set full` captures.  python profiles/ncu_target.py infer|train|edsr_infer|edsr_train [batch]"""
 import os
 import sys
 
@@ -34,6 +34,31 @@ def main():
             eng.stage_inputs(pl, [x.to(dev) for x in inputs], pos.to(dev))
             for _ in range(2):
                 eng.run(pl)
+                torch.cuda.synchronize()
+    elif mode.startswith("edsr"):
+        # EDSR x4, 32 blocks x 256 features (configs/{train,test}/edsr_net/exp1_x4.yaml) - SURVEY 8 f3
+        from src.model.nets import EDSRNet
+        net = EDSRNet(in_channels=1, out_channels=1, num_resblocks=32, num_features=256, upscale_factor=4,
+                      res_scale=0.1).to(dev)
+        net.engine.use_graph = False
+        g = torch.Generator().manual_seed(1234)
+        if mode == "edsr_infer":
+            n = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+            x = torch.randn(n, 1, 54, 63, generator=g).to(dev)
+            net.eval()
+            with torch.no_grad():
+                for _ in range(2):
+                    net(x)
+                    torch.cuda.synchronize()
+        else:
+            from pvsr.optim import FusedAdam
+            net.train()
+            opt = FusedAdam.for_net(net, lr=1e-4)
+            x = torch.randn(16, 1, 32, 32, generator=g).to(dev)
+            t = torch.randn(16, 1, 128, 128, generator=g).to(dev)
+            for _ in range(2):
+                net.engine.loss_and_grads(x, t)
+                opt.step()
                 torch.cuda.synchronize()
     else:
         N = int(sys.argv[2]) if len(sys.argv) > 2 else 16
