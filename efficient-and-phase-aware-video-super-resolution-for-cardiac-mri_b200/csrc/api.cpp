@@ -325,6 +325,10 @@ int pvsr_conv3x3_wgrad(const pvsr_wgrad_desc* d, void* stream) {
   return rc ? rc : pvsr_conv3x3_wgrad_staged(d, 0, stream);
 }
 
+int pvsr_bicubic_upsample(const float* in, float* out, int64_t n_img, int h, int w, int scale, void* stream) {
+  if (h < 1 || w < 1 || scale < 1) return set_error(-2, "bicubic: bad size %dx%d x%d", h, w, scale);
+  return check_cuda(launch_bicubic(in, out, n_img, h, w, scale, static_cast<cudaStream_t>(stream)), "bicubic");
+}
 int pvsr_pad_channel_bf16(const float* x, void* out, int64_t n, void* stream) {
   return check_cuda(launch_pad_channel_bf16(x, out, n, static_cast<cudaStream_t>(stream)), "pad_channel_bf16");
 }

@@ -137,4 +137,59 @@ int launch_table(const pvsr_table_job* jobs, int n_jobs, long long max_n, cudaSt
   return static_cast<int>(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Bicubic up-sampling, the comparison baseline of the reference (src/model/nets/bicubic.py:15:
+// nn.Upsample(scale_factor=s, mode='bicubic', align_corners=True)): source coordinate = dst * (in - 1) / (out - 1),
+// Keys cubic convolution with A = -0.75, border indices clamped (torch upsample_bicubic2d semantics).
+// HBM-bound: 4 B written per output pixel, the 4 x 4 input taps of neighbouring outputs hit L1 / L2.
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x3 = 2.f - t, u = 1.f - t;
+  c[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  c[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+  c[2] = ((A + 2.f) * u - (A + 3.f)) * u * u + 1.f;
+  c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+__global__ void __launch_bounds__(256) bicubic_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                      long long n_img, int h, int w, int H, int W, float sy,
+                                                      float sx) {
+  const long long total = n_img * H * W;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(i % W);
+    const long long r = i / W;
+    const int Y = static_cast<int>(r % H);
+    const float* src = in + (r / H) * h * w;
+    const float ry = sy * Y, rx = sx * X;
+    int iy = static_cast<int>(floorf(ry)), ix = static_cast<int>(floorf(rx));
+    iy = iy < h - 1 ? iy : h - 1;
+    ix = ix < w - 1 ? ix : w - 1;
+    const float ty = fminf(fmaxf(ry - iy, 0.f), 1.f), tx = fminf(fmaxf(rx - ix, 0.f), 1.f);
+    float cy[4], cx[4];
+    cubic_coeffs(ty, cy);
+    cubic_coeffs(tx, cx);
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), h - 1);
+      float row = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) row += cx[b] * __ldg(src + static_cast<long long>(yy) * w + min(max(ix - 1 + b, 0), w - 1));
+      acc += cy[a] * row;
+    }
+    out[i] = acc;
+  }
+}
+int launch_bicubic(const float* in, float* out, long long n_img, int h, int w, int scale, cudaStream_t s) {
+  const int H = h * scale, W = w * scale;
+  const long long total = n_img * H * W;
+  if (total <= 0) return 0;
+  const float sy = H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f;
+  const float sx = W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  bicubic_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(in, out, n_img, h, w, H, W, sy, sx);
+  return static_cast<int>(cudaGetLastError());
+}
+
 }  // namespace pvsr

@@ -21,6 +21,7 @@ int launch_cine_gather(const void* vols, int dtype, const struct pvsr_cine_sampl
 int launch_pad_channel_bf16(const float* x, void* out_bf16, long long n, cudaStream_t s);
 int launch_take_channel0(const float* in, int stride, float* out, long long n, cudaStream_t s);
 int launch_table(const struct pvsr_table_job* jobs, int n_jobs, long long max_n, cudaStream_t s);
+int launch_bicubic(const float* in, float* out, long long n_img, int h, int w, int scale, cudaStream_t s);
 int launch_add_bf16(const void* a, const void* b, void* out, long long n_elems, cudaStream_t s);
 
 

@@ -12,7 +12,7 @@ from pvsr.device_loader import DeviceDataloader  # noqa: F401  (registry name: `
 
 
 def _seed_worker(worker_id):
-    np.random.seed((np.random.get_state()[1][0] + worker_id) % (2 ** 32))
+    np.random.seed((int(np.random.get_state()[1][0]) + worker_id) % (2 ** 32))   # int(): numpy 2 keeps uint32 otherwise
 
 
 class Dataloader(DataLoader):

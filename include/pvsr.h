@@ -212,6 +212,9 @@ typedef struct pvsr_table_job {
   int kind;
 } pvsr_table_job;
 int pvsr_run_table(const pvsr_table_job* jobs_dev, int n_jobs, int64_t max_n, void* stream);
+/* Bicubic baseline (src/model/nets/bicubic.py:15: nn.Upsample(scale_factor, 'bicubic', align_corners=True)):
+ * in fp32 [n_img][h][w] -> out fp32 [n_img][h*scale][w*scale]. */
+int pvsr_bicubic_upsample(const float* in, float* out, int64_t n_img, int h, int w, int scale, void* stream);
 /* x fp32 [n] -> out bf16 [n][64] with channel 0 = x and channels 1..63 = 0: single-channel images / gradients as a
  * 64-channel K block of the tensor-core conv (EDSR head conv edsr_net.py:29 and the adjoint of its tail conv :33). */
 int pvsr_pad_channel_bf16(const float* x, void* out_bf16, int64_t n, void* stream);

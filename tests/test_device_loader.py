@@ -95,6 +95,15 @@ def test_dataset_reads_nifti_tree_without_nibabel(tmp_path):
     assert (seq, a, b, c, d) == (1, T - U, 2 * T + U, 0, T)
 
 
+def test_host_loader_with_worker_processes(tmp_path):
+    """num_workers > 0: every worker re-seeds numpy from the parent's state (reference dataloader.py:48-53)."""
+    from src.data.dataloader import Dataloader
+    pos = _make_acdc_tree(tmp_path, 'train', n_seq=2)
+    dl = Dataloader(_dataset(tmp_path, 'train', pos), batch_size=4, shuffle=True, num_workers=2)
+    batches = list(dl)
+    assert len(batches) == len(dl) and batches[0]['lr_imgs'][0].shape == (4, 1, 8, 6)
+
+
 def _emulate_gather(vol_thw, first, n, aff, mean, std):
     """numpy statement of pvsr_cine_gather for one sample (include/pvsr.h)."""
     T = vol_thw.shape[0]

@@ -181,3 +181,31 @@ def test_full_size_edsr_against_oracle(pvsr_lib):
     from src.utils import denormalize
     a, b = denormalize(out.cpu(), 'acdc'), denormalize(want, 'acdc')
     assert PSNR()(a, b).item() > 45.0          # SR frames agree to within a grey level almost everywhere
+
+
+# ------------------------------------------------------------------------------------------------ Bicubic baseline
+def _bicubic_ref(x, s):
+    """The reference's Bicubic.forward (bicubic.py:15-19), executed by torch on the CPU."""
+    return torch.nn.Upsample(scale_factor=s, mode='bicubic', align_corners=True)(x)
+
+
+def test_bicubic_contract():
+    from src.model.nets import Bicubic
+    from pvsr.lib import PvsrError
+    net = Bicubic(upscale_factor=4)
+    assert len(net.state_dict()) == 0
+    with pytest.raises(PvsrError):
+        net(torch.zeros(1, 1, 4, 4))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,s", [((2, 1, 54, 63), 4), ((1, 1, 72, 84), 3), ((3, 1, 108, 126), 2), ((1, 2, 5, 1), 4),
+                                     ((1, 1, 1, 7), 2)])
+def test_bicubic_matches_torch(shape, s, pvsr_lib):
+    from src.model.nets import Bicubic
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(*shape, generator=g)
+    want = _bicubic_ref(x, s)
+    got = Bicubic(s).cuda()(x.cuda()).cpu()
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
