@@ -57,10 +57,13 @@ class SSIM(nn.Module):
         n, c = x.shape[:2]
         conv = F.conv2d if self.dim == 2 else F.conv3d
         k = self.window.to(x.dtype)
-        for axis in range(self.dim):
-            shape = [1] * self.dim
-            shape[axis] = k.numel()
-            x = conv(x, k.view(1, 1, *shape).expand(c, 1, *shape), groups=c)
+        # exact fp32: cuDNN would otherwise be free to run these convolutions in TF32 (10-bit mantissa), which moves
+        # SSIM in the 3rd-4th digit and makes the score depend on the batch size through the algorithm choice
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            for axis in range(self.dim):
+                shape = [1] * self.dim
+                shape[axis] = k.numel()
+                x = conv(x, k.view(1, 1, *shape).expand(c, 1, *shape), groups=c)
         return x
 
     def forward(self, output, target):

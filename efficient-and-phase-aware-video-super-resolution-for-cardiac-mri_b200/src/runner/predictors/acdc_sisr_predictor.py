@@ -15,7 +15,7 @@ import torch
 from pvsr import parallel
 from src.utils import denormalize
 from .acdc_vsr_refinenet_predictor import AcdcVSRRefineNetPredictor, _write_png
-from .base_predictor import BasePredictor
+from .base_predictor import BasePredictor, per_sample_scores
 
 
 class AcdcSISRPredictor(BasePredictor):
@@ -50,14 +50,9 @@ class AcdcSISRPredictor(BasePredictor):
             with torch.no_grad():
                 sr = self.net(lr)
                 srd, hrd = self._denormalize(sr), self._denormalize(hr)
-                vals = []
-                for n, (index, _) in enumerate(items):
-                    patient = self._name(index)[1]
-                    a, b = srd[n:n + 1], hrd[n:n + 1]
-                    for fn in self.metric_fns:
-                        vals.append(fn(a, b, patient) if 'Cardiac' in fn.__class__.__name__ else fn(a, b))
-                    vals.extend(fn(sr[n:n + 1], hr[n:n + 1]) for fn in self.loss_fns)
-                flat = torch.stack([v.float() for v in vals]).cpu().view(len(items), -1)
+                patients = [self._name(index)[1] for index, _ in items]
+                losses, metrics = per_sample_scores(self.loss_fns, self.metric_fns, sr, hr, srd, hrd, patients)
+                flat = torch.cat([metrics, losses], dim=1).cpu()
                 imgs = srd[:, 0].to(torch.uint8).cpu().numpy() if self.exported else None
             nm = len(self.metric_fns)
             for n, (index, _) in enumerate(items):

@@ -21,7 +21,7 @@ import torch
 
 from pvsr import parallel
 from src.utils import denormalize
-from .base_predictor import BasePredictor
+from .base_predictor import BasePredictor, per_sample_scores
 
 
 def _write_png(path, img):
@@ -119,21 +119,16 @@ class AcdcVSRRefineNetPredictor(BasePredictor):
 
     def _per_sequence(self, outputs, targets, indices):
         """[(index, losses (T, #loss), metrics (T, #metric), sr uint8 (T, H, W) or None)] for every sequence of the
-        launch; all scalars of the launch cross PCIe once."""
-        n = outputs[0].shape[0]
-        sr = [self._denormalize(o) for o in outputs]
-        hr = [self._denormalize(t) for t in targets]
-        vals = []
-        for s in range(n):
-            patient = self._patient(indices[s])[1]
-            for o, t, od, td in zip(outputs, targets, sr, hr):
-                vals.extend(fn(o[s:s + 1], t[s:s + 1]) for fn in self.loss_fns)
-                for fn in self.metric_fns:
-                    args = (od[s:s + 1], td[s:s + 1])
-                    vals.append(fn(*args, patient) if 'Cardiac' in fn.__class__.__name__ else fn(*args))
-        T, nl, nm = len(outputs), len(self.loss_fns), len(self.metric_fns)
-        flat = torch.stack([v.float() for v in vals]).cpu().view(n, T, nl + nm)
-        frames = torch.stack(sr, dim=1)[:, :, 0].to(torch.uint8).cpu().numpy() if self.exported else None
+        launch; every loss / metric scores all n * T frames in one call and all scalars cross PCIe once."""
+        n, T = outputs[0].shape[0], len(outputs)
+        out = torch.stack(outputs, dim=1).flatten(0, 1)          # (n * T, 1, H, W), sequence-major
+        tgt = torch.stack(targets, dim=1).flatten(0, 1)
+        srd, hrd = self._denormalize(out), self._denormalize(tgt)
+        patients = [self._patient(indices[s])[1] for s in range(n) for _ in range(T)]
+        losses, metrics = per_sample_scores(self.loss_fns, self.metric_fns, out, tgt, srd, hrd, patients)
+        nl = losses.shape[1]
+        flat = torch.cat([losses, metrics], dim=1).cpu().view(n, T, -1)
+        frames = srd.view(n, T, *srd.shape[1:])[:, :, 0].to(torch.uint8).cpu().numpy() if self.exported else None
         return [(indices[s], flat[s, :, :nl], flat[s, :, nl:], None if frames is None else frames[s])
                 for s in range(n)]
 

@@ -232,3 +232,32 @@ def test_product_path_refuses_cpu_tensors():
     net.train()
     with pytest.raises(PvsrError):
         net([torch.zeros(1, 1, 8, 8)] * 6, torch.zeros(1, 6, 1))
+
+
+def test_batched_scores_equal_per_frame_calls(tmp_path):
+    """per_sample_scores (one call per loss / metric per launch) == the reference's per-frame calls
+    (acdc_vsr_refinenet_predictor.py:64-75, :123-158), Cardiac* crops and unknown losses included."""
+    import pickle
+    from src.model.metrics import PSNR, SSIM, CardiacPSNR, CardiacSSIM
+    from src.model.losses import HuberLoss
+    from src.runner.predictors.base_predictor import per_sample_scores
+    from src.utils import denormalize
+    box = tmp_path / 'coordinates.pkl'
+    with open(box, 'wb') as f:
+        pickle.dump({'patient001': (3, 30, 4, 36), 'patient002': (0, 25, 10, 40)}, f)
+    g = torch.Generator().manual_seed(5)
+    out = torch.randn(6, 1, 40, 48, generator=g)
+    tgt = out + 0.2 * torch.randn(6, 1, 40, 48, generator=g)
+    od, td = denormalize(out, 'acdc'), denormalize(tgt, 'acdc')
+    patients = ['patient001'] * 3 + ['patient002'] * 3
+    loss_fns = [torch.nn.L1Loss(), torch.nn.MSELoss(), HuberLoss()]
+    metric_fns = [PSNR(), SSIM(), CardiacPSNR(coordinates_path=box), CardiacSSIM(coordinates_path=box)]
+    losses, metrics = per_sample_scores(loss_fns, metric_fns, out, tgt, od, td, patients)
+    assert losses.shape == (6, 3) and metrics.shape == (6, 4)
+    for i in range(6):
+        for k, fn in enumerate(loss_fns):
+            assert float(losses[i, k]) == pytest.approx(float(fn(out[i:i + 1], tgt[i:i + 1])), rel=1e-5)
+        for k, fn in enumerate(metric_fns):
+            extra = (patients[i],) if k >= 2 else ()
+            assert float(metrics[i, k]) == pytest.approx(float(fn(od[i:i + 1], td[i:i + 1], *extra)), rel=1e-5)
+    assert all(fn.size_average for fn in metric_fns[:2]) and metric_fns[2].inner.size_average
