@@ -29,6 +29,7 @@ class AcdcSISRTrainer(BaseTrainer):
                        and len(self.loss_fns) == 1 and type(self.loss_fns[0]) is torch.nn.L1Loss
                        and self.loss_fns[0].reduction == 'mean')
         self._dp = parallel.DataParallelStep(self.net, self.optimizer) if fused_opt else None
+        self.log_every = 10
 
     def _run_epoch(self, mode):
         training = mode == 'training'
@@ -39,8 +40,10 @@ class AcdcSISRTrainer(BaseTrainer):
             sampler.set_epoch(self.epoch)
         trange = self._progress(dataloader, mode)
         log, count = self._init_log(), 0
+        names = list(log)
+        acc = torch.zeros(len(names), dtype=torch.float64, device=self.device)     # weighted sums, device-resident
         batch, outputs = None, None
-        for batch in trange:
+        for step, batch in enumerate(trange):
             batch = self._allocate_data(batch)
             inputs, targets = self._get_inputs_targets(batch)
             if training and self._fused:
@@ -64,13 +67,15 @@ class AcdcSISRTrainer(BaseTrainer):
                     loss = (torch.stack(losses) * self.loss_weights).sum()
             metrics = self._compute_metrics(outputs.detach(), targets)
             batch_size = dataloader.batch_size
+            # weighted sums stay on the device; they cross PCIe every `log_every` steps (the reference's per-step
+            # .item() calls serialise host and GPU)
             vals = torch.stack([loss.detach().float()] + [l.detach().float() for l in losses] +
-                               [m.detach().float() for m in metrics]).tolist()      # one D2H transfer per step
-            names = ['Loss'] + [fn.__class__.__name__ for fn in self.loss_fns + self.metric_fns]
-            for name, v in zip(names, vals):
-                log[name] += v * batch_size
+                               [m.detach().float() for m in metrics])
+            acc += vals.double() * batch_size
             count += batch_size
-            trange.set_postfix(**{k: f'{v / count: .3f}' for k, v in log.items()})
+            if (step + 1) % self.log_every == 0:
+                trange.set_postfix(**{k: f'{v / count: .3f}' for k, v in zip(names, acc.tolist())})
+        log = dict(zip(names, acc.tolist()))
         log, count = parallel.reduce_log(log, count, self.device)
         return {k: v / max(count, 1) for k, v in log.items()}, batch, outputs
 

@@ -31,6 +31,7 @@ class AcdcVSRRefineNetTrainer(BaseTrainer):
         self._fused = (isinstance(self.optimizer, FusedAdam) and len(self.loss_fns) == 1
                        and type(self.loss_fns[0]) is torch.nn.L1Loss and self.loss_fns[0].reduction == 'mean')
         self._dp = parallel.DataParallelStep(self.net, self.optimizer) if isinstance(self.optimizer, FusedAdam) else None
+        self.log_every = 10
 
     def _run_epoch(self, mode):
         training = mode == 'training'
@@ -41,8 +42,10 @@ class AcdcVSRRefineNetTrainer(BaseTrainer):
             sampler.set_epoch(self.epoch)
         trange = self._progress(dataloader, mode)
         log, count = self._init_log(), 0
+        names = list(log)
+        acc = torch.zeros(len(names), dtype=torch.float64, device=self.device)     # weighted sums, device-resident
         batch, outputs = None, None
-        for batch in trange:
+        for step, batch in enumerate(trange):
             batch = self._allocate_data(batch)
             inputs, targets, pos_codes = self._get_inputs_targets(batch)
             T = len(inputs)
@@ -62,9 +65,15 @@ class AcdcVSRRefineNetTrainer(BaseTrainer):
                     loss = (torch.stack(losses) * self.loss_weights).sum()
             metrics = self._compute_metrics(outputs, targets)
             batch_size = dataloader.batch_size
-            self._update_log(log, batch_size, T, loss, losses, metrics)
+            # the reference reads every scalar back with .item() each step (:60-66), which serialises host and GPU;
+            # here the weighted sums stay on the device and cross PCIe every `log_every` steps for the progress bar
+            vals = torch.stack([loss.detach().float()] + [l.detach().float() for l in losses] +
+                               [m.detach().float() for m in metrics])
+            acc += vals.double() * (batch_size * T)
             count += batch_size * T
-            trange.set_postfix(**{k: f'{v / count: .3f}' for k, v in log.items()})
+            if (step + 1) % self.log_every == 0:
+                trange.set_postfix(**{k: f'{v / count: .3f}' for k, v in zip(names, acc.tolist())})
+        log = dict(zip(names, acc.tolist()))
         log, count = parallel.reduce_log(log, count, self.device)
         return {k: v / max(count, 1) for k, v in log.items()}, batch, outputs[-1] if outputs is not None else None
 
@@ -106,10 +115,12 @@ class AcdcVSRRefineNetTrainer(BaseTrainer):
         return losses
 
     def _compute_metrics(self, outputs, targets):
+        """Mean over the T frames of each metric's batch mean (:103-120) - all T * N frames in ONE call per metric
+        (equal sample counts per frame make the two means identical)."""
         with torch.no_grad():
-            sr = [self._denormalize(o.detach()) for o in outputs[-1]]
-            hr = [self._denormalize(t) for t in targets]
-            return [torch.stack([fn(o, t) for o, t in zip(sr, hr)]).mean() for fn in self.metric_fns]
+            sr = self._denormalize(torch.stack([o.detach() for o in outputs[-1]]).flatten(0, 1))
+            hr = self._denormalize(torch.stack(list(targets)).flatten(0, 1))
+            return [fn(sr, hr).mean() for fn in self.metric_fns]
 
     def _update_log(self, log, batch_size, T, loss, losses, metrics):
         weight = batch_size * T
