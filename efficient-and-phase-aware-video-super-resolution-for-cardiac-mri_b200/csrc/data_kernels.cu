@@ -16,13 +16,16 @@
 
 namespace pvsr {
 
-template <typename T>
+// Thread = 4 consecutive output pixels of one row (w % 4 == 0: one row/column division per 4 pixels, four independent
+// loads in flight, one 16-byte store) or 1 pixel (any w).  First version (1 pixel per thread, grid-stride with a
+// division per pixel): 1.96 TB/s on 32 whole cycles (ncu, profiles/r01/ncu_r01s5_loader_*.txt).
+template <typename T, int V>
 __global__ void __launch_bounds__(256) cine_gather_kernel(const T* __restrict__ vols,
                                                           const pvsr_cine_sample* __restrict__ samples, int n_samples,
                                                           int n_frames, int h, int w, float mean, float stdv,
                                                           float* __restrict__ out, const float* __restrict__ pos_codes,
                                                           float* __restrict__ pos_out) {
-  // blockIdx.y = frame * n_samples + sample; blockIdx.x strides over the pixels of that image
+  // blockIdx.y = frame * n_samples + sample; blockIdx.x strides over the pixel groups of that image
   const int img = blockIdx.y;
   const int f = img / n_samples, n = img - f * n_samples;
   const pvsr_cine_sample s = samples[n];
@@ -30,11 +33,17 @@ __global__ void __launch_bounds__(256) cine_gather_kernel(const T* __restrict__ 
   if (t < 0) t += s.T;
   const T* __restrict__ src = vols + s.vol_off + static_cast<int64_t>(t) * s.Hs * s.Ws;
   float* __restrict__ dst = out + static_cast<int64_t>(img) * h * w;
-  const int n_pix = h * w;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += gridDim.x * blockDim.x) {
-    const int y = p / w, x = p - y * w;
-    const float v = static_cast<float>(src[static_cast<int64_t>(s.ay * y + s.by) * s.Ws + (s.ax * x + s.bx)]);
-    dst[p] = __fdiv_rn(__fsub_rn(v, mean), stdv);
+  const int wg = w / V, n_grp = h * wg;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n_grp; g += gridDim.x * blockDim.x) {
+    const int y = g / wg, x = (g - y * wg) * V;
+    const T* __restrict__ row = src + (s.ay * y + s.by) * s.Ws + s.bx;     // a frame is far below 2^31 elements
+    float v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = static_cast<float>(row[s.ax * (x + k)]);
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = __fdiv_rn(__fsub_rn(v[k], mean), stdv);
+    if constexpr (V == 4) *reinterpret_cast<float4*>(dst + y * w + x) = make_float4(v[0], v[1], v[2], v[3]);
+    else dst[y * w + x] = v[0];
   }
   if (pos_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
     pos_out[static_cast<int64_t>(n) * n_frames + f] = s.pos_off >= 0 ? pos_codes[s.pos_off + t] : 0.f;
@@ -46,11 +55,18 @@ int launch_cine_gather(const void* vols, int dtype, const pvsr_cine_sample* samp
   if (n_samples <= 0 || n_frames <= 0 || h <= 0 || w <= 0) return 0;
   const long long imgs = static_cast<long long>(n_samples) * n_frames;
   if (imgs > 65535) return static_cast<int>(cudaErrorInvalidValue);
-  const int bx = (h * w + 256 * 4 - 1) / (256 * 4);   // ~4 pixels per thread
-  dim3 grid(bx < 1 ? 1 : bx, static_cast<unsigned>(imgs));
+  const bool vec = (w % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  const int groups = vec ? h * (w / 4) : h * w;
+  int bx = (groups + 256 * 2 - 1) / (256 * 2);         // ~2 groups per thread
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, static_cast<unsigned>(imgs));
 #define PVSR_GATHER(T) \
-  cine_gather_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(vols), samples, n_samples, n_frames, h, w, mean, \
-                                             stdv, out, pos_codes, pos_out)
+  do { \
+    if (vec) cine_gather_kernel<T, 4><<<grid, 256, 0, st>>>(static_cast<const T*>(vols), samples, n_samples, n_frames, h, \
+                                                            w, mean, stdv, out, pos_codes, pos_out); \
+    else cine_gather_kernel<T, 1><<<grid, 256, 0, st>>>(static_cast<const T*>(vols), samples, n_samples, n_frames, h, w, \
+                                                        mean, stdv, out, pos_codes, pos_out); \
+  } while (0)
   switch (dtype) {
     case PVSR_DT_F32: PVSR_GATHER(float); break;
     case PVSR_DT_I16: PVSR_GATHER(int16_t); break;

@@ -35,6 +35,16 @@ def main():
             for _ in range(2):
                 eng.run(pl)
                 torch.cuda.synchronize()
+    elif mode == "loader":
+        # HBM-resident input pipeline: two fetches of 32 whole ACDCSR x4 cycles (pvsr_cine_gather x 2 each)
+        from src.data.dataloader import DeviceDataloader
+        from src.data.datasets import SyntheticCineDataset
+        ds = SyntheticCineDataset(type='test', downscale_factor=4, num_sequences=32, num_phases=30, lr_size=(54, 63),
+                                  num_frames=7, num_updated_frames=6)
+        dl = DeviceDataloader(ds, batch_size=1)
+        for _ in range(2):
+            dl.fetch(list(range(32)))
+            torch.cuda.synchronize()
     elif mode.startswith("edsr"):
         # EDSR x4, 32 blocks x 256 features (configs/{train,test}/edsr_net/exp1_x4.yaml) - SURVEY 8 f3
         from src.model.nets import EDSRNet
