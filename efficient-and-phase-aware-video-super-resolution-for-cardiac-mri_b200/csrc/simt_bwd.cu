@@ -33,17 +33,30 @@ __device__ __forceinline__ float warp_sum(float v) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// lstm_bwd_pointwise.  One block per 128-pixel tile of one cell; thread = (4 consecutive tile rows, 8 channels).
-// Tile-transposed tensors ([tile][ch][128]) are read as 8/16-byte vectors over the 4 rows (7 vector loads per channel
-// instead of 28 scalar ones); dh / dgates are NHWC: the 8 channel-group threads of a pixel cover whole 128-byte lines.
-__global__ void __launch_bounds__(256, 2) lstm_bwd_pointwise_kernel(const __grid_constant__ LstmBwdParams p) {
+// lstm_bwd_pointwise.  One block per HALF 128-pixel tile of one cell; thread = (4 consecutive tile rows, 4 channels):
+// warp = 4 row quads x 8 channel groups, so for a fixed channel the 4 row-quad lanes read 64 (fp32) / 32 (bf16)
+// contiguous bytes of the tile-transposed tensors ([tile][ch][128]) = whole 32-byte sectors, and the 8 channel-group
+// lanes of a pixel cover a whole 128-byte line of the NHWC dh / 64 bytes per gate of dgates.
+// The first form (4 rows x 8 channels per thread, 128 registers, 2 blocks of 256 threads per SM = 25 % occupancy; ncu:
+// 69 us per 6-cell launch, 22 % warps active, 33 % of DRAM peak, sm throughput 14 %) was latency-bound: halving the
+// per-thread tile cuts the registers to 80 (3 blocks per SM) and issues all 32 loads of a thread up front.  tanh(c_t) uses the
+// same MUFU form as the forward epilogue (conv3x3_tc.cu: tanh_from_scaled).
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));   // 2^(2 log2(e) x)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return fmaf(-2.f, r, 1.f);
+}
+
+__global__ void __launch_bounds__(256, 3) lstm_bwd_pointwise_kernel(const __grid_constant__ LstmBwdParams p) {
   // PDL: this kernel alternates with the tcgen05 data-gradient launches of the reverse wavefront
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const LstmBwdProb& pr = p.prob[blockIdx.y];
-  const int tile = blockIdx.x;
-  const int cg = threadIdx.x & 7;          // channels [8*cg, 8*cg + 8)
-  const int rq = threadIdx.x >> 3;         // tile rows [4*rq, 4*rq + 4)
+  const int tile = blockIdx.x >> 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = (warp & 1) * 8 + (lane & 7);                       // channels [4*cg, 4*cg + 4)
+  const int rq = (blockIdx.x & 1) * 16 + (warp >> 1) * 4 + (lane >> 3);   // tile rows [4*rq, 4*rq + 4)
   size_t pix[4];
   bool valid[4];
   if (p.wp > 0) {
@@ -76,76 +89,74 @@ __global__ void __launch_bounds__(256, 2) lstm_bwd_pointwise_kernel(const __grid
   const float* cpt = pr.c_prev ? pr.c_prev + static_cast<size_t>(tile) * 64 * 128 + rq * 4 : nullptr;
   float* dct = pr.dc + static_cast<size_t>(tile) * 64 * 128 + rq * 4;
 
-  float dh[4][8];
+  // every load of the thread is issued before the first use: 4 (dh) + 4 x 7 independent requests in flight
+  float4 dh4[4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    if (valid[r]) {
-      const float4* q = reinterpret_cast<const float4*>(pr.dh + pix[r] * 64 + cg * 8);
-      const float4 v0 = q[0], v1 = q[1];
-      dh[r][0] = v0.x; dh[r][1] = v0.y; dh[r][2] = v0.z; dh[r][3] = v0.w;
-      dh[r][4] = v1.x; dh[r][5] = v1.y; dh[r][6] = v1.z; dh[r][7] = v1.w;
-    } else {
+  for (int r = 0; r < 4; ++r)
+    dh4[r] = valid[r] ? *reinterpret_cast<const float4*>(pr.dh + pix[r] * 64 + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  uint2 ui[4], uf[4], uo[4], ug[4];
+  float4 cn4[4], cp4[4], dc4[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dh[r][j] = 0.f;
-    }
+  for (int j = 0; j < 4; ++j) {
+    const int ch = cg * 4 + j;
+    ui[j] = *reinterpret_cast<const uint2*>(gt + ch * 128);
+    uf[j] = *reinterpret_cast<const uint2*>(gt + (64 + ch) * 128);
+    uo[j] = *reinterpret_cast<const uint2*>(gt + (128 + ch) * 128);
+    ug[j] = *reinterpret_cast<const uint2*>(gt + (192 + ch) * 128);
+    cn4[j] = *reinterpret_cast<const float4*>(ct + ch * 128);
+    cp4[j] = cpt ? *reinterpret_cast<const float4*>(cpt + ch * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dc4[j] = pr.dc_zero ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(dct + ch * 128);
   }
-  uint32_t oi[4][4], of[4][4], oo[4][4], og[4][4];   // [row][channel pair] packed bf16
+  const float dh[4][4] = {{dh4[0].x, dh4[0].y, dh4[0].z, dh4[0].w}, {dh4[1].x, dh4[1].y, dh4[1].z, dh4[1].w},
+                          {dh4[2].x, dh4[2].y, dh4[2].z, dh4[2].w}, {dh4[3].x, dh4[3].y, dh4[3].z, dh4[3].w}};
+  uint32_t oi[4][2], of[4][2], oo[4][2], og[4][2];   // [row][channel pair] packed bf16 (packed as soon as a pair is done)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ch = cg * 8 + j;
-    const uint2 ui = *reinterpret_cast<const uint2*>(gt + ch * 128);
-    const uint2 uf = *reinterpret_cast<const uint2*>(gt + (64 + ch) * 128);
-    const uint2 uo = *reinterpret_cast<const uint2*>(gt + (128 + ch) * 128);
-    const uint2 ug = *reinterpret_cast<const uint2*>(gt + (192 + ch) * 128);
-    const float4 cn4 = *reinterpret_cast<const float4*>(ct + ch * 128);
-    const float4 cp4 = cpt ? *reinterpret_cast<const float4*>(cpt + ch * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 dc4 = pr.dc_zero ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(dct + ch * 128);
-    const float gi[4] = {bf16lo(ui.x), bf16hi(ui.x), bf16lo(ui.y), bf16hi(ui.y)};
-    const float gf[4] = {bf16lo(uf.x), bf16hi(uf.x), bf16lo(uf.y), bf16hi(uf.y)};
-    const float go[4] = {bf16lo(uo.x), bf16hi(uo.x), bf16lo(uo.y), bf16hi(uo.y)};
-    const float gg[4] = {bf16lo(ug.x), bf16hi(ug.x), bf16lo(ug.y), bf16hi(ug.y)};
-    const float cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
-    const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
-    const float dcin[4] = {dc4.x, dc4.y, dc4.z, dc4.w};
-    float dco[4], ai[4], af[4], ao[4], ag[4];
+  for (int jp = 0; jp < 2; ++jp) {
+    float ai[4][2], af[4][2], ao[4][2], ag[4][2];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float tc = tanhf(cn[r]);
-      const float dcv = fmaf(dh[r][j] * go[r], 1.f - tc * tc, dcin[r]);
-      ao[r] = dh[r][j] * tc * go[r] * (1.f - go[r]);
-      ai[r] = dcv * gg[r] * gi[r] * (1.f - gi[r]);
-      af[r] = dcv * cp[r] * gf[r] * (1.f - gf[r]);
-      ag[r] = dcv * gi[r] * (1.f - gg[r] * gg[r]);
-      dco[r] = dcv * gf[r];
-    }
-    *reinterpret_cast<float4*>(dct + ch * 128) = make_float4(dco[0], dco[1], dco[2], dco[3]);
-    // pack channel pairs: even j fills the low half, odd j the high half
+    for (int u = 0; u < 2; ++u) {
+      const int j = jp * 2 + u;
+      const float gi[4] = {bf16lo(ui[j].x), bf16hi(ui[j].x), bf16lo(ui[j].y), bf16hi(ui[j].y)};
+      const float gf[4] = {bf16lo(uf[j].x), bf16hi(uf[j].x), bf16lo(uf[j].y), bf16hi(uf[j].y)};
+      const float go[4] = {bf16lo(uo[j].x), bf16hi(uo[j].x), bf16lo(uo[j].y), bf16hi(uo[j].y)};
+      const float gg[4] = {bf16lo(ug[j].x), bf16hi(ug[j].x), bf16lo(ug[j].y), bf16hi(ug[j].y)};
+      const float cn[4] = {cn4[j].x, cn4[j].y, cn4[j].z, cn4[j].w};
+      const float cp[4] = {cp4[j].x, cp4[j].y, cp4[j].z, cp4[j].w};
+      const float dcin[4] = {dc4[j].x, dc4[j].y, dc4[j].z, dc4[j].w};
+      float dco[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if ((j & 1) == 0) {
-        oi[r][j >> 1] = pack2(ai[r], 0.f) & 0xFFFFu; of[r][j >> 1] = pack2(af[r], 0.f) & 0xFFFFu;
-        oo[r][j >> 1] = pack2(ao[r], 0.f) & 0xFFFFu; og[r][j >> 1] = pack2(ag[r], 0.f) & 0xFFFFu;
-      } else {
-        oi[r][j >> 1] |= pack2(0.f, ai[r]) & 0xFFFF0000u; of[r][j >> 1] |= pack2(0.f, af[r]) & 0xFFFF0000u;
-        oo[r][j >> 1] |= pack2(0.f, ao[r]) & 0xFFFF0000u; og[r][j >> 1] |= pack2(0.f, ag[r]) & 0xFFFF0000u;
+      for (int r = 0; r < 4; ++r) {
+        const float tc = tanh_mufu(cn[r]);
+        const float dcv = fmaf(dh[r][j] * go[r], 1.f - tc * tc, dcin[r]);
+        ao[r][u] = dh[r][j] * tc * go[r] * (1.f - go[r]);
+        ai[r][u] = dcv * gg[r] * gi[r] * (1.f - gi[r]);
+        af[r][u] = dcv * cp[r] * gf[r] * (1.f - gf[r]);
+        ag[r][u] = dcv * gi[r] * (1.f - gg[r] * gg[r]);
+        dco[r] = dcv * gf[r];
       }
+      *reinterpret_cast<float4*>(dct + (cg * 4 + j) * 128) = make_float4(dco[0], dco[1], dco[2], dco[3]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      oi[r][jp] = pack2(ai[r][0], ai[r][1]); of[r][jp] = pack2(af[r][0], af[r][1]);
+      oo[r][jp] = pack2(ao[r][0], ao[r][1]); og[r][jp] = pack2(ag[r][0], ag[r][1]);
     }
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     if (!valid[r]) continue;
-    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(pr.dgates) + pix[r] * 256 + cg * 8;
-    *reinterpret_cast<uint4*>(dst) = make_uint4(oi[r][0], oi[r][1], oi[r][2], oi[r][3]);
-    *reinterpret_cast<uint4*>(dst + 64) = make_uint4(of[r][0], of[r][1], of[r][2], of[r][3]);
-    *reinterpret_cast<uint4*>(dst + 128) = make_uint4(oo[r][0], oo[r][1], oo[r][2], oo[r][3]);
-    *reinterpret_cast<uint4*>(dst + 192) = make_uint4(og[r][0], og[r][1], og[r][2], og[r][3]);
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(pr.dgates) + pix[r] * 256 + cg * 4;
+    *reinterpret_cast<uint2*>(dst) = make_uint2(oi[r][0], oi[r][1]);
+    *reinterpret_cast<uint2*>(dst + 64) = make_uint2(of[r][0], of[r][1]);
+    *reinterpret_cast<uint2*>(dst + 128) = make_uint2(oo[r][0], oo[r][1]);
+    *reinterpret_cast<uint2*>(dst + 192) = make_uint2(og[r][0], og[r][1]);
   }
 }
 
 int launch_lstm_bwd_pointwise(const LstmBwdParams& p, cudaStream_t s) {
   if (p.n_prob <= 0 || p.n_img <= 0) return 0;
   const int tiles = p.wp > 0 ? p.tiles_per_img : p.tiles_x * p.tiles_y;
-  dim3 grid(static_cast<unsigned>(p.n_img * tiles), static_cast<unsigned>(p.n_prob));
+  dim3 grid(static_cast<unsigned>(2 * p.n_img * tiles), static_cast<unsigned>(p.n_prob));   // two blocks per tile
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(256);

@@ -275,13 +275,16 @@ def test_fused_step_matches_autograd_and_adam(pvsr_lib):
         torch.cuda.synchronize()
         # step 0: identical parameters -> identical kernels (only atomic ordering differs); later steps: the two
         # Adam implementations have moved single elements apart by O(lr), so the comparison is statistical
-        ltol, gtol = (1e-5, 1e-3) if step == 0 else (2e-3, 4e-2)
+        # (a near-zero gradient element whose sign differs gets +-lr from either Adam: bias gradients of ~1e-6 reach
+        # rel-L2 0.05 at step 2 while staying collinear, hence the cosine gate next to the looser norm gate)
+        ltol, gtol = (1e-5, 1e-3) if step == 0 else (2e-3, 8e-2)
         assert abs(loss_a.item() - loss_b.item()) <= ltol * abs(loss_a.item()), (step, loss_a.item(), loss_b.item())
         for (k, pa), (_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
             if pa.grad is None:
                 assert float(pb.grad.abs().sum()) == 0.0
                 continue
             assert rel_l2(pb.grad, pa.grad) < gtol, (step, k, rel_l2(pb.grad, pa.grad))
+            assert cosine(pb.grad, pa.grad) > 0.997, (step, k, cosine(pb.grad, pa.grad))
         opt_a.step()
         opt_b.step()
     torch.cuda.synchronize()
