@@ -114,3 +114,76 @@ def test_two_gpu_data_parallel_matches_single_gpu(pvsr_lib):
         assert r[4] == list(range(r[0], 2 * world, world))
         # rank weights after the step equal the single-GPU weights up to Adam's sensitivity; compare loosely
         assert ((r[5] - full[:, r[4]]).norm() / full[:, r[4]].norm()).item() <= 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ EDSR
+EDSR_KW = dict(in_channels=1, out_channels=1, num_resblocks=2, num_features=64, upscale_factor=4, res_scale=0.1)
+
+
+def _edsr_batch(n):
+    g = torch.Generator().manual_seed(21)
+    return torch.randn(n, 1, 12, 10, generator=g), torch.randn(n, 1, 48, 40, generator=g)
+
+
+def _edsr_worker(rank, world, port, q):
+    import sys
+    for p in (PKG, ROOT, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    from pvsr import parallel
+    from pvsr.optim import FusedAdam
+    from src.model.nets import EDSRNet
+    parallel.init()
+    dev = torch.device("cuda", rank)
+    x, t = _edsr_batch(2 * world)
+    sl = slice(2 * rank, 2 * rank + 2)
+    torch.manual_seed(rank)                                  # different seeds: the broadcast must equalise them
+    net = EDSRNet(**EDSR_KW).to(dev).train()
+    opt = FusedAdam.for_net(net, lr=1e-3)
+    dp = parallel.DataParallelStep(net, opt)
+    loss, _ = net.engine.loss_and_grads(x[sl].to(dev), t[sl].to(dev))
+    parallel.allreduce_sum_(dp.flat_grad)
+    grads = {k: (p.grad / world).cpu() for k, p in net.named_parameters()}
+    opt.step()
+    net.engine.params_changed()
+    torch.cuda.synchronize()
+    weights = {k: p.detach().cpu() for k, p in net.named_parameters()}
+    q.put((rank, loss.item(), grads, weights))
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_gpu_edsr_data_parallel_matches_single_gpu(pvsr_lib):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from pvsr.optim import FusedAdam
+    from src.model.nets import EDSRNet
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_edsr_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(60)
+    assert all(p.exitcode == 0 for p in procs)
+    x, t = _edsr_batch(2 * world)
+    torch.manual_seed(0)
+    net = EDSRNet(**EDSR_KW).cuda().train()
+    FusedAdam.for_net(net, lr=1e-3)
+    loss, _ = net.engine.loss_and_grads(x.cuda(), t.cuda())
+    torch.cuda.synchronize()
+    # nn.L1Loss averages over the batch: the mean of the two half-batch losses is the full-batch loss
+    assert abs(sum(r[1] for r in res) / world - loss.item()) <= 1e-4 * abs(loss.item())
+    for k, p in net.named_parameters():
+        g = p.grad.cpu()
+        for r in res:
+            rel = ((r[2][k] - g).norm() / g.norm()).item()
+            assert rel <= 5e-3, (k, rel)
+        assert torch.equal(res[0][2][k], res[1][2][k])
+        assert torch.equal(res[0][3][k], res[1][3][k]), k        # ranks stay in lock-step
