@@ -212,6 +212,11 @@ int pvsr_set_pdl(int enable) {
   return 0;
 }
 int pvsr_get_pdl(void) { return get_pdl(); }
+int pvsr_set_head_tma(int enable) {
+  set_head_tma(enable);
+  return 0;
+}
+int pvsr_get_head_tma(void) { return get_head_tma(); }
 
 int pvsr_choose_tile(int H, int W, int* tw_log2_out) {
   if (H <= 0 || W <= 0 || !tw_log2_out) return set_error(-2, "bad image size");

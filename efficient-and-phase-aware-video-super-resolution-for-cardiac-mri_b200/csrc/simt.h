@@ -11,6 +11,8 @@ int launch_in_conv_prelu(const float* x, const float* w, const float* b, const f
                          long long n_img, int H, int W, cudaStream_t s);
 int launch_head_conv_last(const void* in_bf16_nhwc, const float* w, const float* b, float* out, const float* target,
                           float* l1_partial, long long n_img, int H, int W, cudaStream_t s);
+void set_head_tma(int enable);   // A/B switch of the head_conv_last forms (TMA ring / cp.async)
+int get_head_tma();
 int launch_posterm(const float* w1, const float* b1, const float* pos, float* table, int n_frames_out, int B, int L,
                    int window, int c_out, int c_in, int feat2, int n_total, cudaStream_t s);
 int launch_pack_weights(const float* w, const int* idx, const int* idx2, void* out_bf16, long long n, cudaStream_t s);

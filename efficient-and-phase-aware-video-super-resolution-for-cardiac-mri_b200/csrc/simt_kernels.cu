@@ -12,6 +12,8 @@
 
 #include <stdlib.h>
 
+#include "conv.h"
+#include "ptx.cuh"
 #include "simt.h"
 #include "stencil.cuh"
 
@@ -205,9 +207,179 @@ __global__ void __launch_bounds__(256, 1) head_conv_last_kernel(const __nv_bfloa
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// head_conv_last, TMA form.  Same arithmetic; the halo tile arrives as ONE cp.async.bulk.tensor box (64 ch x 32 x 16
+// pixels, 128B swizzle, zero fill outside the image = the conv padding) into a 3-deep ring, so that two 64 KB tiles
+// are in flight per SM while a third is being multiplied (the cp.async form above holds one: 148 x 64 KB in flight
+// cap it at ~4 TB/s by Little's law; 144-byte pixel pitch + 2 stages already used 165 KB of shared memory).
+// ldmatrix rows address the swizzled tile directly: 16-byte chunk ck of halo pixel hp lives at hp*128 + ((ck ^ (hp&7))*16).
+constexpr int kLastStages = 3;
+constexpr int kLastTileBytes = kLastHaloPix * 128;          // 65536
+
+__global__ void __launch_bounds__(256, 1) head_conv_last_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                    const float* __restrict__ w,
+                                                                    const float* __restrict__ b, float* __restrict__ out,
+                                                                    const float* __restrict__ target,
+                                                                    float* __restrict__ l1_partial, int H, int W,
+                                                                    int tiles_x, int tiles_y, int n_tiles) {
+  extern __shared__ uint8_t sm_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+  float* P = reinterpret_cast<float*>(sm + kLastStages * kLastTileBytes);      // [9][516] fp32
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + kLastStages * kLastTileBytes + 9 * kLastPStride * 4);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t sm_s = ptx::smem_u32(sm);
+
+  auto issue = [&](int t, int stage) {      // thread 0 only
+    const int tx = t % tiles_x;
+    const int q = t / tiles_x;
+    const int ty = q % tiles_y, img = q / tiles_y;
+    ptx::mbar_arrive_expect_tx(&full[stage], kLastTileBytes);
+    ptx::tma_load_4d(sm + stage * kLastTileBytes, &tmap, &full[stage], 0, tx * kLastTW - 1, ty * kLastTH - 1, img);
+  };
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmap);
+    for (int i = 0; i < kLastStages; ++i) ptx::mbar_init(&full[i], 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kLastStages - 1; ++i) {
+      const long long t = static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x;
+      if (t < n_tiles) issue(static_cast<int>(t), i);
+    }
+  }
+
+  // B fragments of the [64 x 16] weight matrix (taps 9..15 are zero): parameter layout (1, 64, 3, 3) -> w[c*9 + tap]
+  uint32_t bw[4][2][2];
+  {
+    const int n = lane >> 2, k0 = (lane & 3) * 2;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int tap = nt * 8 + n;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int c = ks * 16 + k0 + hh * 8;
+          const float lo = tap < 9 ? __ldg(w + c * 9 + tap) : 0.f;
+          const float hi = tap < 9 ? __ldg(w + (c + 1) * 9 + tap) : 0.f;
+          bw[ks][nt][hh] = f2_to_bf16x2(lo, hi);
+        }
+      }
+  }
+  const float bias = b[0];
+
+  int it = 0;
+  for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++it) {
+    const int t = static_cast<int>(tl);
+    const int stage = it % kLastStages;
+    // ring slot (it + 2) % 3 held tile it - 1, whose last reader passed the barrier that closed iteration it - 1
+    if (threadIdx.x == 0) {
+      const long long tn = tl + static_cast<long long>(kLastStages - 1) * gridDim.x;
+      if (tn < n_tiles) issue(static_cast<int>(tn), (it + kLastStages - 1) % kLastStages);
+    }
+    ptx::mbar_wait(&full[stage], (it / kLastStages) & 1);
+    const uint32_t tile_s = sm_s + stage * kLastTileBytes;
+    int q = t;
+    const int tx = q % tiles_x;
+    q /= tiles_x;
+    const int ty = q % tiles_y;
+    const int img = q / tiles_y;
+    const int y0 = ty * kLastTH - 1, x0 = tx * kLastTW - 1;                  // image coordinates of halo pixel (0, 0)
+
+    // P for this warp's 64 halo pixels: 4 m16 tiles x 4 k16 steps x 2 n8 tiles
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const int px0 = warp * 64 + mt * 16;
+      float acc[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+      const int hp = px0 + (lane & 7) + 8 * ((lane >> 3) & 1);
+      const uint32_t arow = tile_s + hp * 128;
+      const int sw = hp & 7, ck0 = lane >> 4;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                     : "r"(arow + (((ks * 2 + ck0) ^ sw) << 4)));
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+              "{%0, %1, %2, %3};"
+              : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+              : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bw[ks][nt][0]), "r"(bw[ks][nt][1]));
+      }
+      const int r = px0 + (lane >> 2), c = (lane & 3) * 2;
+      P[c * kLastPStride + r] = acc[0][0];
+      P[(c + 1) * kLastPStride + r] = acc[0][1];
+      P[c * kLastPStride + r + 8] = acc[0][2];
+      P[(c + 1) * kLastPStride + r + 8] = acc[0][3];
+      if ((lane & 3) == 0) {
+        P[8 * kLastPStride + r] = acc[1][0];
+        P[8 * kLastPStride + r + 8] = acc[1][2];
+      }
+    }
+    __syncthreads();                     // P complete; every ldmatrix read of this ring slot is done
+
+    float l1 = 0.f;
+    for (int i = threadIdx.x; i < kLastTH * kLastTW; i += 256) {
+      const int ly = i / kLastTW, lx = i - ly * kLastTW;
+      const int y = y0 + 1 + ly, x = x0 + 1 + lx;
+      float acc = bias;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) acc += P[tap * kLastPStride + (ly + tap / 3) * kLastHaloW + lx + tap % 3];
+      if (y < H && x < W) {
+        const size_t o = (static_cast<size_t>(img) * H + y) * W + x;
+        out[o] = acc;
+        if (target) l1 += fabsf(acc - target[o]);
+      }
+    }
+    if (l1_partial) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, d);
+      if (lane == 0) atomicAdd(l1_partial + img, l1);
+    }
+    __syncthreads();                     // P consumed before the next tile's products overwrite it
+  }
+}
+
+static int g_head_tma = 1;   // 1: TMA ring form of head_conv_last, 0: cp.async double-buffer form (A/B: PVSR_HEAD_TMA)
+void set_head_tma(int enable) { g_head_tma = enable ? 1 : 0; }
+int get_head_tma() { return g_head_tma; }
+
+static int launch_head_conv_last_tma(const void* in, const float* w, const float* b, float* out, const float* target,
+                                     float* l1_partial, long long n_img, int H, int W, cudaStream_t s) {
+  const int tiles_x = (W + kLastTW - 1) / kLastTW, tiles_y = (H + kLastTH - 1) / kLastTH;
+  const size_t smem = 1024 + kLastStages * kLastTileBytes + 9 * kLastPStride * sizeof(float) + 64;
+  static bool attr = false;
+  static int num_sms = 0;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(head_conv_last_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr = true;
+  }
+  CUtensorMap tmap;
+  if (make_act_tmap(&tmap, in, 64, W, H, n_img, kLastHaloW, kLastHaloH, 1) != 0) return static_cast<int>(cudaErrorInvalidValue);
+  const long long blocks = n_img * tiles_x * tiles_y;
+  if (blocks >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
+  const unsigned grid = static_cast<unsigned>(blocks < num_sms ? blocks : num_sms);
+  head_conv_last_tma_kernel<<<grid, 256, smem, s>>>(tmap, w, b, out, target, l1_partial, H, W, tiles_x, tiles_y,
+                                                   static_cast<int>(blocks));
+  return static_cast<int>(cudaGetLastError());
+}
+
 int launch_head_conv_last(const void* in, const float* w, const float* b, float* out, const float* target,
                           float* l1_partial, long long n_img, int H, int W, cudaStream_t s) {
   if (n_img == 0) return 0;
+  if (g_head_tma) return launch_head_conv_last_tma(in, w, b, out, target, l1_partial, n_img, H, W, s);
   const int tiles_x = (W + kLastTW - 1) / kLastTW, tiles_y = (H + kLastTH - 1) / kLastTH;
   const size_t smem = 2 * kLastHaloPix * kLastPitch + 9 * kLastPStride * sizeof(float);
   static bool attr = false;

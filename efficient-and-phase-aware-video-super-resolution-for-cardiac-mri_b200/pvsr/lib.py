@@ -102,6 +102,8 @@ SIGNATURES = {
     "pvsr_get_halo_mode": (c_int, []),
     "pvsr_set_pdl": (c_int, [c_int]),
     "pvsr_get_pdl": (c_int, []),
+    "pvsr_set_head_tma": (c_int, [c_int]),
+    "pvsr_get_head_tma": (c_int, []),
     "pvsr_choose_tile": (c_int, [c_int, c_int, C.POINTER(c_int)]),
     "pvsr_pack_index_count": (c_int64, [C.POINTER(PackSpec)]),
     "pvsr_pack_index_host": (c_int, [C.POINTER(PackSpec), c_void_p]),
@@ -187,6 +189,8 @@ def load():
         fn.argtypes = args
     if os.environ.get("PVSR_HALO") is not None:           # A/B switch of the halo (slab) conv kernel
         lib.pvsr_set_halo_mode(int(os.environ["PVSR_HALO"]))
+    if os.environ.get("PVSR_HEAD_TMA") is not None:       # A/B switch of the head_conv_last forms
+        lib.pvsr_set_head_tma(int(os.environ["PVSR_HEAD_TMA"]))
     if os.environ.get("PVSR_PDL") is not None:            # A/B switch of programmatic dependent launch
         lib.pvsr_set_pdl(int(os.environ["PVSR_PDL"]))
     if os.environ.get("PVSR_CTA_PAIR") is not None:       # A/B switch of the cta_group::2 conv kernel

@@ -52,6 +52,9 @@ int pvsr_get_halo_mode(void);
  * plan (captured CUDA graphs keep the setting they were captured with).  Process-wide. */
 int pvsr_set_pdl(int enable);
 int pvsr_get_pdl(void);
+/* head_conv_last form: 1 = 3-stage TMA ring (default), 0 = cp.async double buffer (A/B switch; env PVSR_HEAD_TMA). */
+int pvsr_set_head_tma(int enable);
+int pvsr_get_head_tma(void);
 
 /* ---- host-side packing logic (pure CPU; usable without a GPU) ------------------------------------------------ */
 /* Tile choice of the implicit GEMM: tile = (128 >> tw_log2) x (1 << tw_log2) output pixels. */
