@@ -44,6 +44,7 @@ class _Plan:
         self.target = torch.empty(self.T, cfg.batch, self.Hs, self.Ws, dtype=torch.float32,
                                   device=device) if self.train else None
         self.packed_version = None
+        self.outs, self.out_idx = [self.out], 0     # output ring (RefineNetEngine.output_slots)
 
     def class_stats(self, bwd=False):
         n = L.NUM_CLASSES_BWD if bwd else NUM_CLASSES
@@ -69,6 +70,9 @@ class RefineNetEngine:
         self.net = net
         self.plans = {}
         self.use_graph = True
+        # inference plans rotate over this many output buffers: with 2, the device->host copy of step i (on a copy
+        # stream, pvsr.hostio.HostFrameRing) overlaps the whole forward of step i + 1 instead of blocking it
+        self.output_slots = 1
         self._flat = None   # (flat_param, flat_grad, views) once flatten_parameters() ran
         self._grad_buf = None
         self._aux = {}
@@ -174,10 +178,24 @@ class RefineNetEngine:
         [lists, T, N, H*s, W*s] (reused by the next call)."""
         P, keep = self._params_struct()
         self._ensure_packed(pl, P)
+        pl.out = self._next_out(pl, advance=True)
         L.check(pl.lib.pvsr_plan_forward(pl.handle, C.byref(P), L.ptr(pl.packed), L.ptr(pl.lr), L.ptr(pl.pos),
                                          L.ptr(pl.out), L.ptr(pl.workspace), int(self.use_graph),
                                          L.current_stream()), "pvsr_plan_forward")
         return pl.out
+
+    def _next_out(self, pl, advance=False):
+        slots = 1 if pl.train else max(1, int(self.output_slots))
+        while len(pl.outs) < slots:
+            pl.outs.append(torch.empty_like(pl.outs[0]))
+        buf = pl.outs[pl.out_idx % slots]
+        if advance:
+            pl.out_idx += 1
+        return buf
+
+    def next_output_ptr(self, pl):
+        """Device address of the buffer the next run(pl) writes (for HostFrameRing.before_launch)."""
+        return self._next_out(pl).data_ptr()
 
     def _check_inputs(self, inputs):
         x0 = inputs[0]

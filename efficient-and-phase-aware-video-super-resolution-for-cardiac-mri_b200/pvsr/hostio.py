@@ -32,14 +32,18 @@ class HostFrameRing:
         self.slots = slots
         self.host = [None] * slots
         self.done = [None] * slots        # event: copy into slot finished
+        self.src = [None] * slots         # device address each outstanding copy reads from
         self.next = 0
         self.bytes_per_step = 0
 
-    def before_launch(self):
-        """Call before enqueueing a forward that overwrites the buffer earlier submits read from."""
+    def before_launch(self, dst_ptr=None):
+        """Call before enqueueing a forward that overwrites a buffer earlier submits read from: the compute stream
+        waits for the copies still reading `dst_ptr` (RefineNetEngine.next_output_ptr) - or for all of them when the
+        address is not given.  With engine.output_slots = 2 the copy of step i never reads what step i + 1 writes, so
+        the forward starts immediately and the copy overlaps it."""
         cur = torch.cuda.current_stream(self.device)
-        for ev in self.done:
-            if ev is not None:
+        for ev, src in zip(self.done, self.src):
+            if ev is not None and (dst_ptr is None or src == dst_ptr):
                 cur.wait_event(ev)
 
     def submit(self, frames):
@@ -61,6 +65,7 @@ class HostFrameRing:
             ev = torch.cuda.Event()
             ev.record(self.stream)
         self.done[s] = ev
+        self.src[s] = src.data_ptr()
         self.bytes_per_step = src.numel() * src.element_size()
         return s
 
