@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "conv.h"
+#include "ptx.cuh"
 #include "simt.h"
 #include "stencil.cuh"
 
@@ -374,9 +375,195 @@ __global__ void __launch_bounds__(256, 2) head_last_bwd_weight_kernel(const __nv
   if (threadIdx.x == 0) atomicAdd(db, sacc[576]);
 }
 
+// TMA form of head_last_bwd_weight: the `in` tile (64 ch x 32 x 8 px, 128B swizzle) arrives as one bulk tensor box
+// through a 4-deep ring - three tiles (96 KB) in flight per SM where the cp.async form above loads, waits, multiplies,
+// one tile at a time (same lesson as head_conv_last_tma_kernel).  The small fp32 dOut halo (34 x 10) of tile i + 1 is
+// fetched into registers at the top of iteration i and parked in the other half of a double-buffered shared array at
+// its end, so its latency hides behind the MMAs of tile i.  (A 3-D fp32 tensor map with a 36-element box faulted with
+// "illegal instruction" at the cp.async.bulk.tensor - not pursued.)
+constexpr int kWStages = 4;
+constexpr int kWTileBytes = kWTH * kWTW * 128;                       // 32768
+constexpr int kWHaloPitch = 1536;
+
+__global__ void __launch_bounds__(256, 1) head_last_bwd_weight_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                                          const float* __restrict__ dout,
+                                                                          float* __restrict__ dw, float* __restrict__ db,
+                                                                          int H, int W, int tiles_x, int tiles_y,
+                                                                          int total) {
+  extern __shared__ uint8_t smw_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smw_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* halos = sm + kWStages * kWTileBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(halos + kWStages * kWHaloPitch);
+  float* sacc = reinterpret_cast<float*>(full + kWStages);           // [577]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t sm_s = ptx::smem_u32(sm);
+  auto issue = [&](int t, int stage) {      // thread 0 only
+    const int tx = t % tiles_x;
+    const int q = t / tiles_x;
+    const int ty = q % tiles_y, img = q / tiles_y;
+    ptx::mbar_arrive_expect_tx(&full[stage], kWTileBytes);
+    ptx::tma_load_4d(sm + stage * kWTileBytes, &tm_in, &full[stage], 0, tx * kWTW, ty * kWTH, img);
+  };
+  // this thread's (up to two) elements of the 34 x 10 dOut halo of tile t, zero outside the image
+  auto halo_fetch = [&](long long t, float (&v)[2]) {
+    const int tx = static_cast<int>(t % tiles_x);
+    const long long q = t / tiles_x;
+    const int ty = static_cast<int>(q % tiles_y);
+    const float* dsrc = dout + (q / tiles_y) * H * W;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = threadIdx.x + k * 256;
+      const int hy = i / (kWTW + 2), hx = i - hy * (kWTW + 2);
+      const int y = ty * kWTH + hy - 1, x = tx * kWTW + hx - 1;
+      v[k] = (i < (kWTH + 2) * (kWTW + 2) && y >= 0 && y < H && x >= 0 && x < W)
+                 ? __ldg(dsrc + static_cast<size_t>(y) * W + x) : 0.f;
+    }
+  };
+  auto halo_store = [&](int buf, const float (&v)[2]) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < (kWTH + 2) * (kWTW + 2)) {
+        const int hy = i / (kWTW + 2), hx = i - hy * (kWTW + 2);
+        reinterpret_cast<float*>(halos + buf * kWHaloPitch)[hy * kWHaloW + hx] = v[k];
+      }
+    }
+  };
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tm_in);
+    for (int i = 0; i < kWStages; ++i) ptx::mbar_init(&full[i], 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWStages - 1; ++i) {
+      const long long t = static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x;
+      if (t < total) issue(static_cast<int>(t), i);
+    }
+  }
+  {
+    float v[2];
+    if (blockIdx.x < total) {
+      halo_fetch(blockIdx.x, v);
+      halo_store(0, v);
+    }
+  }
+  __syncthreads();
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+  float bsum = 0.f;
+  int it = 0;
+  for (long long tl = blockIdx.x; tl < total; tl += gridDim.x, ++it) {
+    const int stage = it % kWStages;
+    if (threadIdx.x == 0) {                 // slot (it + 3) % 4 held tile it - 1: released by the barrier below
+      const long long tn = tl + static_cast<long long>(kWStages - 1) * gridDim.x;
+      if (tn < total) issue(static_cast<int>(tn), (it + kWStages - 1) % kWStages);
+    }
+    float hnext[2];
+    const bool has_next = tl + gridDim.x < total;
+    if (has_next) halo_fetch(tl + gridDim.x, hnext);          // in flight during this tile's MMAs
+    ptx::mbar_wait(&full[stage], (it / kWStages) & 1);
+    const uint32_t tile_s = sm_s + stage * kWTileBytes;
+    const float* halo = reinterpret_cast<const float*>(halos + (it & 1) * kWHaloPitch);
+    bsum += halo[(1 + (threadIdx.x >> 5)) * kWHaloW + 1 + (threadIdx.x & 31)];      // one interior pixel per thread
+
+    const int ly = warp;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int lx0 = ks * 16;
+      uint32_t ahi[4], alo[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int tap = (lane >> 2) + (f & 1) * 8;
+        const int k = (lane & 3) * 2 + (f >> 1) * 8;
+        float v0 = 0.f, v1 = 0.f;
+        if (tap < 9) {
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const float* hrow = halo + (ly - dy + 1) * kWHaloW + (lx0 + k - dx + 1);
+          v0 = hrow[0];
+          v1 = hrow[1];
+        }
+        const uint32_t hi = pack2(v0, v1);
+        ahi[f] = hi;
+        alo[f] = pack2(v0 - bf16lo(hi), v1 - bf16hi(hi));
+      }
+      const int hp = ly * kWTW + lx0 + (lane & 7) + 8 * ((lane >> 3) & 1);
+      const uint32_t arow = tile_s + hp * 128;
+      const int sw = hp & 7;
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(arow + (((2 * np + (lane >> 4)) ^ sw) << 4)));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t bb0 = h ? b2 : b0, bb1 = h ? b3 : b1;
+          float* c = acc[2 * np + h];
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+              "{%0, %1, %2, %3};"
+              : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+              : "r"(ahi[0]), "r"(ahi[1]), "r"(ahi[2]), "r"(ahi[3]), "r"(bb0), "r"(bb1));
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+              "{%0, %1, %2, %3};"
+              : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+              : "r"(alo[0]), "r"(alo[1]), "r"(alo[2]), "r"(alo[3]), "r"(bb0), "r"(bb1));
+        }
+      }
+    }
+    if (has_next) halo_store((it + 1) & 1, hnext);   // the other halo buffer: its readers finished an iteration ago
+    __syncthreads();   // every read of this ring slot is done before thread 0 refills it next iteration
+  }
+  for (int i = threadIdx.x; i < 577; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int ch = nt * 8 + (lane & 3) * 2, tap = lane >> 2;
+    atomicAdd(&sacc[ch * 9 + tap], acc[nt][0]);
+    atomicAdd(&sacc[(ch + 1) * 9 + tap], acc[nt][1]);
+    if (tap == 0) {
+      atomicAdd(&sacc[ch * 9 + 8], acc[nt][2]);
+      atomicAdd(&sacc[(ch + 1) * 9 + 8], acc[nt][3]);
+    }
+  }
+  bsum = warp_sum(bsum);
+  if (lane == 0) atomicAdd(&sacc[576], bsum);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 576; i += 256) atomicAdd(dw + i, sacc[i]);
+  if (threadIdx.x == 0) atomicAdd(db, sacc[576]);
+}
+
+static int launch_head_last_bwd_weight_tma(const void* in_bf16, const float* dout, float* dw, float* db, long long n_img,
+                                           int H, int W, int num_sms, cudaStream_t s) {
+  const int tiles_x = (W + kWTW - 1) / kWTW, tiles_y = (H + kWTH - 1) / kWTH;
+  const size_t smem = 1024 + kWStages * (kWTileBytes + kWHaloPitch) + 64 + 577 * sizeof(float) + 16;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(head_last_bwd_weight_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = true;
+  }
+  CUtensorMap tm_in;
+  if (make_act_tmap(&tm_in, in_bf16, 64, W, H, n_img, kWTW, kWTH, 1) != 0) return static_cast<int>(cudaErrorInvalidValue);
+  const long long total = n_img * tiles_x * tiles_y;
+  if (total >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
+  const long long cap = num_sms > 0 ? num_sms : 148;
+  head_last_bwd_weight_tma_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, smem, s>>>(
+      tm_in, dout, dw, db, H, W, tiles_x, tiles_y, static_cast<int>(total));
+  return static_cast<int>(cudaGetLastError());
+}
+
 int launch_head_last_bwd_weight(const void* in_bf16, const float* dout, float* dw, float* db, long long n_img, int H,
                                 int W, int num_sms, cudaStream_t s) {
   if (n_img * H * W == 0) return 0;
+  if (get_head_tma())
+    return launch_head_last_bwd_weight_tma(in_bf16, dout, dw, db, n_img, H, W, num_sms, s);
   const int tiles_x = (W + kWTW - 1) / kWTW, tiles_y = (H + kWTH - 1) / kWTH;
   long long blocks = n_img * tiles_x * tiles_y;
   const long long cap = 4LL * (num_sms > 0 ? num_sms : 148);
