@@ -33,7 +33,10 @@ import torch  # noqa: E402
 T_FRAMES, U_FRAMES, LR_H, LR_W, SCALE = 30, 6, 54, 63, 4
 # BASELINE.json configs: [1] ACDC x4 (the headline workload), [2] the x2 / x3 scale variants, [3] DSB15SR-shaped x4
 WORKLOADS = {"acdc_x4": (54, 63, 4, "ACDCSR"), "acdc_x3": (72, 84, 3, "ACDCSR"), "acdc_x2": (108, 126, 2, "ACDCSR"),
-             "dsb15_x4": (63, 48, 4, "DSB15SR")}
+             "dsb15_x4": (63, 48, 4, "DSB15SR"),
+             # EDSRNet x4 of configs/{train,test}/edsr_net/exp1_x4.yaml on the same conv core
+             "edsr_x4": (54, 63, 4, "ACDCSR")}
+EDSR_FRAMES = 60
 NET_KW = dict(in_channels=1, out_channels=1, num_features=[64, 64, 64], upscale_factor=SCALE, num_stages=3,
               update_memory=True, num_updated_frames=U_FRAMES, refine_window_size=5, positional_encoding=True)
 METRIC = "SR frames/s at x4"
@@ -133,6 +136,70 @@ def cpu_oracle_time(n_seq_steps, warmup, threads):
             if i >= warmup:
                 times.append(dt)
     return times
+
+
+def edsr_cpu_time(frames):
+    """CPU oracle of EDSR x4 (32 x 256) on `frames` ACDCSR-shaped LR frames: (seconds, cores)."""
+    from oracle import edsr_oracle as O
+    from src.model.nets import EDSRNet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = EDSRNet(in_channels=1, out_channels=1, num_resblocks=32, num_features=256, upscale_factor=4,
+                 res_scale=0.1).state_dict()
+    x = torch.randn(frames, 1, LR_H, LR_W, generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        O.edsr_forward(sd, x[:1], 32, 4, 0.1)
+        t0 = time.perf_counter()
+        O.edsr_forward(sd, x, 32, 4, 0.1)
+        return time.perf_counter() - t0, cores
+
+
+def run_edsr(args, rank, world):
+    """`--workload edsr_x4`: single-GPU line for the EDSR widening row (profiles/bench_edsr.py does the device timing)."""
+    if rank != 0:
+        return
+    metric = "SR frames/s at x4 (EDSRNet 32 x 256)"
+    cfg = {"workload": f"EDSRNet x4 inference (32 residual blocks x 256 features, 43 M parameters, random init), "
+                       f"{EDSR_FRAMES} synthetic ACDCSR-shaped LR frames {LR_H}x{LR_W} per step -> SR frames 216x252",
+           "name": "edsr_x4", "frames_per_step": EDSR_FRAMES, "parallelism": "single GPU",
+           "l2": "256 MiB flush write between steps"}
+    if args.impl == "reference":
+        times = []
+        for _ in range(max(1, args.steps)):
+            dt, cores = edsr_cpu_time(2)
+            times.append(dt)
+        value = 2 * len(times) / sum(times)
+        sample = f"{len(times)} step(s) x 2 LR frames {LR_H}x{LR_W} through the fp32 torch CPU oracle (oracle/edsr_oracle.py)"
+        print(json.dumps({"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": len(times), "warmup": 1, "ms_per_step": 1e3 * sum(times) / len(times),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": dict(cfg, frames_per_step=2),
+                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import bench_edsr
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    res = bench_edsr.measure(argparse.Namespace(frames=EDSR_FRAMES, steps=args.steps, warmup=args.warmup))
+    clocks = sampler.stop()
+    inf = res["inference"]
+    line = {"metric": metric, "value": inf["frames_per_s"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": inf["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "e2e": {"value": inf["e2e_frames_per_s"], "unit": UNIT, "h2d_bytes_per_step": inf["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": inf["d2h_bytes_per_step"], "ms_per_step": inf["ms_per_step_e2e"]},
+            "gpu_launches": inf["launches_per_step"] * args.steps, "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "conv3x3_halo_kernel<256, EPI_STORE / EPI_PS> (all 71 launches of a step)",
+                         "achieved": inf["tflops"], "peak": res["peak_tflops"], "unit": "TFLOP/s",
+                         "frac": inf["frac_of_peak"], "traffic": None, "peak_source": res["peak_source"]},
+            "train_step": res["train_step"]}
+    if not args.no_cpu_baseline:
+        dt, cores = edsr_cpu_time(2)
+        line["cpu_baseline"] = {"value": 2 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "2 LR frames 54x63 through the fp32 torch CPU oracle (oracle/edsr_oracle.py)"}
+    print(json.dumps(line), flush=True)
 
 
 def run_reference(args, rank):
@@ -265,6 +332,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "edsr_x4":
+        run_edsr(args, rank, world)
+        return
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -3,7 +3,7 @@
 parameters) on the RefineNet conv core - SURVEY section 8 f3.  Not the headline bench (bench.py); same timing rules:
 CUDA events on the launching stream, >= 3 warm-up steps, 256 MiB L2 flush between steps.
 
-  python profiles/bench_edsr.py [--frames 60] [--steps 10] [--no-cpu]
+  python profiles/bench_edsr.py [--frames 60] [--steps 10]        (contract-shaped line + CPU leg: bench.py --workload edsr_x4)
 
 inference: one step = `--frames` ACDCSR-shaped LR frames 54x63 -> SR frames 216x252 through the public module call
 training : one step = forward + L1 + backward + fused Adam on N = 16 patches of 32x32 (HR 128x128)
@@ -14,7 +14,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "efficient-and-phase-aware-video-super-resolution-for-cardiac-mri_b200")
@@ -51,13 +50,9 @@ def timed(fn, steps, warmup, flush):
     return e0.elapsed_time(e1) / steps
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=60)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--no-cpu", action="store_true")
-    args = ap.parse_args()
+def measure(args):
+    """Device-timed EDSR x4 inference + training step; returns the result dict (no CPU leg: the CPU oracle is timed by
+    `bench.py --workload edsr_x4`, the only bench that may execute oracle/)."""
     import build as pvsr_build
     pvsr_build.build()
     from pvsr.optim import FusedAdam
@@ -89,7 +84,8 @@ def main():
     out["inference"] = {"frames_per_step": args.frames, "ms_per_step": ms, "frames_per_s": args.frames / ms * 1e3,
                         "e2e_frames_per_s": args.frames / ms_e2e * 1e3, "tflop_per_step": fl / 1e12,
                         "tflops": fl / ms / 1e9, "frac_of_peak": fl / ms / 1e9 / peak,
-                        "launches_per_step": 2 * 32 + 7}
+                        "launches_per_step": 2 * 32 + 7, "ms_per_step_e2e": ms_e2e,
+                        "h2d_bytes_per_step": x_h.numel() * 4, "d2h_bytes_per_step": y_h.numel() * 4}
     del net
     torch.cuda.empty_cache()
 
@@ -112,18 +108,16 @@ def main():
                          "tflops": total / ms / 1e9, "frac_of_peak": total / ms / 1e9 / peak,
                          "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
 
-    if not args.no_cpu:
-        from oracle import edsr_oracle as O
-        torch.set_num_threads(os.cpu_count() or 1)
-        sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
-        xc = x_h[:2].clone()
-        with torch.no_grad():
-            O.edsr_forward(sd, xc[:1], 32, 4, 0.1)
-            t0 = time.perf_counter()
-            O.edsr_forward(sd, xc, 32, 4, 0.1)
-            dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"frames_per_s": 2 / dt, "cores": os.cpu_count(), "kind": "port",
-                               "sample": "2 frames 54x63 through the fp32 torch CPU oracle (edsr_oracle.py)"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    out = measure(args)
     print(json.dumps(out), flush=True)
 
 
