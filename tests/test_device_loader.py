@@ -206,3 +206,18 @@ def test_device_loader_feeds_trainer_and_predictor(tmp_path, pvsr_lib):
     assert logs[0].keys() == logs[1].keys()
     for k in logs[0]:
         assert logs[0][k] == pytest.approx(logs[1][k], rel=1e-6), k
+
+
+@pytest.mark.gpu
+def test_device_loader_shards_cover_the_dataset_once(tmp_path, pvsr_lib):
+    """shard=(rank, world): the ranks' batches partition the training items (DistributedSampler semantics)."""
+    from src.data.dataloader import DeviceDataloader
+    pos = _make_acdc_tree(tmp_path, 'train', n_seq=2)
+    seen = []
+    for rank in range(2):
+        dl = DeviceDataloader(_dataset(tmp_path, 'train', pos), batch_size=3, shuffle=False, shard=(rank, 2))
+        for batch in dl:
+            assert batch['lr_imgs'][0].is_cuda
+            seen.extend(batch['index'].tolist())
+    n = len(_dataset(tmp_path, 'train', pos))
+    assert sorted(set(seen)) == list(range(n)) and len(seen) in (n, n + 1)      # odd sizes are padded by one item

@@ -209,3 +209,32 @@ def test_bicubic_matches_torch(shape, s, pvsr_lib):
     got = Bicubic(s).cuda()(x.cuda()).cpu()
     assert got.shape == want.shape
     assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw,shape", [
+    (dict(num_resblocks=1, num_features=192, upscale_factor=2), (2, 1, 10, 14)),     # BN = 64 x 3 column tiles
+    (dict(num_resblocks=2, num_features=64, upscale_factor=8), (1, 1, 6, 5)),        # three conv + PixelShuffle(2) stages
+    (dict(num_resblocks=0, num_features=128, upscale_factor=3), (3, 1, 7, 9)),       # no residual block at all
+])
+def test_other_widths_and_factors_against_oracle(kw, shape, pvsr_lib):
+    """Configurations without a golden file: the CUDA path against the (golden-pinned) oracle, forward and gradients."""
+    from oracle import edsr_oracle as O
+    full = dict(in_channels=1, out_channels=1, res_scale=0.1, **kw)
+    net = _net(full)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    s = kw["upscale_factor"]
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(*shape, generator=g)
+    target = torch.randn(shape[0], 1, shape[2] * s, shape[3] * s, generator=g)
+    want, loss, grads = O.edsr_loss_and_grads(sd, x, target, kw["num_resblocks"], s, 0.1)
+    net = net.cuda().train()
+    out = net(x.cuda())
+    got_loss = torch.nn.L1Loss()(out, target.cuda())
+    got_loss.backward()
+    _check_out(out.detach().cpu(), want)
+    assert got_loss.item() == pytest.approx(loss.item(), rel=2e-3)
+    for k, p in net.named_parameters():
+        a, b = p.grad.cpu(), grads[k]
+        rel = ((a - b).norm() / b.norm()).item()
+        assert rel <= 0.12, (k, rel)
