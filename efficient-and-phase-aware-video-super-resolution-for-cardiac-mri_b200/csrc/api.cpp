@@ -330,6 +330,13 @@ int pvsr_conv3x3_wgrad(const pvsr_wgrad_desc* d, void* stream) {
   return rc ? rc : pvsr_conv3x3_wgrad_staged(d, 0, stream);
 }
 
+int pvsr_frame_scores(const float* sr, const float* hr, const int32_t* rects, int64_t n, int H, int W, float mean,
+                      float std, const float* window11, float value_range, double* sums, void* stream) {
+  if (H < 1 || W < 1 || !window11 || !sums) return set_error(-2, "frame_scores: bad arguments");
+  if (n > 65535) return set_error(-2, "frame_scores: at most 65535 frames per call");
+  return check_cuda(launch_frame_scores(sr, hr, rects, n, H, W, mean, std, window11, value_range, sums,
+                                        static_cast<cudaStream_t>(stream)), "frame_scores");
+}
 int pvsr_bicubic_upsample(const float* in, float* out, int64_t n_img, int h, int w, int scale, void* stream) {
   if (h < 1 || w < 1 || scale < 1) return set_error(-2, "bicubic: bad size %dx%d x%d", h, w, scale);
   return check_cuda(launch_bicubic(in, out, n_img, h, w, scale, static_cast<cudaStream_t>(stream)), "bicubic");

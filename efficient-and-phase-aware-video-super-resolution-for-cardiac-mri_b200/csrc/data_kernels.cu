@@ -154,6 +154,138 @@ int launch_table(const pvsr_table_job* jobs, int n_jobs, long long max_n, cudaSt
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Per-frame scores of the runners in one pass over the SR / HR frames: the reference calls
+// L1Loss, denormalize (src/utils.py:1-20), PSNR (metrics.py:20-36) and SSIM (metrics.py:86-113: five dense 11x11
+// Gaussian convolutions) once per frame and reads every scalar back with .item().  Here two launches score N frames:
+//   sums[n][0] = sum |sr - hr|                     (normalised frames, over the rectangle)
+//   sums[n][1] = sum (D(sr) - D(hr))^2             D(x) = clamp(rint(x * std + mean), 0, 255)
+//   sums[n][2] = sum of the SSIM map               (valid 11x11 window positions inside the rectangle)
+// rects[n] = (h0, hn, w0, wn) restricts a frame to its cardiac bounding box (CardiacPSNR / CardiacSSIM, :116-165).
+// Accumulation: fp32 inside a block, fp64 atomics across blocks.  HBM-bound: 8 B read per pixel and launch.
+__device__ __forceinline__ float denorm255(float x, float mean, float stdv) {
+  // two roundings like torch's `imgs * std + mean` (src/utils.py:19), then round-half-even like Tensor.round_()
+  return fminf(fmaxf(rintf(__fadd_rn(__fmul_rn(x, stdv), mean)), 0.f), 255.f);
+}
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int d = 4; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+  }
+  return t;   // valid in thread 0
+}
+
+__global__ void __launch_bounds__(256) frame_l1_mse_kernel(const float* __restrict__ sr, const float* __restrict__ hr,
+                                                           const int* __restrict__ rects, int H, int W, float mean,
+                                                           float stdv, double* __restrict__ sums) {
+  __shared__ float red[8];
+  const int n = blockIdx.y;
+  const int h0 = rects ? rects[4 * n] : 0, hn = rects ? rects[4 * n + 1] : H;
+  const int w0 = rects ? rects[4 * n + 2] : 0, wn = rects ? rects[4 * n + 3] : W;
+  const int rw = wn - w0, area = (hn - h0) * rw;
+  const float* a = sr + static_cast<long long>(n) * H * W;
+  const float* b = hr + static_cast<long long>(n) * H * W;
+  float l1 = 0.f, se = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < area; i += gridDim.x * blockDim.x) {
+    const int y = i / rw, x = i - y * rw;
+    const int o = (h0 + y) * W + w0 + x;
+    const float va = a[o], vb = b[o];
+    l1 += fabsf(va - vb);
+    const float dd = denorm255(va, mean, stdv) - denorm255(vb, mean, stdv);
+    se = fmaf(dd, dd, se);
+  }
+  const float t0 = block_sum_256(l1, red);
+  const float t1 = block_sum_256(se, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums + 3 * n, static_cast<double>(t0));
+    atomicAdd(sums + 3 * n + 1, static_cast<double>(t1));
+  }
+}
+
+constexpr int kSsTH = 16, kSsTW = 32, kSsK = 11;
+constexpr int kSsIH = kSsTH + kSsK - 1, kSsIW = kSsTW + kSsK - 1;      // 26 x 42 input tile
+
+__global__ void __launch_bounds__(256) frame_ssim_kernel(const float* __restrict__ sr, const float* __restrict__ hr,
+                                                         const int* __restrict__ rects, int H, int W, float mean,
+                                                         float stdv, const float* __restrict__ window, float c1, float c2,
+                                                         int tiles_x, double* __restrict__ sums) {
+  __shared__ float ta[kSsIH][kSsIW + 1], tb[kSsIH][kSsIW + 1];
+  __shared__ float hp[5][kSsIH][kSsTW + 1];
+  __shared__ float wk[kSsK];
+  __shared__ float red[8];
+  const int n = blockIdx.y;
+  const int h0 = rects ? rects[4 * n] : 0, hn = rects ? rects[4 * n + 1] : H;
+  const int w0 = rects ? rects[4 * n + 2] : 0, wn = rects ? rects[4 * n + 3] : W;
+  const int oh = hn - h0 - (kSsK - 1), ow = wn - w0 - (kSsK - 1);      // valid window positions
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int oy0 = ty * kSsTH, ox0 = tx * kSsTW;
+  if (oy0 >= oh || ox0 >= ow) return;                                  // tile outside this frame's (smaller) rectangle
+  if (threadIdx.x < kSsK) wk[threadIdx.x] = window[threadIdx.x];
+  const float* a = sr + static_cast<long long>(n) * H * W;
+  const float* b = hr + static_cast<long long>(n) * H * W;
+  for (int i = threadIdx.x; i < kSsIH * kSsIW; i += 256) {
+    const int ly = i / kSsIW, lx = i - ly * kSsIW;
+    const int y = h0 + oy0 + ly, x = w0 + ox0 + lx;
+    const bool ok = y < hn && x < wn;
+    const int o = y * W + x;
+    ta[ly][lx] = ok ? denorm255(a[o], mean, stdv) : 0.f;
+    tb[ly][lx] = ok ? denorm255(b[o], mean, stdv) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSsIH * kSsTW; i += 256) {             // horizontal pass
+    const int ly = i / kSsTW, lx = i - ly * kSsTW;
+    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kSsK; ++k) {
+      const float w = wk[k], va = ta[ly][lx + k], vb = tb[ly][lx + k];
+      m1 = fmaf(w, va, m1); m2 = fmaf(w, vb, m2);
+      s11 = fmaf(w, va * va, s11); s22 = fmaf(w, vb * vb, s22); s12 = fmaf(w, va * vb, s12);
+    }
+    hp[0][ly][lx] = m1; hp[1][ly][lx] = m2; hp[2][ly][lx] = s11; hp[3][ly][lx] = s22; hp[4][ly][lx] = s12;
+  }
+  __syncthreads();
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < kSsTH * kSsTW; i += 256) {             // vertical pass + SSIM map
+    const int ly = i / kSsTW, lx = i - ly * kSsTW;
+    if (oy0 + ly >= oh || ox0 + lx >= ow) continue;
+    float q[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < kSsK; ++k) {
+      const float w = wk[k];
+#pragma unroll
+      for (int c = 0; c < 5; ++c) q[c] = fmaf(w, hp[c][ly + k][lx], q[c]);
+    }
+    const float mu1 = q[0], mu2 = q[1];
+    const float v1 = q[2] - mu1 * mu1, v2 = q[3] - mu2 * mu2, cov = q[4] - mu1 * mu2;
+    acc += ((2.f * mu1 * mu2 + c1) * (2.f * cov + c2)) / ((mu1 * mu1 + mu2 * mu2 + c1) * (v1 + v2 + c2));
+  }
+  const float t = block_sum_256(acc, red);
+  if (threadIdx.x == 0) atomicAdd(sums + 3 * n + 2, static_cast<double>(t));
+}
+
+int launch_frame_scores(const float* sr, const float* hr, const int* rects, long long n, int H, int W, float mean,
+                        float stdv, const float* window, float value_range, double* sums, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if (n > 65535) return static_cast<int>(cudaErrorInvalidValue);
+  cudaError_t e = cudaMemsetAsync(sums, 0, static_cast<size_t>(n) * 3 * sizeof(double), s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int bx = (H * W + 256 * 8 - 1) / (256 * 8);
+  frame_l1_mse_kernel<<<dim3(bx < 1 ? 1 : bx, static_cast<unsigned>(n)), 256, 0, s>>>(sr, hr, rects, H, W, mean, stdv, sums);
+  if (H >= kSsK && W >= kSsK) {
+    const int tiles_x = (W - kSsK + 1 + kSsTW - 1) / kSsTW, tiles_y = (H - kSsK + 1 + kSsTH - 1) / kSsTH;
+    const float c1 = (0.01f * value_range) * (0.01f * value_range), c2 = (0.03f * value_range) * (0.03f * value_range);
+    frame_ssim_kernel<<<dim3(static_cast<unsigned>(tiles_x * tiles_y), static_cast<unsigned>(n)), 256, 0, s>>>(
+        sr, hr, rects, H, W, mean, stdv, window, c1, c2, tiles_x, sums);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Bicubic up-sampling, the comparison baseline of the reference (src/model/nets/bicubic.py:15:
 // nn.Upsample(scale_factor=s, mode='bicubic', align_corners=True)): source coordinate = dst * (in - 1) / (out - 1),
 // Keys cubic convolution with A = -0.75, border indices clamped (torch upsample_bicubic2d semantics).

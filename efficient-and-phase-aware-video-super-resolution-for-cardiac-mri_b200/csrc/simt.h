@@ -23,6 +23,8 @@ int launch_cine_gather(const void* vols, int dtype, const struct pvsr_cine_sampl
 int launch_pad_channel_bf16(const float* x, void* out_bf16, long long n, cudaStream_t s);
 int launch_take_channel0(const float* in, int stride, float* out, long long n, cudaStream_t s);
 int launch_table(const struct pvsr_table_job* jobs, int n_jobs, long long max_n, cudaStream_t s);
+int launch_frame_scores(const float* sr, const float* hr, const int* rects, long long n, int H, int W, float mean,
+                        float stdv, const float* window, float value_range, double* sums, cudaStream_t s);
 int launch_bicubic(const float* in, float* out, long long n_img, int h, int w, int scale, cudaStream_t s);
 int launch_add_bf16(const void* a, const void* b, void* out, long long n_elems, cudaStream_t s);
 

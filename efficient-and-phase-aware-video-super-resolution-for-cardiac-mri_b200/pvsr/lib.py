@@ -121,6 +121,8 @@ SIGNATURES = {
     "pvsr_conv3x3_wgrad_staged": (c_int, [C.POINTER(WgradDesc), c_int, c_void_p]),
     "pvsr_conv3x3_wgrad_multi": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "pvsr_run_table": (c_int, [c_void_p, c_int, c_int64, c_void_p]),
+    "pvsr_frame_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, C.c_float, C.c_float, c_void_p,
+                                  C.c_float, c_void_p, c_void_p]),
     "pvsr_bicubic_upsample": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "pvsr_pad_channel_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "pvsr_take_channel0_f32": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p]),

@@ -51,7 +51,8 @@ class AcdcSISRPredictor(BasePredictor):
                 sr = self.net(lr)
                 srd, hrd = self._denormalize(sr), self._denormalize(hr)
                 patients = [self._name(index)[1] for index, _ in items]
-                losses, metrics = per_sample_scores(self.loss_fns, self.metric_fns, sr, hr, srd, hrd, patients)
+                losses, metrics = per_sample_scores(self.loss_fns, self.metric_fns, sr, hr, srd, hrd, patients,
+                                                    dataset=self.dataset_name)
                 flat = torch.cat([metrics, losses], dim=1).cpu()
                 imgs = srd[:, 0].to(torch.uint8).cpu().numpy() if self.exported else None
             nm = len(self.metric_fns)

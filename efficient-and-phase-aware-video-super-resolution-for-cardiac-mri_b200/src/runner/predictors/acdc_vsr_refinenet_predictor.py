@@ -123,12 +123,15 @@ class AcdcVSRRefineNetPredictor(BasePredictor):
         n, T = outputs[0].shape[0], len(outputs)
         out = torch.stack(outputs, dim=1).flatten(0, 1)          # (n * T, 1, H, W), sequence-major
         tgt = torch.stack(targets, dim=1).flatten(0, 1)
-        srd, hrd = self._denormalize(out), self._denormalize(tgt)
         patients = [self._patient(indices[s])[1] for s in range(n) for _ in range(T)]
-        losses, metrics = per_sample_scores(self.loss_fns, self.metric_fns, out, tgt, srd, hrd, patients)
+        losses, metrics = per_sample_scores(self.loss_fns, self.metric_fns, out, tgt, lambda: self._denormalize(out),
+                                            lambda: self._denormalize(tgt), patients, dataset=self.dataset_name)
         nl = losses.shape[1]
         flat = torch.cat([losses, metrics], dim=1).cpu().view(n, T, -1)
-        frames = srd.view(n, T, *srd.shape[1:])[:, :, 0].to(torch.uint8).cpu().numpy() if self.exported else None
+        frames = None
+        if self.exported:
+            srd = self._denormalize(out)
+            frames = srd.view(n, T, *srd.shape[1:])[:, :, 0].to(torch.uint8).cpu().numpy()
         return [(indices[s], flat[s, :, :nl], flat[s, :, nl:], None if frames is None else frames[s])
                 for s in range(n)]
 

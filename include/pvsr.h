@@ -215,6 +215,15 @@ typedef struct pvsr_table_job {
   int kind;
 } pvsr_table_job;
 int pvsr_run_table(const pvsr_table_job* jobs_dev, int n_jobs, int64_t max_n, void* stream);
+/* Per-frame scores of n SR / HR frame pairs (fp32 [n][H][W], normalised) in two launches - what the runners compute
+ * per frame with L1Loss + denormalize (src/utils.py:1-20) + PSNR (src/model/metrics.py:20-36) + SSIM (:86-113) and, with
+ * rects, CardiacPSNR / CardiacSSIM (:116-165).  sums fp64 [n][3] (zeroed here):
+ *   [0] sum |sr - hr|,  [1] sum (D(sr) - D(hr))^2 with D(x) = clamp(rint(x*std + mean), 0, 255),
+ *   [2] sum of the SSIM map over the valid positions of the 11-tap window `window11` (device, normalised), constants
+ *       c1 = (0.01 value_range)^2, c2 = (0.03 value_range)^2.
+ * rects int32 [n][4] = (h0, hn, w0, wn) per frame, or NULL for the whole frame. */
+int pvsr_frame_scores(const float* sr, const float* hr, const int32_t* rects, int64_t n, int H, int W, float mean,
+                      float std, const float* window11, float value_range, double* sums, void* stream);
 /* Bicubic baseline (src/model/nets/bicubic.py:15: nn.Upsample(scale_factor, 'bicubic', align_corners=True)):
  * in fp32 [n_img][h][w] -> out fp32 [n_img][h*scale][w*scale]. */
 int pvsr_bicubic_upsample(const float* in, float* out, int64_t n_img, int h, int w, int scale, void* stream);
