@@ -15,6 +15,7 @@ import torch
 from pvsr import parallel
 from pvsr.optim import FusedAdam
 from src.utils import denormalize
+from ..scores import _fusable, per_sample_scores
 from .base_trainer import BaseTrainer
 
 
@@ -97,6 +98,10 @@ class AcdcSISRTrainer(BaseTrainer):
 
     def _compute_metrics(self, output, target):
         with torch.no_grad():
+            if _fusable([], self.metric_fns, output) and not any(hasattr(fn, 'inner') for fn in self.metric_fns):
+                _, scores = per_sample_scores([], self.metric_fns, output.detach(), target, None, None, None,
+                                              dataset=self.dataset_name)
+                return list(scores.mean(dim=0))
             output, target = self._denormalize(output), self._denormalize(target)
             return [metric_fn(output, target) for metric_fn in self.metric_fns]
 

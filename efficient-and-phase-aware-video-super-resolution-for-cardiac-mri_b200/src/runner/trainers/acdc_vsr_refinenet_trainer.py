@@ -19,6 +19,7 @@ import torch
 from pvsr import parallel
 from pvsr.optim import FusedAdam
 from src.utils import denormalize
+from ..scores import _fusable, per_sample_scores
 from .base_trainer import BaseTrainer
 
 
@@ -118,8 +119,14 @@ class AcdcVSRRefineNetTrainer(BaseTrainer):
         """Mean over the T frames of each metric's batch mean (:103-120) - all T * N frames in ONE call per metric
         (equal sample counts per frame make the two means identical)."""
         with torch.no_grad():
-            sr = self._denormalize(torch.stack([o.detach() for o in outputs[-1]]).flatten(0, 1))
-            hr = self._denormalize(torch.stack(list(targets)).flatten(0, 1))
+            out = torch.stack([o.detach() for o in outputs[-1]]).flatten(0, 1)
+            tgt = torch.stack(list(targets)).flatten(0, 1)
+            if _fusable([], self.metric_fns, out) and not any(hasattr(fn, 'inner') for fn in self.metric_fns):
+                # PSNR / SSIM of all frames in two launches (pvsr_frame_scores)
+                _, scores = per_sample_scores([], self.metric_fns, out, tgt, None, None, None,
+                                              dataset=self.dataset_name)
+                return list(scores.mean(dim=0))
+            sr, hr = self._denormalize(out), self._denormalize(tgt)
             return [fn(sr, hr).mean() for fn in self.metric_fns]
 
     def _update_log(self, log, batch_size, T, loss, losses, metrics):

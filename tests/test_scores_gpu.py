@@ -64,7 +64,7 @@ def test_fused_scores_equal_generic_path(shape, tmp_path, pvsr_lib):
 def test_unfusable_configurations_take_the_generic_path(pvsr_lib):
     from src.model.losses import HuberLoss
     from src.model.metrics import PSNR
-    from src.runner.predictors.base_predictor import _fusable
+    from src.runner.scores import _fusable
     x = torch.zeros(2, 1, 32, 32, device='cuda')
     assert _fusable([torch.nn.L1Loss()], [PSNR()], x)
     assert not _fusable([HuberLoss()], [PSNR()], x)
