@@ -41,6 +41,7 @@ NET_KW = dict(in_channels=1, out_channels=1, num_features=[64, 64, 64], upscale_
               update_memory=True, num_updated_frames=U_FRAMES, refine_window_size=5, positional_encoding=True)
 METRIC = "SR frames/s at x4"
 UNIT = "frames/s"
+WORKLOADS_NAME = "ACDCSR"
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -119,23 +120,72 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_oracle_time(n_seq_steps, warmup, threads):
-    """Times the CPU oracle (all 3*S heads, as the reference predictor executes them) on one sequence per step."""
-    from oracle import refinenet_oracle as O
-    torch.set_num_threads(threads)
-    sd = O.init_state_dict(upscale_factor=SCALE, positional_encoding=True, seed=0)
-    inputs, pos = synthetic_sequences(1, 1234)
-    kw = dict(num_stages=3, num_updated_frames=U_FRAMES, refine_window_size=5, upscale_factor=SCALE,
+def cpu_model(state_dict=None, scale=None):
+    """The CPU implementation of the path: (forward(inputs, pos) -> 3*S lists, kind).  kind = "reference": the
+    UNMODIFIED reference RefineNet staged under oracle/_ref by oracle/make_ref.py (all 3*S heads, exactly what the
+    reference predictor executes); kind = "port": the pinned restatement oracle/refinenet_oracle.py when the staged
+    copy is absent.  `state_dict`: weights to load (default: seed-0 initialisation of the x`SCALE` config)."""
+    from oracle import ref_model, refinenet_oracle as O
+    scale = scale or SCALE
+    if ref_model.available():
+        net = ref_model.build_net(state_dict, seed=0, upscale_factor=scale)
+        return (lambda inputs, pos: net(inputs, pos)), "reference"
+    sd = state_dict if state_dict is not None else O.init_state_dict(upscale_factor=scale, positional_encoding=True, seed=0)
+    sd = {k: v.detach().cpu() for k, v in sd.items()}
+    kw = dict(num_stages=3, num_updated_frames=U_FRAMES, refine_window_size=5, upscale_factor=scale,
               positional_encoding=True, memory=True, num_layers=3)
+    return (lambda inputs, pos: O.refinenet_forward(sd, inputs, pos, **kw)), "port"
+
+
+def cpu_oracle_time(n_seq_steps, warmup, threads):
+    """Times the CPU implementation (all 3*S heads, as the reference predictor executes them) on one sequence per
+    step.  Returns (times, kind)."""
+    torch.set_num_threads(threads)
+    fwd, kind = cpu_model()
+    inputs, pos = synthetic_sequences(1, 1234)
     times = []
     with torch.no_grad():
         for i in range(warmup + n_seq_steps):
             t0 = time.perf_counter()
-            O.refinenet_forward(sd, inputs, pos, **kw)
+            fwd(inputs, pos)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-    return times
+    return times, kind
+
+
+# SURVEY.md section 8c gates (bf16 operands, fp32 accumulate / state) - the same numbers tests/test_model_gpu.py uses
+GATES = {"max_abs": 2e-2, "rel_l2": 1.5e-2, "psnr_delta_db": 0.01, "ssim_delta": 1e-4}
+
+
+def inference_parity(frames_host, inputs_h, pos_h, hr_h, seqs, state_dict, threads):
+    """Checks SR frames of the LAST TIMED e2e step (host copy read back through the HostFrameRing: B sequences x CUDA
+    graph replay x rotating output buffers) against the CPU implementation run on the same sequences' own inputs.
+    frames_host: [T, B, 1, H, W].  Returns (parity dict, per-run CPU seconds, kind)."""
+    from oracle import refinenet_oracle as O
+    torch.set_num_threads(threads)
+    fwd, kind = cpu_model(state_dict)
+    dataset = "dsb15" if WORKLOADS_NAME == "DSB15SR" else "acdc"
+    worst = {"max_abs": 0.0, "rel_l2": 0.0, "psnr_delta_db": 0.0, "ssim_delta": 0.0}
+    times = []
+    with torch.no_grad():
+        for i in seqs:
+            t0 = time.perf_counter()
+            ref = fwd([x[i:i + 1] for x in inputs_h], pos_h[i:i + 1])[-1]
+            times.append(time.perf_counter() - t0)
+            for t, r in enumerate(ref):
+                g = frames_host[t, i:i + 1].float()
+                worst["max_abs"] = max(worst["max_abs"], (g - r).abs().max().item())
+                worst["rel_l2"] = max(worst["rel_l2"], ((g - r).norm() / r.norm()).item())
+                tgt = O.denormalize(hr_h[t][i:i + 1], dataset)
+                dg, dr = O.denormalize(g, dataset), O.denormalize(r, dataset)
+                worst["psnr_delta_db"] = max(worst["psnr_delta_db"], abs(float(O.psnr(dg, tgt)) - float(O.psnr(dr, tgt))))
+                worst["ssim_delta"] = max(worst["ssim_delta"], abs(float(O.ssim(dg, tgt)) - float(O.ssim(dr, tgt))))
+    ok = all(worst[k] <= GATES[k] for k in GATES)
+    par = dict(worst, ok=ok, gates=GATES, checked_against=kind,
+               what=f"SR frames of sequences {list(seqs)} of the last timed e2e step (graph replay, output ring, D2H) "
+                    f"vs the CPU {kind} on the same inputs; PSNR / SSIM deltas against a synthetic HR target")
+    return par, times, kind
 
 
 def edsr_cpu_time(frames):
@@ -206,18 +256,19 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    times = cpu_oracle_time(args.steps, args.warmup, cores)
+    times, kind = cpu_oracle_time(args.steps, args.warmup, cores)
     total = sum(times)
     value = T_FRAMES * len(times) / total
     sample = (f"{len(times)} step(s) x 1 {args.workload} sequence (42 LR frames {LR_H}x{LR_W} -> 30 SR frames), "
-              "all 9 heads, fp32")
+              "all 9 heads, fp32, " + ("the unmodified reference RefineNet (oracle/_ref)" if kind == "reference"
+                                       else "oracle port (oracle/_ref not staged)"))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"RefineNet x{SCALE} inference, synthetic cine sequences (LR {LR_H}x{LR_W}, T=30, U=6), "
                                    "1 sequence per step on the host CPU", "name": args.workload,
                        "sequences_per_step": 1},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -226,7 +277,89 @@ def run_reference(args, rank):
 TRAIN_N, TRAIN_T, TRAIN_HW = 16, 7, 32     # configs/train/refine_net/exp1_x4.yaml:20-33: batch 16, 7 frames, 32x32 patches
 
 
-def bench_train(args, dev, rank, world, distributed, barrier):
+def nccl_tuning_lines():
+    """AllReduce algorithm / protocol lines from this process's NCCL log when bench.py itself turned the log on
+    (NCCL_DEBUG unset by the caller -> INFO + TUNING into a private file); [] otherwise."""
+    path = os.environ.get("PVSR_NCCL_LOG")
+    if not path:
+        return []
+    path = path.replace("%p", str(os.getpid()))
+    try:
+        with open(path) as f:
+            lines = [l.strip() for l in f if "AllReduce" in l and ("Algo" in l or "algo" in l)]
+    except OSError:
+        return []
+    seen, out = set(), []
+    for l in lines:
+        key = l.split("NCCL INFO", 1)[-1].strip()
+        if key not in seen:
+            seen.add(key)
+            out.append(key)
+    return out[-4:]
+
+
+GRAD_GATES = {"grad_rel_l2": 4e-2, "grad_cos": 0.999, "loss_rel": 2e-3, "out_rel_l2": 1.5e-2}
+
+
+def train_parity(net, eng, inputs_d, pos_d, targets_d, inputs_h, pos_h, threads):
+    """Parity of the BENCHMARKED training plan (N = 16 per GPU, its own weight-gradient split counts) at the current
+    weights, on rank 0, outside the timed region:
+      (1) gradients of the fused N=16 step vs the mean of two N=8 steps through the generic autograd path (their own
+          plans; the loss is a mean over samples, so the two must agree) - per-tensor rel-L2 and cosine;
+      (2) the fused loss vs the trainer's loss formula (acdc_vsr_refinenet_trainer.py:83-93) evaluated on the step's own
+          output frames;
+      (3) output frames of samples 0 and N-1 (all 9 lists, train mode) vs the CPU implementation's forward."""
+    from oracle import refinenet_oracle as O
+    N = inputs_d[0].shape[0]
+    flat_p, flat_g = eng.flatten_parameters()
+    loss16, out16 = eng.loss_and_grads(inputs_d, pos_d, targets_d)
+    g16 = flat_g.clone()
+    out16 = out16.clone()
+    names = [(k, p) for k, p in net.named_parameters()]
+    flat_g.zero_()
+    h = N // 2
+    for lo in (0, h):
+        out = net([x[lo:lo + h] for x in inputs_d], pos_d[lo:lo + h])
+        O.trainer_loss(out, [t[lo:lo + h] for t in targets_d], training=True).backward()
+    torch.cuda.synchronize()
+    worst_rel, worst_cos, worst_name = 0.0, 1.0, None
+    off = 0
+    for k, p_ in names:
+        n = p_.numel()
+        a = g16[off:off + n].double()
+        b = p_.grad.reshape(-1).double() * 0.5 if p_.grad is not None else torch.zeros_like(a)
+        off += (n + 3) // 4 * 4
+        if float(b.norm()) == 0.0:
+            continue
+        rel = float((a - b).norm() / b.norm())
+        cos = float((a * b).sum() / (a.norm() * b.norm()))
+        if rel > worst_rel:
+            worst_rel, worst_name = rel, k
+        worst_cos = min(worst_cos, cos)
+    lists = tuple([out16[l, t].unsqueeze(1) for t in range(out16.shape[1])] for l in range(out16.shape[0]))
+    loss_formula = float(O.trainer_loss(lists, targets_d, training=True))
+    loss_rel = abs(float(loss16) - loss_formula) / abs(loss_formula)
+    # forward of the training plan vs the CPU implementation (train-mode forward == eval forward: no dropout / BN)
+    torch.set_num_threads(threads)
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    fwd, kind = cpu_model(sd, scale=4)
+    out_rel = 0.0
+    with torch.no_grad():
+        for i in (0, N - 1):
+            ref = fwd([x[i:i + 1] for x in inputs_h], pos_h[i:i + 1])
+            ref = torch.stack([torch.stack(list(o)) for o in ref])[:, :, 0, 0]
+            got = out16[:, :, i].cpu()
+            out_rel = max(out_rel, float((got - ref).norm() / ref.norm()))
+    flat_g.zero_()
+    res = {"grad_rel_l2": worst_rel, "grad_rel_l2_tensor": worst_name, "grad_cos": worst_cos, "loss_rel": loss_rel,
+           "out_rel_l2": out_rel, "gates": GRAD_GATES, "checked_against": f"two N={h} autograd steps (gradients), trainer "
+           f"loss formula on the step's own frames (loss), CPU {kind} forward of samples 0 and {N - 1} (frames)"}
+    res["ok"] = bool(worst_rel <= GRAD_GATES["grad_rel_l2"] and worst_cos >= GRAD_GATES["grad_cos"] and
+                     loss_rel <= GRAD_GATES["loss_rel"] and out_rel <= GRAD_GATES["out_rel_l2"])
+    return res
+
+
+def bench_train(args, dev, rank, world, distributed, barrier, parity=True):
     """One RefineNet x4 training step (forward + multi-stage L1 + backward + gradient all-reduce + Adam) per step at
     the reference's training shapes: N=16 per GPU, 7 target frames + 2x6 warm-up frames of 32x32 LR patches.
     Returns a dict for the JSON line (rank 0) - SURVEY.md section 8 config 5."""
@@ -235,13 +368,14 @@ def bench_train(args, dev, rank, world, distributed, barrier):
     from pvsr.parallel import DataParallelStep
     from pvsr.synthetic import cine_batch
     from src.model.nets import RefineNet
+    kw = dict(NET_KW, upscale_factor=4)
     torch.manual_seed(0)
-    net = RefineNet(**NET_KW).to(dev).train()
+    net = RefineNet(**kw).to(dev).train()
     opt = FusedAdam.for_net(net, lr=1e-4)
     dp = DataParallelStep(net, opt)
     eng = net.engine
     eng.use_graph = not args.no_graph
-    inputs_h, pos_h, targets_h = cine_batch(TRAIN_N, T=TRAIN_T, U=U_FRAMES, h=TRAIN_HW, w=TRAIN_HW, scale=SCALE,
+    inputs_h, pos_h, targets_h = cine_batch(TRAIN_N, T=TRAIN_T, U=U_FRAMES, h=TRAIN_HW, w=TRAIN_HW, scale=4,
                                             seed=4321 + rank, end_systole=3, with_targets=True)
     inputs_h = [x.pin_memory() for x in inputs_h]
     targets_h = [x.pin_memory() for x in targets_h]
@@ -266,11 +400,13 @@ def bench_train(args, dev, rank, world, distributed, barrier):
         loss_h.copy_(loss, non_blocking=True)
         return loss
 
-    res = {}
+    res, ar_ms = {}, None
     for name, fn in (("device", device_step), ("e2e", e2e_step)):
         for _ in range(max(args.warmup, 3)):
             fn()
         barrier()
+        dp.time_allreduce = name == "device"
+        dp.allreduce_ms()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
@@ -278,34 +414,46 @@ def bench_train(args, dev, rank, world, distributed, barrier):
         e1.record()
         barrier()
         res[name] = e0.elapsed_time(e1)
-    t = torch.tensor([res["device"], res["e2e"]], dtype=torch.float64, device=dev)
+        if name == "device":
+            ar_ms = dp.allreduce_ms()
+        dp.time_allreduce = False
+    t = torch.tensor([res["device"], res["e2e"], ar_ms or 0.0], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ar_ms = t.tolist()
+    loss_val = float(loss)
     pl = eng.train_plan(inputs_d)
     prof_f = eng.profile(pl)
     prof_b = eng.profile_backward(pl)
     flops = pl.flops + pl.flops_bwd
     frames = world * TRAIN_N * TRAIN_T
     h2d = sum(x.numel() * 4 for x in inputs_h + targets_h) + pos_h.numel() * 4
-    return {
+    out = {
         "metric": "training target frames/s at x4", "value": frames * args.steps / (ms / 1e3), "unit": "frames/s",
-        "ms_per_step": ms / args.steps, "steps_per_s": args.steps / (ms / 1e3),
+        "ms_per_step": ms / args.steps, "steps_per_s": args.steps / (ms / 1e3), "n_gpus": world,
         "config": {"workload": f"RefineNet x4 training step, N={TRAIN_N} per GPU, {TRAIN_T} target frames + 2x{U_FRAMES} "
                                f"warm-up frames of {TRAIN_HW}x{TRAIN_HW} LR patches (HR 128x128), all 9 heads, L1 multi-stage "
                                "loss, fused Adam", "global_batch": world * TRAIN_N,
                    "parallelism": f"data-parallel x{world}, one NCCL all-reduce of the flat fp32 gradient per step"},
         "e2e": {"value": frames * args.steps / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "allreduce": {"collective": "ncclAllReduce (SUM, fp32) via torch.distributed" if distributed else "none (1 GPU)",
+                      "bytes": dp.allreduce_bytes(), "ms_per_step": ar_ms if distributed else 0.0,
+                      "timing": "CUDA events on the compute stream around dist.all_reduce, max over ranks, mean over "
+                                "the timed steps (includes waiting for the slowest rank's backward)",
+                      "nccl_tuning": nccl_tuning_lines() if distributed else []},
         "gpu_launches": int((pl.launches + pl.launches_bwd + 3) * args.steps),
         "algorithmic_tflop_per_step_per_gpu": flops / 1e12,
         "whole_step_tflops_per_gpu": flops / (ms / args.steps / 1e3) / 1e12,
-        "loss": float(loss),
+        "loss": loss_val,
         "kernel_ms_per_step": {**{k: round(v[0], 3) for k, v in prof_f.items()},
                                **{k: round(v[0], 3) for k, v in prof_b.items()}},
         "kernel_tflops": {k: round(v[2] / (v[0] / 1e3) / 1e12, 1) for k, v in {**prof_f, **prof_b}.items()
                           if v[2] > 0 and v[0] > 0},
     }
+    if parity and rank == 0:
+        out["parity"] = train_parity(net, eng, inputs_d, pos_d, targets_d, inputs_h, pos_h, os.cpu_count() or 1)
+    return out
 
 
 def main():
@@ -317,6 +465,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the B = 1 / 8 operating points of the N=1 line")
+    ap.add_argument("--no-train", action="store_true", help="skip the train_step object")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-line parity check of the timed frames")
     ap.add_argument("--workload", default="acdc_x4", choices=sorted(WORKLOADS),
                     help="inference workload shape (default: the BASELINE.json headline config)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train", "both"],
@@ -324,8 +475,9 @@ def main():
                          "train: the training-step line; both: inference line with the train_step object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
-    global LR_H, LR_W, SCALE, METRIC
+    global LR_H, LR_W, SCALE, METRIC, WORKLOADS_NAME
     LR_H, LR_W, SCALE, shape_name = WORKLOADS[args.workload]
+    WORKLOADS_NAME = shape_name
     NET_KW["upscale_factor"] = SCALE
     METRIC = f"SR frames/s at x{SCALE}"
 
@@ -352,6 +504,13 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if "NCCL_DEBUG" not in os.environ and "NCCL_DEBUG_FILE" not in os.environ:
+            # algorithm / protocol of the gradient all-reduce for the train_step object (private per-process log file;
+            # left alone when the caller configured NCCL logging itself)
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ["NCCL_DEBUG_SUBSYS"] = "INIT,TUNING"
+            os.environ["PVSR_NCCL_LOG"] = f"/tmp/pvsr_nccl_{os.getppid()}_%p.log"
+            os.environ["NCCL_DEBUG_FILE"] = os.environ["PVSR_NCCL_LOG"]
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -369,6 +528,7 @@ def main():
                     "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": tr["ms_per_step"],
                     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                     "data": "synthetic", "config": tr["config"], "e2e": tr["e2e"], "gpu_launches": tr["gpu_launches"],
+                    "allreduce": tr["allreduce"], "parity": tr.get("parity"),
                     "clocks": sampler.stop(),
                     "roofline": {"bound": "tensor", "kernel": "whole training step (all tcgen05 conv / dgrad / wgrad launches)",
                                  "achieved": tr["whole_step_tflops_per_gpu"], "peak": peak, "unit": "TFLOP/s",
@@ -379,6 +539,8 @@ def main():
             print(json.dumps(line), flush=True)
         if distributed:
             dist.destroy_process_group()
+        if rank == 0 and tr.get("parity") and not tr["parity"]["ok"]:
+            raise SystemExit("bench.py: training parity check FAILED: " + json.dumps(tr["parity"]))
         return
 
     torch.manual_seed(0)
@@ -389,7 +551,9 @@ def main():
     B = args.batch
 
     # this rank's shard of the synthetic job: B sequences, host-resident (pinned) for the e2e leg
-    inputs_h, pos_h = synthetic_sequences(B, 1234 + rank)
+    from pvsr.synthetic import cine_batch
+    inputs_h, pos_h, hr_h = cine_batch(B, T=T_FRAMES, U=U_FRAMES, h=LR_H, w=LR_W, scale=SCALE, seed=1234 + rank,
+                                       with_targets=True)     # hr_h: synthetic HR targets (PSNR / SSIM deltas only)
     inputs_h = [x.pin_memory() for x in inputs_h]
     stacked_h = torch.stack(inputs_h).pin_memory()      # the same frames as ONE pinned buffer (a collated batch)
     pos_h = pos_h.pin_memory()
@@ -408,6 +572,8 @@ def main():
     ring = HostFrameRing(dev, slots=2)      # pinned host slots + copy stream: the D2H of step i overlaps step i+1
     eng.output_slots = 2                    # ... which needs a second output buffer for step i+1 to write into
 
+    last_slot = [0]
+
     def e2e_step():
         flush.fill_(1)
         ring.before_launch(eng.next_output_ptr(plan))                    # output buffer reuse vs copies in flight
@@ -415,7 +581,7 @@ def main():
         ps = pos_h.to(dev, non_blocking=True)
         with torch.no_grad():
             frames = net(xs, ps)[-1]                                     # the public module call
-        ring.submit(frames)                                              # D2H read of all SR frames of the step
+        last_slot[0] = ring.submit(frames)                               # D2H read of all SR frames of the step
         return frames
 
     with torch.no_grad():
@@ -453,18 +619,50 @@ def main():
         f1.record()
         barrier()
         ms_e2e = f0.elapsed_time(f1)
+        # what the LAST TIMED e2e step delivered to the host (checked against the CPU implementation below)
+        frames_last = ring.result(last_slot[0]).clone() if rank == 0 else None
+
+        # small-batch operating points (SURVEY.md 8d sweep; the reference predictor runs B = 1): device-timed like `value`
+        sweep = {}
+        if world == 1 and not args.no_sweep:
+            for b in (1, 8):
+                if b == B:
+                    continue
+                pb = eng.plan_for(b, len(inputs_d), LR_H, LR_W, False, dev)
+                eng.stage_inputs(pb, [x[:b] for x in inputs_d], pos_d[:b])
+                for _ in range(args.warmup):
+                    flush.fill_(1)
+                    eng.run(pb)
+                torch.cuda.synchronize()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_rep = max(args.steps, 10)
+                g0.record()
+                for _ in range(n_rep):
+                    flush.fill_(1)
+                    eng.run(pb)
+                g1.record()
+                torch.cuda.synchronize()
+                msb = g0.elapsed_time(g1) / n_rep
+                sweep[str(b)] = {"sequences_per_step": b, "ms_per_step": msb, "value": b * T_FRAMES / (msb / 1e3),
+                                 "unit": UNIT, "tflops": pb.flops / (msb / 1e3) / 1e12, "launches_per_step": pb.launches}
+                del pb
+                eng.plans.pop((b, len(inputs_d), LR_H, LR_W, False, str(dev), False), None)
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
-    # the training step of config 5 (short, same process) rides along on the single-GPU line
+    # the training step of config 5 (short, same process) rides along on the line at every N: data-parallel with the
+    # NCCL gradient all-reduce (acdc_vsr_refinenet_trainer.py:44-47 is the step it replaces)
     train_res = None
-    if args.mode == "both" or (args.mode == "infer" and world == 1 and args.workload == "acdc_x4"):
+    if args.mode == "both" or (args.mode == "infer" and args.workload == "acdc_x4" and not args.no_train):
         targs = argparse.Namespace(**vars(args))
-        targs.steps = min(args.steps, 5)
+        targs.steps = min(args.steps, 10)
+        sd_infer = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()} if rank == 0 else None
         train_res = bench_train(targs, dev, rank, world, distributed, barrier)
+    else:
+        sd_infer = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()} if rank == 0 else None
 
     if rank == 0:
         peaks = measured_peaks()
@@ -493,7 +691,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(plan.launches * args.steps),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel<256, EPI_LSTM> (ConvLSTM cell wavefront)",
+            "roofline": {"bound": "tensor", "kernel": "conv3x3_halo_kernel<256, EPI_LSTM, cta_group::2> (ConvLSTM cell wavefront)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peaks["_source"] + ", sustained bf16",
@@ -503,19 +701,48 @@ def main():
                          "whole_step_tflops": step_flops / (ms / args.steps / 1e3) / 1e12},
             "kernel_ms_per_step": {k: round(v[0], 3) for k, v in prof.items()},
         }
+        line["roofline"]["timing"] = ("per-launch CUDA events of an eager pass over the same schedule (the timed region "
+                                      "replays these launches as one CUDA graph); share_of_step agrees with the ncu "
+                                      "launch list of this command under profiles/")
+        if sweep:
+            line["batch_sweep"] = sweep
+            line["batch_sweep"][str(B)] = {"sequences_per_step": B, "ms_per_step": ms / args.steps, "value": value,
+                                           "unit": UNIT, "tflops": step_flops / (ms / args.steps / 1e3) / 1e12,
+                                           "launches_per_step": plan.launches}
         if train_res is not None:
             line["train_step"] = {k: train_res[k] for k in ("metric", "value", "unit", "ms_per_step", "steps_per_s",
-                                                            "config", "e2e", "algorithmic_tflop_per_step_per_gpu",
+                                                            "n_gpus", "config", "e2e", "allreduce",
+                                                            "algorithmic_tflop_per_step_per_gpu",
                                                             "whole_step_tflops_per_gpu", "kernel_ms_per_step",
-                                                            "kernel_tflops", "loss")}
+                                                            "kernel_tflops", "loss") if k in train_res}
+            if "parity" in train_res:
+                line["train_step"]["parity"] = train_res["parity"]
+        cores = os.cpu_count() or 1
+        failed = []
+        if not args.no_parity:
+            # sequences 0 and B-1 of the last timed step at N=1; sequence 0 only when other ranks share the host cores
+            seqs = [0, B - 1] if (world == 1 and B > 1) else [0]
+            par, ptimes, kind = inference_parity(frames_last, inputs_h, pos_h, hr_h, seqs, sd_infer, cores)
+            line["parity"] = par
+            if not par["ok"]:
+                failed.append("inference")
+        if train_res is not None and train_res.get("parity") and not train_res["parity"]["ok"]:
+            failed.append("training")
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            times = cpu_oracle_time(3, 1, cores)       # 1 warm-up + 3 timed runs, median
+            times, kind = cpu_oracle_time(3, 1, cores)       # 1 warm-up + 3 timed runs, median
             line["cpu_baseline"] = {"value": T_FRAMES / statistics.median(times), "unit": UNIT, "cores": cores,
-                                    "kind": "port",
-                                    "sample": "1 ACDCSR x4 sequence (30 SR frames) per run, all 9 heads as the reference "
-                                              "executes them, fp32 torch CPU oracle, 1 warm-up + 3 timed runs, median"}
+                                    "kind": kind,
+                                    "sample": f"1 {shape_name} x{SCALE} sequence (30 SR frames) per run, all 9 heads as the "
+                                              "reference executes them, fp32 on the host CPU ("
+                                              + ("the unmodified reference RefineNet staged under oracle/_ref"
+                                                 if kind == "reference" else "pinned oracle port")
+                                              + "), 1 warm-up + 3 timed runs, median"}
         print(json.dumps(line), flush=True)
+        if failed:
+            if distributed:
+                dist.destroy_process_group()
+            raise SystemExit(f"bench.py: parity check FAILED ({', '.join(failed)}): " +
+                             json.dumps({"inference": line.get("parity"), "training": (train_res or {}).get("parity")}))
     if distributed:
         dist.destroy_process_group()
 

@@ -117,9 +117,32 @@ class DataParallelStep:
             optimizer.grad_scale = 1.0 / self.world
         broadcast_(self.flat_param, 0)      # identical initial weights on every rank
         net.engine.params_changed()
+        # optional device timing of the exchange: set `time_allreduce = True`, read allreduce_ms() after a synchronize
+        self.time_allreduce = False
+        self._ar_events = []
+
+    def allreduce_bytes(self):
+        return self.flat_grad.numel() * self.flat_grad.element_size()
+
+    def allreduce_ms(self, reset=True):
+        """Mean device time (CUDA events on the compute stream, which waits for NCCL's stream) of the gradient
+        all-reduce over the steps recorded since the last reset; None when nothing was recorded."""
+        if not self._ar_events:
+            return None
+        ms = [a.elapsed_time(b) for a, b in self._ar_events]
+        if reset:
+            self._ar_events = []
+        return sum(ms) / len(ms)
 
     def step(self):
-        allreduce_sum_(self.flat_grad)
+        if self.time_allreduce and is_distributed():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            allreduce_sum_(self.flat_grad)
+            e1.record()
+            self._ar_events.append((e0, e1))
+        else:
+            allreduce_sum_(self.flat_grad)
         if not hasattr(self.optimizer, 'grad_scale') and self.world > 1:
             self.flat_grad.mul_(1.0 / self.world)
         self.optimizer.step()
