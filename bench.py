@@ -576,7 +576,7 @@ def main():
 
     def e2e_step():
         flush.fill_(1)
-        ring.before_launch(eng.next_output_ptr(plan))                    # output buffer reuse vs copies in flight
+        ring.before_launch(eng.next_output_ptr(plan), eng.next_output_bytes(plan))   # buffer reuse vs copies in flight
         xs = list(stacked_h.to(dev, non_blocking=True).unbind(0))        # H2D from pinned host memory (one copy)
         ps = pos_h.to(dev, non_blocking=True)
         with torch.no_grad():

@@ -212,6 +212,11 @@ int pvsr_set_pdl(int enable) {
   return 0;
 }
 int pvsr_get_pdl(void) { return get_pdl(); }
+int pvsr_set_two_branch(int enable) {
+  set_two_branch(enable);
+  return 0;
+}
+int pvsr_get_two_branch(void) { return get_two_branch(); }
 int pvsr_set_head_tma(int enable) {
   set_head_tma(enable);
   return 0;
@@ -469,12 +474,12 @@ int pvsr_head_conv_last_fwd(const void* in, const float* w, const float* b, floa
 }
 
 int pvsr_cine_gather(const void* volumes, int vol_dtype, const pvsr_cine_sample* samples, int n_samples, int n_frames,
-                     int h, int w, float mean, float std, float* out, const float* pos_codes, float* pos_out,
+                     int h, int w, double mean, double std, float* out, const float* pos_codes, float* pos_out,
                      void* stream) {
-  if (vol_dtype < PVSR_DT_F32 || vol_dtype > PVSR_DT_U8) return set_error(-2, "unknown volume dtype %d", vol_dtype);
+  if (vol_dtype < PVSR_DT_F32 || vol_dtype > PVSR_DT_F64) return set_error(-2, "unknown volume dtype %d", vol_dtype);
   if (static_cast<long long>(n_samples) * n_frames > 65535)
     return set_error(-2, "cine_gather: n_samples * n_frames = %lld exceeds 65535", static_cast<long long>(n_samples) * n_frames);
-  if (std == 0.f) return set_error(-2, "cine_gather: std must be non-zero");
+  if (std == 0.0) return set_error(-2, "cine_gather: std must be non-zero");
   return check_cuda(launch_cine_gather(volumes, vol_dtype, samples, n_samples, n_frames, h, w, mean, std, out,
                                        pos_codes, pos_out, static_cast<cudaStream_t>(stream)), "cine_gather");
 }

@@ -98,6 +98,11 @@ inline int cta_pair_factor() { return get_cta_pair() ? 2 : 1; }
 void set_pdl(int enable);
 int get_pdl();
 
+// Two-branch schedules of training plans (plan.cpp: Ctx::side): weight-gradient launches and the HBM-bound head
+// kernels on a second stream / graph branch.  1 = on (default), 0 = single chain (A/B measurements).
+void set_two_branch(int enable);
+int get_two_branch();
+
 // Slab ("halo") variant of the 3x3 launches: one activation slab per source instead of nine shifted boxes. 0 = off.
 void set_halo_mode(int mode);
 int get_halo_mode();

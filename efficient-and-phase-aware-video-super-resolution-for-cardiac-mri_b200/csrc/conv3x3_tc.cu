@@ -856,6 +856,10 @@ static int g_pdl = 0;   // programmatic dependent launch between consecutive ker
 void set_pdl(int enable) { g_pdl = enable ? 1 : 0; }
 int get_pdl() { return g_pdl; }
 
+static int g_two_branch = 1;
+void set_two_branch(int enable) { g_two_branch = enable ? 1 : 0; }
+int get_two_branch() { return g_two_branch; }
+
 void set_cta_pair(int enable) { g_cta_pair = enable ? 1 : 0; }
 int get_cta_pair() { return g_cta_pair; }
 

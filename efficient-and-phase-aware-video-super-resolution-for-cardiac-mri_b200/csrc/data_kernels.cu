@@ -5,6 +5,8 @@
 //                 for a whole batch in one launch.  The random decisions are drawn on the host (same numpy stream as
 //                 the host path) and arrive as one descriptor per sample; the kernel is a pure gather:
 //                     out[f][n][y][x] = (float(vol_n[(t_first_n + f) mod T_n][ay*y + by][ax*x + bx]) - mean) / std
+//                 (IEEE sub + div in fp32; fp64 volumes in fp64 then rounded once, which is what numpy's
+//                 `(img - mean) / (std + 1e-10)` followed by ToTensor's `.float()` gives for either dtype)
 //                 HBM-bound: 2-4 B read + 4 B written per output pixel, rows contiguous (reversed rows under a
 //                 horizontal flip still cover whole 128 B lines per warp).
 #include <cuda_bf16.h>
@@ -22,7 +24,7 @@ namespace pvsr {
 template <typename T, int V>
 __global__ void __launch_bounds__(256) cine_gather_kernel(const T* __restrict__ vols,
                                                           const pvsr_cine_sample* __restrict__ samples, int n_samples,
-                                                          int n_frames, int h, int w, float mean, float stdv,
+                                                          int n_frames, int h, int w, double mean_d, double std_d,
                                                           float* __restrict__ out, const float* __restrict__ pos_codes,
                                                           float* __restrict__ pos_out) {
   // blockIdx.y = frame * n_samples + sample; blockIdx.x strides over the pixel groups of that image
@@ -38,10 +40,17 @@ __global__ void __launch_bounds__(256) cine_gather_kernel(const T* __restrict__ 
     const int y = g / wg, x = (g - y * wg) * V;
     const T* __restrict__ row = src + (s.ay * y + s.by) * s.Ws + s.bx;     // a frame is far below 2^31 elements
     float v[V];
+    if constexpr (sizeof(T) == 8) {
 #pragma unroll
-    for (int k = 0; k < V; ++k) v[k] = static_cast<float>(row[s.ax * (x + k)]);
+      for (int k = 0; k < V; ++k)
+        v[k] = static_cast<float>(__ddiv_rn(__dsub_rn(static_cast<double>(row[s.ax * (x + k)]), mean_d), std_d));
+    } else {
+      const float mean = static_cast<float>(mean_d), stdv = static_cast<float>(std_d);
 #pragma unroll
-    for (int k = 0; k < V; ++k) v[k] = __fdiv_rn(__fsub_rn(v[k], mean), stdv);
+      for (int k = 0; k < V; ++k) v[k] = static_cast<float>(row[s.ax * (x + k)]);
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = __fdiv_rn(__fsub_rn(v[k], mean), stdv);
+    }
     if constexpr (V == 4) *reinterpret_cast<float4*>(dst + y * w + x) = make_float4(v[0], v[1], v[2], v[3]);
     else dst[y * w + x] = v[0];
   }
@@ -50,7 +59,7 @@ __global__ void __launch_bounds__(256) cine_gather_kernel(const T* __restrict__ 
 }
 
 int launch_cine_gather(const void* vols, int dtype, const pvsr_cine_sample* samples, int n_samples, int n_frames, int h,
-                       int w, float mean, float stdv, float* out, const float* pos_codes, float* pos_out,
+                       int w, double mean, double stdv, float* out, const float* pos_codes, float* pos_out,
                        cudaStream_t st) {
   if (n_samples <= 0 || n_frames <= 0 || h <= 0 || w <= 0) return 0;
   const long long imgs = static_cast<long long>(n_samples) * n_frames;
@@ -72,6 +81,7 @@ int launch_cine_gather(const void* vols, int dtype, const pvsr_cine_sample* samp
     case PVSR_DT_I16: PVSR_GATHER(int16_t); break;
     case PVSR_DT_U16: PVSR_GATHER(uint16_t); break;
     case PVSR_DT_U8: PVSR_GATHER(uint8_t); break;
+    case PVSR_DT_F64: PVSR_GATHER(double); break;
     default: return static_cast<int>(cudaErrorInvalidValue);
   }
 #undef PVSR_GATHER

@@ -156,6 +156,10 @@ struct pvsr_plan {
       bm_head_wg[PVSR_MAX_HEAD_CONVS];
   std::map<GraphKey, cudaGraphExec_t> graphs;
   cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's stream may be the legacy stream)
+  // Second stream of the two-branch schedules (Ctx::side): weight-gradient launches and the HBM-bound 64 <-> 1 channel
+  // head kernels leave the critical path and overlap with it; `side_stream` serves eager runs, `cap_side` captures.
+  cudaStream_t side_stream = nullptr, cap_side = nullptr;
+  std::vector<cudaEvent_t> ev_pool;    // fork / join events of the two-branch schedules (timing disabled)
 
   // ---- accounting (filled by dry runs at creation)
   long long launches[kNumClasses];
@@ -271,6 +275,48 @@ struct Ctx {
   std::vector<cudaEvent_t>* events = nullptr;
   std::vector<int>* event_cls = nullptr;
   int rc = 0;
+  // Two-branch schedule: launches bracketed by to_side() / to_main() go to `side` (ordered after everything enqueued on
+  // `main` so far); main waits for side work only where it is about to overwrite a buffer the side branch reads
+  // (main_wait) and at the end (join).  side == nullptr (profiling runs, dry runs): a single stream, same results.
+  cudaStream_t main = nullptr, side = nullptr;
+  int ev_next = 0;
+  bool on_side = false;
+
+  cudaEvent_t next_event() {
+    if (ev_next >= static_cast<int>(p->ev_pool.size())) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      p->ev_pool.push_back(e);
+    }
+    return p->ev_pool[ev_next++];
+  }
+  void to_side() {
+    if (dry || !side || on_side) return;
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, main);
+    cudaStreamWaitEvent(side, e, 0);
+    stream = side;
+    on_side = true;
+  }
+  void to_main() {
+    if (!on_side) return;
+    stream = main;
+    on_side = false;
+  }
+  // Event marking "everything enqueued on the side branch so far" (nullptr when there is no side branch)
+  cudaEvent_t side_mark() {
+    if (dry || !side) return nullptr;
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, side);
+    return e;
+  }
+  void main_wait(cudaEvent_t e) {
+    if (e) cudaStreamWaitEvent(main, e, 0);
+  }
+  void join() {
+    to_main();
+    main_wait(side_mark());
+  }
 
   void begin(int cls) {
     (void)cls;
@@ -508,6 +554,9 @@ void schedule(Ctx& c) {
         run_conv(c, CLS_HEAD_PS, p->ps_bn[q], EPI_PS, p->maps_head[q], cp,
                  2.0 * 9 * kFeat * (kFeat * p->ps_r[q] * p->ps_r[q]) * p->ps_h[q] * p->ps_w[q] * n_head);
       }
+      // Training plans keep one head-intermediate slot per list, so the HBM-bound 64 -> 1 conv of list k can run on the
+      // side branch underneath the tensor-bound launches that follow (next list's head convs, next stage's ConvLSTM).
+      if (p->train) c.to_side();
       c.begin(CLS_HEAD_LAST);
       if (!c.dry && !c.rc) {
         float* o = c.out + static_cast<size_t>(list) * T * B * p->Hs * p->Ws;
@@ -517,6 +566,7 @@ void schedule(Ctx& c) {
         if (e) c.rc = check_cuda(e, "head_conv_last launch");
       }
       c.end(CLS_HEAD_LAST, 2.0 * 9 * kFeat * static_cast<double>(p->Hs) * p->Ws * n_head);
+      c.to_main();
     }
 
     // ---------------------------------------------------------------- edge-frame feature updates (:120-131)
@@ -526,6 +576,7 @@ void schedule(Ctx& c) {
               p->img_x[s + 1] + static_cast<long long>(L - half) * B, static_cast<long long>(half) * B);
     }
   }
+  c.join();
 }
 
 // ------------------------------------------------------------------------------------------------ backward helpers
@@ -594,6 +645,13 @@ void schedule_backward(Ctx& c) {
   float* wg = reinterpret_cast<float*>(c.ws + p->off_wg);
   __nv_bfloat16* gr = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_gr);
 
+  // Two-branch schedule (Ctx::side).  Main branch = the dependent chain of data gradients: head adjoints -> refine
+  // dgrad -> reverse ConvLSTM wavefront (gate adjoint + dgrad per diagonal).  Side branch = everything that only
+  // produces parameter gradients: every tcgen05 weight-gradient launch and the 64 -> 1 head weight adjoint.  The
+  // HBM-bound main-branch kernels (head_last_bwd_data, casts, the gate adjoints) then run underneath tensor-bound
+  // side-branch work instead of leaving the tensor pipe idle.  The side branch of stage s may still be reading the
+  // per-stage gradient buffers when the main branch reaches stage s - 1: ev_* mark the three places it must wait.
+  cudaEvent_t ev_head = nullptr, ev_refine = nullptr, ev_lstm = nullptr;
   for (int s = S - 1; s >= 0 && !c.rc; --s) {
     run_memset(c, p->off_dh, static_cast<size_t>(2 * NL) * p->dh_stride);
     const size_t dh_top_f = p->off_dh + static_cast<size_t>(0 * NL + NL - 1) * p->dh_stride;
@@ -603,19 +661,25 @@ void schedule_backward(Ctx& c) {
     const int last = p->n_ps - 1;
     const float* dout_s = c.dout ? c.dout + static_cast<size_t>(3 * s) * TB * p->Hs * p->Ws : nullptr;
     const uint8_t* head_last_in = c.ws + p->off_head[last] + static_cast<size_t>(3 * s) * p->head_stride[last];
+    c.main_wait(ev_head);     // head weight gradients of stage s + 1 read dhead[*]
     run_simt(c, BCLS_HEAD_LAST, "head_last_bwd_data", [&] {
       return launch_head_last_bwd_data(dout_s, c.P->head_w[p->n_ps], c.ws + p->off_dhead[last], 3 * TB, p->Hs, p->Ws,
                                        c.stream);
     });
-    if (c.dry || (c.G->head_w[p->n_ps] && c.G->head_b[p->n_ps]))
+    if (c.dry || (c.G->head_w[p->n_ps] && c.G->head_b[p->n_ps])) {
+      c.to_side();
       run_simt(c, BCLS_HEAD_LAST, "head_last_bwd_weight", [&] {
         return launch_head_last_bwd_weight(head_last_in, dout_s, c.G->head_w[p->n_ps], c.G->head_b[p->n_ps], 3 * TB,
                                            p->Hs, p->Ws, p->num_sms, c.stream);
       });
+      c.to_main();
+    }
     for (int q = last; q >= 0; --q) {
       const int r = p->ps_r[q];
       const double conv_fl = 2.0 * 9 * kFeat * (kFeat * r * r) * p->ps_h[q] * p->ps_w[q] * 3.0 * TB;
+      c.to_side();
       run_wgrad(c, BCLS_HEAD_WGRAD, p->bm_head_wg[q], p->wl_head[s][q], p->ps_h[q], p->ps_w[q], conv_fl);
+      c.to_main();
       ConvParams cp;
       base_params(p->bw_tile[q], p->ps_h[q], p->ps_w[q], &cp);
       set_slab(&cp, p->geo_hdg[q]);
@@ -642,6 +706,7 @@ void schedule_backward(Ctx& c) {
           pr.grad1 = nullptr;
         }
         run_conv(c, BCLS_HEAD_DGRAD, 64, EPI_GRAD, p->bm_head_dg[0], cp, conv_fl / 3);
+        c.main_wait(ev_refine);   // refine weight gradients of stage s + 1 read gr / gm
         run_simt(c, BCLS_MISC, "cast gx", [&] {
           return launch_cast_f32_bf16(grad_stack(c, p->off_gx, 0), gr + static_cast<size_t>(half) * B * px * kFeat,
                                       TB * px * kFeat, c.stream);
@@ -657,12 +722,15 @@ void schedule_backward(Ctx& c) {
         run_conv(c, BCLS_HEAD_DGRAD, 64, EPI_GRAD, p->bm_head_dg[0], cp, conv_fl * 2 / 3);
       }
     }
+    ev_head = c.side_mark();
 
     // ---------------------------------------------------------------- refine block
     if (pos) {
       const double c2_fl = 2.0 * 9 * (2 * kFeat + 1) * kFeat * px * TB;
       const double c1_fl = 2.0 * 9 * (2 * kFeat + 1) * Wn * (2 * kFeat + 1) * px * TB;
+      c.to_side();
       run_wgrad(c, BCLS_REFINE_WGRAD, p->bm_c2_wg, p->wl_c2[s], p->h, p->w, c2_fl);
+      c.to_main();
       {
         ConvParams cp;
         base_params(p->lr, p->h, p->w, &cp);
@@ -682,7 +750,9 @@ void schedule_backward(Ctx& c) {
                                     c.pos, reinterpret_cast<float*>(c.ws + p->off_sums), c.G->ref_w1, T, B, L, U - half,
                                     Wn, p->h, p->w, 2 * kFeat + 1, (2 * kFeat + 1) * Wn, 2 * kFeat, 144, c.stream);
         });
+      c.to_side();
       run_wgrad(c, BCLS_REFINE_WGRAD, p->bm_c1_wg, p->wl_c1[s], p->h, p->w, c1_fl);
+      c.to_main();
       {
         ConvParams cp;
         base_params(p->lr, p->h, p->w, &cp);
@@ -701,7 +771,9 @@ void schedule_backward(Ctx& c) {
       }
     } else {
       const double c1_fl = 2.0 * (2 * kFeat) * Wn * kFeat * px * TB;
+      c.to_side();
       run_wgrad(c, BCLS_REFINE_WGRAD, p->bm_c1_wg, p->wl_c1[s], p->h, p->w, c1_fl);
+      c.to_main();
       ConvParams cp;
       base_params(p->lr, p->h, p->w, &cp);
       cp.n_img = static_cast<int>(TB);
@@ -717,7 +789,9 @@ void schedule_backward(Ctx& c) {
       run_conv(c, BCLS_REFINE_DGRAD, 128, EPI_GRAD, p->bm_c1_dg, cp, c1_fl);
     }
 
+    ev_refine = c.side_mark();
     // ---------------------------------------------------------------- ConvLSTM: reverse wavefront over the T frames
+    c.main_wait(ev_lstm);       // the ConvLSTM weight gradient of stage s + 1 reads dgates
     const double lstm_fl = 2.0 * 9 * 2 * kFeat * 4 * kFeat;
     for (int d = 0; d < T + NL - 1; ++d) {
       LstmBwdParams lp{};
@@ -769,7 +843,10 @@ void schedule_backward(Ctx& c) {
       run_simt(c, BCLS_LSTM_POINT, "lstm_bwd_pointwise", [&] { return launch_lstm_bwd_pointwise(lp, c.stream); });
       run_conv(c, BCLS_LSTM_DGRAD, p->lstm_dg_bn, EPI_GRAD, p->bm_lstm_dg, cp, lstm_fl * px * B * np);
     }
+    c.to_side();
     run_wgrad(c, BCLS_LSTM_WGRAD, p->bm_lstm_wg, p->wl_lstm[s], p->h, p->w, lstm_fl * px * TB * 2 * NL);
+    c.to_main();
+    ev_lstm = c.side_mark();
   }
 
   // ---------------------------------------------------------------- in_block (refine_net.py:188-192), gradient frames
@@ -781,6 +858,7 @@ void schedule_backward(Ctx& c) {
     });
 
   // ---------------------------------------------------------------- packed gradients -> parameter layout
+  c.join();
   const int32_t* idx = reinterpret_cast<const int32_t*>(c.pk + p->pk_idx);
   for (const auto& j : p->sc_jobs) {
     float* dst = c.dry ? nullptr : job_grad(j.kind, j.a, j.b, c.G, j.is_bias);
@@ -986,12 +1064,18 @@ void build_wg_jobs(pvsr_plan* p) {
 // the kernel attributes) followed by a capture of the same schedule on an internal stream for later replays.
 template <typename F>
 static int run_or_replay(pvsr_plan* p, const GraphKey& key, int use_graph, cudaStream_t s, F&& eager) {
-  if (!use_graph) return eager(s);
+  int e = 0;
+  const bool two = get_two_branch() != 0 && p->train;
+  if (two && !p->side_stream) {
+    e = cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking);
+    if (!e) e = cudaStreamCreateWithFlags(&p->cap_side, cudaStreamNonBlocking);
+    if (e) return check_cuda(e, "side stream");
+  }
+  if (!use_graph) return eager(s, two ? p->side_stream : nullptr);
   auto it = p->graphs.find(key);
   if (it != p->graphs.end()) return check_cuda(cudaGraphLaunch(it->second, s), "graph launch");
-  int rc = eager(s);
+  int rc = eager(s, two ? p->side_stream : nullptr);
   if (rc) return rc;
-  int e = 0;
   if (!p->cap_stream) {
     e = cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking);
     if (e) return check_cuda(e, "capture stream");
@@ -999,7 +1083,7 @@ static int run_or_replay(pvsr_plan* p, const GraphKey& key, int use_graph, cudaS
   cudaGraph_t graph = nullptr;
   e = cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal);
   if (e) return check_cuda(e, "begin capture");
-  rc = eager(p->cap_stream);
+  rc = eager(p->cap_stream, two ? p->cap_side : nullptr);
   e = cudaStreamEndCapture(p->cap_stream, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
   if (e) return check_cuda(e, "end capture");
@@ -1289,6 +1373,9 @@ void pvsr_plan_destroy(pvsr_plan* p) {
   if (!p) return;
   for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+  if (p->side_stream) cudaStreamDestroy(p->side_stream);
+  if (p->cap_side) cudaStreamDestroy(p->cap_side);
+  for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   delete p;
 }
 
@@ -1357,20 +1444,21 @@ static int ensure_device(pvsr_plan* p) {
 }
 
 static Ctx make_ctx(pvsr_plan* p, const pvsr_net_params* P, const void* packed, const float* lr, const float* pos,
-                    void* ws, cudaStream_t s, std::vector<cudaEvent_t>* ev, std::vector<int>* ev_cls) {
+                    void* ws, cudaStream_t s, cudaStream_t side, std::vector<cudaEvent_t>* ev, std::vector<int>* ev_cls) {
   Ctx c{};
   c.p = p; c.dry = false; c.P = P;
   c.ws = static_cast<uint8_t*>(ws);
   c.pk = static_cast<const uint8_t*>(packed);
   c.lr = lr; c.pos = pos; c.stream = s;
+  c.main = s; c.side = ev ? nullptr : side;     // per-launch timing runs are single-stream
   c.events = ev; c.event_cls = ev_cls;
   return c;
 }
 
 static int forward_eager(pvsr_plan* p, const pvsr_net_params* P, const void* packed, const float* lr,
-                         const float* pos, float* out, void* ws, cudaStream_t s, std::vector<cudaEvent_t>* ev,
-                         std::vector<int>* ev_cls) {
-  Ctx c = make_ctx(p, P, packed, lr, pos, ws, s, ev, ev_cls);
+                         const float* pos, float* out, void* ws, cudaStream_t s, cudaStream_t side,
+                         std::vector<cudaEvent_t>* ev, std::vector<int>* ev_cls) {
+  Ctx c = make_ctx(p, P, packed, lr, pos, ws, s, side, ev, ev_cls);
   c.out = out;
   c.cnt_launches = p->launches; c.cnt_flops = p->flops;
   schedule(c);
@@ -1379,8 +1467,8 @@ static int forward_eager(pvsr_plan* p, const pvsr_net_params* P, const void* pac
 
 static int backward_eager(pvsr_plan* p, const pvsr_net_params* P, const void* packed, const float* lr,
                           const float* pos, const float* dout, const pvsr_net_grads* G, void* ws, cudaStream_t s,
-                          std::vector<cudaEvent_t>* ev, std::vector<int>* ev_cls) {
-  Ctx c = make_ctx(p, P, packed, lr, pos, ws, s, ev, ev_cls);
+                          cudaStream_t side, std::vector<cudaEvent_t>* ev, std::vector<int>* ev_cls) {
+  Ctx c = make_ctx(p, P, packed, lr, pos, ws, s, side, ev, ev_cls);
   c.dout = dout; c.G = G;
   c.cnt_launches = p->launches_bwd; c.cnt_flops = p->flops_bwd;
   schedule_backward(c);
@@ -1396,8 +1484,8 @@ int pvsr_plan_forward(pvsr_plan* p, const pvsr_net_params* P, const void* packed
   rc = build_maps(p, ws, packed);
   if (rc) return rc;
   GraphKey key{{ws, packed, lr, pos, out, hash_bytes(P, sizeof(*P)), nullptr, nullptr}};
-  return run_or_replay(p, key, use_graph, static_cast<cudaStream_t>(stream), [&](cudaStream_t s) {
-    return forward_eager(p, P, packed, lr, pos, out, ws, s, nullptr, nullptr);
+  return run_or_replay(p, key, use_graph, static_cast<cudaStream_t>(stream), [&](cudaStream_t s, cudaStream_t side) {
+    return forward_eager(p, P, packed, lr, pos, out, ws, s, side, nullptr, nullptr);
   });
 }
 
@@ -1426,8 +1514,8 @@ int pvsr_plan_backward(pvsr_plan* p, const pvsr_net_params* P, const void* packe
   if (rc) return rc;
   GraphKey key{{ws, packed, lr, pos, dout, hash_bytes(P, sizeof(*P)), hash_bytes(G, sizeof(*G)),
                 reinterpret_cast<const void*>(1)}};
-  return run_or_replay(p, key, use_graph, s, [&](cudaStream_t st) {
-    return backward_eager(p, P, packed, lr, pos, dout, G, ws, st, nullptr, nullptr);
+  return run_or_replay(p, key, use_graph, s, [&](cudaStream_t st, cudaStream_t side) {
+    return backward_eager(p, P, packed, lr, pos, dout, G, ws, st, side, nullptr, nullptr);
   });
 }
 
@@ -1456,7 +1544,7 @@ int pvsr_plan_profile(pvsr_plan* p, const pvsr_net_params* P, const void* packed
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   std::vector<cudaEvent_t> ev;
   std::vector<int> cls;
-  rc = forward_eager(p, P, packed, lr, pos, out, ws, s, &ev, &cls);
+  rc = forward_eager(p, P, packed, lr, pos, out, ws, s, nullptr, &ev, &cls);
   return finish_profile(s, ev, cls, kNumClasses, ms_by_class, rc);
 }
 
@@ -1473,7 +1561,7 @@ int pvsr_plan_profile_bwd(pvsr_plan* p, const pvsr_net_params* P, const void* pa
   if (rc) return rc;
   std::vector<cudaEvent_t> ev;
   std::vector<int> cls;
-  rc = backward_eager(p, P, packed, lr, pos, dout, G, ws, s, &ev, &cls);
+  rc = backward_eager(p, P, packed, lr, pos, dout, G, ws, s, nullptr, &ev, &cls);
   return finish_profile(s, ev, cls, kNumClassesBwd, ms_by_class, rc);
 }
 

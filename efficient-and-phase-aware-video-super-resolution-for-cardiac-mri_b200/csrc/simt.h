@@ -18,7 +18,7 @@ int launch_posterm(const float* w1, const float* b1, const float* pos, float* ta
 int launch_pack_weights(const float* w, const int* idx, const int* idx2, void* out_bf16, long long n, cudaStream_t s);
 int launch_gather_f32(const float* src, const int* idx, float* out, long long n, cudaStream_t s);
 int launch_cine_gather(const void* vols, int dtype, const struct pvsr_cine_sample* samples, int n_samples, int n_frames,
-                       int h, int w, float mean, float stdv, float* out, const float* pos_codes, float* pos_out,
+                       int h, int w, double mean, double stdv, float* out, const float* pos_codes, float* pos_out,
                        cudaStream_t s);
 int launch_pad_channel_bf16(const float* x, void* out_bf16, long long n, cudaStream_t s);
 int launch_take_channel0(const float* in, int stride, float* out, long long n, cudaStream_t s);

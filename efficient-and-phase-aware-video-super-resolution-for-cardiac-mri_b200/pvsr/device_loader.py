@@ -6,8 +6,9 @@ pickle, normalises every frame of the cycle, flips and crops on the host, and 8 
 src/data/dataloader.py:6-53).  At ~15 k SR frames/s per GPU that pipeline cannot keep one B200 busy, let alone eight.
 Here the decoded volumes are uploaded ONCE in their stored dtype (the whole preprocessed ACDC set is a few GB; a B200
 has 180 GB), and a batch is one `pvsr_cine_gather` launch per resolution: the host only draws the random decisions -
-from the SAME numpy stream, in the same order as the host transform chain, so a seeded run produces bit-identical
-batches on either path - and ships one 48-byte descriptor per sample.
+from the SAME Python `random` stream, with the reference's calls in the reference's order (src/data/transforms.py:
+`decide()`), so a seeded run produces bit-identical batches on either path, and both reproduce the items recorded from
+the unmodified reference pipeline (tests/golden/data_pipeline.npz) - and ships one 48-byte descriptor per sample.
 
 The loader yields the dataset's batch contract: {'lr_imgs': list of L x (N,1,h,w), 'hr_imgs': list of T x (N,1,sh,sw),
 'pos_code': (N,L,1), 'index': (N,)} with all tensors on the device.
@@ -22,8 +23,9 @@ from torch.utils.data.distributed import DistributedSampler
 from . import lib as L
 
 _DT = {np.dtype(np.float32): L.DT_F32, np.dtype(np.int16): L.DT_I16, np.dtype(np.uint16): L.DT_U16,
-       np.dtype(np.uint8): L.DT_U8}
-_TORCH_DT = {L.DT_F32: torch.float32, L.DT_I16: torch.int16, L.DT_U16: torch.int16, L.DT_U8: torch.uint8}   # u16 bits kept in an int16 tensor
+       np.dtype(np.uint8): L.DT_U8, np.dtype(np.float64): L.DT_F64}
+_TORCH_DT = {L.DT_F32: torch.float32, L.DT_I16: torch.int16, L.DT_U16: torch.int16, L.DT_U8: torch.uint8,
+             L.DT_F64: torch.float64}   # u16 bits kept in an int16 tensor
 
 
 class Affine:
@@ -76,7 +78,7 @@ class DeviceDataloader:
     `transform_plan()` and `window(index)` (AcdcVSRRefineNetDataset / SyntheticCineDataset do)."""
 
     def __init__(self, dataset, batch_size=1, shuffle=False, sampler=None, batch_sampler=None, drop_last=False,
-                 shard=None, device=None, **_ignored):
+                 shard=None, shard_pad=True, device=None, **_ignored):
         for need in ('sequence_table', 'transform_plan', 'window'):
             if not hasattr(dataset, need):
                 raise TypeError(f'{type(dataset).__name__} has no {need}(): it cannot be served from device memory')
@@ -88,9 +90,12 @@ class DeviceDataloader:
         if batch_sampler is None:
             if sampler is None:
                 rank, world = shard if shard is not None else (0, 1)
-                if world > 1:
+                if world > 1 and shard_pad:
                     sampler = DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=shuffle,
                                                  drop_last=drop_last)
+                elif world > 1:
+                    from .parallel import ShardSampler
+                    sampler = ShardSampler(len(dataset), rank, world)      # validation: every sample exactly once
                 else:
                     sampler = RandomSampler(dataset) if shuffle else SequentialSampler(dataset)
             batch_sampler = BatchSampler(sampler, batch_size, drop_last)
@@ -120,7 +125,7 @@ class DeviceDataloader:
 
     # ------------------------------------------------------------------ batches
     def decide(self, index):
-        """Draws the augmentation decisions of one item (numpy global RNG, same order as the host transform chain)
+        """Draws the augmentation decisions of one item (Python `random`, same order as the host transform chain)
         and returns (seq, lr_first, n_lr, hr_first, n_hr, lr Affine, hr Affine)."""
         seq, a, b, c, d = self.dataset.window(index)
         T, H, W = self._lr.shapes[seq]

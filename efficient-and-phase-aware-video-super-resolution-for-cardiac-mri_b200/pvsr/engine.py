@@ -197,6 +197,10 @@ class RefineNetEngine:
         """Device address of the buffer the next run(pl) writes (for HostFrameRing.before_launch)."""
         return self._next_out(pl).data_ptr()
 
+    def next_output_bytes(self, pl):
+        buf = self._next_out(pl)
+        return buf.numel() * buf.element_size()
+
     def _check_inputs(self, inputs):
         x0 = inputs[0]
         if not x0.is_cuda:

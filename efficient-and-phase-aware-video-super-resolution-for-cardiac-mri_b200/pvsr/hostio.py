@@ -32,19 +32,28 @@ class HostFrameRing:
         self.slots = slots
         self.host = [None] * slots
         self.done = [None] * slots        # event: copy into slot finished
-        self.src = [None] * slots         # device address each outstanding copy reads from
+        self.src = [None] * slots         # device byte range [begin, end) each outstanding copy reads from
         self.next = 0
         self.bytes_per_step = 0
 
-    def before_launch(self, dst_ptr=None):
+    def before_launch(self, dst_ptr=None, dst_bytes=None):
         """Call before enqueueing a forward that overwrites a buffer earlier submits read from: the compute stream
-        waits for the copies still reading `dst_ptr` (RefineNetEngine.next_output_ptr) - or for all of them when the
-        address is not given.  With engine.output_slots = 2 the copy of step i never reads what step i + 1 writes, so
-        the forward starts immediately and the copy overlaps it."""
+        waits for the copies still reading any byte of [dst_ptr, dst_ptr + dst_bytes)
+        (RefineNetEngine.next_output_ptr / next_output_bytes) - or for all of them when the address is not given.
+        A submitted tensor may be a sub-view of the output buffer (e.g. the last list of an all-heads forward), so
+        the test is a range overlap, not pointer equality; without `dst_bytes` any copy whose source starts at or
+        after `dst_ptr` is waited for.  With engine.output_slots = 2 the copy of step i never reads what step i + 1
+        writes, so the forward starts immediately and the copy overlaps it."""
         cur = torch.cuda.current_stream(self.device)
         for ev, src in zip(self.done, self.src):
-            if ev is not None and (dst_ptr is None or src == dst_ptr):
-                cur.wait_event(ev)
+            if ev is None:
+                continue
+            if dst_ptr is not None:
+                s0, s1 = src
+                d1 = dst_ptr + dst_bytes if dst_bytes is not None else None
+                if s1 <= dst_ptr or (d1 is not None and s0 >= d1):
+                    continue
+            cur.wait_event(ev)
 
     def submit(self, frames):
         """Enqueues the D2H of `frames` (list of tensors or one tensor); returns the slot index."""
@@ -65,7 +74,7 @@ class HostFrameRing:
             ev = torch.cuda.Event()
             ev.record(self.stream)
         self.done[s] = ev
-        self.src[s] = src.data_ptr()
+        self.src[s] = (src.data_ptr(), src.data_ptr() + src.numel() * src.element_size())
         self.bytes_per_step = src.numel() * src.element_size()
         return s
 

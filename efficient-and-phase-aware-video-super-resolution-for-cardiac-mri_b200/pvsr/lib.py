@@ -88,7 +88,7 @@ class TableJob(C.Structure):
 
 
 TJ_PACK, TJ_GATHER, TJ_SCATTER = 0, 1, 2
-DT_F32, DT_I16, DT_U16, DT_U8 = 0, 1, 2, 3
+DT_F32, DT_I16, DT_U16, DT_U8, DT_F64 = 0, 1, 2, 3, 4
 NUM_CLASSES, NUM_CLASSES_BWD = 7, 9
 
 # name -> (restype, argtypes); every symbol declared in include/pvsr.h
@@ -100,6 +100,8 @@ SIGNATURES = {
     "pvsr_get_cta_pair": (c_int, []),
     "pvsr_set_halo_mode": (c_int, [c_int]),
     "pvsr_get_halo_mode": (c_int, []),
+    "pvsr_set_two_branch": (c_int, [c_int]),
+    "pvsr_get_two_branch": (c_int, []),
     "pvsr_set_pdl": (c_int, [c_int]),
     "pvsr_get_pdl": (c_int, []),
     "pvsr_set_head_tma": (c_int, [c_int]),
@@ -131,7 +133,7 @@ SIGNATURES = {
                                     c_int, c_int, c_int, c_void_p]),
     "pvsr_head_conv_last_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                         c_int, c_void_p]),
-    "pvsr_cine_gather": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, C.c_float, C.c_float, c_void_p,
+    "pvsr_cine_gather": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, C.c_double, C.c_double, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
     "pvsr_add_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "pvsr_lstm_cell_bwd_pointwise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64,
@@ -193,6 +195,8 @@ def load():
         lib.pvsr_set_halo_mode(int(os.environ["PVSR_HALO"]))
     if os.environ.get("PVSR_HEAD_TMA") is not None:       # A/B switch of the head_conv_last forms
         lib.pvsr_set_head_tma(int(os.environ["PVSR_HEAD_TMA"]))
+    if os.environ.get("PVSR_TWO_BRANCH") is not None:     # A/B switch of the two-branch training schedules
+        lib.pvsr_set_two_branch(int(os.environ["PVSR_TWO_BRANCH"]))
     if os.environ.get("PVSR_PDL") is not None:            # A/B switch of programmatic dependent launch
         lib.pvsr_set_pdl(int(os.environ["PVSR_PDL"]))
     if os.environ.get("PVSR_CTA_PAIR") is not None:       # A/B switch of the cta_group::2 conv kernel

@@ -69,6 +69,21 @@ def shard_indices(n_items, rank, world, sizes=None):
     return sorted(mine)
 
 
+class ShardSampler(torch.utils.data.Sampler):
+    """Rank `rank`'s items of a dataset WITHOUT padding: i -> rank i % world, in order.  For loops with no per-step
+    collective (validation, test): DistributedSampler would repeat samples to equalise the shards, and the summed
+    log would then count them twice (the validation score feeds Monitor.is_best and ReduceLROnPlateau)."""
+
+    def __init__(self, n_items, rank, world):
+        self.indices = shard_indices(n_items, rank, world)
+
+    def __iter__(self):
+        return iter(self.indices)
+
+    def __len__(self):
+        return len(self.indices)
+
+
 def bucket_by_shape(shapes):
     """Groups item indices by identical (frames, h, w): sequences of one bucket can be batched into one plan launch
     (the plan geometry is static).  Returns {shape: [indices]} with deterministic ordering."""

@@ -8,6 +8,8 @@ import numpy as np
 from torch.utils.data import DataLoader
 from torch.utils.data.distributed import DistributedSampler
 
+from pvsr.parallel import ShardSampler
+
 from pvsr.device_loader import DeviceDataloader  # noqa: F401  (registry name: `dataloader: {name: DeviceDataloader}`)
 
 
@@ -17,12 +19,15 @@ def _seed_worker(worker_id):
 
 class Dataloader(DataLoader):
     def __init__(self, dataset, batch_size=1, shuffle=False, sampler=None, batch_sampler=None, num_workers=0,
-                 collate_fn=None, pin_memory=False, drop_last=False, timeout=0, worker_init_fn=None, shard=None):
+                 collate_fn=None, pin_memory=False, drop_last=False, timeout=0, worker_init_fn=None, shard=None,
+                 shard_pad=True):
         if shard is not None and sampler is None and batch_sampler is None:
             rank, world = shard
             if world > 1:
+                # training: equal step counts on every rank (one all-reduce per step) -> padded shards;
+                # shard_pad=False (validation): every sample exactly once, ranks may differ by one item
                 sampler = DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=shuffle,
-                                             drop_last=drop_last)
+                                             drop_last=drop_last) if shard_pad else ShardSampler(len(dataset), rank, world)
                 shuffle = False
         kwargs = dict(batch_size=batch_size, shuffle=shuffle, sampler=sampler, batch_sampler=batch_sampler,
                       num_workers=num_workers, pin_memory=pin_memory, drop_last=drop_last, timeout=timeout,

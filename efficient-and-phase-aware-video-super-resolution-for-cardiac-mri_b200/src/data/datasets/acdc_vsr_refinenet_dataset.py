@@ -40,12 +40,13 @@ def window_slices(T, t, num_frames, num_updated_frames, train):
 
 def device_transform_plan(transforms, augments):
     from ..transforms import Normalize, ToTensor
-    mean, std = np.float32(0), np.float32(1)
+    mean, std = 0.0, 1.0
     for step in transforms.steps:
         if isinstance(step, Normalize):
             if step.means is None or step.means.size != 1:
                 raise TypeError('per-image statistics / multi-channel Normalize cannot be served from device memory')
-            mean, std = step.means.reshape(-1)[0], (step.stds + 1e-10).astype(np.float32).reshape(-1)[0]
+            # float64 masters: the kernel rounds them to the volume's dtype exactly like Normalize does on the host
+            mean, std = float(step.means.reshape(-1)[0]), float((step.stds + 1e-10).reshape(-1)[0])
         elif not isinstance(step, ToTensor):
             raise TypeError(f'transform {type(step).__name__} cannot be served from device memory')
     for step in augments.steps:

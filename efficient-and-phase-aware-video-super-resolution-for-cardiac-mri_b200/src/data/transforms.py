@@ -4,8 +4,15 @@ RandomCropPatch, resolved by name through `compose` (reference src/data/transfor
 
 Every transform takes any number of numpy images (H, W, C) - the LR frames followed by the HR frames of one cine
 sequence - and returns the same number, applying ONE random decision to all of them.
+
+Parity with the reference is pinned by tests/golden/data_pipeline.npz (oracle/make_golden_data.py runs the unmodified
+reference classes): the random decisions are drawn from Python's `random` module with the reference's calls in the
+reference's order (`random.random() < prob` per flip, transforms.py:340,369; `random.randint(0, h - ht)` then
+`random.randint(0, w - wt)` per crop, :443), and Normalize computes in the image's own floating dtype like numpy does
+for `img[..., c] = (img[..., c] - mean) / (std + 1e-10)` (:165-168) before ToTensor's `.float()`.
 """
 import importlib
+import random
 
 import numpy as np
 import torch
@@ -57,20 +64,29 @@ class Normalize(BaseTransform):
     def __init__(self, means=None, stds=None):
         if (means is None) != (stds is None):
             raise ValueError('means and stds should be both None or both given.')
-        self.means = None if means is None else np.asarray(means, dtype=np.float32)
-        self.stds = None if stds is None else np.asarray(stds, dtype=np.float32)
+        if means is not None and len(means) != len(stds):
+            raise ValueError('The number of the means should be the same as the standard deviations.')
+        # float64 masters (the YAML numbers); cast to the image's dtype at use, which is what numpy does with the
+        # reference's Python-float operands
+        self.means = None if means is None else np.asarray(means, dtype=np.float64)
+        self.stds = None if stds is None else np.asarray(stds, dtype=np.float64)
 
     def __call__(self, *imgs, normalize_tags=None, **kwargs):
         tags = normalize_tags if normalize_tags is not None else [True] * len(imgs)
         out = []
         for img, tag in zip(imgs, tags):
             if tag:
-                img = np.asarray(img, dtype=np.float32)
+                img = np.asarray(img)
+                if not np.issubdtype(img.dtype, np.floating):
+                    # the preprocessing scripts only write float32 volumes (acdc_preprocess.py:40); the reference would
+                    # truncate the normalised values back into an integer array - integer volumes are promoted instead
+                    img = img.astype(np.float32)
+                dt = img.dtype
                 if self.means is None:
                     axes = tuple(range(img.ndim - 1))
-                    img = (img - img.mean(axis=axes)) / (img.std(axis=axes) + 1e-10)
+                    img = ((img - img.mean(axis=axes)) / (img.std(axis=axes) + 1e-10)).astype(dt, copy=False)
                 else:
-                    img = (img - self.means) / (self.stds + 1e-10)
+                    img = ((img - self.means.astype(dt)) / (self.stds + 1e-10).astype(dt)).astype(dt, copy=False)
             out.append(img)
         return tuple(out)
 
@@ -79,11 +95,11 @@ class _RandomFlip(BaseTransform):
     axis = 0
 
     def __init__(self, prob=0.5):
-        self.prob = prob
+        self.prob = max(0, min(prob, 1))
 
     def decide(self, h, w):
         """Draws this step's decision for an (h, w) LR image: ('flip', axis) or None (pvsr.device_loader)."""
-        return ('flip', self.axis) if np.random.rand() < self.prob else None
+        return ('flip', self.axis) if random.random() < self.prob else None
 
     def __call__(self, *imgs, **kwargs):
         if self.decide(*imgs[0].shape[:2]) is not None:
@@ -111,8 +127,8 @@ class RandomCropPatch(BaseTransform):
         ph, pw = self.size
         if ph > h or pw > w:
             raise ValueError(f'The crop size {self.size} exceeds the LR image size {(h, w)}.')
-        y0 = np.random.randint(0, h - ph + 1)
-        x0 = np.random.randint(0, w - pw + 1)
+        y0 = random.randint(0, h - ph)       # inclusive bounds, rows first (transforms.py:443)
+        x0 = random.randint(0, w - pw)
         return ('crop', y0, x0, ph, pw, self.ratio)
 
     def __call__(self, *imgs, **kwargs):

@@ -125,7 +125,7 @@ def main(args):
                                                                       shard=(rank, world)))
         loader_cfg.kwargs.update(batch_size=train_bs)
         train_dataloader = _get_instance(src.data.dataloader, loader_cfg, datasets['train'])
-        loader_cfg.kwargs.update(batch_size=valid_bs)
+        loader_cfg.kwargs.update(batch_size=valid_bs, shard_pad=False)   # under DDP: each validation sample counted once
         valid_dataloader = _get_instance(src.data.dataloader, loader_cfg, datasets['valid'])
 
         net = _get_instance(src.model.nets, config.net)

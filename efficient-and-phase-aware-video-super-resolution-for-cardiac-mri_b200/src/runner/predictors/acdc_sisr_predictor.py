@@ -36,10 +36,23 @@ class AcdcSISRPredictor(BasePredictor):
         patient, _, sid, fid = filename.split('_')
         return filename, patient, sid, fid
 
+    def _my_indices(self, n_items):
+        """Frames of this rank: whole (patient, slice) groups, cost-balanced by frame count, so that every slice's
+        GIF (and its PNGs) is written by exactly one rank from ALL of that slice's frames."""
+        if self.world <= 1:
+            return list(range(n_items))
+        groups = {}
+        for index in range(n_items):
+            _, patient, sid, _ = self._name(index)
+            groups.setdefault((patient, sid), []).append(index)
+        keys = sorted(groups)
+        owned = parallel.shard_indices(len(keys), self.rank, self.world, sizes=[len(groups[k]) for k in keys])
+        return sorted(i for g in owned for i in groups[keys[g]])
+
     def predict(self):
         self.net.eval()
         dataset = self.test_dataloader.dataset
-        mine = parallel.shard_indices(len(dataset), self.rank, self.world)
+        mine = self._my_indices(len(dataset))
         names = [fn.__class__.__name__ for fn in self.metric_fns + self.loss_fns]
         log, count, rows, frames = self._init_log(), 0, [], {}
 

@@ -51,6 +51,10 @@ class BaseTrainer:
             self.np_random_seeds = random.sample(range(10000000), k=self.num_epochs)
         while self.epoch <= self.num_epochs:
             np.random.seed(self.np_random_seeds[self.epoch - 1] + self.rank)
+            if self.world > 1:
+                # the augmentation decisions follow the reference's Python `random` calls (src/data/transforms.py); one
+                # process = the reference's stream untouched, several ranks = one stream per rank and epoch
+                random.seed(self.np_random_seeds[self.epoch - 1] * 1000003 + self.rank)
             logging.info(f'Epoch {self.epoch}.')
             train_log, train_batch, train_outputs = self._run_epoch('training')
             logging.info(f'Train log: {train_log}.')

@@ -52,6 +52,11 @@ int pvsr_get_halo_mode(void);
  * plan (captured CUDA graphs keep the setting they were captured with).  Process-wide. */
 int pvsr_set_pdl(int enable);
 int pvsr_get_pdl(void);
+/* Two-branch schedules of training plans: the tcgen05 weight-gradient launches and the HBM-bound 64 <-> 1 channel head
+ * kernels run on a second stream (a second branch of the captured CUDA graph) underneath the dependent chain of data
+ * gradients.  1 = on (default), 0 = one chain (A/B switch; env PVSR_TWO_BRANCH).  Set BEFORE the first run of a plan. */
+int pvsr_set_two_branch(int enable);
+int pvsr_get_two_branch(void);
 /* head_conv_last form: 1 = 3-stage TMA ring (default), 0 = cp.async double buffer (A/B switch; env PVSR_HEAD_TMA). */
 int pvsr_set_head_tma(int enable);
 int pvsr_get_head_tma(void);
@@ -251,6 +256,7 @@ int pvsr_scatter_add_scaled(float* param_grad, const int32_t* idx, const float* 
 #define PVSR_DT_I16 1
 #define PVSR_DT_U16 2
 #define PVSR_DT_U8 3
+#define PVSR_DT_F64 4   /* normalised in fp64, rounded to fp32 once (numpy semantics of the reference's Normalize) */
 typedef struct pvsr_cine_sample {
   int64_t vol_off;         /* element offset of frame 0 of the sequence inside `volumes` */
   int64_t pos_off;         /* element offset of the sequence's code [T] inside `pos_codes`, or -1 */
@@ -261,7 +267,7 @@ typedef struct pvsr_cine_sample {
   int32_t ax, bx;          /* source column = ax * x + bx */
 } pvsr_cine_sample;
 int pvsr_cine_gather(const void* volumes, int vol_dtype, const pvsr_cine_sample* samples, int n_samples, int n_frames,
-                     int h, int w, float mean, float std, float* out, const float* pos_codes, float* pos_out,
+                     int h, int w, double mean, double std, float* out, const float* pos_codes, float* pos_out,
                      void* stream);
 
 /* Number of fp32 elements of a tile-transposed ConvLSTM cell-state buffer for n_img images of H x W. */

@@ -137,18 +137,36 @@ def metrics_golden():
     seeds by the tests, only the expected values are stored)."""
     metrics = importlib.import_module("src.model.metrics")
     utils = importlib.import_module("src.utils")
+    import pickle
+    import tempfile
     out = []
     for seed, (n, h, w) in enumerate([(1, 216, 252), (2, 40, 37), (1, 11, 11), (3, 64, 48)]):
         g = torch.Generator().manual_seed(100 + seed)
         a = torch.randn(n, 1, h, w, generator=g)
         b = a + 0.1 * torch.randn(n, 1, h, w, generator=g)
         rec = {"seed": 100 + seed, "shape": [n, 1, h, w]}
+        # cardiac bounding box (h0, hn, w0, wn) of the one patient these frames belong to (metrics.py:116-165 reads it
+        # from a pickle keyed by patient name); at least the 11-pixel SSIM window in both directions
+        box = [h // 5, max(h // 5 + 11, (4 * h) // 5), w // 4, max(w // 4 + 11, (3 * w) // 4)] if min(h, w) > 11 \
+            else [0, h, 0, w]
+        rec["cardiac_box"] = box
+        with tempfile.TemporaryDirectory() as td:
+            cp = os.path.join(td, "coordinates.pkl")
+            with open(cp, "wb") as f:
+                pickle.dump({"patient_g": tuple(box)}, f)
+            cpsnr = metrics.CardiacPSNR(coordinates_path=cp, size_average=False)
+            cssim = metrics.CardiacSSIM(coordinates_path=cp, size_average=False)
+            cpsnr_avg, cssim_avg = metrics.CardiacPSNR(coordinates_path=cp), metrics.CardiacSSIM(coordinates_path=cp)
         for ds in ("acdc", "dsb15"):
             da, db = utils.denormalize(a, ds), utils.denormalize(b, ds)
             rec[ds] = {"denorm_sum": float(da.double().sum()), "psnr": float(metrics.PSNR()(da, db)),
                        "ssim": float(metrics.SSIM()(da, db)),
                        "psnr_per_sample": [float(v) for v in metrics.PSNR(size_average=False)(da, db)],
-                       "ssim_per_sample": [float(v) for v in metrics.SSIM(size_average=False)(da, db)]}
+                       "ssim_per_sample": [float(v) for v in metrics.SSIM(size_average=False)(da, db)],
+                       "cardiac_psnr": float(cpsnr_avg(da, db, "patient_g")),
+                       "cardiac_ssim": float(cssim_avg(da, db, "patient_g")),
+                       "cardiac_psnr_per_sample": [float(v) for v in cpsnr(da, db, "patient_g")],
+                       "cardiac_ssim_per_sample": [float(v) for v in cssim(da, db, "patient_g")]}
         out.append(rec)
     with open(os.path.join(OUT, "metrics.json"), "w") as f:
         json.dump(out, f, indent=1)
@@ -159,7 +177,8 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ref = load_reference()
-    for name, (kw, N, T, h, w) in CASES.items():
-        make_case(ref, name, kw, N, T, h, w)
-    known_answers(ref)
+    if "--metrics" not in sys.argv:        # --metrics: only rewrite metrics.json
+        for name, (kw, N, T, h, w) in CASES.items():
+            make_case(ref, name, kw, N, T, h, w)
+        known_answers(ref)
     metrics_golden()

@@ -75,3 +75,31 @@ def test_two_rank_gloo():
         p.join(100)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert sorted(q.get(timeout=5) for _ in range(2)) == [0, 1]
+
+
+def test_unpadded_validation_shards_and_slice_level_sisr_shards():
+    """ShardSampler: every item exactly once over the ranks (no DistributedSampler padding in validation / test);
+    AcdcSISRPredictor._my_indices: whole (patient, slice) groups per rank, so one rank writes each slice's GIF."""
+    import types
+    from pvsr.parallel import ShardSampler
+    from src.runner.predictors.acdc_sisr_predictor import AcdcSISRPredictor
+    for n, world in ((7, 2), (10, 4), (3, 8)):
+        seen = [i for r in range(world) for i in ShardSampler(n, r, world)]
+        assert sorted(seen) == list(range(n))
+    # 3 patients x 2 slices x ragged frame counts
+    names = []
+    for p in range(3):
+        for s in range(2):
+            for f in range(4 + p + s):
+                names.append((f'patient{p:03d}_2d_slice{s:02d}_frame{f:02d}', f'patient{p:03d}', f'slice{s:02d}', f'frame{f:02d}'))
+    owners = {}
+    covered = []
+    for rank in range(4):
+        stub = types.SimpleNamespace(world=4, rank=rank, _name=lambda i: names[i])
+        mine = AcdcSISRPredictor._my_indices(stub, len(names))
+        covered.extend(mine)
+        for i in mine:
+            assert owners.setdefault(names[i][1:3], rank) == rank          # a slice never spans two ranks
+    assert sorted(covered) == list(range(len(names)))
+    one = AcdcSISRPredictor._my_indices(types.SimpleNamespace(world=1, rank=0, _name=lambda i: names[i]), len(names))
+    assert one == list(range(len(names)))

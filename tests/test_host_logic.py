@@ -110,9 +110,11 @@ def test_config_registry_resolves_reference_configs():
 
 
 def test_metrics_match_reference_values():
-    """PSNR / SSIM / denormalize against numbers produced by the reference's src/model/metrics.py and src/utils.py
-    (oracle/make_golden.py: metrics_golden)."""
-    from src.model.metrics import PSNR, SSIM
+    """PSNR / SSIM / CardiacPSNR / CardiacSSIM / denormalize against numbers produced by the reference's
+    src/model/metrics.py (:9-165) and src/utils.py (oracle/make_golden.py: metrics_golden)."""
+    import pickle
+    import tempfile
+    from src.model.metrics import PSNR, SSIM, CardiacPSNR, CardiacSSIM
     from src.utils import denormalize
     with open(os.path.join(GOLDEN, "metrics.json")) as f:
         recs = json.load(f)
@@ -121,8 +123,19 @@ def test_metrics_match_reference_values():
         a = torch.randn(*rec["shape"], generator=g)
         b = a + 0.1 * torch.randn(*rec["shape"], generator=g)
         a0 = a.clone()
+        with tempfile.TemporaryDirectory() as td:       # metrics.py:116-165: per-patient box read from a pickle
+            cp = os.path.join(td, "coordinates.pkl")
+            with open(cp, "wb") as f:
+                pickle.dump({"patient_g": tuple(rec["cardiac_box"])}, f)
+            cpsnr, cssim = CardiacPSNR(coordinates_path=cp), CardiacSSIM(coordinates_path=cp)
+            cpsnr_n = CardiacPSNR(coordinates_path=cp, size_average=False)
+            cssim_n = CardiacSSIM(coordinates_path=cp, size_average=False)
         for ds in ("acdc", "dsb15"):
             da, db = denormalize(a, ds), denormalize(b, ds)
+            assert abs(float(cpsnr(da, db, "patient_g")) - rec[ds]["cardiac_psnr"]) <= 1e-4
+            assert abs(float(cssim(da, db, "patient_g")) - rec[ds]["cardiac_ssim"]) <= 2e-6
+            assert np.allclose(cpsnr_n(da, db, "patient_g").tolist(), rec[ds]["cardiac_psnr_per_sample"], atol=1e-4)
+            assert np.allclose(cssim_n(da, db, "patient_g").tolist(), rec[ds]["cardiac_ssim_per_sample"], atol=2e-6)
             assert torch.equal(a, a0)                                        # input untouched
             assert float(da.double().sum()) == rec[ds]["denorm_sum"]
             assert abs(float(PSNR()(da, db)) - rec[ds]["psnr"]) <= 1e-4       # the 0.01 dB parity bar, with margin

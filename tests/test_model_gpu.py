@@ -98,7 +98,8 @@ def test_errors_like_reference(pvsr_lib):
             net2.eval()([torch.zeros(1, 1, 8, 8)] * 6, torch.zeros(1, 6, 1))   # CPU tensors: no fallback
 
 
-@pytest.mark.parametrize("scale,h,w,pos", [(4, 54, 63, True), (4, 63, 48, True), (3, 72, 84, True)])
+@pytest.mark.parametrize("scale,h,w,pos", [(4, 54, 63, True), (4, 63, 48, True), (3, 72, 84, True),
+                                           (2, 108, 126, True)])   # BASELINE.json configs[1..3]: ACDC x4/x3/x2, DSB15 x4
 def test_full_size_sequence_vs_oracle(pvsr_lib, scale, h, w, pos):
     """One ACDCSR / DSB15SR-shaped cine sequence (T=30, U=6): SR frames and PSNR/SSIM against the CPU oracle."""
     from oracle import refinenet_oracle as O
@@ -177,3 +178,38 @@ def test_host_frame_ring_overlapped_readback(pvsr_lib):
         ring.drain()
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_batched_full_size_graph_replay_through_host_ring(pvsr_lib):
+    """The benchmarked combination at B = 8: full ACDCSR x4 shape x CUDA-graph replay x last-head-only x rotating output
+    buffers x overlapped HostFrameRing read-back, checked against the CPU oracle for 2 of the 8 sequences of the LAST
+    of three pipelined steps (so the frames compared went through a replayed graph and a reused host slot)."""
+    from oracle import refinenet_oracle as O
+    from pvsr.hostio import HostFrameRing
+    from pvsr.synthetic import cine_batch
+    T, U, h, w, B = 30, 6, 54, 63, 8
+    kw = dict(in_channels=1, out_channels=1, num_features=[64, 64, 64], num_stages=3, update_memory=True,
+              num_updated_frames=U, refine_window_size=5, upscale_factor=4, positional_encoding=True)
+    net = build_net(kw)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.cuda().eval()
+    net.only_last_head = True
+    net.reuse_output_buffers = True
+    net.engine.output_slots = 2
+    ring = HostFrameRing("cuda", slots=2)
+    steps = [cine_batch(B, T=T, U=U, h=h, w=w, scale=4, seed=900 + i) for i in range(3)]
+    slot = None
+    with torch.no_grad():
+        for inputs, pos in steps:
+            pl = net.engine.plan_for(B, len(inputs), h, w, False, torch.device("cuda", torch.cuda.current_device()))
+            ring.before_launch(net.engine.next_output_ptr(pl))
+            frames = net([x.cuda(non_blocking=True) for x in inputs], pos.cuda(non_blocking=True))[-1]
+            slot = ring.submit(frames)
+        got = ring.result(slot).clone()          # [T, B, 1, H, W] of the last step
+        ring.drain()
+        inputs, pos = steps[-1]
+        for i in (0, B - 1):
+            ref = O.refinenet_forward(sd, [x[i:i + 1] for x in inputs], pos[i:i + 1], **oracle_kwargs(kw))[-1]
+            for t, r in enumerate(ref):
+                g = got[t, i:i + 1]
+                assert (g - r).abs().max().item() <= MAX_ABS and ((g - r).norm() / r.norm()).item() <= REL_L2, (i, t)

@@ -19,21 +19,33 @@ def _scores(loss_fns, metric_fns, a, b, patients, dataset, fused):
                              patients, dataset=dataset if fused else None)
 
 
-def test_fused_scores_match_reference_metric_values(pvsr_lib):
-    from src.model.metrics import PSNR, SSIM
+def test_fused_scores_match_reference_metric_values(pvsr_lib, tmp_path):
+    """Fused kernel AND generic torch path against the reference's own PSNR / SSIM / CardiacPSNR / CardiacSSIM values
+    (metrics.py:9-165; golden written by oracle/make_golden.py from the unmodified reference classes)."""
+    from src.model.metrics import PSNR, SSIM, CardiacPSNR, CardiacSSIM
     with open(os.path.join(GOLDEN, "metrics.json")) as f:
         recs = json.load(f)
-    for rec in recs:
+    for i, rec in enumerate(recs):
         g = torch.Generator().manual_seed(rec["seed"])
         a = torch.randn(*rec["shape"], generator=g)
         b = a + 0.1 * torch.randn(*rec["shape"], generator=g)
+        box = tmp_path / f"coordinates{i}.pkl"
+        with open(box, "wb") as f:
+            pickle.dump({"patient_g": tuple(rec["cardiac_box"])}, f)
+        fns = [PSNR().cuda(), SSIM().cuda(), CardiacPSNR(coordinates_path=box).cuda(),
+               CardiacSSIM(coordinates_path=box).cuda()]
         for ds in ("acdc", "dsb15"):
-            losses, metrics = _scores([torch.nn.L1Loss()], [PSNR().cuda(), SSIM().cuda()], a.cuda(), b.cuda(),
-                                      ["p"] * a.shape[0], ds, True)
-            l1 = (a - b).abs().flatten(1).mean(dim=1)
-            assert torch.allclose(losses[:, 0].cpu(), l1, rtol=1e-5, atol=0)
-            assert torch.allclose(metrics[:, 0].cpu(), torch.tensor(rec[ds]["psnr_per_sample"]), atol=1e-4)
-            assert torch.allclose(metrics[:, 1].cpu(), torch.tensor(rec[ds]["ssim_per_sample"]), atol=2e-6)
+            for fused in (True, False):
+                losses, metrics = _scores([torch.nn.L1Loss()], fns, a.cuda(), b.cuda(), ["patient_g"] * a.shape[0], ds,
+                                          fused)
+                l1 = (a - b).abs().flatten(1).mean(dim=1)
+                assert torch.allclose(losses[:, 0].cpu(), l1, rtol=1e-5, atol=0)
+                assert torch.allclose(metrics[:, 0].cpu(), torch.tensor(rec[ds]["psnr_per_sample"]), atol=1e-4)
+                assert torch.allclose(metrics[:, 1].cpu(), torch.tensor(rec[ds]["ssim_per_sample"]), atol=2e-6)
+                assert torch.allclose(metrics[:, 2].cpu(), torch.tensor(rec[ds]["cardiac_psnr_per_sample"]), atol=1e-4), \
+                    (rec["shape"], ds, fused)
+                assert torch.allclose(metrics[:, 3].cpu(), torch.tensor(rec[ds]["cardiac_ssim_per_sample"]), atol=2e-6), \
+                    (rec["shape"], ds, fused)
 
 
 @pytest.mark.parametrize("shape", [(6, 1, 216, 252), (4, 1, 40, 48), (3, 1, 11, 75), (2, 1, 128, 128)])

@@ -6,6 +6,8 @@ Tolerances (measured drift of the reference itself under b
 rel-L2 0.7-2.6e-2, cosine >= 0.9998): gradients rel-L2 <= 4e-2 and cosine >= 0.999; loss |delta| <= 2e-3 relative.
 """
 import numpy as np
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -316,3 +318,105 @@ def test_training_shape_vs_oracle(pvsr_lib):
     got = {k: p.grad for k, p in net.named_parameters()}
     worst = _check_grads(got, {k: ref_grads.get(k) for k in got}, "train-shape")
     print({k: (round(v[0], 4), round(v[1], 6)) for k, v in worst.items()})
+
+
+def test_fused_adam_checkpoint_roundtrip_and_torch_interchange(pvsr_lib):
+    """FusedAdam.state_dict / load_state_dict: the checkpoint has torch.optim.Adam's layout, a resumed
+    run continues exactly like the uninterrupted one (moments + step count restored, so bias correction is right),
+    and a torch.optim.Adam checkpoint of the same net loads into FusedAdam (and back)."""
+    import io
+    from pvsr.optim import FusedAdam
+    z, meta = load_golden("x4_pos")
+    kw = meta["kwargs"]
+    inputs = [torch.from_numpy(x).cuda() for x in z["inputs"]]
+    pos = torch.from_numpy(z["pos"]).cuda()
+    targets = [torch.from_numpy(t).cuda() for t in z["targets"]]
+
+    def steps(net, opt, n):
+        for _ in range(n):
+            net.engine.loss_and_grads(inputs, pos, targets)
+            opt.step()
+
+    net_a = build_net(kw).cuda().train()
+    opt_a = FusedAdam.for_net(net_a, lr=1e-3)
+    steps(net_a, opt_a, 2)
+    buf = io.BytesIO()
+    torch.save({"net": net_a.state_dict(), "optimizer": opt_a.state_dict()}, buf)     # base_trainer.py:230 layout
+    steps(net_a, opt_a, 2)                                                           # uninterrupted: 4 steps
+
+    ck = torch.load(io.BytesIO(buf.getvalue()), weights_only=False)
+    sd = ck["optimizer"]
+    named = [k for k, _ in net_a.named_parameters()]
+    assert set(sd["state"]) == set(range(len(named)))
+    st = sd["state"][named.index("out_block.conv1.weight")]
+    assert set(st) == {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 2.0
+    assert st["exp_avg"].shape == net_a.out_block.conv1.weight.shape and float(st["exp_avg"].abs().sum()) > 0
+
+    net_b = build_net(kw).cuda().train()
+    net_b.load_state_dict(ck["net"])
+    opt_b = FusedAdam.for_net(net_b, lr=1e-3)
+    opt_b.load_state_dict(sd)
+    assert opt_b.step_count.item() == 2.0
+    steps(net_b, opt_b, 2)                                                           # resumed: 2 + 2 steps
+    torch.cuda.synchronize()
+    for (k, pa), (_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        # same kernels, same inputs: only the order of the fp32 atomics in the gradient kernels differs
+        assert (pa - pb).abs().max().item() <= 1e-4, (k, (pa - pb).abs().max().item())
+
+    # a fresh FusedAdam WITHOUT the state restarts at step 0 and must differ (this is the bug the override fixes)
+    net_c = build_net(kw).cuda().train()
+    net_c.load_state_dict(ck["net"])
+    opt_c = FusedAdam.for_net(net_c, lr=1e-3)
+    steps(net_c, opt_c, 2)
+    torch.cuda.synchronize()
+    assert (net_c.out_block.conv1.weight - net_a.out_block.conv1.weight).abs().max().item() > 3e-4
+
+    # interchange with torch.optim.Adam (the reference's optimiser, src/main.py:76)
+    net_t = build_net(kw).cuda().train()
+    net_t.load_state_dict(ck["net"])
+    opt_t = torch.optim.Adam(net_t.parameters(), lr=1e-3)
+    sd_t = {"state": {i: v for i, v in sd["state"].items() if named[i] != "refine_block.prelu.weight"},
+            "param_groups": sd["param_groups"]}
+    opt_t.load_state_dict(sd_t)                                                     # FusedAdam checkpoint -> torch Adam
+    from oracle import refinenet_oracle as O
+    for _ in range(2):
+        opt_t.zero_grad()
+        O.trainer_loss(net_t(inputs, pos), targets, training=True).backward()
+        opt_t.step()
+    torch.cuda.synchronize()
+    for (k, pa), (_, pt) in zip(net_a.named_parameters(), net_t.named_parameters()):
+        assert (pa - pt).abs().max().item() <= 3e-3 + 1e-6, k       # statistical, as in test_fused_step_matches_autograd_and_adam
+    net_d = build_net(kw).cuda().train()
+    net_d.load_state_dict(net_t.state_dict())
+    opt_d = FusedAdam.for_net(net_d, lr=1e-3)
+    opt_d.load_state_dict(opt_t.state_dict())                                       # torch Adam checkpoint -> FusedAdam
+    assert opt_d.step_count.item() == 4.0
+    i = named.index("out_block.conv1.weight")
+    off = dict((id(p), o) for p, o in opt_d._slices())[id(net_d.out_block.conv1.weight)]
+    n = net_d.out_block.conv1.weight.numel()
+    assert torch.equal(opt_d.exp_avg[off:off + n].view_as(net_d.out_block.conv1.weight),
+                       opt_t.state_dict()["state"][i]["exp_avg"])
+
+
+def test_benchmarked_training_plan_vs_oracle(pvsr_lib):
+    """The N = 16 plan bench.py times (configs/train/refine_net/exp1_x4.yaml shapes: 7 target + 2x6 warm-up frames of
+    32x32 patches; its own wgrad split counts and two-branch schedule) against the CPU oracle's loss, frames and
+    full-batch gradients - not just the N = 2 case above."""
+    from oracle import refinenet_oracle as O
+    from pvsr.synthetic import cine_batch
+    kw = dict(in_channels=1, out_channels=1, num_features=[64, 64, 64], num_stages=3, update_memory=True,
+              num_updated_frames=6, refine_window_size=5, upscale_factor=4, positional_encoding=True)
+    net = build_net(kw)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    inputs, pos, targets = cine_batch(16, T=7, U=6, h=32, w=32, scale=4, seed=4321, end_systole=3, with_targets=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref_loss, ref_grads, ref_out = _oracle_grads(kw, sd, inputs, pos, targets)
+    net = net.cuda().train()
+    for rep in range(2):                       # rep 1 = CUDA-graph replay of both schedules
+        loss, out = net.engine.loss_and_grads([x.cuda() for x in inputs], pos.cuda(), [t.cuda() for t in targets])
+        torch.cuda.synchronize()
+        assert abs(loss.item() - ref_loss) <= LOSS_REL * abs(ref_loss), (rep, loss.item(), ref_loss)
+        ref_stack = torch.stack([torch.stack(o) for o in ref_out]).detach()[:, :, :, 0]
+        assert rel_l2(out.cpu(), ref_stack) <= 1.5e-2
+        got = {k: p.grad for k, p in net.named_parameters()}
+        _check_grads(got, {k: ref_grads.get(k) for k in got}, f"train N=16 rep {rep}")
