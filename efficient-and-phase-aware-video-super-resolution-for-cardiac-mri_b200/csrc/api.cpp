@@ -212,6 +212,11 @@ int pvsr_set_pdl(int enable) {
   return 0;
 }
 int pvsr_get_pdl(void) { return get_pdl(); }
+int pvsr_set_w_resident(int enable) {
+  set_w_resident(enable);
+  return 0;
+}
+int pvsr_get_w_resident(void) { return get_w_resident(); }
 int pvsr_set_two_branch(int enable) {
   set_two_branch(enable);
   return 0;
@@ -313,6 +318,7 @@ int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream) {
   int bw = tw, bh = th;
   if (slab) {
     p.halo = 1; p.pr_wp = g.wp; p.pr_rows = g.rows; p.tiles_x = 1; p.tiles_y = g.tiles;
+    p.w_resident = get_w_resident();
     bw = g.wp; bh = g.rows;
   }
   for (int v = 0; v < d->n_views; ++v) {

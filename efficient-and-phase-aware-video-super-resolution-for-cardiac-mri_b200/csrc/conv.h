@@ -81,6 +81,7 @@ struct ConvParams {
   int halo;          // != 0: padded-raster slab kernel (below); tiles_x = 1, tiles_y = pr_tiles
   int pr_wp;         // padded row pitch Wp >= W + 1: output position p = y * Wp + x, tile t covers [128 t, 128 t + 128)
   int pr_rows;       // rows of the activation box = rows a tile can span + 2 (the maps carry (64, Wp, pr_rows, 1) boxes)
+  int w_resident;    // slab kernel: keep the whole weight operand in shared memory when it fits (single problem, one N tile)
   ConvProblem prob[kMaxProb];
 };
 
@@ -97,6 +98,10 @@ inline int cta_pair_factor() { return get_cta_pair() ? 2 : 1; }
 // Programmatic dependent launch (griddepcontrol) on the tcgen05 launches and the LSTM gate-adjoint kernel: 0 = off.
 void set_pdl(int enable);
 int get_pdl();
+
+// Resident weight operand of narrow slab launches (conv3x3_tc.cu: halo_resident_blocks).  1 = on (default).
+void set_w_resident(int enable);
+int get_w_resident();
 
 // Two-branch schedules of training plans (plan.cpp: Ctx::side): weight-gradient launches and the HBM-bound head
 // kernels on a second stream / graph branch.  1 = on (default), 0 = single chain (A/B measurements).

@@ -587,6 +587,18 @@ __host__ __device__ inline int halo_num_a(int slab_bytes, int b_bytes) {
   return halo_num_b(slab_bytes, b_bytes, 3) >= 6 ? 3 : 2;
 }
 
+// Resident weights: a launch with ONE problem and one N tile whose whole packed weight operand (this CTA's share) fits
+// next to two activation slabs keeps it in shared memory for the life of the persistent CTA instead of re-streaming it
+// from L2 for every tile.  The narrow-N launches are bound by L2 -> SMEM delivery, not by the tensor pipe: refine conv2
+// (N = 64, 27 K blocks) moved 110 KB of weights + 96 KB of activations per 2.6 k-cycle tile = 5.2 KB / cycle chip-wide
+// against the ~6.3 KB / cycle the L2 slices deliver (B300_MICROARCH.md: LTS throughput cap); resident: 96 KB.
+__host__ __device__ inline int halo_resident_blocks(const ConvParams& p, int b_bytes, int slab_bytes) {
+  if (p.w_resident == 0 || p.n_prob != 1 || p.n_tiles_n != 1) return 0;
+  const int kb = p.prob[0].n_src * 9 * p.kb_per_src;
+  const long long need = static_cast<long long>(kb) * b_bytes + 2LL * (slab_bytes + kHaloGuard) + kHaloGuard;
+  return need <= kHaloBudget ? kb : 0;
+}
+
 template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
@@ -598,8 +610,9 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
   const int slab_bytes = halo_slab_bytes(p.pr_rows * Wp);
   constexpr int G = halo_group(C::kBBytes);        // taps per weight stage
   constexpr int kBStage = G * C::kBBytes;
-  const int NA = halo_num_a(slab_bytes, C::kBBytes);
-  const int NB = halo_num_b(slab_bytes, kBStage, NA);
+  const int RES = halo_resident_blocks(p, C::kBBytes, slab_bytes);   // > 0: K blocks held resident (all of them)
+  const int NA = RES ? 2 : halo_num_a(slab_bytes, C::kBBytes);
+  const int NB = RES ? 1 : halo_num_b(slab_bytes, kBStage, NA);
   // [guard][slab 0][guard] .. [slab NA-1][guard][B stage 0 .. NB-1][barriers][LSTM biases]
   uint8_t* slab0 = smem + kHaloGuard;
   const int slab_pitch = slab_bytes + kHaloGuard;
@@ -659,6 +672,16 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
     if (elect_one()) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      if (RES && item0 < total_items) {
+        // the whole weight operand once: bfull[0] collects every box (both CTAs' halves on the leader's barrier)
+        const int wcol = p.prob[0].w_row_base + rank * (BN / CG);
+        if (CG == 1 || rank == 0) mbar_arrive_expect_tx(&bfull[0], CG * RES * C::kBBytes);
+        for (int kb = 0; kb < RES; ++kb) {
+          uint8_t* bdst = smem_b + kb * C::kBBytes;
+          if constexpr (CG == 2) tma_load_2d_cg2(bdst, &maps.w, mapa(smem_u32(&bfull[0]), 0), 0, wcol + kb * p.n_total);
+          else tma_load_2d(bdst, &maps.w, &bfull[0], 0, wcol + kb * p.n_total);
+        }
+      }
       for (int t = item0; t < total_items; t += item_step) {
         const TileCoord tc = decode_item(p, t, groups, tiles_m, CG, rank);
         const ConvProblem& pr = p.prob[tc.z];
@@ -680,7 +703,7 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
               tma_load_4d(dst, tm, &afull[sa], sv.ch0 + cb * kBlockK, cx, cy, sv.img_base + tc.img);
             }
             if (++sa == NA) { sa = 0; pa ^= 1; }
-            for (int tg = 0; tg < 9 / G; ++tg) {
+            for (int tg = 0; tg < (RES ? 0 : 9 / G); ++tg) {
               mbar_wait(&bempty[sb], pb ^ 1);
               if constexpr (CG == 2) {
                 if (rank == 0) mbar_arrive_expect_tx(&bfull[sb], 2 * kBStage);
@@ -709,6 +732,10 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
+      if (RES && item0 < total_items) {
+        mbar_wait(&bfull[0], 0);          // resident weights have landed (in both CTAs of a pair)
+        tc_fence_after();
+      }
       for (int t = item0; t < total_items; t += item_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -727,6 +754,30 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
             const uint32_t slab = slab_base + sa * slab_pitch + (o0 - 1) * 128;
             const int nk16 = (cb == p.kb_per_src - 1) ? p.k16_last : 4;
             const bool last_a = (s == n_src - 1) && (cb == p.kb_per_src - 1);
+            if (RES) {
+              tc_fence_after();
+              const uint64_t bsrc = bdesc0 + static_cast<uint32_t>(((s * 9 * p.kb_per_src + cb) * C::kBBytes) >> 4);
+              const uint32_t bstep = static_cast<uint32_t>((p.kb_per_src * C::kBBytes) >> 4);   // next tap, same channel block
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const int dyp = tap / 3, dxp = tap - 3 * dyp;
+                const uint64_t adesc = make_desc_k_sw128(slab + (dyp * Wp + dxp) * 128);
+                const uint64_t bdesc = bsrc + tap * bstep;
+                mma_ss<CG>(tmem_d, adesc, bdesc, idesc, acc);
+                acc = 1;
+                if (nk16 == 4) {
+                  mma_ss<CG>(tmem_d, adesc + 2, bdesc + 2, idesc, 1);
+                  mma_ss<CG>(tmem_d, adesc + 4, bdesc + 4, idesc, 1);
+                  mma_ss<CG>(tmem_d, adesc + 6, bdesc + 6, idesc, 1);
+                } else {
+                  for (int k = 1; k < nk16; ++k) mma_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+                }
+              }
+              mma_commit_t<CG>(&aempty[sa]);
+              if (last_a) mma_commit_t<CG>(&tfull[as]);
+              if (++sa == NA) { sa = 0; pa ^= 1; }
+              continue;
+            }
             for (int tg = 0; tg < 9 / G; ++tg) {
               mbar_wait(&bfull[sb], pb);
               tc_fence_after();
@@ -855,6 +906,10 @@ int get_halo_mode() { return g_halo; }
 static int g_pdl = 0;   // programmatic dependent launch between consecutive kernels (measured: no gain; off)
 void set_pdl(int enable) { g_pdl = enable ? 1 : 0; }
 int get_pdl() { return g_pdl; }
+
+static int g_w_resident = 1;   // resident weight operand for launches where it fits (halo_resident_blocks)
+void set_w_resident(int enable) { g_w_resident = enable ? 1 : 0; }
+int get_w_resident() { return g_w_resident; }
 
 static int g_two_branch = 1;
 void set_two_branch(int enable) { g_two_branch = enable ? 1 : 0; }

@@ -369,6 +369,7 @@ void base_params(const Tiling& t, int H, int W, ConvParams* cp) {
 void set_slab(ConvParams* cp, const pvsr_plan::Geo& g) {
   if (!g.on) return;
   cp->halo = 1;
+  cp->w_resident = get_w_resident();
   cp->pr_wp = g.g.wp;
   cp->pr_rows = g.g.rows;
   cp->tiles_x = 1;

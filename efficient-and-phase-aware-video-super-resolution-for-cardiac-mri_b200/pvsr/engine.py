@@ -62,6 +62,26 @@ class _Plan:
             pass
 
 
+def bind_reference_module(net):
+    """RefineNetEngine for an instance of the REFERENCE's own `RefineNet` (src/model/nets/refine_net.py:10-135), i.e.
+    a module this package did not construct.  The engine reads seven scalars and
+    `named_parameters()`; the reference stores four of them on the module (:21-28) and the other three are derived
+    from its sub-modules here: `memory` (ConvLSTMCell.memory, :231), `positional_encoding` (_RefineBlock, :145) and
+    the number of convolutions in `_OutBlock` (:194-205)."""
+    if not hasattr(net, 'memory'):
+        net.memory = bool(net.forward_lstm_block.cell_list[0].memory)
+    if not hasattr(net, 'positional_encoding'):
+        net.positional_encoding = bool(net.refine_block.positional_encoding)
+    if not hasattr(net, 'num_head_convs'):
+        net.num_head_convs = sum(1 for m in net.out_block.children() if isinstance(m, torch.nn.Conv2d))
+    if net.in_channels != 1 or net.out_channels != 1 or any(f != 64 for f in net.num_features):
+        raise ValueError('The B200 path implements the 1 -> 64 -> 1 channel configuration of the reference configs '
+                         f'(got in/out channels {net.in_channels}/{net.out_channels}, features {net.num_features}).')
+    engine = RefineNetEngine(net)
+    net.engine = engine          # pvsr.autograd.refinenet_train_forward looks the engine up on the module
+    return engine
+
+
 class RefineNetEngine:
     """Runs RefineNet.forward / backward (reference refine_net.py:61-135) for a module exposing the reference's
     parameters."""

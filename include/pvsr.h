@@ -52,6 +52,11 @@ int pvsr_get_halo_mode(void);
  * plan (captured CUDA graphs keep the setting they were captured with).  Process-wide. */
 int pvsr_set_pdl(int enable);
 int pvsr_get_pdl(void);
+/* Resident weight operand: slab launches with one problem and one N tile whose packed weights fit next to two activation
+ * slabs (refine conv2: 27 K blocks x 4 KB per CTA; its data gradient) load them ONCE per persistent CTA instead of once
+ * per tile - those launches are bound by L2 -> shared-memory delivery.  1 = on (default); env PVSR_W_RESIDENT. */
+int pvsr_set_w_resident(int enable);
+int pvsr_get_w_resident(void);
 /* Two-branch schedules of training plans: the tcgen05 weight-gradient launches and the HBM-bound 64 <-> 1 channel head
  * kernels run on a second stream (a second branch of the captured CUDA graph) underneath the dependent chain of data
  * gradients.  1 = on (default), 0 = one chain (A/B switch; env PVSR_TWO_BRANCH).  Set BEFORE the first run of a plan. */

@@ -213,3 +213,75 @@ def test_batched_full_size_graph_replay_through_host_ring(pvsr_lib):
             for t, r in enumerate(ref):
                 g = got[t, i:i + 1]
                 assert (g - r).abs().max().item() <= MAX_ABS and ((g - r).norm() / r.norm()).item() <= REL_L2, (i, t)
+
+
+def _plain_reference_tree(kw):
+    """A plain nn.Module tree with ONLY what INTEGRATION.md section B says the engine needs: the reference's attribute
+    names (refine_net.py:21-28), its sub-module attributes (`cell.memory`, `refine_block.positional_encoding`) and its
+    parameter names - none of this package's RefineNet code."""
+    import torch.nn as nn
+    s = kw["upscale_factor"]
+    net = nn.Module()
+    for k in ("in_channels", "out_channels", "num_features", "num_stages", "refine_window_size", "upscale_factor",
+              "update_memory", "num_updated_frames"):
+        setattr(net, k, kw[k])
+    net.in_block = nn.Module()
+    net.in_block.conv = nn.Conv2d(1, 64, 3, padding=1)
+    net.in_block.prelu = nn.PReLU(1, 0.2)
+    for name in ("forward_lstm_block", "backward_lstm_block"):
+        blk = nn.Module()
+        cells = []
+        for _ in kw["num_features"]:
+            c = nn.Module()
+            c.conv = nn.Conv2d(128, 256, 3, padding=1)
+            c.memory = True
+            cells.append(c)
+        blk.cell_list = nn.ModuleList(cells)
+        setattr(net, name, blk)
+    rb = nn.Module()
+    rb.positional_encoding = True
+    rb.body = nn.Sequential()
+    rb.body.add_module("conv1", nn.Conv2d(645, 129, 3, padding=1))
+    rb.body.add_module("conv2", nn.Conv2d(129, 64, 3, padding=1))
+    rb.prelu = nn.PReLU(1, 0.2)
+    net.refine_block = rb
+    ob = nn.Module()
+    n_ps = {2: 1, 3: 1, 4: 2, 8: 3}[s]
+    for q in range(n_ps):
+        setattr(ob, f"conv{q + 1}", nn.Conv2d(64, 64 * (9 if s == 3 else 4), 3, padding=1))
+    setattr(ob, f"conv{n_ps + 1}", nn.Conv2d(64, 1, 3, padding=1))
+    net.out_block = ob
+    return net
+
+
+@pytest.mark.parametrize("scale", [2, 3, 4, 8])
+def test_engine_binds_the_reference_module(pvsr_lib, scale):
+    """`pvsr.engine.bind_reference_module` on (a) the UNMODIFIED reference RefineNet class
+    (staged under oracle/_ref, when present) and (b) a plain nn.Module tree with only the attributes section B lists -
+    both against the CPU oracle on the module's own weights, every scale (2 / 2 / 3 / 4 head convolutions)."""
+    from oracle import ref_model, refinenet_oracle as O
+    from pvsr.engine import bind_reference_module
+    kw = dict(in_channels=1, out_channels=1, num_features=[64, 64, 64], num_stages=2, update_memory=True,
+              num_updated_frames=3, refine_window_size=5, upscale_factor=scale, positional_encoding=True)
+    g = torch.Generator().manual_seed(11)
+    inputs = [torch.randn(2, 1, 9, 7, generator=g) for _ in range(8)]
+    pos = torch.randn(2, 8, 1, generator=g)
+    nets = [("plain tree", _plain_reference_tree(kw))]
+    if ref_model.available():
+        torch.manual_seed(3)
+        nets.append(("reference class", ref_model.load().RefineNet(**kw)))
+    for what, net in nets:
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        assert len(sd) == 26 - 2 * (3 - {2: 2, 3: 2, 4: 3, 8: 4}[scale])
+        with torch.no_grad():
+            ref = O.refinenet_forward(sd, inputs, pos, **oracle_kwargs(kw))
+        net = net.cuda().eval()
+        eng = bind_reference_module(net)
+        assert net.num_head_convs == {2: 2, 3: 2, 4: 3, 8: 4}[scale] and net.engine is eng
+        with torch.no_grad():
+            out = eng.forward([x.cuda() for x in inputs], pos.cuda())
+        torch.cuda.synchronize()
+        assert len(out) == 6
+        got, want = _stack(out), torch.stack([torch.stack(list(o)) for o in ref])
+        rel = ((got - want).norm() / want.norm()).item()
+        assert (got - want).abs().max().item() <= MAX_ABS and rel <= REL_L2, (what, scale, rel)
