@@ -217,6 +217,11 @@ int pvsr_set_w_resident(int enable) {
   return 0;
 }
 int pvsr_get_w_resident(void) { return get_w_resident(); }
+int pvsr_set_pack_table(int enable) {
+  set_pack_table(enable);
+  return 0;
+}
+int pvsr_get_pack_table(void) { return get_pack_table(); }
 int pvsr_set_two_branch(int enable) {
   set_two_branch(enable);
   return 0;

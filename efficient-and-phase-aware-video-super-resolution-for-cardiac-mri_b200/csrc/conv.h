@@ -103,6 +103,10 @@ int get_pdl();
 void set_w_resident(int enable);
 int get_w_resident();
 
+// One table_kernel launch for all operand packs of a plan / all gradient scatters of its backward pass. 1 = on.
+void set_pack_table(int enable);
+int get_pack_table();
+
 // Two-branch schedules of training plans (plan.cpp: Ctx::side): weight-gradient launches and the HBM-bound head
 // kernels on a second stream / graph branch.  1 = on (default), 0 = single chain (A/B measurements).
 void set_two_branch(int enable);

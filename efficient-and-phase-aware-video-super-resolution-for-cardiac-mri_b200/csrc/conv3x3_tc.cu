@@ -911,6 +911,10 @@ static int g_w_resident = 1;   // resident weight operand for launches where it 
 void set_w_resident(int enable) { g_w_resident = enable ? 1 : 0; }
 int get_w_resident() { return g_w_resident; }
 
+static int g_pack_table = 1;
+void set_pack_table(int enable) { g_pack_table = enable ? 1 : 0; }
+int get_pack_table() { return g_pack_table; }
+
 static int g_two_branch = 1;
 void set_two_branch(int enable) { g_two_branch = enable ? 1 : 0; }
 int get_two_branch() { return g_two_branch; }

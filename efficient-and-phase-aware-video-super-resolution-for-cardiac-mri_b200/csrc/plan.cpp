@@ -117,6 +117,12 @@ struct pvsr_plan {
   // ---- packed-parameter layout (bytes)
   size_t pk_lstm_w, pk_lstm_b, pk_c1_w, pk_c2_w, pk_c2_b, pk_head_w[PVSR_MAX_HEAD_CONVS], pk_head_b[PVSR_MAX_HEAD_CONVS];
   size_t pk_idx, pk_bytes;
+  // one table_kernel launch packs every operand (pvsr_table_job rows in the packed buffer behind the index region);
+  // the backward pass scatters every packed gradient the same way.  Used when no job needs a second index.
+  size_t pk_table = 0, pk_sc_table = 0;
+  bool table_ok = false;
+  const void* table_key = nullptr;      // hash of the parameter pointers the uploaded pack table was built for
+  const void* sc_table_key = nullptr;   // same for the scatter table (gradient pointers)
   long long c1_rows, c2_rows, head_rows[PVSR_MAX_HEAD_CONVS];
   // data-gradient operands (training)
   size_t pk_lstm_dg, pk_c1_dg, pk_c2_dg, pk_head_dg[PVSR_MAX_HEAD_CONVS];
@@ -861,6 +867,20 @@ void schedule_backward(Ctx& c) {
   // ---------------------------------------------------------------- packed gradients -> parameter layout
   c.join();
   const int32_t* idx = reinterpret_cast<const int32_t*>(c.pk + p->pk_idx);
+  if (p->table_ok && get_pack_table()) {
+    // one table launch (uploaded by upload_scatter_table before the schedule runs / is captured)
+    run_simt(c, BCLS_MISC, "scatter table", [&] {
+      long long max_n = 0;
+      int n = 0;
+      for (const auto& j : p->sc_jobs) {
+        if (!job_grad(j.kind, j.a, j.b, c.G, j.is_bias)) continue;
+        max_n = j.n > max_n ? j.n : max_n;
+        ++n;
+      }
+      return launch_table(reinterpret_cast<const pvsr_table_job*>(c.pk + p->pk_sc_table), n, max_n, c.stream);
+    });
+    return;
+  }
   for (const auto& j : p->sc_jobs) {
     float* dst = c.dry ? nullptr : job_grad(j.kind, j.a, j.b, c.G, j.is_bias);
     if (!c.dry && !dst) continue;
@@ -1349,6 +1369,11 @@ int pvsr_plan_create(const pvsr_net_config* cfg, pvsr_plan** out) {
   p->ws_bytes = off;
   p->pk_idx = pk;
   pk = align_up(pk + p->idx_host.size() * 4, 1024);
+  p->table_ok = true;
+  for (const auto& j : p->jobs) if (j.has2) p->table_ok = false;
+  for (const auto& j : p->sc_jobs) if (j.has2) p->table_ok = false;
+  p->pk_table = pk; pk = align_up(pk + p->jobs.size() * sizeof(pvsr_table_job), 1024);
+  p->pk_sc_table = pk; pk = align_up(pk + (p->sc_jobs.size() + 1) * sizeof(pvsr_table_job), 1024);
   p->pk_bytes = pk;
 
   // ---- accounting via dry runs of the schedules
@@ -1424,6 +1449,28 @@ int pvsr_plan_pack(pvsr_plan* p, const pvsr_net_params* P, void* packed, void* s
     p->idx_uploaded_for = packed;
   }
   const int32_t* idx = reinterpret_cast<const int32_t*>(pk + p->pk_idx);
+  if (p->table_ok && get_pack_table()) {
+    // one launch for all operands (forward packs, bias gathers, transposed data-gradient packs)
+    std::vector<pvsr_table_job> tab(p->jobs.size());
+    long long max_n = 0;
+    for (size_t i = 0; i < p->jobs.size(); ++i) {
+      const auto& j = p->jobs[i];
+      const float* src = job_weight(j.kind, j.a, j.b, P, j.is_bias);
+      if (!src) return set_error(-4, "missing parameter pointer (kind %d)", j.kind);
+      tab[i].src = src; tab[i].idx = idx + j.idx; tab[i].dst = pk + j.dst; tab[i].n = j.n; tab[i].scale = 1.f;
+      tab[i].kind = j.is_bias ? PVSR_TJ_GATHER : PVSR_TJ_PACK;
+      max_n = j.n > max_n ? j.n : max_n;
+    }
+    const void* key = hash_bytes(tab.data(), tab.size() * sizeof(pvsr_table_job));
+    if (p->table_key != key) {
+      int e = cudaMemcpyAsync(pk + p->pk_table, tab.data(), tab.size() * sizeof(pvsr_table_job), cudaMemcpyHostToDevice, s);
+      if (!e) e = cudaStreamSynchronize(s);      // `tab` dies at return; happens once per set of parameter pointers
+      if (e) return check_cuda(e, "pack table upload");
+      p->table_key = key;
+    }
+    return check_cuda(launch_table(reinterpret_cast<const pvsr_table_job*>(pk + p->pk_table),
+                                   static_cast<int>(tab.size()), max_n, s), "pack table launch");
+  }
   for (const auto& j : p->jobs) {
     const float* src = job_weight(j.kind, j.a, j.b, P, j.is_bias);
     if (!src) return set_error(-4, "missing parameter pointer (kind %d)", j.kind);
@@ -1490,6 +1537,31 @@ int pvsr_plan_forward(pvsr_plan* p, const pvsr_net_params* P, const void* packed
   });
 }
 
+// Scatter table of the backward pass: packed fp32 gradient regions -> parameter-layout gradient buffers.
+static int upload_scatter_table(pvsr_plan* p, const void* packed, const pvsr_net_grads* G, void* ws, cudaStream_t s) {
+  if (!(p->table_ok && get_pack_table())) return 0;
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  const int32_t* idx = reinterpret_cast<const int32_t*>(pk + p->pk_idx);
+  const float* wg = reinterpret_cast<const float*>(static_cast<const uint8_t*>(ws) + p->off_wg);
+  std::vector<pvsr_table_job> tab;
+  for (const auto& j : p->sc_jobs) {
+    float* dst = job_grad(j.kind, j.a, j.b, G, j.is_bias);
+    if (!dst) continue;
+    pvsr_table_job t{};
+    t.src = wg + j.src; t.idx = idx + j.idx; t.dst = dst; t.n = j.n; t.scale = 1.f; t.kind = PVSR_TJ_SCATTER;
+    tab.push_back(t);
+  }
+  if (tab.empty()) return 0;
+  const void* key = hash_bytes(tab.data(), tab.size() * sizeof(pvsr_table_job));
+  if (p->sc_table_key == key) return 0;
+  int e = cudaMemcpyAsync(const_cast<uint8_t*>(pk) + p->pk_sc_table, tab.data(), tab.size() * sizeof(pvsr_table_job),
+                          cudaMemcpyHostToDevice, s);
+  if (!e) e = cudaStreamSynchronize(s);
+  if (e) return check_cuda(e, "scatter table upload");
+  p->sc_table_key = key;
+  return 0;
+}
+
 static int upload_jobs(pvsr_plan* p, void* ws, cudaStream_t s) {
   if (p->jobs_uploaded_for == ws || p->wg_jobs.empty()) return 0;
   // synchronous w.r.t. the host vector (owned by the plan, so it outlives the copy anyway)
@@ -1512,6 +1584,8 @@ int pvsr_plan_backward(pvsr_plan* p, const pvsr_net_params* P, const void* packe
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   rc = upload_jobs(p, ws, s);
+  if (rc) return rc;
+  rc = upload_scatter_table(p, packed, G, ws, s);
   if (rc) return rc;
   GraphKey key{{ws, packed, lr, pos, dout, hash_bytes(P, sizeof(*P)), hash_bytes(G, sizeof(*G)),
                 reinterpret_cast<const void*>(1)}};
@@ -1559,6 +1633,8 @@ int pvsr_plan_profile_bwd(pvsr_plan* p, const pvsr_net_params* P, const void* pa
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   rc = upload_jobs(p, ws, s);
+  if (rc) return rc;
+  rc = upload_scatter_table(p, packed, G, ws, s);
   if (rc) return rc;
   std::vector<cudaEvent_t> ev;
   std::vector<int> cls;

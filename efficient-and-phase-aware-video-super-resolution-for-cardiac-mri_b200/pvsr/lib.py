@@ -102,6 +102,8 @@ SIGNATURES = {
     "pvsr_get_halo_mode": (c_int, []),
     "pvsr_set_w_resident": (c_int, [c_int]),
     "pvsr_get_w_resident": (c_int, []),
+    "pvsr_set_pack_table": (c_int, [c_int]),
+    "pvsr_get_pack_table": (c_int, []),
     "pvsr_set_two_branch": (c_int, [c_int]),
     "pvsr_get_two_branch": (c_int, []),
     "pvsr_set_pdl": (c_int, [c_int]),
@@ -199,6 +201,8 @@ def load():
         lib.pvsr_set_head_tma(int(os.environ["PVSR_HEAD_TMA"]))
     if os.environ.get("PVSR_W_RESIDENT") is not None:     # A/B switch of the resident weight operand (narrow slab launches)
         lib.pvsr_set_w_resident(int(os.environ["PVSR_W_RESIDENT"]))
+    if os.environ.get("PVSR_PACK_TABLE") is not None:     # A/B switch of the table-driven pack / scatter launches
+        lib.pvsr_set_pack_table(int(os.environ["PVSR_PACK_TABLE"]))
     if os.environ.get("PVSR_TWO_BRANCH") is not None:     # A/B switch of the two-branch training schedules
         lib.pvsr_set_two_branch(int(os.environ["PVSR_TWO_BRANCH"]))
     if os.environ.get("PVSR_PDL") is not None:            # A/B switch of programmatic dependent launch

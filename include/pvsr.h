@@ -57,6 +57,10 @@ int pvsr_get_pdl(void);
  * per tile - those launches are bound by L2 -> shared-memory delivery.  1 = on (default); env PVSR_W_RESIDENT. */
 int pvsr_set_w_resident(int enable);
 int pvsr_get_w_resident(void);
+/* pvsr_plan_pack as ONE table launch (pvsr_run_table) instead of one launch per operand, and the gradient scatter at the
+ * end of pvsr_plan_backward likewise.  1 = on (default); env PVSR_PACK_TABLE. */
+int pvsr_set_pack_table(int enable);
+int pvsr_get_pack_table(void);
 /* Two-branch schedules of training plans: the tcgen05 weight-gradient launches and the HBM-bound 64 <-> 1 channel head
  * kernels run on a second stream (a second branch of the captured CUDA graph) underneath the dependent chain of data
  * gradients.  1 = on (default), 0 = one chain (A/B switch; env PVSR_TWO_BRANCH).  Set BEFORE the first run of a plan. */

@@ -130,7 +130,12 @@ def test_full_size_sequence_vs_oracle(pvsr_lib, scale, h, w, pos):
         ta = O.denormalize(t, dataset)
         dp.append(abs(float(O.psnr(O.denormalize(a, dataset), ta)) - float(O.psnr(O.denormalize(b, dataset), ta))))
         ds.append(abs(float(O.ssim(O.denormalize(a, dataset), ta)) - float(O.ssim(O.denormalize(b, dataset), ta))))
-    assert max(dp) <= 0.01 and max(ds) <= 1e-4, (max(dp), max(ds))
+    # SSIM gate = 2x the drift of the REFERENCE ITSELF under torch.autocast(bf16) vs fp32 on the same sequence and
+    # target (SURVEY 8c derived 1e-4 that way at x4; measured here with the unmodified reference, CPU, seed 1234:
+    # x4 54x63: SSIM 4.9e-5, PSNR 2.2e-4 dB;  x2 108x126: SSIM 1.02e-4, PSNR 3.2e-4 dB - the x2 frames are random-noise
+    # targets 4x larger than the LR grid, where single uint8 flips move the 11x11-window SSIM more)
+    ssim_gate = 2e-4 if scale == 2 else 1e-4
+    assert max(dp) <= 0.01 and max(ds) <= ssim_gate, (max(dp), max(ds))
 
 
 def test_batched_sequences_are_independent(pvsr_lib):
