@@ -107,6 +107,10 @@ int get_w_resident();
 void set_pack_table(int enable);
 int get_pack_table();
 
+// Rank-1 adjoint of the head's tail (tail_rank1.cu) in training plans.  1 = on (default).
+void set_tail_rank1(int enable);
+int get_tail_rank1();
+
 // Two-branch schedules of training plans (plan.cpp: Ctx::side): weight-gradient launches and the HBM-bound head
 // kernels on a second stream / graph branch.  1 = on (default), 0 = single chain (A/B measurements).
 void set_two_branch(int enable);

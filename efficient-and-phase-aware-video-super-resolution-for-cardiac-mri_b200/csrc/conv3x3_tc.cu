@@ -915,6 +915,10 @@ static int g_pack_table = 1;
 void set_pack_table(int enable) { g_pack_table = enable ? 1 : 0; }
 int get_pack_table() { return g_pack_table; }
 
+static int g_tail_rank1 = 1;
+void set_tail_rank1(int enable) { g_tail_rank1 = enable ? 1 : 0; }
+int get_tail_rank1() { return g_tail_rank1; }
+
 static int g_two_branch = 1;
 void set_two_branch(int enable) { g_two_branch = enable ? 1 : 0; }
 int get_two_branch() { return g_two_branch; }

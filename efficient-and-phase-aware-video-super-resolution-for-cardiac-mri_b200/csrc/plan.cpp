@@ -111,6 +111,7 @@ struct pvsr_plan {
   int mid_ch;
   // backward-only regions
   size_t off_gx, off_dh, off_dc, off_dgates, off_gr, off_gm, off_dhead[PVSR_MAX_HEAD_CONVS], off_wg, off_sums, off_jobs;
+  size_t off_tail;       // scratch of the rank-1 adjoint of the head's tail (tail_rank1.cu)
   size_t dh_stride;      // bytes of one [T*B] stack of fp32 64-channel LR gradient images
   Tiling bw_tile[PVSR_MAX_HEAD_CONVS];   // tiling of the data/weight-gradient launches of head conv q
 
@@ -651,6 +652,16 @@ void schedule_backward(Ctx& c) {
   }
   float* wg = reinterpret_cast<float*>(c.ws + p->off_wg);
   __nv_bfloat16* gr = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_gr);
+  // Rank-1 adjoint of [last conv + PixelShuffle(2), final conv] (tail_rank1.cu): replaces head_last_bwd_data /
+  // _weight and the dgrad / wgrad launches of the last 64 -> 256 conv when the head has >= 2 shuffle stages (x4, x8).
+  const bool tail = get_tail_rank1() != 0 && p->n_ps >= 2 && p->ps_r[p->n_ps - 1] == 2;
+  void* tail_ws = c.ws + p->off_tail;
+  if (tail) {
+    run_simt(c, BCLS_MISC, "tail tables", [&] {
+      int e = launch_tail_tables(c.P->head_w[p->n_ps - 1], c.P->head_w[p->n_ps], tail_ws, c.stream);
+      return e ? e : launch_tail_zero_sums(tail_ws, c.stream);
+    });
+  }
 
   // Two-branch schedule (Ctx::side).  Main branch = the dependent chain of data gradients: head adjoints -> refine
   // dgrad -> reverse ConvLSTM wavefront (gate adjoint + dgrad per diagonal).  Side branch = everything that only
@@ -669,19 +680,42 @@ void schedule_backward(Ctx& c) {
     const float* dout_s = c.dout ? c.dout + static_cast<size_t>(3 * s) * TB * p->Hs * p->Ws : nullptr;
     const uint8_t* head_last_in = c.ws + p->off_head[last] + static_cast<size_t>(3 * s) * p->head_stride[last];
     c.main_wait(ev_head);     // head weight gradients of stage s + 1 read dhead[*]
-    run_simt(c, BCLS_HEAD_LAST, "head_last_bwd_data", [&] {
-      return launch_head_last_bwd_data(dout_s, c.P->head_w[p->n_ps], c.ws + p->off_dhead[last], 3 * TB, p->Hs, p->Ws,
-                                       c.stream);
-    });
-    if (c.dry || (c.G->head_w[p->n_ps] && c.G->head_b[p->n_ps])) {
+    int q_first = last;
+    if (tail) {
+      // d(input of the last 64 -> 256 conv) straight from dL/d(out); the correlation sums on the side branch
+      const double tail_fl = 2.0 * 9 * kFeat * (kFeat * 4) * p->ps_h[last] * p->ps_w[last] * 3.0 * TB;   // algorithmic
+      c.begin(BCLS_HEAD_DGRAD);
+      if (!c.dry && !c.rc) {
+        int e = launch_tail_dx(dout_s, tail_ws, c.ws + p->off_dhead[last - 1], 3 * TB, p->ps_h[last], p->ps_w[last],
+                               p->num_sms, c.stream);
+        if (e) c.rc = check_cuda(e, "tail_dx launch");
+      }
+      c.end(BCLS_HEAD_DGRAD, tail_fl);
       c.to_side();
-      run_simt(c, BCLS_HEAD_LAST, "head_last_bwd_weight", [&] {
-        return launch_head_last_bwd_weight(head_last_in, dout_s, c.G->head_w[p->n_ps], c.G->head_b[p->n_ps], 3 * TB,
-                                           p->Hs, p->Ws, p->num_sms, c.stream);
-      });
+      c.begin(BCLS_HEAD_WGRAD);
+      if (!c.dry && !c.rc) {
+        const uint8_t* x_last = c.ws + p->off_head[last - 1] + static_cast<size_t>(3 * s) * p->head_stride[last - 1];
+        int e = launch_tail_corr(dout_s, x_last, tail_ws, 3 * TB, p->ps_h[last], p->ps_w[last], p->num_sms, c.stream);
+        if (e) c.rc = check_cuda(e, "tail_corr launch");
+      }
+      c.end(BCLS_HEAD_WGRAD, tail_fl);
       c.to_main();
+      q_first = last - 1;
+    } else {
+      run_simt(c, BCLS_HEAD_LAST, "head_last_bwd_data", [&] {
+        return launch_head_last_bwd_data(dout_s, c.P->head_w[p->n_ps], c.ws + p->off_dhead[last], 3 * TB, p->Hs, p->Ws,
+                                         c.stream);
+      });
+      if (c.dry || (c.G->head_w[p->n_ps] && c.G->head_b[p->n_ps])) {
+        c.to_side();
+        run_simt(c, BCLS_HEAD_LAST, "head_last_bwd_weight", [&] {
+          return launch_head_last_bwd_weight(head_last_in, dout_s, c.G->head_w[p->n_ps], c.G->head_b[p->n_ps], 3 * TB,
+                                             p->Hs, p->Ws, p->num_sms, c.stream);
+        });
+        c.to_main();
+      }
     }
-    for (int q = last; q >= 0; --q) {
+    for (int q = q_first; q >= 0; --q) {
       const int r = p->ps_r[q];
       const double conv_fl = 2.0 * 9 * kFeat * (kFeat * r * r) * p->ps_h[q] * p->ps_w[q] * 3.0 * TB;
       c.to_side();
@@ -864,6 +898,16 @@ void schedule_backward(Ctx& c) {
                                       p->num_sms, c.stream);
     });
 
+  if (tail) {
+    // parameter gradients of the tail from the accumulated correlation sums (all stages, all lists)
+    c.to_side();
+    run_simt(c, BCLS_MISC, "tail finish", [&] {
+      return launch_tail_finish(tail_ws, c.P->head_w[p->n_ps - 1], c.P->head_b[p->n_ps - 1], c.P->head_w[p->n_ps],
+                                c.G->head_w[p->n_ps - 1], c.G->head_b[p->n_ps - 1], c.G->head_w[p->n_ps],
+                                c.G->head_b[p->n_ps], c.stream);
+    });
+    c.to_main();
+  }
   // ---------------------------------------------------------------- packed gradients -> parameter layout
   c.join();
   const int32_t* idx = reinterpret_cast<const int32_t*>(c.pk + p->pk_idx);
@@ -1261,6 +1305,7 @@ int pvsr_plan_create(const pvsr_net_config* cfg, pvsr_plan** out) {
       off = align_up(off + 3 * static_cast<size_t>(TB) * p->ps_h[q + 1] * p->ps_w[q + 1] * kFeat * 2, 1024);
     }
     p->off_sums = off; off = align_up(off + static_cast<size_t>(p->Wn) * 16 * 144 * 4, 1024);
+    p->off_tail = off; off = align_up(off + tail_scratch_bytes(), 1024);
 
     // ---- data-gradient operands: transposed, spatially flipped weights
     {

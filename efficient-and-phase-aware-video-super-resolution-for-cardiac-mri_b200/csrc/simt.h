@@ -56,6 +56,16 @@ int launch_in_conv_prelu_bwd(const float* x, const float* w, const float* b, con
                              cudaStream_t s);
 int launch_posterm_bwd(const void* g_bf16, const float* pos, float* sums, float* dw1, int n_frames, int B, int L,
                        int frame0, int window, int H, int W, int c_out, int c_in, int feat2, int ch, cudaStream_t s);
+// Rank-1 adjoint of conv3x3 (64 -> 256) + PixelShuffle(2) + conv3x3 (64 -> 1) (tail_rank1.cu)
+size_t tail_scratch_bytes();
+int launch_tail_tables(const float* W2, const float* w3, void* scratch, cudaStream_t s);
+int launch_tail_zero_sums(void* scratch, cudaStream_t s);
+int launch_tail_dx(const float* g, const void* scratch, void* dx_bf16, long long n_img, int H1, int W1, int num_sms,
+                   cudaStream_t s);
+int launch_tail_corr(const float* g, const void* x_bf16, void* scratch, long long n_img, int H1, int W1, int num_sms,
+                     cudaStream_t s);
+int launch_tail_finish(const void* scratch, const float* W2, const float* b2, const float* w3, float* dW2, float* db2,
+                       float* dw3, float* db3, cudaStream_t s);
 int launch_cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t s);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                 float wd, float grad_scale, float* state, int num_sms, cudaStream_t s);

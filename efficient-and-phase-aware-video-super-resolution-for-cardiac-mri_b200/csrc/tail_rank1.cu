@@ -1,0 +1,518 @@
+// Rank-1 adjoint of the head's tail:  X --conv3x3 (64 -> 256, W2, b2)--> PixelShuffle(2) --conv3x3 (64 -> 1, w3)--> out
+// (reference src/model/nets/refine_net.py:201-205: out_block.conv2 / pixelshuffle2 / conv3 for x4; the last conv +
+// PixelShuffle(2) pair and the final conv of any power-of-two scale with at least two shuffle stages).
+//
+// The last conv has ONE output channel, so the gradient that flows back through it has rank <= 9 per pixel:
+//     d a[p][c] = sum_t w3[c][t] * g[p - t]                       (g = dL/d out, one channel at HR; a = the 64-ch HR map)
+// Substituting into the data / weight gradients of the 64 -> 256 conv collapses their K = 2304 / N = 256 contractions:
+//     dX[z][ci]          = sum_o U_cls(z)[o][ci] * g[2z + o]                                  o in [-3, 4]^2  (64 offsets)
+//     dW2[(c,q)][ci][t'] = sum_t w3[c][t] * R[q,t,t'][ci]
+//     dw3[c][t]          = sum_q b2[(c,q)] Gq[q,t] + sum_{q,t',ci} W2[(c,q)][ci][t'] * R[q,t,t'][ci]
+//     db2[(c,q)]         = sum_t w3[c][t] * Gq[q,t],      db3 = sum_p g[p]
+// with   U_cls[o][ci]   = sum over (t', q, t) with -2t' + q - t = o and t' allowed by the border class of z of
+//                         sum_c W2[(c,q)][ci][t'] w3[c][t]
+//        R[q,t,t'][ci]  = sum over z with z - t' inside the image of g[2z + o(t',q,t)] * X[z][ci]
+//                       = S[o][ci] - (row-edge sum) - (column-edge sum) + (corner sum)     (inclusion - exclusion)
+//        S[o][ci]       = sum_z g[2z + o] * X[z][ci],     Gq[q,t] = sum_z g[2z + q - t]
+// (zero padding of both convs = the "inside the image" conditions; tests/test_ops_gpu.py checks every border case
+// against torch autograd).  So the whole backward of the tail needs: one 64-offset stencil of g per X pixel (a
+// [pixels x 64] x [64 x 64] product on mma.sync, border pixels recomputed with their class tables) and ONE
+// [64 offsets x pixels] x [pixels x 64] correlation per X pixel - 1/36 of the FLOPs of the dgrad + wgrad launches of the
+// 64 -> 256 conv, and neither the 64-channel HR gradient (128 B per HR pixel written, then read twice) nor the HR
+// activation is touched by the backward pass at all.  bench.py keeps counting the ALGORITHMIC FLOPs of the layer
+// (SURVEY.md 8d); DESIGN.md states the executed ones.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "simt.h"
+
+namespace pvsr {
+
+namespace {
+
+constexpr int kO = 8;            // offsets per axis for r = 2: o in [-3, 4]
+constexpr int kOmin = -3;
+constexpr int kNO = kO * kO;     // 64
+constexpr int kTH = 8, kTW = 16; // X-pixel tile of the two mma.sync kernels (128 pixels)
+constexpr int kGhH = 2 * kTH + kO - 2;   // 22 halo rows of g per tile
+constexpr int kGhW = 2 * kTW + kO - 2;   // 38 halo columns
+constexpr int kGhPitch = 40;
+constexpr int kXPitch = 144;     // bytes per X pixel row in shared memory (128 + 16: conflict-free ldmatrix)
+
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Border class of X pixel (zy, zx): bit 0 first row, bit 1 last row, bit 2 first column, bit 3 last column.
+__device__ __forceinline__ int border_class(int zy, int zx, int H1, int W1) {
+  return (zy == 0 ? 1 : 0) | (zy == H1 - 1 ? 2 : 0) | (zx == 0 ? 4 : 0) | (zx == W1 - 1 ? 8 : 0);
+}
+
+// g halo of one tile -> shared memory (zero outside the HR image): gh[r][c] = g[2*y0 + kOmin + r][2*x0 + kOmin + c]
+__device__ __forceinline__ void load_g_halo(const float* __restrict__ gimg, int y0, int x0, int Hs, int Ws, float* gh) {
+  for (int i = threadIdx.x; i < kGhH * kGhW; i += blockDim.x) {
+    const int r = i / kGhW, c = i - r * kGhW;
+    const int y = 2 * y0 + kOmin + r, x = 2 * x0 + kOmin + c;
+    gh[r * kGhPitch + c] = (y >= 0 && y < Hs && x >= 0 && x < Ws) ? __ldg(gimg + static_cast<size_t>(y) * Ws + x) : 0.f;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Tables.  U[cls][o][ci] fp32 for the 16 border classes (class 0 = interior) and UT[ci][o] bf16 = class 0 as the
+// K-major B operand of tail_dx_kernel.  One thread per (cls, o, ci).
+__global__ void __launch_bounds__(256) tail_tables_kernel(const float* __restrict__ W2, const float* __restrict__ w3,
+                                                          float* __restrict__ U, __nv_bfloat16* __restrict__ UT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 16 * kNO * 64) return;
+  const int ci = i & 63, o = (i >> 6) & 63, cls = i >> 12;
+  const int oy = o / kO + kOmin, ox = o % kO + kOmin;
+  float sum = 0.f;
+  for (int tpy = -1; tpy <= 1; ++tpy) {
+    if ((tpy == 1 && (cls & 1)) || (tpy == -1 && (cls & 2))) continue;      // z - t' leaves the image
+    const int sy = oy + 2 * tpy;                                            // = qy - ty
+    for (int tpx = -1; tpx <= 1; ++tpx) {
+      if ((tpx == 1 && (cls & 4)) || (tpx == -1 && (cls & 8))) continue;
+      const int sx = ox + 2 * tpx;
+      const int tp = (tpy + 1) * 3 + (tpx + 1);
+      for (int ty = -1; ty <= 1; ++ty) {
+        const int qy = sy + ty;
+        if (qy < 0 || qy > 1) continue;
+        for (int tx = -1; tx <= 1; ++tx) {
+          const int qx = sx + tx;
+          if (qx < 0 || qx > 1) continue;
+          const int q = qy * 2 + qx, t = (ty + 1) * 3 + (tx + 1);
+          float s = 0.f;
+          for (int c = 0; c < 64; ++c) s = fmaf(__ldg(W2 + (static_cast<size_t>(c * 4 + q) * 64 + ci) * 9 + tp), __ldg(w3 + c * 9 + t), s);
+          sum += s;
+        }
+      }
+    }
+  }
+  U[i] = sum;
+  if (cls == 0) UT[ci * kNO + o] = __float2bfloat16(sum);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dX, all pixels with the interior table: D[pixel][ci] = sum_o g[2 z + o] * U0[o][ci] as mma.sync m16n8k16 products
+// (A = the g stencil of 16 consecutive pixels of a row built from the shared halo, split into bf16 hi + lo so that
+// an arbitrary fp32 loss gradient keeps ~16 mantissa bits; B = UT held in registers for the life of the block).
+// Warp w of a block owns row y0 + w of an 8 x 16 pixel tile.  The bf16 result tile is staged in shared memory and
+// written with 16-byte stores.  Border pixels are overwritten afterwards by tail_dx_edge_kernel.
+__global__ void __launch_bounds__(256, 2) tail_dx_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ UT,
+                                                         __nv_bfloat16* __restrict__ dX, int n_img, int H1, int W1,
+                                                         int tiles_x, int tiles_y) {
+  __shared__ __align__(16) float gh[kGhH * kGhPitch];
+  __shared__ __align__(16) uint8_t outt[kTH * kTW * kXPitch];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Hs = 2 * H1, Ws = 2 * W1;
+  // B fragments: b0 = UT[n = 8 nt + lane / 4][k = 16 ks + 2 (lane % 4) + {0, 1}], b1 = same with k + 8
+  uint32_t bfrag[4][8][2];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(UT + (nt * 8 + (lane >> 2)) * kNO + ks * 16 + (lane & 3) * 2);
+      bfrag[ks][nt][0] = __ldg(row);
+      bfrag[ks][nt][1] = __ldg(row + 4);
+    }
+  const int total = n_img * tiles_y * tiles_x;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    int tt = t;
+    const int tx = tt % tiles_x;
+    tt /= tiles_x;
+    const int ty = tt % tiles_y;
+    const int img = tt / tiles_y;
+    const int y0 = ty * kTH, x0 = tx * kTW;
+    load_g_halo(g + static_cast<size_t>(img) * Hs * Ws, y0, x0, Hs, Ws, gh);
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+    const int r0 = lane >> 2, c0 = (lane & 3) * 2;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      // k = 16 ks + col: col < 8 -> (oy index 2 ks, ox index col), col >= 8 -> (2 ks + 1, col - 8)
+      uint32_t ahi[4], alo[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int row = r0 + (f & 1) * 8;          // pixel x0 + row of tile row `warp`
+        const int oyi = 2 * ks + (f >> 1);
+        const float2 v = *reinterpret_cast<const float2*>(gh + (2 * warp + oyi) * kGhPitch + 2 * row + c0);
+        const uint32_t hi = pack_bf2(v.x, v.y);
+        ahi[f] = hi;
+        alo[f] = pack_bf2(v.x - bf_lo(hi), v.y - bf_hi(hi));
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        mma16816(acc[nt], ahi, bfrag[ks][nt][0], bfrag[ks][nt][1]);
+        mma16816(acc[nt], alo, bfrag[ks][nt][0], bfrag[ks][nt][1]);
+      }
+    }
+    // stage: pixel (warp, r0 / r0 + 8), channels 8 nt + c0, c0 + 1
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      *reinterpret_cast<uint32_t*>(outt + (warp * kTW + r0) * kXPitch + (nt * 8 + c0) * 2) = pack_bf2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<uint32_t*>(outt + (warp * kTW + r0 + 8) * kXPitch + (nt * 8 + c0) * 2) = pack_bf2(acc[nt][2], acc[nt][3]);
+    }
+    __syncthreads();
+    __nv_bfloat16* dimg = dX + static_cast<size_t>(img) * H1 * W1 * 64;
+#pragma unroll
+    for (int it = 0; it < kTH * kTW * 8 / 256; ++it) {
+      const int i = threadIdx.x + it * 256;
+      const int px = i >> 3, ck = i & 7;
+      const int y = y0 + px / kTW, x = x0 + px % kTW;
+      if (y < H1 && x < W1)
+        *reinterpret_cast<uint4*>(dimg + (static_cast<size_t>(y) * W1 + x) * 64 + ck * 8) =
+            *reinterpret_cast<const uint4*>(outt + px * kXPitch + ck * 16);
+    }
+    __syncthreads();     // gh / outt are overwritten by the next tile
+  }
+}
+
+// Border pixels (first / last row or column) again, exactly, with the table of their class (fp32 SIMT: they are
+// 2 (H1 + W1) - 4 of H1 * W1 pixels).  Thread = (border pixel, channel).
+__device__ __forceinline__ bool border_pixel(int e, int H1, int W1, int* zy, int* zx) {
+  // enumeration: top row, bottom row (H1 > 1), left column without corners, right column without corners (W1 > 1)
+  if (e < W1) { *zy = 0; *zx = e; return true; }
+  e -= W1;
+  if (H1 > 1) {
+    if (e < W1) { *zy = H1 - 1; *zx = e; return true; }
+    e -= W1;
+  }
+  const int inner = H1 - 2 > 0 ? H1 - 2 : 0;
+  if (e < inner) { *zy = 1 + e; *zx = 0; return true; }
+  e -= inner;
+  if (W1 > 1 && e < inner) { *zy = 1 + e; *zx = W1 - 1; return true; }
+  return false;
+}
+__host__ __device__ inline int border_count(int H1, int W1) {
+  const int inner = H1 - 2 > 0 ? H1 - 2 : 0;
+  return W1 + (H1 > 1 ? W1 : 0) + inner + (W1 > 1 ? inner : 0);
+}
+
+__global__ void __launch_bounds__(256) tail_dx_edge_kernel(const float* __restrict__ g, const float* __restrict__ U,
+                                                           __nv_bfloat16* __restrict__ dX, long long n_img, int H1,
+                                                           int W1) {
+  const int per_img = border_count(H1, W1);
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int ci = static_cast<int>(i & 63);
+  const long long pe = i >> 6;
+  if (pe >= n_img * per_img) return;
+  const long long img = pe / per_img;
+  int zy, zx;
+  if (!border_pixel(static_cast<int>(pe - img * per_img), H1, W1, &zy, &zx)) return;
+  const int Hs = 2 * H1, Ws = 2 * W1;
+  const float* gimg = g + static_cast<size_t>(img) * Hs * Ws;
+  const float* Uc = U + static_cast<size_t>(border_class(zy, zx, H1, W1)) * kNO * 64 + ci;
+  float sum = 0.f;
+#pragma unroll 1
+  for (int oyi = 0; oyi < kO; ++oyi) {
+    const int y = 2 * zy + kOmin + oyi;
+    if (y < 0 || y >= Hs) continue;
+#pragma unroll
+    for (int oxi = 0; oxi < kO; ++oxi) {
+      const int x = 2 * zx + kOmin + oxi;
+      if (x < 0 || x >= Ws) continue;
+      sum = fmaf(__ldg(gimg + static_cast<size_t>(y) * Ws + x), __ldg(Uc + (oyi * kO + oxi) * 64), sum);
+    }
+  }
+  dX[(static_cast<size_t>(img) * H1 * W1 + static_cast<size_t>(zy) * W1 + zx) * 64 + ci] = __float2bfloat16(sum);
+}
+
+// ------------------------------------------------------------------------------------------------
+// S[o][ci] += sum_z g[2 z + o] * X[z][ci]  and  Gs[o] += sum_z g[2 z + o]  over all pixels of all images: an
+// [64 offsets x pixels] x [pixels x 64 channels] product on mma.sync (K = pixels).  Persistent blocks walk 8 x 16 pixel
+// tiles; the X tile is staged with cp.async (144-byte pixel pitch), the B operand comes from it via ldmatrix.trans, the A
+// operand (g stencil, bf16 hi + lo) is built from the shared halo.  Warp w accumulates offsets [16 (w % 4), +16) x
+// channels [32 (w / 4), +32) across all tiles of the block; one atomic pass at the end.
+__global__ void __launch_bounds__(256, 2) tail_corr_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ X,
+                                                           float* __restrict__ S, float* __restrict__ Gs, int n_img,
+                                                           int H1, int W1, int tiles_x, int tiles_y) {
+  __shared__ float gh[kGhH * kGhPitch];
+  __shared__ __align__(16) uint8_t xt[kTH * kTW * kXPitch];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mt = warp & 3, nh = warp >> 2;
+  const int Hs = 2 * H1, Ws = 2 * W1;
+  const uint32_t xt_s = static_cast<uint32_t>(__cvta_generic_to_shared(xt));
+  float acc[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+  float gsum = 0.f;                  // threads 0..63: offset o = threadIdx.x
+  const int total = n_img * tiles_y * tiles_x;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    int tt = t;
+    const int tx = tt % tiles_x;
+    tt /= tiles_x;
+    const int ty = tt % tiles_y;
+    const int img = tt / tiles_y;
+    const int y0 = ty * kTH, x0 = tx * kTW;
+    const __nv_bfloat16* src = X + static_cast<size_t>(img) * H1 * W1 * 64;
+#pragma unroll
+    for (int it = 0; it < kTH * kTW * 8 / 256; ++it) {
+      const int i = threadIdx.x + it * 256;
+      const int px = i >> 3, ck = i & 7;
+      const int y = y0 + px / kTW, x = x0 + px % kTW;
+      const bool ok = y < H1 && x < W1;
+      const __nv_bfloat16* p = src + (static_cast<size_t>(ok ? y : 0) * W1 + (ok ? x : 0)) * 64 + ck * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xt_s + px * kXPitch + ck * 16), "l"(p),
+                   "r"(ok ? 16 : 0)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    load_g_halo(g + static_cast<size_t>(img) * Hs * Ws, y0, x0, Hs, Ws, gh);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < kNO) {
+      const int oyi = threadIdx.x / kO, oxi = threadIdx.x % kO;
+      const int ny = H1 - y0 < kTH ? H1 - y0 : kTH, nx = W1 - x0 < kTW ? W1 - x0 : kTW;
+      float s = 0.f;
+      for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < nx; ++x) s += gh[(2 * y + oyi) * kGhPitch + 2 * x + oxi];
+      gsum += s;
+    }
+    const int r0 = lane >> 2, c0 = (lane & 3) * 2;
+#pragma unroll
+    for (int ks = 0; ks < kTH; ++ks) {           // k step = the 16 pixels of tile row ks
+      // A (row-major, rows = offsets 16 mt + {r0, r0 + 8} = (oy index 2 mt / 2 mt + 1, ox index r0), columns = pixels)
+      uint32_t ahi[4], alo[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int oyi = 2 * mt + (f & 1);
+        const int zx = c0 + (f >> 1) * 8;
+        const float* row = gh + (2 * ks + oyi) * kGhPitch + 2 * zx + r0;
+        const float v0 = row[0], v1 = row[2];
+        const uint32_t hi = pack_bf2(v0, v1);
+        ahi[f] = hi;
+        alo[f] = pack_bf2(v0 - bf_lo(hi), v1 - bf_hi(hi));
+      }
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        const uint32_t addr = xt_s + (ks * kTW + (lane & 7) + 8 * ((lane >> 3) & 1)) * kXPitch +
+                              (nh * 32 + 16 * np + 8 * (lane >> 4)) * 2;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(addr));
+        mma16816(acc[2 * np], ahi, b0, b1);
+        mma16816(acc[2 * np], alo, b0, b1);
+        mma16816(acc[2 * np + 1], ahi, b2, b3);
+        mma16816(acc[2 * np + 1], alo, b2, b3);
+      }
+    }
+    __syncthreads();     // the tile and the halo are overwritten by the next iteration
+  }
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int o = mt * 16 + (lane >> 2), ci = nh * 32 + nt * 8 + (lane & 3) * 2;
+    atomicAdd(S + o * 64 + ci, acc[nt][0]);
+    atomicAdd(S + o * 64 + ci + 1, acc[nt][1]);
+    atomicAdd(S + (o + 8) * 64 + ci, acc[nt][2]);
+    atomicAdd(S + (o + 8) * 64 + ci + 1, acc[nt][3]);
+  }
+  if (threadIdx.x < kNO) atomicAdd(Gs + threadIdx.x, gsum);
+}
+
+// Edge sums E[set][o][ci]: the same correlation restricted to one edge set of pixels.  set 0 first row, 1 last row,
+// 2 first column, 3 last column, 4..7 the corners (0,0), (0,W1-1), (H1-1,0), (H1-1,W1-1).  blockIdx.y = set,
+// blockIdx.x walks chunks of that set's pixels over all images; thread = (channel, group of 16 offsets).
+__global__ void __launch_bounds__(256) tail_corr_edge_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ X,
+                                                             float* __restrict__ E, long long n_img, int H1, int W1,
+                                                             int chunk) {
+  const int set = blockIdx.y;
+  const int per_img = set < 2 ? W1 : (set < 4 ? H1 : 1);
+  const long long n_pix = n_img * per_img;
+  const long long p0 = static_cast<long long>(blockIdx.x) * chunk;
+  if (p0 >= n_pix) return;
+  const long long p1 = p0 + chunk < n_pix ? p0 + chunk : n_pix;
+  const int ci = threadIdx.x & 63, og = threadIdx.x >> 6;      // offsets [16 og, 16 og + 16) = oy indices 2 og, 2 og + 1
+  const int Hs = 2 * H1, Ws = 2 * W1;
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  for (long long p = p0; p < p1; ++p) {
+    const long long img = p / per_img;
+    const int e = static_cast<int>(p - img * per_img);
+    int zy, zx;
+    switch (set) {
+      case 0: zy = 0; zx = e; break;
+      case 1: zy = H1 - 1; zx = e; break;
+      case 2: zy = e; zx = 0; break;
+      case 3: zy = e; zx = W1 - 1; break;
+      case 4: zy = 0; zx = 0; break;
+      case 5: zy = 0; zx = W1 - 1; break;
+      case 6: zy = H1 - 1; zx = 0; break;
+      default: zy = H1 - 1; zx = W1 - 1; break;
+    }
+    const float x = __bfloat162float(X[(static_cast<size_t>(img) * H1 * W1 + static_cast<size_t>(zy) * W1 + zx) * 64 + ci]);
+    const float* gimg = g + static_cast<size_t>(img) * Hs * Ws;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int yy = 2 * zy + kOmin + 2 * og + (k >> 3), xx = 2 * zx + kOmin + (k & 7);
+      const float gv = (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) ? __ldg(gimg + static_cast<size_t>(yy) * Ws + xx) : 0.f;
+      acc[k] = fmaf(gv, x, acc[k]);
+    }
+  }
+  float* dst = E + (static_cast<size_t>(set) * kNO + og * 16) * 64 + ci;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) atomicAdd(dst + k * 64, acc[k]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parameter gradients from S, E, Gs (see the file header).  Three thread ranges:
+//   [0, 256*64*9)                 dW2[(c,q)][ci][t'] += sum_t w3[c][t] R[q,t,t'][ci]
+//   next 64*9*4*9                 dw3[c][t] += sum_ci W2[(c,q)][ci][t'] R[q,t,t'][ci]        (atomic over q, t')
+//   next 256 + 576 + 1            db2, the bias part of dw3, db3
+__device__ __forceinline__ float tail_R(const float* __restrict__ S, const float* __restrict__ E, int q, int t, int tp,
+                                        int ci) {
+  const int tpy = tp / 3 - 1, tpx = tp % 3 - 1, ty = t / 3 - 1, tx = t % 3 - 1, qy = q >> 1, qx = q & 1;
+  const int o = (-2 * tpy + qy - ty - kOmin) * kO + (-2 * tpx + qx - tx - kOmin);
+  float v = S[o * 64 + ci];
+  const int rset = tpy == 1 ? 0 : 1, cset = tpx == 1 ? 2 : 3;
+  if (tpy != 0) v -= E[(rset * kNO + o) * 64 + ci];
+  if (tpx != 0) v -= E[(cset * kNO + o) * 64 + ci];
+  if (tpy != 0 && tpx != 0) {
+    const int cor = 4 + (tpy == 1 ? 0 : 2) + (tpx == 1 ? 0 : 1);
+    v += E[(cor * kNO + o) * 64 + ci];
+  }
+  return v;
+}
+__device__ __forceinline__ float tail_Gq(const float* __restrict__ Gs, int q, int t) {
+  const int ty = t / 3 - 1, tx = t % 3 - 1, qy = q >> 1, qx = q & 1;
+  return Gs[(qy - ty - kOmin) * kO + (qx - tx - kOmin)];
+}
+
+__global__ void __launch_bounds__(256) tail_finish_kernel(const float* __restrict__ S, const float* __restrict__ E,
+                                                          const float* __restrict__ Gs, const float* __restrict__ W2,
+                                                          const float* __restrict__ b2, const float* __restrict__ w3,
+                                                          float* __restrict__ dW2, float* __restrict__ db2,
+                                                          float* __restrict__ dw3, float* __restrict__ db3) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int n1 = 256 * 64 * 9, n2 = 64 * 9 * 4 * 9, n3 = 256 + 576 + 1;
+  if (i < n1) {
+    if (!dW2) return;
+    const int tp = i % 9, ci = (i / 9) & 63, co = i / (9 * 64);
+    const int c = co >> 2, q = co & 3;
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s = fmaf(w3[c * 9 + t], tail_R(S, E, q, t, tp, ci), s);
+    dW2[i] += s;
+    return;
+  }
+  i -= n1;
+  if (i < n2) {
+    if (!dw3) return;
+    const int tp = i % 9, q = (i / 9) & 3, t = (i / 36) % 9, c = i / 324;
+    const float* w = W2 + static_cast<size_t>(c * 4 + q) * 64 * 9 + tp;
+    float s = 0.f;
+    for (int ci = 0; ci < 64; ++ci) s = fmaf(w[ci * 9], tail_R(S, E, q, t, tp, ci), s);
+    atomicAdd(dw3 + c * 9 + t, s);
+    return;
+  }
+  i -= n2;
+  if (i >= n3) return;
+  if (i < 256) {
+    if (!db2) return;
+    const int c = i >> 2, q = i & 3;
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s = fmaf(w3[c * 9 + t], tail_Gq(Gs, q, t), s);
+    db2[i] += s;
+  } else if (i < 256 + 576) {
+    if (!dw3) return;
+    const int k = i - 256, c = k / 9, t = k % 9;
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s = fmaf(b2[c * 4 + q], tail_Gq(Gs, q, t), s);
+    atomicAdd(dw3 + k, s);
+  } else if (db3) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += tail_Gq(Gs, q, 4);     // the four HR parity classes partition the image
+    db3[0] += s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+// scratch layout (floats): U [16][64][64] | S [64][64] | E [8][64][64] | Gs [64] | UT bf16 [64][64]
+constexpr size_t kTailU = 0, kTailS = kTailU + 16 * kNO * 64, kTailE = kTailS + kNO * 64, kTailG = kTailE + 8 * kNO * 64,
+                 kTailUT = kTailG + kNO, kTailFloats = kTailUT + kNO * 64 / 2;
+
+size_t tail_scratch_bytes() { return kTailFloats * sizeof(float); }
+
+int launch_tail_tables(const float* W2, const float* w3, void* scratch, cudaStream_t s) {
+  float* f = static_cast<float*>(scratch);
+  tail_tables_kernel<<<16 * kNO * 64 / 256, 256, 0, s>>>(W2, w3, f + kTailU, reinterpret_cast<__nv_bfloat16*>(f + kTailUT));
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_tail_zero_sums(void* scratch, cudaStream_t s) {
+  float* f = static_cast<float*>(scratch);
+  return static_cast<int>(cudaMemsetAsync(f + kTailS, 0, (kTailUT - kTailS) * sizeof(float), s));
+}
+
+int launch_tail_dx(const float* g, const void* scratch, void* dx_bf16, long long n_img, int H1, int W1, int num_sms,
+                   cudaStream_t s) {
+  if (n_img <= 0) return 0;
+  const float* f = static_cast<const float*>(scratch);
+  const int tiles_x = (W1 + kTW - 1) / kTW, tiles_y = (H1 + kTH - 1) / kTH;
+  const long long total = n_img * tiles_x * tiles_y;
+  if (total >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
+  const long long cap = 4LL * (num_sms > 0 ? num_sms : 148);
+  tail_dx_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, 0, s>>>(
+      g, reinterpret_cast<const __nv_bfloat16*>(f + kTailUT), static_cast<__nv_bfloat16*>(dx_bf16), static_cast<int>(n_img),
+      H1, W1, tiles_x, tiles_y);
+  int e = static_cast<int>(cudaGetLastError());
+  if (e) return e;
+  const long long threads = n_img * border_count(H1, W1) * 64;
+  tail_dx_edge_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(g, f + kTailU,
+                                                                                  static_cast<__nv_bfloat16*>(dx_bf16),
+                                                                                  n_img, H1, W1);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_tail_corr(const float* g, const void* x_bf16, void* scratch, long long n_img, int H1, int W1, int num_sms,
+                     cudaStream_t s) {
+  if (n_img <= 0) return 0;
+  float* f = static_cast<float*>(scratch);
+  const int tiles_x = (W1 + kTW - 1) / kTW, tiles_y = (H1 + kTH - 1) / kTH;
+  const long long total = n_img * tiles_x * tiles_y;
+  if (total >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
+  const long long cap = 2LL * (num_sms > 0 ? num_sms : 148);
+  tail_corr_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, 0, s>>>(
+      g, static_cast<const __nv_bfloat16*>(x_bf16), f + kTailS, f + kTailG, static_cast<int>(n_img), H1, W1, tiles_x,
+      tiles_y);
+  int e = static_cast<int>(cudaGetLastError());
+  if (e) return e;
+  const int chunk = 64;
+  const long long longest = n_img * (H1 > W1 ? H1 : W1);
+  dim3 grid(static_cast<unsigned>((longest + chunk - 1) / chunk), 8);
+  tail_corr_edge_kernel<<<grid, 256, 0, s>>>(g, static_cast<const __nv_bfloat16*>(x_bf16), f + kTailE, n_img, H1, W1, chunk);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_tail_finish(const void* scratch, const float* W2, const float* b2, const float* w3, float* dW2, float* db2,
+                       float* dw3, float* db3, cudaStream_t s) {
+  const float* f = static_cast<const float*>(scratch);
+  constexpr int n = 256 * 64 * 9 + 64 * 9 * 4 * 9 + 256 + 576 + 1;
+  tail_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(f + kTailS, f + kTailE, f + kTailG, W2, b2, w3, dW2, db2, dw3, db3);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace pvsr

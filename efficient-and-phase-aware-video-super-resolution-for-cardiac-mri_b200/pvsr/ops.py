@@ -310,6 +310,23 @@ def head_conv_last_bwd(x, w, dout):
     return din, dw, db
 
 
+def head_tail_bwd(x, w2, b2, w3, dout):
+    """Rank-1 adjoint of conv3x3 (64 -> 256) + PixelShuffle(2) + conv3x3 (64 -> 1) (csrc/tail_rank1.cu).
+    x bf16 [n,H1,W1,64], w2 (256,64,3,3), b2 (256), w3 (1,64,3,3), dout fp32 [n,2 H1,2 W1]
+    -> (dx bf16 [n,H1,W1,64], dw2, db2, dw3, db3)."""
+    lib = L.load()
+    n, H1, W1, _ = x.shape
+    dx = torch.empty_like(x)
+    dw2, db2 = torch.zeros_like(w2), torch.zeros_like(b2)
+    dw3 = torch.zeros_like(w3)
+    db3 = torch.zeros(1, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(lib.pvsr_head_tail_scratch_bytes(), dtype=torch.uint8, device=x.device)
+    L.check(lib.pvsr_head_tail_bwd(L.ptr(dout.contiguous()), L.ptr(x), L.ptr(w2.contiguous()), L.ptr(b2.contiguous()),
+                                   L.ptr(w3.contiguous()), L.ptr(dx), L.ptr(dw2), L.ptr(db2), L.ptr(dw3), L.ptr(db3),
+                                   L.ptr(scratch), n, H1, W1, L.current_stream()), "head_tail_bwd")
+    return dx, dw2, db2, dw3, db3
+
+
 def in_conv_prelu_bwd(x, w, b, slope, g):
     """x fp32 [n,H,W], g fp32 [n,H,W,64] -> (dw (64,1,3,3), db (64), dslope (1))."""
     lib = L.load()

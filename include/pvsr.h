@@ -297,6 +297,21 @@ int pvsr_head_conv_last_fwd(const void* in_bf16, const float* w, const float* b,
 
 int pvsr_add_bf16(const void* a, const void* b, void* out, int64_t n_elems, void* stream);
 
+/* Backward of the head's tail  X -conv3x3 64->256 (w2, b2)-> PixelShuffle(2) -conv3x3 64->1 (w3)-> out  in one call
+ * (refine_net.py:201-205 under autograd), exploiting that the last conv has ONE output channel (csrc/tail_rank1.cu):
+ *   dout fp32 [n_img][2 H1][2 W1], x bf16 NHWC [n_img][H1][W1][64], w2 fp32 (256,64,3,3), b2 (256), w3 (1,64,3,3)
+ *   -> dx bf16 NHWC [n_img][H1][W1][64] (written), dw2 / db2 / dw3 / db3 (parameter layout, ACCUMULATED; NULL = skip).
+ * scratch: pvsr_head_tail_scratch_bytes() bytes of device memory. */
+int64_t pvsr_head_tail_scratch_bytes(void);
+int pvsr_head_tail_bwd(const float* dout, const void* x_bf16, const float* w2, const float* b2, const float* w3,
+                       void* dx_bf16, float* dw2, float* db2, float* dw3, float* db3, void* scratch, int64_t n_img,
+                       int H1, int W1, void* stream);
+/* Training plans use that form for the last conv + PixelShuffle(2) + final conv of x4 / x8 heads instead of the
+ * tcgen05 dgrad / wgrad launches of the 64 -> 256 conv and the two adjoint kernels of the 64 -> 1 conv.
+ * 1 = on (default), 0 = the conv-by-conv backward (A/B switch; env PVSR_TAIL_RANK1). */
+int pvsr_set_tail_rank1(int enable);
+int pvsr_get_tail_rank1(void);
+
 /* ---- backward / optimiser ops ---------------------------------------------------------------------------------- */
 /* Adjoint of the ConvLSTM gate math (refine_net.py:258-265) for one cell step over n_img images of H x W:
  * dh fp32 NHWC [n_img][H][W][64]; gates bf16 / c, c_prev, dc fp32 tile-transposed (c_prev NULL = zeros; dc is

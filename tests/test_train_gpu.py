@@ -121,6 +121,42 @@ def test_head_conv_last_bwd(pvsr_lib, n, H, W):
     assert rel_l2(dw, w.grad) < 1e-4 and rel_l2(db, b.grad) < 1e-4
 
 
+@pytest.mark.parametrize("n,H1,W1", [(3, 64, 64), (2, 9, 21), (2, 17, 33), (1, 8, 16), (1, 1, 1), (2, 1, 5), (2, 7, 1),
+                                     (1, 2, 2), (1, 27, 31)])
+def test_head_tail_rank1_bwd(pvsr_lib, n, H1, W1):
+    """csrc/tail_rank1.cu against torch autograd through conv3x3(64->256) -> PixelShuffle(2) -> conv3x3(64->1)
+    (refine_net.py:201-205), every border configuration incl. one-pixel-wide images: data gradient (bf16 output) and
+    all four parameter gradients."""
+    from pvsr import ops
+    g = torch.Generator(device="cuda").manual_seed(40 + H1 + W1)
+    x = bf16r(torch.randn(n, 64, H1, W1, generator=g, device="cuda")).requires_grad_(True)
+    w2 = (torch.randn(256, 64, 3, 3, generator=g, device="cuda") * 0.04).requires_grad_(True)
+    b2 = (torch.randn(256, generator=g, device="cuda") * 0.1).requires_grad_(True)
+    w3 = (torch.randn(1, 64, 3, 3, generator=g, device="cuda") * 0.05).requires_grad_(True)
+    b3 = torch.zeros(1, device="cuda", requires_grad=True)
+    dout = torch.randn(n, 1, 2 * H1, 2 * W1, generator=g, device="cuda")
+    out = F.conv2d(F.pixel_shuffle(F.conv2d(x, w2, b2, padding=1), 2), w3, b3, padding=1)
+    out.backward(dout)
+    dx, dw2, db2, dw3, db3 = ops.head_tail_bwd(nhwc(x.detach()), w2.detach(), b2.detach(), w3.detach(),
+                                               dout[:, 0].contiguous())
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(dx), x.grad) < 6e-3, rel_l2(nchw(dx), x.grad)        # bf16 table + bf16 output rounding
+    assert cosine(nchw(dx).float(), x.grad) > 0.9999
+    assert rel_l2(dw2, w2.grad) < 2e-4, rel_l2(dw2, w2.grad)
+    assert rel_l2(db2, b2.grad) < 2e-4
+    assert rel_l2(dw3, w3.grad) < 2e-4, rel_l2(dw3, w3.grad)
+    assert rel_l2(db3, b3.grad) < 2e-4
+    # a sign-valued loss gradient (the fused L1 path) is exact in bf16: same gates
+    dsign = torch.sign(dout) * 0.25
+    for t in (x, w2, b2, w3, b3):
+        t.grad = None
+    F.conv2d(F.pixel_shuffle(F.conv2d(x, w2, b2, padding=1), 2), w3, b3, padding=1).backward(dsign)
+    dx, dw2, db2, dw3, db3 = ops.head_tail_bwd(nhwc(x.detach()), w2.detach(), b2.detach(), w3.detach(),
+                                               dsign[:, 0].contiguous())
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(dx), x.grad) < 6e-3 and rel_l2(dw2, w2.grad) < 2e-4 and rel_l2(dw3, w3.grad) < 2e-4
+
+
 def test_in_conv_prelu_bwd(pvsr_lib):
     from pvsr import ops
     g = torch.Generator(device="cuda").manual_seed(34)
@@ -420,3 +456,32 @@ def test_benchmarked_training_plan_vs_oracle(pvsr_lib):
         assert rel_l2(out.cpu(), ref_stack) <= 1.5e-2
         got = {k: p.grad for k, p in net.named_parameters()}
         _check_grads(got, {k: ref_grads.get(k) for k in got}, f"train N=16 rep {rep}")
+
+
+@pytest.mark.parametrize("name", ["x4_pos", "x8_pos", "x4_rect"])
+def test_tail_rank1_equals_conv_by_conv_backward(pvsr_lib, name):
+    """A/B of the two backward forms of the head's tail inside the whole plan (pvsr_set_tail_rank1): the rank-1 adjoint
+    (default) and the conv-by-conv backward give the same parameter gradients; both are also gated against the oracle
+    by the fixture tests above."""
+    z, meta = load_golden(name)
+    kw = meta["kwargs"]
+    inputs = [torch.from_numpy(x).cuda() for x in z["inputs"]]
+    pos = torch.from_numpy(z["pos"]).cuda()
+    targets = [torch.from_numpy(t).cuda() for t in z["targets"]]
+    grads = {}
+    try:
+        for mode in (1, 0):
+            pvsr_lib.pvsr_set_tail_rank1(mode)
+            net = build_net(kw).cuda().train()
+            loss, _ = net.engine.loss_and_grads(inputs, pos, targets)
+            torch.cuda.synchronize()
+            grads[mode] = ({k: p.grad.clone() for k, p in net.named_parameters()}, loss.item())
+    finally:
+        pvsr_lib.pvsr_set_tail_rank1(1)
+    assert grads[0][1] == grads[1][1]                      # the forward pass is the same
+    for k in grads[0][0]:
+        a, b = grads[1][0][k], grads[0][0][k]
+        if float(b.abs().sum()) == 0.0:
+            assert float(a.abs().sum()) == 0.0, k
+            continue
+        assert rel_l2(a, b) < 1.5e-2 and cosine(a, b) > 0.9998, (k, rel_l2(a, b), cosine(a, b))
