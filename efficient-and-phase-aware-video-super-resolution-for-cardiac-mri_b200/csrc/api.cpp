@@ -242,6 +242,23 @@ int pvsr_head_tail_bwd(const float* dout, const void* x_bf16, const float* w2, c
   if (!e) e = launch_tail_finish(scratch, w2, b2, w3, dw2, db2, dw3, db3, s);
   return check_cuda(e, "head_tail_bwd");
 }
+int pvsr_set_tail_fwd(int enable) {
+  set_tail_fwd(enable);
+  return 0;
+}
+int pvsr_get_tail_fwd(void) { return get_tail_fwd(); }
+int64_t pvsr_head_tail_fwd_table_bytes(void) { return static_cast<int64_t>(tail_fwd_table_bytes()); }
+int pvsr_head_tail_fwd_tables(const float* w2, const float* b2, const float* w3, const float* b3, void* tables,
+                              void* stream) {
+  if (!w2 || !b2 || !w3 || !b3 || !tables) return set_error(-2, "null argument");
+  return check_cuda(launch_tail_fwd_tables(w2, b2, w3, b3, tables, static_cast<cudaStream_t>(stream)), "tail_fwd_tables");
+}
+int pvsr_head_tail_fwd(const void* x_bf16, const void* tables, float* out, int64_t n_img, int H1, int W1, void* stream) {
+  if (!x_bf16 || !tables || !out) return set_error(-2, "null argument");
+  if (n_img < 0 || H1 < 1 || W1 < 1) return set_error(-2, "bad shape");
+  return check_cuda(launch_tail_fwd(x_bf16, tables, out, n_img, H1, W1, device_num_sms(), static_cast<cudaStream_t>(stream)),
+                    "tail_fwd");
+}
 int pvsr_set_two_branch(int enable) {
   set_two_branch(enable);
   return 0;

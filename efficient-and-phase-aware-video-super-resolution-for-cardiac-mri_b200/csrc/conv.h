@@ -111,6 +111,10 @@ int get_pack_table();
 void set_tail_rank1(int enable);
 int get_tail_rank1();
 
+// Composite forward of the head's tail (tail_rank1.cu: one 64 -> 4 channel 5x5 conv instead of conv + shuffle + conv).
+void set_tail_fwd(int enable);
+int get_tail_fwd();
+
 // Two-branch schedules of training plans (plan.cpp: Ctx::side): weight-gradient launches and the HBM-bound head
 // kernels on a second stream / graph branch.  1 = on (default), 0 = single chain (A/B measurements).
 void set_two_branch(int enable);

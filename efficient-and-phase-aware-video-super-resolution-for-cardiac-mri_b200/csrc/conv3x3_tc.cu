@@ -919,6 +919,10 @@ static int g_tail_rank1 = 1;
 void set_tail_rank1(int enable) { g_tail_rank1 = enable ? 1 : 0; }
 int get_tail_rank1() { return g_tail_rank1; }
 
+static int g_tail_fwd = 1;
+void set_tail_fwd(int enable) { g_tail_fwd = enable ? 1 : 0; }
+int get_tail_fwd() { return g_tail_fwd; }
+
 static int g_two_branch = 1;
 void set_two_branch(int enable) { g_two_branch = enable ? 1 : 0; }
 int get_two_branch() { return g_two_branch; }

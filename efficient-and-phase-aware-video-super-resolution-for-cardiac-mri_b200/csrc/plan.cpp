@@ -121,6 +121,7 @@ struct pvsr_plan {
   // one table_kernel launch packs every operand (pvsr_table_job rows in the packed buffer behind the index region);
   // the backward pass scatters every packed gradient the same way.  Used when no job needs a second index.
   size_t pk_table = 0, pk_sc_table = 0;
+  size_t pk_tail_fwd = 0;               // tables of the composite forward of the head's tail (tail_rank1.cu)
   bool table_ok = false;
   const void* table_key = nullptr;      // hash of the parameter pointers the uploaded pack table was built for
   const void* sc_table_key = nullptr;   // same for the scatter table (gradient pointers)
@@ -543,7 +544,12 @@ void schedule(Ctx& c) {
                 (k == 0 ? hf_top : hb_top) + static_cast<long long>(U) * B, in_img, static_cast<long long>(T) * B);
       }
       const long long n_head = static_cast<long long>(T) * B;
-      for (int q = 0; q < p->n_ps; ++q) {
+      // x4 / x8: the last conv + PixelShuffle(2) and the final 64 -> 1 conv run as ONE composite 5x5 conv (tail_rank1.cu);
+      // training plans only together with the rank-1 backward (the conv-by-conv backward reads the 64-channel HR map)
+      const bool tailf = get_tail_fwd() != 0 && p->n_ps >= 2 && p->ps_r[p->n_ps - 1] == 2 &&
+                         (!p->train || get_tail_rank1() != 0);
+      const int n_ps_run = tailf ? p->n_ps - 1 : p->n_ps;
+      for (int q = 0; q < n_ps_run; ++q) {
         ConvParams cp;
         base_params(q == 0 ? p->lr : p->ps_tile[q], p->ps_h[q], p->ps_w[q], &cp);
         cp.n_img = static_cast<int>(n_head);
@@ -565,6 +571,20 @@ void schedule(Ctx& c) {
       // Training plans keep one head-intermediate slot per list, so the HBM-bound 64 -> 1 conv of list k can run on the
       // side branch underneath the tensor-bound launches that follow (next list's head convs, next stage's ConvLSTM).
       if (p->train) c.to_side();
+      if (tailf) {
+        const int last = p->n_ps - 1;
+        c.begin(CLS_HEAD_PS);
+        if (!c.dry && !c.rc) {
+          float* o = c.out + static_cast<size_t>(list) * T * B * p->Hs * p->Ws;
+          int e = launch_tail_fwd(c.ws + p->off_head[last - 1] + lslot * p->head_stride[last - 1], c.pk + p->pk_tail_fwd, o,
+                                  n_head, p->ps_h[last], p->ps_w[last], p->num_sms, c.stream);
+          if (e) c.rc = check_cuda(e, "tail_fwd launch");
+        }
+        c.end(CLS_HEAD_PS, (2.0 * 9 * kFeat * (kFeat * 4) * p->ps_h[last] * p->ps_w[last] +
+                            2.0 * 9 * kFeat * static_cast<double>(p->Hs) * p->Ws) * n_head);     // algorithmic FLOPs
+        c.to_main();
+        continue;
+      }
       c.begin(CLS_HEAD_LAST);
       if (!c.dry && !c.rc) {
         float* o = c.out + static_cast<size_t>(list) * T * B * p->Hs * p->Ws;
@@ -1419,6 +1439,7 @@ int pvsr_plan_create(const pvsr_net_config* cfg, pvsr_plan** out) {
   for (const auto& j : p->sc_jobs) if (j.has2) p->table_ok = false;
   p->pk_table = pk; pk = align_up(pk + p->jobs.size() * sizeof(pvsr_table_job), 1024);
   p->pk_sc_table = pk; pk = align_up(pk + (p->sc_jobs.size() + 1) * sizeof(pvsr_table_job), 1024);
+  p->pk_tail_fwd = pk; pk = align_up(pk + tail_fwd_table_bytes(), 1024);
   p->pk_bytes = pk;
 
   // ---- accounting via dry runs of the schedules
@@ -1485,6 +1506,17 @@ int pvsr_plan_class_stats_bwd(const pvsr_plan* p, int64_t* launches, double* flo
   return kNumClassesBwd;
 }
 
+// Composite-forward tables of the head's tail (x4 / x8 heads): functions of the last two convs' parameters only.
+static bool plan_has_tail(const pvsr_plan* p) { return p->n_ps >= 2 && p->ps_r[p->n_ps - 1] == 2; }
+static int pack_tail_tables(pvsr_plan* p, const pvsr_net_params* P, uint8_t* pk, cudaStream_t s) {
+  if (!plan_has_tail(p)) return 0;
+  const int last = p->n_ps - 1;
+  if (!P->head_w[last] || !P->head_b[last] || !P->head_w[p->n_ps] || !P->head_b[p->n_ps])
+    return set_error(-4, "missing head parameter pointer");
+  return check_cuda(launch_tail_fwd_tables(P->head_w[last], P->head_b[last], P->head_w[p->n_ps], P->head_b[p->n_ps],
+                                           pk + p->pk_tail_fwd, s), "tail forward tables");
+}
+
 int pvsr_plan_pack(pvsr_plan* p, const pvsr_net_params* P, void* packed, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint8_t* pk = static_cast<uint8_t*>(packed);
@@ -1513,8 +1545,9 @@ int pvsr_plan_pack(pvsr_plan* p, const pvsr_net_params* P, void* packed, void* s
       if (e) return check_cuda(e, "pack table upload");
       p->table_key = key;
     }
-    return check_cuda(launch_table(reinterpret_cast<const pvsr_table_job*>(pk + p->pk_table),
-                                   static_cast<int>(tab.size()), max_n, s), "pack table launch");
+    int e = launch_table(reinterpret_cast<const pvsr_table_job*>(pk + p->pk_table), static_cast<int>(tab.size()), max_n, s);
+    if (e) return check_cuda(e, "pack table launch");
+    return pack_tail_tables(p, P, pk, s);
   }
   for (const auto& j : p->jobs) {
     const float* src = job_weight(j.kind, j.a, j.b, P, j.is_bias);
@@ -1524,7 +1557,7 @@ int pvsr_plan_pack(pvsr_plan* p, const pvsr_net_params* P, void* packed, void* s
     else e = launch_pack_weights(src, idx + j.idx, j.has2 ? idx + j.idx2 : nullptr, pk + j.dst, j.n, s);
     if (e) return check_cuda(e, "pack launch");
   }
-  return 0;
+  return pack_tail_tables(p, P, pk, s);
 }
 
 static int ensure_device(pvsr_plan* p) {

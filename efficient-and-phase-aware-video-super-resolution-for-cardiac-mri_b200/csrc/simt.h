@@ -66,6 +66,12 @@ int launch_tail_corr(const float* g, const void* x_bf16, void* scratch, long lon
                      cudaStream_t s);
 int launch_tail_finish(const void* scratch, const float* W2, const float* b2, const float* w3, float* dW2, float* db2,
                        float* dw3, float* db3, cudaStream_t s);
+// ... and its forward as one composite 64 -> 4 channel 5x5 convolution (tables: tail_fwd_table_bytes() of device memory)
+size_t tail_fwd_table_bytes();
+int launch_tail_fwd_tables(const float* W2, const float* b2, const float* w3, const float* b3, void* tables,
+                           cudaStream_t s);
+int launch_tail_fwd(const void* x_bf16, const void* tables, float* out, long long n_img, int H1, int W1, int num_sms,
+                    cudaStream_t s);
 int launch_cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t s);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                 float wd, float grad_scale, float* state, int num_sms, cudaStream_t s);

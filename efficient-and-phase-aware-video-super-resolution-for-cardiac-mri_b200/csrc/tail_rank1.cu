@@ -449,6 +449,194 @@ __global__ void __launch_bounds__(256) tail_finish_kernel(const float* __restric
   }
 }
 
+// ================================================================================================
+// FORWARD of the same tail as ONE composite convolution.  Both convs are linear with nothing between them but the
+// pixel shuffle, and the second has a single output channel, so for every X pixel z and sub-pixel q in {0,1}^2
+//     out[2z + q] = b3 + biasT_cls(z)[q] + sum_{d in [-2,2]^2} sum_ci Kf_cls(z)[q][d][ci] * X[z + d][ci]
+//     Kf_cls[q][d][ci] = sum over taps t of the last conv with 2z + q + t inside the HR image, d1 = floor((q + t) / 2),
+//                        q' = (q + t) mod 2, t' = d - d1 in [-1,1]^2  of  sum_c w3[c][t] W2[(c,q')][ci][t']
+// (zero padding of the 64-channel HR map = the "inside" condition = the border class of z; zero padding of X is the
+// zero fill of the halo tile).  A 64 -> 4 channel 5x5 convolution: 12.8 kFLOP per X pixel instead of 295 k + 4.6 k,
+// and the 64-channel HR map (128 B per HR pixel written by the shuffle conv, read by the last conv) never exists.
+// N = 4 is far too narrow for tcgen05 (N >= 16 at M = 128); warp-level mma.sync m16n8k16 with the upper half of the
+// n8 tile zero does it at ~25.6 kFLOP executed per pixel.  Interior table on the tensor cores for every pixel, border
+// pixels recomputed exactly afterwards with their class tables (SIMT, ~3 % of the pixels).
+namespace {
+constexpr int kFT = 16;                         // tile = 16 x 16 X pixels
+constexpr int kFH = kFT + 4;                    // halo tile 20 x 20
+constexpr int kFK = 25 * 64;                    // K of the composite conv
+constexpr int kFBPitch = kFK + 8;               // bf16 elements per table row in shared memory (conflict-free)
+constexpr int kFSmem = kFH * kFH * kXPitch + 4 * kFBPitch * 2;
+}  // namespace
+
+// Kf fp32 [16 cls][4 q][25 d][64 ci], KB bf16 [4 q][25*64] (class 0), biasT fp32 [16][4] (b3 included).
+__global__ void __launch_bounds__(256) tail_fwd_tables_kernel(const float* __restrict__ W2, const float* __restrict__ b2,
+                                                              const float* __restrict__ w3, const float* __restrict__ b3,
+                                                              float* __restrict__ Kf, __nv_bfloat16* __restrict__ KB,
+                                                              float* __restrict__ biasT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 16 * 4) {
+    const int cls = i >> 2, q = i & 3, qy = q >> 1, qx = q & 1;
+    float s = b3[0];
+    for (int ty = -1; ty <= 1; ++ty) {
+      const int d1y = (qy + ty + 2) / 2 - 1, qpy = (qy + ty + 2) & 1;
+      if ((d1y == -1 && (cls & 1)) || (d1y == 1 && (cls & 2))) continue;
+      for (int tx = -1; tx <= 1; ++tx) {
+        const int d1x = (qx + tx + 2) / 2 - 1, qpx = (qx + tx + 2) & 1;
+        if ((d1x == -1 && (cls & 4)) || (d1x == 1 && (cls & 8))) continue;
+        const int t = (ty + 1) * 3 + (tx + 1), qp = qpy * 2 + qpx;
+        for (int c = 0; c < 64; ++c) s = fmaf(w3[c * 9 + t], b2[c * 4 + qp], s);
+      }
+    }
+    biasT[i] = s;
+  }
+  if (i >= 16 * 4 * 25 * 64) return;
+  const int ci = i & 63, d = (i >> 6) % 25, q = (i / (64 * 25)) & 3, cls = i / (64 * 25 * 4);
+  const int dy = d / 5 - 2, dx = d % 5 - 2, qy = q >> 1, qx = q & 1;
+  float sum = 0.f;
+  for (int ty = -1; ty <= 1; ++ty) {
+    const int d1y = (qy + ty + 2) / 2 - 1, qpy = (qy + ty + 2) & 1;
+    if ((d1y == -1 && (cls & 1)) || (d1y == 1 && (cls & 2))) continue;
+    const int tpy = dy - d1y;
+    if (tpy < -1 || tpy > 1) continue;
+    for (int tx = -1; tx <= 1; ++tx) {
+      const int d1x = (qx + tx + 2) / 2 - 1, qpx = (qx + tx + 2) & 1;
+      if ((d1x == -1 && (cls & 4)) || (d1x == 1 && (cls & 8))) continue;
+      const int tpx = dx - d1x;
+      if (tpx < -1 || tpx > 1) continue;
+      const int t = (ty + 1) * 3 + (tx + 1), qp = qpy * 2 + qpx, tp = (tpy + 1) * 3 + (tpx + 1);
+      float s = 0.f;
+      for (int c = 0; c < 64; ++c) s = fmaf(__ldg(w3 + c * 9 + t), __ldg(W2 + (static_cast<size_t>(c * 4 + qp) * 64 + ci) * 9 + tp), s);
+      sum += s;
+    }
+  }
+  Kf[i] = sum;
+  if (cls == 0) KB[q * kFK + d * 64 + ci] = __float2bfloat16(sum);
+}
+
+// out fp32 [n_img][2 H1][2 W1] for every X pixel with the interior table.  Block = 16 x 16 pixel tile, warp w = tile
+// rows 2w, 2w + 1 (two m16 tiles); per (tap d, 16-channel step) one B fragment from the shared table serves both.
+__global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ KB,
+                                                          const float* __restrict__ biasT, float* __restrict__ out,
+                                                          int n_img, int H1, int W1, int tiles_x, int tiles_y) {
+  extern __shared__ __align__(16) uint8_t fsm[];
+  uint8_t* xt = fsm;                                                 // [20 * 20][144 B]
+  __nv_bfloat16* bs = reinterpret_cast<__nv_bfloat16*>(fsm + kFH * kFH * kXPitch);   // [4][kFBPitch]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t xt_s = static_cast<uint32_t>(__cvta_generic_to_shared(xt));
+  for (int i = threadIdx.x; i < 4 * kFK / 8; i += 256) {             // 16-byte chunks of the table
+    const int q = i / (kFK / 8), k8 = i - q * (kFK / 8);
+    *reinterpret_cast<uint4*>(bs + q * kFBPitch + k8 * 8) = __ldg(reinterpret_cast<const uint4*>(KB + q * kFK + k8 * 8));
+  }
+  const float bias0 = biasT[(lane & 3) < 2 ? (lane & 3) * 2 : 0], bias1 = biasT[(lane & 3) < 2 ? (lane & 3) * 2 + 1 : 0];
+  const int Hs = 2 * H1, Ws = 2 * W1;
+  const int total = n_img * tiles_y * tiles_x;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    int tt = t;
+    const int tx = tt % tiles_x;
+    tt /= tiles_x;
+    const int ty = tt % tiles_y;
+    const int img = tt / tiles_y;
+    const int y0 = ty * kFT, x0 = tx * kFT;
+    const __nv_bfloat16* src = X + static_cast<size_t>(img) * H1 * W1 * 64;
+    for (int i = threadIdx.x; i < kFH * kFH * 8; i += 256) {
+      const int hp = i >> 3, ck = i & 7;
+      const int y = y0 - 2 + hp / kFH, x = x0 - 2 + hp % kFH;
+      const bool ok = y >= 0 && y < H1 && x >= 0 && x < W1;
+      const __nv_bfloat16* p = src + (static_cast<size_t>(ok ? y : 0) * W1 + (ok ? x : 0)) * 64 + ck * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xt_s + hp * kXPitch + ck * 16), "l"(p),
+                   "r"(ok ? 16 : 0)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    float acc[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[mt][j] = 0.f;
+    const uint32_t* brow = reinterpret_cast<const uint32_t*>(bs + (lane >> 2 & 3) * kFBPitch) + (lane & 3);
+    const bool bval = lane < 16;                                     // n8 columns 4..7 are zero
+    const uint32_t a_lane = ((lane & 7) + 8 * ((lane >> 3) & 1)) * kXPitch + 16 * (lane >> 4);
+#pragma unroll 1
+    for (int d = 0; d < 25; ++d) {
+      const int dy = d / 5, dx = d - dy * 5;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int kk = d * 64 + ks * 16;
+        const uint32_t b0 = bval ? brow[kk / 2] : 0u, b1 = bval ? brow[kk / 2 + 4] : 0u;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t a[4];
+          const uint32_t addr = xt_s + ((2 * warp + mt + dy) * kFH + dx) * kXPitch + a_lane + ks * 32;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+                       : "r"(addr));
+          mma16816(acc[mt], a, b0, b1);
+        }
+      }
+    }
+    // columns 2 (lane % 4) + {0, 1} = sub-pixel (qy = lane % 4, qx = 0 / 1) for lane % 4 < 2
+    if ((lane & 3) < 2) {
+      const int qy = lane & 3;
+      float* oimg = out + static_cast<size_t>(img) * Hs * Ws;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int zy = y0 + 2 * warp + mt;
+        if (zy >= H1) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int zx = x0 + (lane >> 2) + 8 * h;
+          if (zx < W1)
+            *reinterpret_cast<float2*>(oimg + static_cast<size_t>(2 * zy + qy) * Ws + 2 * zx) =
+                make_float2(acc[mt][2 * h] + bias0, acc[mt][2 * h + 1] + bias1);
+        }
+      }
+    }
+    __syncthreads();     // the tile is overwritten by the next iteration
+  }
+}
+
+// Border pixels again with the table of their class: warp = one border pixel, lane = two channels.
+__global__ void __launch_bounds__(256) tail_fwd_edge_kernel(const __nv_bfloat16* __restrict__ X, const float* __restrict__ Kf,
+                                                            const float* __restrict__ biasT, float* __restrict__ out,
+                                                            long long n_img, int H1, int W1) {
+  const int per_img = border_count(H1, W1);
+  const long long pe = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pe >= n_img * per_img) return;
+  const long long img = pe / per_img;
+  int zy, zx;
+  if (!border_pixel(static_cast<int>(pe - img * per_img), H1, W1, &zy, &zx)) return;
+  const int cls = border_class(zy, zx, H1, W1);
+  const __nv_bfloat16* ximg = X + static_cast<size_t>(img) * H1 * W1 * 64;
+  const float* K = Kf + static_cast<size_t>(cls) * 4 * kFK + 2 * lane;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int d = 0; d < 25; ++d) {
+    const int y = zy + d / 5 - 2, x = zx + d % 5 - 2;
+    if (y < 0 || y >= H1 || x < 0 || x >= W1) continue;
+    const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(ximg + (static_cast<size_t>(y) * W1 + x) * 64 + 2 * lane);
+    const float2 xf = __bfloat1622float2(xv);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 kv = __ldg(reinterpret_cast<const float2*>(K + q * kFK + d * 64));
+      acc[q] = fmaf(xf.x, kv.x, fmaf(xf.y, kv.y, acc[q]));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], s);
+  if (lane < 4) {
+    const int qy = lane >> 1, qx = lane & 1;
+    const float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+    out[(static_cast<size_t>(img) * 2 * H1 + 2 * zy + qy) * (2 * W1) + 2 * zx + qx] = v + biasT[cls * 4 + lane];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 // scratch layout (floats): U [16][64][64] | S [64][64] | E [8][64][64] | Gs [64] | UT bf16 [64][64]
 constexpr size_t kTailU = 0, kTailS = kTailU + 16 * kNO * 64, kTailE = kTailS + kNO * 64, kTailG = kTailE + 8 * kNO * 64,
@@ -512,6 +700,48 @@ int launch_tail_finish(const void* scratch, const float* W2, const float* b2, co
   const float* f = static_cast<const float*>(scratch);
   constexpr int n = 256 * 64 * 9 + 64 * 9 * 4 * 9 + 256 + 576 + 1;
   tail_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(f + kTailS, f + kTailE, f + kTailG, W2, b2, w3, dW2, db2, dw3, db3);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ---- forward: tables live in the packed-parameter buffer (they change only when the weights do)
+// layout (bytes): Kf fp32 [16][4][1600] | biasT fp32 [16][4] | KB bf16 [4][1600]
+constexpr size_t kTailFwdKf = 0, kTailFwdBias = kTailFwdKf + 16 * 4 * kFK * 4, kTailFwdKB = kTailFwdBias + 16 * 4 * 4,
+                 kTailFwdBytes = kTailFwdKB + 4 * kFK * 2;
+
+size_t tail_fwd_table_bytes() { return kTailFwdBytes; }
+
+int launch_tail_fwd_tables(const float* W2, const float* b2, const float* w3, const float* b3, void* tables,
+                           cudaStream_t s) {
+  uint8_t* t = static_cast<uint8_t*>(tables);
+  tail_fwd_tables_kernel<<<(16 * 4 * kFK + 255) / 256, 256, 0, s>>>(
+      W2, b2, w3, b3, reinterpret_cast<float*>(t + kTailFwdKf), reinterpret_cast<__nv_bfloat16*>(t + kTailFwdKB),
+      reinterpret_cast<float*>(t + kTailFwdBias));
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_tail_fwd(const void* x_bf16, const void* tables, float* out, long long n_img, int H1, int W1, int num_sms,
+                    cudaStream_t s) {
+  if (n_img <= 0) return 0;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = true;
+  }
+  const uint8_t* t = static_cast<const uint8_t*>(tables);
+  const int tiles_x = (W1 + kFT - 1) / kFT, tiles_y = (H1 + kFT - 1) / kFT;
+  const long long total = n_img * tiles_x * tiles_y;
+  if (total >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
+  const long long cap = 2LL * (num_sms > 0 ? num_sms : 148);
+  tail_fwd_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, kFSmem, s>>>(
+      static_cast<const __nv_bfloat16*>(x_bf16), reinterpret_cast<const __nv_bfloat16*>(t + kTailFwdKB),
+      reinterpret_cast<const float*>(t + kTailFwdBias), out, static_cast<int>(n_img), H1, W1, tiles_x, tiles_y);
+  int e = static_cast<int>(cudaGetLastError());
+  if (e) return e;
+  const long long warps = n_img * border_count(H1, W1);
+  tail_fwd_edge_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(x_bf16), reinterpret_cast<const float*>(t + kTailFwdKf),
+      reinterpret_cast<const float*>(t + kTailFwdBias), out, n_img, H1, W1);
   return static_cast<int>(cudaGetLastError());
 }
 

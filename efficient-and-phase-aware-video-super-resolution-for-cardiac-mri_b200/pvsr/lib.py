@@ -108,6 +108,11 @@ SIGNATURES = {
     "pvsr_get_tail_rank1": (c_int, []),
     "pvsr_head_tail_scratch_bytes": (c_int64, []),
     "pvsr_head_tail_bwd": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_void_p]),
+    "pvsr_set_tail_fwd": (c_int, [c_int]),
+    "pvsr_get_tail_fwd": (c_int, []),
+    "pvsr_head_tail_fwd_table_bytes": (c_int64, []),
+    "pvsr_head_tail_fwd_tables": (c_int, [c_void_p] * 6),
+    "pvsr_head_tail_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "pvsr_set_two_branch": (c_int, [c_int]),
     "pvsr_get_two_branch": (c_int, []),
     "pvsr_set_pdl": (c_int, [c_int]),
@@ -209,6 +214,8 @@ def load():
         lib.pvsr_set_pack_table(int(os.environ["PVSR_PACK_TABLE"]))
     if os.environ.get("PVSR_TAIL_RANK1") is not None:     # A/B switch of the rank-1 adjoint of the head's tail
         lib.pvsr_set_tail_rank1(int(os.environ["PVSR_TAIL_RANK1"]))
+    if os.environ.get("PVSR_TAIL_FWD") is not None:       # A/B switch of the composite forward of the head's tail
+        lib.pvsr_set_tail_fwd(int(os.environ["PVSR_TAIL_FWD"]))
     if os.environ.get("PVSR_TWO_BRANCH") is not None:     # A/B switch of the two-branch training schedules
         lib.pvsr_set_two_branch(int(os.environ["PVSR_TWO_BRANCH"]))
     if os.environ.get("PVSR_PDL") is not None:            # A/B switch of programmatic dependent launch

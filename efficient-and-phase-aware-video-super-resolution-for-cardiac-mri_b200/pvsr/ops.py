@@ -327,6 +327,19 @@ def head_tail_bwd(x, w2, b2, w3, dout):
     return dx, dw2, db2, dw3, db3
 
 
+def head_tail_fwd(x, w2, b2, w3, b3):
+    """Composite forward of conv3x3 (64 -> 256) + PixelShuffle(2) + conv3x3 (64 -> 1) (csrc/tail_rank1.cu).
+    x bf16 [n,H1,W1,64] -> out fp32 [n, 2 H1, 2 W1]."""
+    lib = L.load()
+    n, H1, W1, _ = x.shape
+    tables = torch.empty(lib.pvsr_head_tail_fwd_table_bytes(), dtype=torch.uint8, device=x.device)
+    L.check(lib.pvsr_head_tail_fwd_tables(L.ptr(w2.contiguous()), L.ptr(b2.contiguous()), L.ptr(w3.contiguous()),
+                                          L.ptr(b3.contiguous()), L.ptr(tables), L.current_stream()), "head_tail_fwd_tables")
+    out = torch.empty(n, 2 * H1, 2 * W1, dtype=torch.float32, device=x.device)
+    L.check(lib.pvsr_head_tail_fwd(L.ptr(x), L.ptr(tables), L.ptr(out), n, H1, W1, L.current_stream()), "head_tail_fwd")
+    return out
+
+
 def in_conv_prelu_bwd(x, w, b, slope, g):
     """x fp32 [n,H,W], g fp32 [n,H,W,64] -> (dw (64,1,3,3), db (64), dslope (1))."""
     lib = L.load()

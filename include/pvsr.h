@@ -311,6 +311,18 @@ int pvsr_head_tail_bwd(const float* dout, const void* x_bf16, const float* w2, c
  * 1 = on (default), 0 = the conv-by-conv backward (A/B switch; env PVSR_TAIL_RANK1). */
 int pvsr_set_tail_rank1(int enable);
 int pvsr_get_tail_rank1(void);
+/* Forward of the same tail as ONE composite 64 -> 4 channel 5x5 convolution (both convs are linear, the second has one
+ * output channel): out fp32 [n_img][2 H1][2 W1] from x bf16 NHWC [n_img][H1][W1][64]; the 64-channel HR map is never
+ * materialised.  tables: pvsr_head_tail_fwd_table_bytes() of device memory, refreshed by pvsr_head_tail_fwd_tables
+ * whenever w2 / b2 / w3 / b3 change (pvsr_plan_pack does it for plans). */
+int64_t pvsr_head_tail_fwd_table_bytes(void);
+int pvsr_head_tail_fwd_tables(const float* w2, const float* b2, const float* w3, const float* b3, void* tables,
+                              void* stream);
+int pvsr_head_tail_fwd(const void* x_bf16, const void* tables, float* out, int64_t n_img, int H1, int W1, void* stream);
+/* Plans: 1 = composite forward for x4 / x8 heads (default; training plans only together with pvsr_set_tail_rank1(1)),
+ * 0 = conv + shuffle + conv (A/B switch; env PVSR_TAIL_FWD). */
+int pvsr_set_tail_fwd(int enable);
+int pvsr_get_tail_fwd(void);
 
 /* ---- backward / optimiser ops ---------------------------------------------------------------------------------- */
 /* Adjoint of the ConvLSTM gate math (refine_net.py:258-265) for one cell step over n_img images of H x W:
