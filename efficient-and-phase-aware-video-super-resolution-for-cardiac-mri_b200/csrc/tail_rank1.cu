@@ -24,6 +24,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "simt.h"
 
@@ -638,6 +639,21 @@ __global__ void __launch_bounds__(256) tail_fwd_edge_kernel(const __nv_bfloat16*
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
+// Measured on B200 (profiles/r02/README.md, stress_train.py): with the two-branch training schedule the graph hung
+// after 20-30 replays as soon as these mma.sync kernels could share an SM with a CTA of a tcgen05 kernel (wgrad_tc_kernel:
+// 193 KB of shared memory leaves room for one 23 KB block); the SIMT kernels that shared SMs with it before (gate adjoint,
+// stencils) never did, and neither form hangs alone.  The mma.sync kernels therefore ask for kTailExclusiveSmem bytes
+// of (unused) dynamic shared memory: 23 KB + 16 KB + 193 KB does not fit one SM, so they only ever run on SMs without
+// a tcgen05 CTA.  PVSR_TAIL_EXCLUSIVE=0 removes the padding (reproduces the hang).
+constexpr int kTailExclusiveSmem = 16 * 1024;
+static int tail_pad_bytes() {
+  static int pad = -1;
+  if (pad < 0) {
+    const char* e = getenv("PVSR_TAIL_EXCLUSIVE");
+    pad = (e && e[0] == '0') ? 0 : kTailExclusiveSmem;
+  }
+  return pad;
+}
 // scratch layout (floats): U [16][64][64] | S [64][64] | E [8][64][64] | Gs [64] | UT bf16 [64][64]
 constexpr size_t kTailU = 0, kTailS = kTailU + 16 * kNO * 64, kTailE = kTailS + kNO * 64, kTailG = kTailE + 8 * kNO * 64,
                  kTailUT = kTailG + kNO, kTailFloats = kTailUT + kNO * 64 / 2;
@@ -663,7 +679,7 @@ int launch_tail_dx(const float* g, const void* scratch, void* dx_bf16, long long
   const long long total = n_img * tiles_x * tiles_y;
   if (total >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
   const long long cap = 4LL * (num_sms > 0 ? num_sms : 148);
-  tail_dx_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, 0, s>>>(
+  tail_dx_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, tail_pad_bytes(), s>>>(
       g, reinterpret_cast<const __nv_bfloat16*>(f + kTailUT), static_cast<__nv_bfloat16*>(dx_bf16), static_cast<int>(n_img),
       H1, W1, tiles_x, tiles_y);
   int e = static_cast<int>(cudaGetLastError());
@@ -683,7 +699,7 @@ int launch_tail_corr(const float* g, const void* x_bf16, void* scratch, long lon
   const long long total = n_img * tiles_x * tiles_y;
   if (total >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
   const long long cap = 2LL * (num_sms > 0 ? num_sms : 148);
-  tail_corr_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, 0, s>>>(
+  tail_corr_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, tail_pad_bytes(), s>>>(
       g, static_cast<const __nv_bfloat16*>(x_bf16), f + kTailS, f + kTailG, static_cast<int>(n_img), H1, W1, tiles_x,
       tiles_y);
   int e = static_cast<int>(cudaGetLastError());
