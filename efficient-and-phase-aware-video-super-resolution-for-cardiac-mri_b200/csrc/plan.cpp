@@ -31,6 +31,8 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -263,6 +265,21 @@ float* job_grad(int kind, int a, int b, const pvsr_net_grads* G, bool bias) {
   return nullptr;
 }
 
+// ------------------------------------------------------------------------------------------------ launch trace
+// PVSR_TRACE_LAUNCH=1 (debug aid): every launch of an eager schedule run is followed by an event on its stream;
+// pvsr_debug_dump_trace() then reports, per branch, the first launch that has not completed (hang hunting).
+struct TraceEntry { cudaEvent_t ev; int cls, seq, side, bwd; };
+std::vector<TraceEntry> g_trace;
+bool trace_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("PVSR_TRACE_LAUNCH"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+bool env_flag(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '1';
+}
+
 // ------------------------------------------------------------------------------------------------ launch context
 struct Ctx {
   pvsr_plan* p;
@@ -289,6 +306,7 @@ struct Ctx {
   cudaStream_t main = nullptr, side = nullptr;
   int ev_next = 0;
   bool on_side = false;
+  int trace_seq = 0, trace_bwd = 0;
 
   cudaEvent_t next_event() {
     if (ev_next >= static_cast<int>(p->ev_pool.size())) {
@@ -339,6 +357,18 @@ struct Ctx {
     if (dry) {
       cnt_launches[cls] += 1;
       cnt_flops[cls] += fl;
+    }
+    if (!dry && trace_enabled()) {
+      cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(stream, &st);
+      if (st == cudaStreamCaptureStatusNone) {
+        TraceEntry t{};
+        cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming);
+        cudaEventRecord(t.ev, stream);
+        t.cls = cls; t.seq = trace_seq; t.side = on_side ? 1 : 0; t.bwd = trace_bwd;
+        g_trace.push_back(t);
+      }
+      ++trace_seq;
     }
     if (events && !dry) {
       cudaEvent_t e;
@@ -704,6 +734,7 @@ void schedule_backward(Ctx& c) {
     if (tail) {
       // d(input of the last 64 -> 256 conv) straight from dL/d(out); the correlation sums on the side branch
       const double tail_fl = 2.0 * 9 * kFeat * (kFeat * 4) * p->ps_h[last] * p->ps_w[last] * 3.0 * TB;   // algorithmic
+      if (env_flag("PVSR_TAIL_DX_DRAIN")) c.main_wait(c.side_mark());
       c.begin(BCLS_HEAD_DGRAD);
       if (!c.dry && !c.rc) {
         int e = launch_tail_dx(dout_s, tail_ws, c.ws + p->off_dhead[last - 1], 3 * TB, p->ps_h[last], p->ps_w[last],
@@ -711,7 +742,7 @@ void schedule_backward(Ctx& c) {
         if (e) c.rc = check_cuda(e, "tail_dx launch");
       }
       c.end(BCLS_HEAD_DGRAD, tail_fl);
-      c.to_side();
+      if (!env_flag("PVSR_TAIL_CORR_MAIN")) c.to_side();
       c.begin(BCLS_HEAD_WGRAD);
       if (!c.dry && !c.rc) {
         const uint8_t* x_last = c.ws + p->off_head[last - 1] + static_cast<size_t>(3 * s) * p->head_stride[last - 1];
@@ -1184,6 +1215,28 @@ static int run_or_replay(pvsr_plan* p, const GraphKey& key, int use_graph, cudaS
 
 extern "C" {
 
+int pvsr_debug_dump_trace(void) {
+  int first[2][2] = {{-1, -1}, {-1, -1}}, done = 0;
+  for (size_t i = 0; i < g_trace.size(); ++i) {
+    const TraceEntry& t = g_trace[i];
+    if (cudaEventQuery(t.ev) == cudaSuccess) { ++done; continue; }
+    if (first[t.bwd][t.side] < 0) first[t.bwd][t.side] = static_cast<int>(i);
+  }
+  fprintf(stderr, "[pvsr trace] %zu launches recorded, %d complete\n", g_trace.size(), done);
+  for (int b = 0; b < 2; ++b)
+    for (int sd = 0; sd < 2; ++sd)
+      if (first[b][sd] >= 0) {
+        const TraceEntry& t = g_trace[first[b][sd]];
+        fprintf(stderr, "[pvsr trace] first incomplete: %s schedule, %s branch, launch #%d, class %d\n",
+                b ? "backward" : "forward", sd ? "side" : "main", t.seq, t.cls);
+      }
+  return 0;
+}
+void pvsr_debug_clear_trace(void) {
+  for (auto& t : g_trace) cudaEventDestroy(t.ev);
+  g_trace.clear();
+}
+
 int pvsr_plan_create(const pvsr_net_config* cfg, pvsr_plan** out) {
   if (!cfg || !out) return set_error(-2, "null argument");
   if (cfg->scale != 2 && cfg->scale != 3 && cfg->scale != 4 && cfg->scale != 8)
@@ -1597,6 +1650,7 @@ static int backward_eager(pvsr_plan* p, const pvsr_net_params* P, const void* pa
   Ctx c = make_ctx(p, P, packed, lr, pos, ws, s, side, ev, ev_cls);
   c.dout = dout; c.G = G;
   c.cnt_launches = p->launches_bwd; c.cnt_flops = p->flops_bwd;
+  c.trace_bwd = 1;
   schedule_backward(c);
   return c.rc;
 }

@@ -108,6 +108,8 @@ SIGNATURES = {
     "pvsr_get_tail_rank1": (c_int, []),
     "pvsr_head_tail_scratch_bytes": (c_int64, []),
     "pvsr_head_tail_bwd": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_void_p]),
+    "pvsr_debug_dump_trace": (c_int, []),
+    "pvsr_debug_clear_trace": (None, []),
     "pvsr_set_tail_fwd": (c_int, [c_int]),
     "pvsr_get_tail_fwd": (c_int, []),
     "pvsr_head_tail_fwd_table_bytes": (c_int64, []),

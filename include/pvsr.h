@@ -70,6 +70,12 @@ int pvsr_get_two_branch(void);
 int pvsr_set_head_tma(int enable);
 int pvsr_get_head_tma(void);
 
+/* Debug aid (env PVSR_TRACE_LAUNCH=1): every launch of an EAGER plan run is followed by an event on its stream;
+ * pvsr_debug_dump_trace() prints (stderr) the first launch of each branch that has not completed - callable from a
+ * watchdog thread while the device hangs.  pvsr_debug_clear_trace() forgets the recorded launches. */
+int pvsr_debug_dump_trace(void);
+void pvsr_debug_clear_trace(void);
+
 /* ---- host-side packing logic (pure CPU; usable without a GPU) ------------------------------------------------ */
 /* Tile choice of the implicit GEMM: tile = (128 >> tw_log2) x (1 << tw_log2) output pixels. */
 int pvsr_choose_tile(int H, int W, int* tw_log2_out);

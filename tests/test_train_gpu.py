@@ -511,4 +511,5 @@ def test_tail_rank1_equals_conv_by_conv_backward(pvsr_lib, name):
         if float(b.abs().sum()) == 0.0:
             assert float(a.abs().sum()) == 0.0, k
             continue
-        assert rel_l2(a, b) < 1.5e-2 and cosine(a, b) > 0.9998, (k, rel_l2(a, b), cosine(a, b))
+        # two bf16 evaluation orders of the same gradient: the gates of the oracle comparison apply to their difference
+        assert rel_l2(a, b) < GRAD_REL_L2 and cosine(a, b) > GRAD_COS, (k, rel_l2(a, b), cosine(a, b))
