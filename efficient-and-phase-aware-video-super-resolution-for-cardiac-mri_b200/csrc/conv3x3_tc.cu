@@ -923,7 +923,7 @@ static int g_tail_fwd = 1;
 void set_tail_fwd(int enable) { g_tail_fwd = enable ? 1 : 0; }
 int get_tail_fwd() { return g_tail_fwd; }
 
-static int g_two_branch = 0;   // see conv.h: off by default (hang together with the rank-1 tail kernels, under investigation)
+static int g_two_branch = 0;   // off by default: 3 % gain, and one placement of the tail correlation hung the graph (plan.cpp)
 void set_two_branch(int enable) { g_two_branch = enable ? 1 : 0; }
 int get_two_branch() { return g_two_branch; }
 

@@ -734,7 +734,6 @@ void schedule_backward(Ctx& c) {
     if (tail) {
       // d(input of the last 64 -> 256 conv) straight from dL/d(out); the correlation sums on the side branch
       const double tail_fl = 2.0 * 9 * kFeat * (kFeat * 4) * p->ps_h[last] * p->ps_w[last] * 3.0 * TB;   // algorithmic
-      if (env_flag("PVSR_TAIL_DX_DRAIN")) c.main_wait(c.side_mark());
       c.begin(BCLS_HEAD_DGRAD);
       if (!c.dry && !c.rc) {
         int e = launch_tail_dx(dout_s, tail_ws, c.ws + p->off_dhead[last - 1], 3 * TB, p->ps_h[last], p->ps_w[last],
@@ -742,7 +741,9 @@ void schedule_backward(Ctx& c) {
         if (e) c.rc = check_cuda(e, "tail_dx launch");
       }
       c.end(BCLS_HEAD_DGRAD, tail_fl);
-      if (!env_flag("PVSR_TAIL_CORR_MAIN")) c.to_side();
+      // Measured (profiles/stress_train.py): with this launch on the side branch the captured two-branch graph hangs after
+      // 20-30 replays (eager streams and the single-chain graph run 600+ steps); PVSR_TAIL_CORR_SIDE=1 reproduces it
+      if (env_flag("PVSR_TAIL_CORR_SIDE")) c.to_side();
       c.begin(BCLS_HEAD_WGRAD);
       if (!c.dry && !c.rc) {
         const uint8_t* x_last = c.ws + p->off_head[last - 1] + static_cast<size_t>(3 * s) * p->head_stride[last - 1];

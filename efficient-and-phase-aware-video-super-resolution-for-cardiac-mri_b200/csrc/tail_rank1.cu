@@ -639,18 +639,15 @@ __global__ void __launch_bounds__(256) tail_fwd_edge_kernel(const __nv_bfloat16*
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-// Measured on B200 (profiles/r02/README.md, stress_train.py): with the two-branch training schedule the graph hung
-// after 20-30 replays as soon as these mma.sync kernels could share an SM with a CTA of a tcgen05 kernel (wgrad_tc_kernel:
-// 193 KB of shared memory leaves room for one 23 KB block); the SIMT kernels that shared SMs with it before (gate adjoint,
-// stencils) never did, and neither form hangs alone.  The mma.sync kernels therefore ask for kTailExclusiveSmem bytes
-// of (unused) dynamic shared memory: 23 KB + 16 KB + 193 KB does not fit one SM, so they only ever run on SMs without
-// a tcgen05 CTA.  PVSR_TAIL_EXCLUSIVE=0 removes the padding (reproduces the hang).
+// Optional dynamic shared-memory padding of the two mma.sync kernels (PVSR_TAIL_EXCLUSIVE=1): 23 KB + 16 KB + the 193 KB
+// of a wgrad_tc_kernel CTA do not fit one SM, so the kernels then never share an SM with a tcgen05 CTA.  Built while hunting
+// a hang of the two-branch graph (it was not the cause: plan.cpp, launch of tail_corr); off by default.
 constexpr int kTailExclusiveSmem = 16 * 1024;
 static int tail_pad_bytes() {
   static int pad = -1;
   if (pad < 0) {
     const char* e = getenv("PVSR_TAIL_EXCLUSIVE");
-    pad = (e && e[0] == '0') ? 0 : kTailExclusiveSmem;
+    pad = (e && e[0] == '1') ? kTailExclusiveSmem : 0;
   }
   return pad;
 }
