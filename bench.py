@@ -739,7 +739,10 @@ def main():
             line["train_step"] = {k: train_res[k] for k in ("metric", "value", "unit", "ms_per_step", "steps_per_s",
                                                             "n_gpus", "config", "e2e", "allreduce",
                                                             "algorithmic_tflop_per_step_per_gpu",
-                                                            "whole_step_tflops_per_gpu", "kernel_ms_per_step",
+                                                            "whole_step_tflops_per_gpu",
+                                                            "executed_tflop_per_step_per_gpu",
+                                                            "executed_tflops_per_gpu", "flop_accounting",
+                                                            "kernel_ms_per_step",
                                                             "kernel_tflops", "loss") if k in train_res}
             if "parity" in train_res:
                 line["train_step"]["parity"] = train_res["parity"]
