@@ -919,8 +919,8 @@ static int g_tail_rank1 = 1;
 void set_tail_rank1(int enable) { g_tail_rank1 = enable ? 1 : 0; }
 int get_tail_rank1() { return g_tail_rank1; }
 
-static int g_tail_fwd = 1;
-void set_tail_fwd(int enable) { g_tail_fwd = enable ? 1 : 0; }
+static int g_tail_fwd = 2;   // 0: conv + shuffle + conv, 1: composite 5x5 conv on mma.sync, 2: 36-channel tcgen05 conv + gather
+void set_tail_fwd(int mode) { g_tail_fwd = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 int get_tail_fwd() { return g_tail_fwd; }
 
 static int g_two_branch = 0;   // off by default: 3 % gain, and one placement of the tail correlation hung the graph (plan.cpp)
@@ -936,6 +936,7 @@ int launch_conv3x3(int bn, int epi, const ConvMaps& maps, const ConvParams& p, i
   if (epi == EPI_LSTM && bn == 256) return launch_cg<256, EPI_LSTM>(maps, p, num_sms, stream);
   if (epi == EPI_STORE) {
     switch (bn) {
+      case 48: return launch_cg<48, EPI_STORE>(maps, p, num_sms, stream);
       case 64: return launch_cg<64, EPI_STORE>(maps, p, num_sms, stream);
       case 144: return launch_cg<144, EPI_STORE>(maps, p, num_sms, stream);
       case 256: return launch_cg<256, EPI_STORE>(maps, p, num_sms, stream);

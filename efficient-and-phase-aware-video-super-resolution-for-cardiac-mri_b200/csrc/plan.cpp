@@ -124,6 +124,9 @@ struct pvsr_plan {
   // the backward pass scatters every packed gradient the same way.  Used when no job needs a second index.
   size_t pk_table = 0, pk_sc_table = 0;
   size_t pk_tail_fwd = 0;               // tables of the composite forward of the head's tail (tail_rank1.cu)
+  size_t pk_t36_w = 0, pk_t36_b = 0;    // 36-channel form: packed operand [9][48][64] bf16, bias fp32 [48]
+  size_t off_t36 = 0;                   // workspace: B fp32 [T*B images][H1][W1][48] of one list
+  ConvMaps maps_t36;
   bool table_ok = false;
   const void* table_key = nullptr;      // hash of the parameter pointers the uploaded pack table was built for
   const void* sc_table_key = nullptr;   // same for the scatter table (gradient pointers)
@@ -601,6 +604,34 @@ void schedule(Ctx& c) {
       // Training plans keep one head-intermediate slot per list, so the HBM-bound 64 -> 1 conv of list k can run on the
       // side branch underneath the tensor-bound launches that follow (next list's head convs, next stage's ConvLSTM).
       if (p->train) c.to_side();
+      if (tailf && get_tail_fwd() == 2) {
+        // 36-channel form: one N = 48 tcgen05 launch (fp32 B tile store) + the 9-tap gather
+        const int last = p->n_ps - 1;
+        const double fl = (2.0 * 9 * kFeat * (kFeat * 4) * p->ps_h[last] * p->ps_w[last] +
+                           2.0 * 9 * kFeat * static_cast<double>(p->Hs) * p->Ws) * n_head;              // algorithmic FLOPs
+        float* Bbuf = reinterpret_cast<float*>(c.ws + p->off_t36);
+        ConvParams cp;
+        base_params(last == 0 ? p->lr : p->ps_tile[last], p->ps_h[last], p->ps_w[last], &cp);
+        cp.n_img = static_cast<int>(n_head);
+        cp.n_prob = 1;
+        cp.n_total = 48; cp.n_store = 48; cp.out_ch = 48;
+        ConvProblem& pr = cp.prob[0];
+        pr.n_src = 1;
+        pr.src[0] = view0(static_cast<long long>(lslot) * n_head);
+        pr.bias = reinterpret_cast<const float*>(c.pk + p->pk_t36_b);
+        pr.out_f32 = Bbuf;
+        set_slab(&cp, p->geo_ps[last]);
+        run_conv(c, CLS_HEAD_PS, 48, EPI_STORE, p->maps_t36, cp, fl);
+        c.begin(CLS_HEAD_LAST);
+        if (!c.dry && !c.rc) {
+          float* o = c.out + static_cast<size_t>(list) * T * B * p->Hs * p->Ws;
+          int e = launch_tail36_gather(Bbuf, c.P->head_b[p->n_ps], o, n_head, p->ps_h[last], p->ps_w[last], c.stream);
+          if (e) c.rc = check_cuda(e, "tail36 gather launch");
+        }
+        c.end(CLS_HEAD_LAST, 0.0);
+        c.to_main();
+        continue;
+      }
       if (tailf) {
         const int last = p->n_ps - 1;
         c.begin(CLS_HEAD_PS);
@@ -1027,6 +1058,10 @@ int build_maps(pvsr_plan* p, const void* ws, const void* pk) {
   if (p->cfg.pos_enc) rc |= make_weight_tmap(&p->maps_c2.w, k + p->pk_c2_w, p->c2_rows, 64);
   for (int q = 0; q < p->n_ps; ++q)
     rc |= make_weight_tmap(&p->maps_head[q].w, k + p->pk_head_w[q], p->head_rows[q], p->ps_bn[q]);
+  if (p->n_ps >= 2 && p->ps_r[p->n_ps - 1] == 2) {
+    p->maps_t36.act[0] = p->maps_head[p->n_ps - 1].act[0];      // the input of the last shuffle conv
+    rc |= make_weight_tmap(&p->maps_t36.w, k + p->pk_t36_w, 9LL * 48, 48);
+  }
 
   if (p->train) {
     const int n_pad = p->T + 2 * p->half;
@@ -1485,6 +1520,10 @@ int pvsr_plan_create(const pvsr_net_config* cfg, pvsr_plan** out) {
     build_wg_jobs(p);
     p->off_jobs = off; off = align_up(off + p->wg_jobs.size() * sizeof(WgJob), 1024);
   }
+  if (p->n_ps >= 2 && p->ps_r[p->n_ps - 1] == 2) {
+    p->off_t36 = off;
+    off = align_up(off + static_cast<size_t>(TB) * p->ps_h[p->n_ps - 1] * p->ps_w[p->n_ps - 1] * 48 * 4, 1024);
+  }
   p->ws_bytes = off;
   p->pk_idx = pk;
   pk = align_up(pk + p->idx_host.size() * 4, 1024);
@@ -1494,6 +1533,8 @@ int pvsr_plan_create(const pvsr_net_config* cfg, pvsr_plan** out) {
   p->pk_table = pk; pk = align_up(pk + p->jobs.size() * sizeof(pvsr_table_job), 1024);
   p->pk_sc_table = pk; pk = align_up(pk + (p->sc_jobs.size() + 1) * sizeof(pvsr_table_job), 1024);
   p->pk_tail_fwd = pk; pk = align_up(pk + tail_fwd_table_bytes(), 1024);
+  p->pk_t36_w = pk; pk = align_up(pk + tail36_weight_bytes(), 1024);
+  p->pk_t36_b = pk; pk = align_up(pk + 48 * 4, 1024);
   p->pk_bytes = pk;
 
   // ---- accounting via dry runs of the schedules
@@ -1567,6 +1608,9 @@ static int pack_tail_tables(pvsr_plan* p, const pvsr_net_params* P, uint8_t* pk,
   const int last = p->n_ps - 1;
   if (!P->head_w[last] || !P->head_b[last] || !P->head_w[p->n_ps] || !P->head_b[p->n_ps])
     return set_error(-4, "missing head parameter pointer");
+  int e = launch_tail36_weights(P->head_w[last], P->head_b[last], P->head_w[p->n_ps], pk + p->pk_t36_w,
+                                reinterpret_cast<float*>(pk + p->pk_t36_b), s);
+  if (e) return check_cuda(e, "tail36 weights");
   return check_cuda(launch_tail_fwd_tables(P->head_w[last], P->head_b[last], P->head_w[p->n_ps], P->head_b[p->n_ps],
                                            pk + p->pk_tail_fwd, s), "tail forward tables");
 }

@@ -638,6 +638,65 @@ __global__ void __launch_bounds__(256) tail_fwd_edge_kernel(const __nv_bfloat16*
   }
 }
 
+// ================================================================================================
+// FORWARD, 36-channel form (tcgen05).  The same composite as above, factored the other way round:
+//     B[z'][(q',t)] = bias36[(q',t)] + sum_{t',ci} Wc[t'][(q',t)][ci] X[z'+t'][ci]       (a 3x3 conv 64 -> 36 channels)
+//     Wc[t'][(q',t)][ci] = sum_c w3[c][t] W2[(c,q')][ci][t'],   bias36[(q',t)] = sum_c w3[c][t] b2[(c,q')]
+//     out[p] = b3 + sum over taps t with p + t = 2 z' + q' inside the HR image of B[z'][(q',t)]
+// B[z'][(q',t)] is what HR position 2z'+q' of the (never materialised) 64-channel map contributes to output pixel
+// 2z'+q'-t.  The zero padding of that map is simply "positions outside the image contribute nothing", so there are NO
+// border classes, and the conv is an ordinary N = 48 launch of conv3x3_halo_kernel (weights resident, 41.5 kFLOP per
+// pixel on the tensor cores instead of the 25.6 k of the mma.sync form - but at tcgen05 rate, without re-reading the tile
+// from shared memory per tap).  The 9-tap gather that follows reads 144 B and writes 16 B per input pixel.
+__global__ void __launch_bounds__(256) tail36_weights_kernel(const float* __restrict__ W2, const float* __restrict__ b2,
+                                                             const float* __restrict__ w3, __nv_bfloat16* __restrict__ Wc,
+                                                             float* __restrict__ bias48) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 48) {
+    float s = 0.f;
+    if (i < 36) {
+      const int qp = i / 9, t = i % 9;
+      for (int c = 0; c < 64; ++c) s = fmaf(w3[c * 9 + t], b2[c * 4 + qp], s);
+    }
+    bias48[i] = s;
+  }
+  if (i >= 9 * 48 * 64) return;
+  const int ci = i & 63, n = (i >> 6) % 48, tp = i / (64 * 48);
+  float s = 0.f;
+  if (n < 36) {
+    const int qp = n / 9, t = n % 9;
+    for (int c = 0; c < 64; ++c) s = fmaf(__ldg(w3 + c * 9 + t), __ldg(W2 + (static_cast<size_t>(c * 4 + qp) * 64 + ci) * 9 + tp), s);
+  }
+  Wc[i] = __float2bfloat16(s);          // packed operand layout: [K block = tap t'][N = 48][64 channels]
+}
+
+// out[img][py][px] = b3 + sum_t B[z'][(q',t)],  (2 z' + q') = (py, px) + t inside the HR image.  Thread = HR pixel.
+__global__ void __launch_bounds__(256) tail36_gather_kernel(const float* __restrict__ B, const float* __restrict__ b3,
+                                                            float* __restrict__ out, long long n_px, int H1, int W1) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  const int Hs = 2 * H1, Ws = 2 * W1;
+  const int px = static_cast<int>(i % Ws);
+  const long long r = i / Ws;
+  const int py = static_cast<int>(r % Hs);
+  const long long img = r / Hs;
+  const float* Bimg = B + static_cast<size_t>(img) * H1 * W1 * 48;
+  float s = b3[0];
+#pragma unroll
+  for (int ty = -1; ty <= 1; ++ty) {
+    const int y = py + ty;
+    if (y < 0 || y >= Hs) continue;
+#pragma unroll
+    for (int tx = -1; tx <= 1; ++tx) {
+      const int x = px + tx;
+      if (x < 0 || x >= Ws) continue;
+      const int n = ((y & 1) * 2 + (x & 1)) * 9 + (ty + 1) * 3 + (tx + 1);
+      s += __ldg(Bimg + (static_cast<size_t>(y >> 1) * W1 + (x >> 1)) * 48 + n);
+    }
+  }
+  out[i] = s;
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 // Optional dynamic shared-memory padding of the two mma.sync kernels (PVSR_TAIL_EXCLUSIVE=1): 23 KB + 16 KB + the 193 KB
 // of a wgrad_tc_kernel CTA do not fit one SM, so the kernels then never share an SM with a tcgen05 CTA.  Built while hunting
@@ -755,6 +814,19 @@ int launch_tail_fwd(const void* x_bf16, const void* tables, float* out, long lon
   tail_fwd_edge_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(
       static_cast<const __nv_bfloat16*>(x_bf16), reinterpret_cast<const float*>(t + kTailFwdKf),
       reinterpret_cast<const float*>(t + kTailFwdBias), out, n_img, H1, W1);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// 36-channel forward: packed operand bf16 [9][48][64] | bias fp32 [48] (inside the plan's packed-parameter buffer)
+size_t tail36_weight_bytes() { return 9 * 48 * 64 * 2; }
+int launch_tail36_weights(const float* W2, const float* b2, const float* w3, void* wc_bf16, float* bias48, cudaStream_t s) {
+  tail36_weights_kernel<<<(9 * 48 * 64 + 255) / 256, 256, 0, s>>>(W2, b2, w3, static_cast<__nv_bfloat16*>(wc_bf16), bias48);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_tail36_gather(const float* B, const float* b3, float* out, long long n_img, int H1, int W1, cudaStream_t s) {
+  const long long n_px = n_img * 4 * H1 * W1;
+  if (n_px <= 0) return 0;
+  tail36_gather_kernel<<<static_cast<unsigned>((n_px + 255) / 256), 256, 0, s>>>(B, b3, out, n_px, H1, W1);
   return static_cast<int>(cudaGetLastError());
 }
 

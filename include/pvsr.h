@@ -325,8 +325,9 @@ int64_t pvsr_head_tail_fwd_table_bytes(void);
 int pvsr_head_tail_fwd_tables(const float* w2, const float* b2, const float* w3, const float* b3, void* tables,
                               void* stream);
 int pvsr_head_tail_fwd(const void* x_bf16, const void* tables, float* out, int64_t n_img, int H1, int W1, void* stream);
-/* Plans: 1 = composite forward for x4 / x8 heads (default; training plans only together with pvsr_set_tail_rank1(1)),
- * 0 = conv + shuffle + conv (A/B switch; env PVSR_TAIL_FWD). */
+/* Plans, x4 / x8 heads (training plans only together with pvsr_set_tail_rank1(1)): 2 = the composite as a 64 -> 36
+ * channel tcgen05 conv (B[z'][(q',t)] = what HR position 2z'+q' contributes to output pixel 2z'+q'-t) + a 9-tap gather
+ * (default), 1 = the 5x5 composite on mma.sync above, 0 = conv + shuffle + conv (A/B switch; env PVSR_TAIL_FWD). */
 int pvsr_set_tail_fwd(int enable);
 int pvsr_get_tail_fwd(void);
 

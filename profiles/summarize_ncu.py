@@ -10,7 +10,10 @@ PAT = ("gpu__time_duration.sum", "dram__bytes_read.sum ", "dram__bytes_write.sum
        "sm__inst_executed_pipe_tensor", "sm__warps_active.avg.pct_of_peak_sustained_active",
        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "sm__throughput.avg.pct",
        "sm__cycles_elapsed.avg ", "sm__cycles_active.avg ", "lts__t_bytes.sum ", "smsp__inst_executed.sum ",
-       "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum ")
+       "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum ",
+       "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "lts__t_sectors.sum ",
+       "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "launch__shared_mem_per_block_static",
+       "launch__occupancy_limit", "sm__inst_executed_pipe_tensor_op_hmma.sum ")
 
 
 def main(path):
