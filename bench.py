@@ -278,24 +278,31 @@ TRAIN_N, TRAIN_T, TRAIN_HW = 16, 7, 32     # configs/train/refine_net/exp1_x4.ya
 
 
 def nccl_tuning_lines():
-    """AllReduce algorithm / protocol lines from this process's NCCL log when bench.py itself turned the log on
-    (NCCL_DEBUG unset by the caller -> INFO + TUNING into a private file); [] otherwise."""
+    """What this process's NCCL log says about the gradient all-reduce when bench.py itself turned the log on
+    (NCCL_DEBUG unset by the caller -> INFO + INIT,TUNING into a private file): the tuner's algorithm / protocol lines
+    when NCCL prints them, else the transport summary of the communicator (NVLS / P2P channels, init line); [] otherwise."""
+    import re
     path = os.environ.get("PVSR_NCCL_LOG")
     if not path:
         return []
     path = path.replace("%p", str(os.getpid()))
     try:
         with open(path) as f:
-            lines = [l.strip() for l in f if "AllReduce" in l and ("Algo" in l or "algo" in l)]
+            raw = [l.strip() for l in f]
     except OSError:
         return []
-    seen, out = set(), []
-    for l in lines:
-        key = l.split("NCCL INFO", 1)[-1].strip()
-        if key not in seen:
-            seen.add(key)
-            out.append(key)
-    return out[-4:]
+    def pick(pattern, limit):
+        seen, out = set(), []
+        for l in raw:
+            if re.search(pattern, l):
+                key = re.sub(r"^.*NCCL INFO ", "", l)
+                key = re.sub(r"\b\d+ *-> *\d+\b|\[\d+\]", "", key)
+                if key not in seen:
+                    seen.add(key)
+                    out.append(re.sub(r"^.*NCCL INFO ", "", l))
+        return out[-limit:]
+    tuned = pick(r"(?i)allreduce.*(algo|proto)|algo.*proto", 4)
+    return tuned if tuned else pick(r"(?i)nvls|via P2P|Init COMPLETE|nChannels|Connected all", 5)
 
 
 def tail_flop_saving(n_pixels_r1, backward):
