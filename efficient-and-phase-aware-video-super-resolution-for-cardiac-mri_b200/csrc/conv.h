@@ -111,10 +111,6 @@ int get_pack_table();
 void set_tail_rank1(int enable);
 int get_tail_rank1();
 
-// Data gradient of the head's tail: 2 = tcgen05 conv of the gathered loss gradient (default), 1 = mma.sync stencil.
-void set_tail_dx_mode(int mode);
-int get_tail_dx_mode();
-
 // Composite forward of the head's tail (tail_rank1.cu: one 64 -> 4 channel 5x5 conv instead of conv + shuffle + conv).
 void set_tail_fwd(int enable);
 int get_tail_fwd();

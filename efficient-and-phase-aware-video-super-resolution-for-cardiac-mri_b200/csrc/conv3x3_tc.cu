@@ -9,8 +9,6 @@
 //
 // Reference semantics reproduced (file:line in /root/reference/src/model/nets/refine_net.py):
 //   ConvLSTMCell.forward 247-267 (EPI_LSTM), _RefineBlock.body 147-155 (EPI_STORE), _OutBlock 194-205 (EPI_PS).
-#include <stdlib.h>
-
 #include "conv.h"
 #include "ptx.cuh"
 
@@ -920,18 +918,6 @@ int get_pack_table() { return g_pack_table; }
 static int g_tail_rank1 = 1;
 void set_tail_rank1(int enable) { g_tail_rank1 = enable ? 1 : 0; }
 int get_tail_rank1() { return g_tail_rank1; }
-
-static int g_tail_dx = 2;
-void set_tail_dx_mode(int mode) { g_tail_dx = mode == 1 ? 1 : 2; }
-int get_tail_dx_mode() {
-  static bool init = false;
-  if (!init) {
-    const char* e = getenv("PVSR_TAIL_DX");
-    if (e && e[0] == '1') g_tail_dx = 1;
-    init = true;
-  }
-  return g_tail_dx;
-}
 
 static int g_tail_fwd = 2;   // 0: conv + shuffle + conv, 1: composite 5x5 conv on mma.sync, 2: 36-channel tcgen05 conv + gather
 void set_tail_fwd(int mode) { g_tail_fwd = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }

@@ -125,9 +125,6 @@ struct pvsr_plan {
   size_t pk_table = 0, pk_sc_table = 0;
   size_t pk_tail_fwd = 0;               // tables of the composite forward of the head's tail (tail_rank1.cu)
   size_t pk_t36_w = 0, pk_t36_b = 0;    // 36-channel form: packed operand [9][48][64] bf16, bias fp32 [48]
-  size_t pk_t36_dg = 0;                 // its data-gradient operand [2][9][64][64] bf16 (training plans)
-  size_t off_t36_db = 0;                // workspace: dB bf16 [2 (hi, lo)][3*T*B images][H1][W1][64]
-  ConvMaps bm_t36_dg;
   size_t off_t36 = 0;                   // workspace: B fp32 [T*B images][H1][W1][48] of one list
   ConvMaps maps_t36;
   bool table_ok = false;
@@ -768,33 +765,13 @@ void schedule_backward(Ctx& c) {
     if (tail) {
       // d(input of the last 64 -> 256 conv) straight from dL/d(out); the correlation sums on the side branch
       const double tail_fl = 2.0 * 9 * kFeat * (kFeat * 4) * p->ps_h[last] * p->ps_w[last] * 3.0 * TB;   // algorithmic
-      if (get_tail_dx_mode() == 2) {
-        // tcgen05 form: dB = gather of the loss gradient (bf16 hi | lo), then the 3x3 data-gradient conv of the composite
-        run_simt(c, BCLS_HEAD_DGRAD, "tail36 dB", [&] {
-          return launch_tail36_db(dout_s, c.ws + p->off_t36_db, 3 * TB, p->ps_h[last], p->ps_w[last], c.stream);
-        });
-        ConvParams cp;
-        base_params(p->ps_tile[last], p->ps_h[last], p->ps_w[last], &cp);
-        cp.n_img = static_cast<int>(3 * TB);
-        cp.n_prob = 1;
-        cp.k16_last = 3;                                  // 48 of the 64 channels of a K block (36 real)
-        cp.n_total = 64; cp.n_store = 64; cp.out_ch = 64;
-        ConvProblem& pr = cp.prob[0];
-        pr.n_src = 2;
-        pr.src[0] = view0(0);
-        pr.src[1] = view0(3 * TB);
-        pr.out_bf16 = reinterpret_cast<__nv_bfloat16*>(c.ws + p->off_dhead[last - 1]);
-        set_slab(&cp, p->geo_ps[last]);
-        run_conv(c, BCLS_HEAD_DGRAD, 64, EPI_STORE, p->bm_t36_dg, cp, tail_fl);
-      } else {
-        c.begin(BCLS_HEAD_DGRAD);
-        if (!c.dry && !c.rc) {
-          int e = launch_tail_dx(dout_s, tail_ws, c.ws + p->off_dhead[last - 1], 3 * TB, p->ps_h[last], p->ps_w[last],
-                                 p->num_sms, c.stream);
-          if (e) c.rc = check_cuda(e, "tail_dx launch");
-        }
-        c.end(BCLS_HEAD_DGRAD, tail_fl);
+      c.begin(BCLS_HEAD_DGRAD);
+      if (!c.dry && !c.rc) {
+        int e = launch_tail_dx(dout_s, tail_ws, c.ws + p->off_dhead[last - 1], 3 * TB, p->ps_h[last], p->ps_w[last],
+                               p->num_sms, c.stream);
+        if (e) c.rc = check_cuda(e, "tail_dx launch");
       }
+      c.end(BCLS_HEAD_DGRAD, tail_fl);
       // Measured (profiles/stress_train.py): with this launch on the side branch the captured two-branch graph hangs after
       // 20-30 replays (eager streams and the single-chain graph run 600+ steps); PVSR_TAIL_CORR_SIDE=1 reproduces it
       if (env_flag("PVSR_TAIL_CORR_SIDE")) c.to_side();
@@ -1139,12 +1116,6 @@ int build_maps(pvsr_plan* p, const void* ws, const void* pk) {
         rc |= make_act_tmap(&p->bm_head_wg[q].act[0], w + p->off_head[q - 1], kFeat, p->ps_w[q], p->ps_h[q],
                             static_cast<long long>(p->n_list_slots) * TB, p->bw_tile[q].tw, p->bw_tile[q].th);
       p->bm_head_wg[q].act[1] = tm_dy;
-    }
-    if (p->n_ps >= 2 && p->ps_r[p->n_ps - 1] == 2) {
-      const int last = p->n_ps - 1;
-      rc |= make_act_tmap(&p->bm_t36_dg.act[0], w + p->off_t36_db, kFeat, p->ps_w[last], p->ps_h[last], 2 * 3 * TB,
-                          box_w(p->geo_ps[last], p->ps_tile[last]), box_h(p->geo_ps[last], p->ps_tile[last]));
-      rc |= make_weight_tmap(&p->bm_t36_dg.w, k + p->pk_t36_dg, 2LL * 9 * 64, 64);
     }
   }
   if (rc) return set_error(-20, "tensor map encode failed");
@@ -1552,10 +1523,6 @@ int pvsr_plan_create(const pvsr_net_config* cfg, pvsr_plan** out) {
   if (p->n_ps >= 2 && p->ps_r[p->n_ps - 1] == 2) {
     p->off_t36 = off;
     off = align_up(off + static_cast<size_t>(TB) * p->ps_h[p->n_ps - 1] * p->ps_w[p->n_ps - 1] * 48 * 4, 1024);
-    if (p->train) {
-      p->off_t36_db = off;
-      off = align_up(off + 2 * 3 * static_cast<size_t>(TB) * p->ps_h[p->n_ps - 1] * p->ps_w[p->n_ps - 1] * 64 * 2, 1024);
-    }
   }
   p->ws_bytes = off;
   p->pk_idx = pk;
@@ -1568,7 +1535,6 @@ int pvsr_plan_create(const pvsr_net_config* cfg, pvsr_plan** out) {
   p->pk_tail_fwd = pk; pk = align_up(pk + tail_fwd_table_bytes(), 1024);
   p->pk_t36_w = pk; pk = align_up(pk + tail36_weight_bytes(), 1024);
   p->pk_t36_b = pk; pk = align_up(pk + 48 * 4, 1024);
-  p->pk_t36_dg = pk; pk = align_up(pk + tail36_dgrad_weight_bytes(), 1024);
   p->pk_bytes = pk;
 
   // ---- accounting via dry runs of the schedules
@@ -1643,7 +1609,7 @@ static int pack_tail_tables(pvsr_plan* p, const pvsr_net_params* P, uint8_t* pk,
   if (!P->head_w[last] || !P->head_b[last] || !P->head_w[p->n_ps] || !P->head_b[p->n_ps])
     return set_error(-4, "missing head parameter pointer");
   int e = launch_tail36_weights(P->head_w[last], P->head_b[last], P->head_w[p->n_ps], pk + p->pk_t36_w,
-                                reinterpret_cast<float*>(pk + p->pk_t36_b), p->train ? pk + p->pk_t36_dg : nullptr, s);
+                                reinterpret_cast<float*>(pk + p->pk_t36_b), s);
   if (e) return check_cuda(e, "tail36 weights");
   return check_cuda(launch_tail_fwd_tables(P->head_w[last], P->head_b[last], P->head_w[p->n_ps], P->head_b[p->n_ps],
                                            pk + p->pk_tail_fwd, s), "tail forward tables");

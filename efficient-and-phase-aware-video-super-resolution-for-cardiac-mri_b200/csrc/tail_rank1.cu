@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(256) tail_fwd_edge_kernel(const __nv_bfloat16*
 // from shared memory per tap).  The 9-tap gather that follows reads 144 B and writes 16 B per input pixel.
 __global__ void __launch_bounds__(256) tail36_weights_kernel(const float* __restrict__ W2, const float* __restrict__ b2,
                                                              const float* __restrict__ w3, __nv_bfloat16* __restrict__ Wc,
-                                                             float* __restrict__ bias48, __nv_bfloat16* __restrict__ Wd) {
+                                                             float* __restrict__ bias48) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 48) {
     float s = 0.f;
@@ -668,57 +668,6 @@ __global__ void __launch_bounds__(256) tail36_weights_kernel(const float* __rest
     for (int c = 0; c < 64; ++c) s = fmaf(__ldg(w3 + c * 9 + t), __ldg(W2 + (static_cast<size_t>(c * 4 + qp) * 64 + ci) * 9 + tp), s);
   }
   Wc[i] = __float2bfloat16(s);          // packed operand layout: [K block = tap t'][N = 48][64 channels]
-  if (Wd) {
-    // data-gradient operand, one copy per source (hi, lo): [source][K block = tap u = -t'][N = 64 channels ci][64 K = n]
-    const int u = 8 - tp;
-    Wd[(static_cast<size_t>(u) * 64 + ci) * 64 + n] = __float2bfloat16(s);
-    Wd[(static_cast<size_t>(9 + u) * 64 + ci) * 64 + n] = __float2bfloat16(s);
-    if (n < 16) {                       // K columns 48..63 of the block are never multiplied (k16_last = 3) but keep them zero
-      Wd[(static_cast<size_t>(u) * 64 + ci) * 64 + 48 + n] = __float2bfloat16(0.f);
-      Wd[(static_cast<size_t>(9 + u) * 64 + ci) * 64 + 48 + n] = __float2bfloat16(0.f);
-    }
-  }
-}
-
-// BACKWARD of the same factorisation (data gradient): dB[z'][(q',t)] = g[2z'+q'-t] is a pure gather of the loss gradient,
-// and dX = the ordinary 3x3 data-gradient conv of dB with the transposed, tap-flipped composite weights
-// Wd[u][ci][(q',t)] = Wc[-u][(q',t)][ci] - a K = 9 x 48, N = 64 tcgen05 launch instead of the mma.sync stencil
-// (tail_dx_kernel: warp-level mma.sync runs at ~1/16 of the tcgen05 rate on B200).  The fp32 gradient is split into
-// bf16 hi + lo images (two sources of the conv, same weights), so an arbitrary loss gradient keeps ~16 mantissa bits
-// and a constant-magnitude one (L1: +-w_k) is not biased by its bf16 rounding.
-// dB: bf16 NHWC [2 (hi, lo)][n_img][H1][W1][64], channels 36..63 zero.  Thread = (pixel, 8-channel chunk).
-__global__ void __launch_bounds__(256) tail36_db_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ dB,
-                                                        long long n_px, int H1, int W1) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n_px * 8) return;
-  const int ck = static_cast<int>(i & 7);
-  const long long pix = i >> 3;
-  const int zx = static_cast<int>(pix % W1);
-  const long long r = pix / W1;
-  const int zy = static_cast<int>(r % H1);
-  const long long img = r / H1;
-  const int Hs = 2 * H1, Ws = 2 * W1;
-  const float* gimg = g + static_cast<size_t>(img) * Hs * Ws;
-  float v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int n = ck * 8 + j;
-    float x = 0.f;
-    if (n < 36) {
-      const int qp = n / 9, t = n - qp * 9;
-      const int y = 2 * zy + (qp >> 1) - (t / 3 - 1), xx = 2 * zx + (qp & 1) - (t % 3 - 1);
-      if (y >= 0 && y < Hs && xx >= 0 && xx < Ws) x = __ldg(gimg + static_cast<size_t>(y) * Ws + xx);
-    }
-    v[j] = x;
-  }
-  uint32_t hi[4], lo[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    hi[j] = pack_bf2(v[2 * j], v[2 * j + 1]);
-    lo[j] = pack_bf2(v[2 * j] - bf_lo(hi[j]), v[2 * j + 1] - bf_hi(hi[j]));
-  }
-  *reinterpret_cast<uint4*>(dB + pix * 64 + ck * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(dB + (n_px + pix) * 64 + ck * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // out[img][py][px] = b3 + sum_t B[z'][(q',t)],  (2 z' + q') = (py, px) + t inside the HR image.  Thread = HR pixel.
@@ -870,18 +819,8 @@ int launch_tail_fwd(const void* x_bf16, const void* tables, float* out, long lon
 
 // 36-channel forward: packed operand bf16 [9][48][64] | bias fp32 [48] (inside the plan's packed-parameter buffer)
 size_t tail36_weight_bytes() { return 9 * 48 * 64 * 2; }
-size_t tail36_dgrad_weight_bytes() { return 2 * 9 * 64 * 64 * 2; }
-int launch_tail36_weights(const float* W2, const float* b2, const float* w3, void* wc_bf16, float* bias48, void* wd_bf16,
-                          cudaStream_t s) {
-  tail36_weights_kernel<<<(9 * 48 * 64 + 255) / 256, 256, 0, s>>>(W2, b2, w3, static_cast<__nv_bfloat16*>(wc_bf16), bias48,
-                                                                 static_cast<__nv_bfloat16*>(wd_bf16));
-  return static_cast<int>(cudaGetLastError());
-}
-int launch_tail36_db(const float* g, void* db_bf16, long long n_img, int H1, int W1, cudaStream_t s) {
-  const long long n_px = n_img * H1 * W1;
-  if (n_px <= 0) return 0;
-  tail36_db_kernel<<<static_cast<unsigned>((n_px * 8 + 255) / 256), 256, 0, s>>>(g, static_cast<__nv_bfloat16*>(db_bf16), n_px,
-                                                                                H1, W1);
+int launch_tail36_weights(const float* W2, const float* b2, const float* w3, void* wc_bf16, float* bias48, cudaStream_t s) {
+  tail36_weights_kernel<<<(9 * 48 * 64 + 255) / 256, 256, 0, s>>>(W2, b2, w3, static_cast<__nv_bfloat16*>(wc_bf16), bias48);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_tail36_gather(const float* B, const float* b3, float* out, long long n_img, int H1, int W1, cudaStream_t s) {
