@@ -114,6 +114,8 @@ struct pvsr_plan {
   // backward-only regions
   size_t off_gx, off_dh, off_dc, off_dgates, off_gr, off_gm, off_dhead[PVSR_MAX_HEAD_CONVS], off_wg, off_sums, off_jobs;
   size_t off_tail;       // scratch of the rank-1 adjoint of the head's tail (tail_rank1.cu)
+  // pvsr_plan_set_sign_gradient: dL/d(out) of list k is sign_scale[k] * {-1, 0, +1} (fused L1 path); 0 = arbitrary
+  float sign_scale[3 * kMaxStages] = {0};
   size_t dh_stride;      // bytes of one [T*B] stack of fp32 64-channel LR gradient images
   Tiling bw_tile[PVSR_MAX_HEAD_CONVS];   // tiling of the data/weight-gradient launches of head conv q
 
@@ -765,10 +767,12 @@ void schedule_backward(Ctx& c) {
     if (tail) {
       // d(input of the last 64 -> 256 conv) straight from dL/d(out); the correlation sums on the side branch
       const double tail_fl = 2.0 * 9 * kFeat * (kFeat * 4) * p->ps_h[last] * p->ps_w[last] * 3.0 * TB;   // algorithmic
+      const float sgn = (p->sign_scale[3 * s] != 0.f && p->sign_scale[3 * s] == p->sign_scale[3 * s + 1] &&
+                         p->sign_scale[3 * s] == p->sign_scale[3 * s + 2]) ? p->sign_scale[3 * s] : 0.f;
       c.begin(BCLS_HEAD_DGRAD);
       if (!c.dry && !c.rc) {
         int e = launch_tail_dx(dout_s, tail_ws, c.ws + p->off_dhead[last - 1], 3 * TB, p->ps_h[last], p->ps_w[last],
-                               p->num_sms, c.stream);
+                               p->num_sms, c.stream, sgn);
         if (e) c.rc = check_cuda(e, "tail_dx launch");
       }
       c.end(BCLS_HEAD_DGRAD, tail_fl);
@@ -778,7 +782,7 @@ void schedule_backward(Ctx& c) {
       c.begin(BCLS_HEAD_WGRAD);
       if (!c.dry && !c.rc) {
         const uint8_t* x_last = c.ws + p->off_head[last - 1] + static_cast<size_t>(3 * s) * p->head_stride[last - 1];
-        int e = launch_tail_corr(dout_s, x_last, tail_ws, 3 * TB, p->ps_h[last], p->ps_w[last], p->num_sms, c.stream);
+        int e = launch_tail_corr(dout_s, x_last, tail_ws, 3 * TB, p->ps_h[last], p->ps_w[last], p->num_sms, c.stream, sgn);
         if (e) c.rc = check_cuda(e, "tail_corr launch");
       }
       c.end(BCLS_HEAD_WGRAD, tail_fl);
@@ -1566,6 +1570,16 @@ void pvsr_plan_destroy(pvsr_plan* p) {
   delete p;
 }
 
+int pvsr_plan_set_sign_gradient(pvsr_plan* p, const float* scales, int n_lists) {
+  if (!p) return set_error(-2, "null argument");
+  for (float& v : p->sign_scale) v = 0.f;
+  if (scales) {
+    if (n_lists != p->n_lists || n_lists > 3 * kMaxStages) return set_error(-2, "sign-gradient scales: expected %d lists", p->n_lists);
+    for (int k = 0; k < n_lists; ++k) p->sign_scale[k] = scales[k];
+  }
+  return 0;
+}
+
 int64_t pvsr_plan_workspace_bytes(const pvsr_plan* p) { return static_cast<int64_t>(p->ws_bytes); }
 int64_t pvsr_plan_packed_bytes(const pvsr_plan* p) { return static_cast<int64_t>(p->pk_bytes); }
 int64_t pvsr_plan_output_elems(const pvsr_plan* p) {
@@ -1765,7 +1779,7 @@ int pvsr_plan_backward(pvsr_plan* p, const pvsr_net_params* P, const void* packe
   rc = upload_scatter_table(p, packed, G, ws, s);
   if (rc) return rc;
   GraphKey key{{ws, packed, lr, pos, dout, hash_bytes(P, sizeof(*P)), hash_bytes(G, sizeof(*G)),
-                reinterpret_cast<const void*>(1)}};
+                hash_bytes(p->sign_scale, sizeof(p->sign_scale))}};
   return run_or_replay(p, key, use_graph, s, [&](cudaStream_t st, cudaStream_t side) {
     return backward_eager(p, P, packed, lr, pos, dout, G, ws, st, side, nullptr, nullptr);
   });

@@ -60,10 +60,11 @@ int launch_posterm_bwd(const void* g_bf16, const float* pos, float* sums, float*
 size_t tail_scratch_bytes();
 int launch_tail_tables(const float* W2, const float* w3, void* scratch, cudaStream_t s);
 int launch_tail_zero_sums(void* scratch, cudaStream_t s);
+// sign_scale != 0: g is known to be sign_scale * {-1, 0, +1} (fused L1 gradient) - no bf16 lo half, half the MMAs
 int launch_tail_dx(const float* g, const void* scratch, void* dx_bf16, long long n_img, int H1, int W1, int num_sms,
-                   cudaStream_t s);
+                   cudaStream_t s, float sign_scale = 0.f);
 int launch_tail_corr(const float* g, const void* x_bf16, void* scratch, long long n_img, int H1, int W1, int num_sms,
-                     cudaStream_t s);
+                     cudaStream_t s, float sign_scale = 0.f);
 int launch_tail_finish(const void* scratch, const float* W2, const float* b2, const float* w3, float* dW2, float* db2,
                        float* dw3, float* db3, cudaStream_t s);
 // ... and its forward as one composite 64 -> 4 channel 5x5 convolution (tables: tail_fwd_table_bytes() of device memory)

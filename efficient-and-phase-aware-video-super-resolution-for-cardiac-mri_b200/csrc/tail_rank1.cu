@@ -112,9 +112,12 @@ __global__ void __launch_bounds__(256) tail_tables_kernel(const float* __restric
 // an arbitrary fp32 loss gradient keeps ~16 mantissa bits; B = UT held in registers for the life of the block).
 // Warp w of a block owns row y0 + w of an 8 x 16 pixel tile.  The bf16 result tile is staged in shared memory and
 // written with 16-byte stores.  Border pixels are overwritten afterwards by tail_dx_edge_kernel.
+// SIGN = true: the loss gradient is known to be  scale * {-1, 0, +1}  (the fused L1 path: dout = w_k sign(out - target),
+// all three lists of a stage share w_k): its sign is exact in bf16, so the lo half of the split and half of the MMAs go.
+template <bool SIGN>
 __global__ void __launch_bounds__(256, 2) tail_dx_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ UT,
                                                          __nv_bfloat16* __restrict__ dX, int n_img, int H1, int W1,
-                                                         int tiles_x, int tiles_y) {
+                                                         int tiles_x, int tiles_y, float scale) {
   __shared__ __align__(16) float gh[kGhH * kGhPitch];
   __shared__ __align__(16) uint8_t outt[kTH * kTW * kXPitch];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -153,16 +156,26 @@ __global__ void __launch_bounds__(256, 2) tail_dx_kernel(const float* __restrict
       for (int f = 0; f < 4; ++f) {
         const int row = r0 + (f & 1) * 8;          // pixel x0 + row of tile row `warp`
         const int oyi = 2 * ks + (f >> 1);
-        const float2 v = *reinterpret_cast<const float2*>(gh + (2 * warp + oyi) * kGhPitch + 2 * row + c0);
+        float2 v = *reinterpret_cast<const float2*>(gh + (2 * warp + oyi) * kGhPitch + 2 * row + c0);
+        if (SIGN) {
+          v.x = v.x > 0.f ? 1.f : (v.x < 0.f ? -1.f : 0.f);
+          v.y = v.y > 0.f ? 1.f : (v.y < 0.f ? -1.f : 0.f);
+        }
         const uint32_t hi = pack_bf2(v.x, v.y);
         ahi[f] = hi;
-        alo[f] = pack_bf2(v.x - bf_lo(hi), v.y - bf_hi(hi));
+        if (!SIGN) alo[f] = pack_bf2(v.x - bf_lo(hi), v.y - bf_hi(hi));
       }
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         mma16816(acc[nt], ahi, bfrag[ks][nt][0], bfrag[ks][nt][1]);
-        mma16816(acc[nt], alo, bfrag[ks][nt][0], bfrag[ks][nt][1]);
+        if (!SIGN) mma16816(acc[nt], alo, bfrag[ks][nt][0], bfrag[ks][nt][1]);
       }
+    }
+    if (SIGN) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[nt][j] *= scale;
     }
     // stage: pixel (warp, r0 / r0 + 8), channels 8 nt + c0, c0 + 1
 #pragma unroll
@@ -241,9 +254,10 @@ __global__ void __launch_bounds__(256) tail_dx_edge_kernel(const float* __restri
 // tiles; the X tile is staged with cp.async (144-byte pixel pitch), the B operand comes from it via ldmatrix.trans, the A
 // operand (g stencil, bf16 hi + lo) is built from the shared halo.  Warp w accumulates offsets [16 (w % 4), +16) x
 // channels [32 (w / 4), +32) across all tiles of the block; one atomic pass at the end.
+template <bool SIGN>
 __global__ void __launch_bounds__(256, 2) tail_corr_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ X,
                                                            float* __restrict__ S, float* __restrict__ Gs, int n_img,
-                                                           int H1, int W1, int tiles_x, int tiles_y) {
+                                                           int H1, int W1, int tiles_x, int tiles_y, float scale) {
   __shared__ float gh[kGhH * kGhPitch];
   __shared__ __align__(16) uint8_t xt[kTH * kTW * kXPitch];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -298,10 +312,14 @@ __global__ void __launch_bounds__(256, 2) tail_corr_kernel(const float* __restri
         const int oyi = 2 * mt + (f & 1);
         const int zx = c0 + (f >> 1) * 8;
         const float* row = gh + (2 * ks + oyi) * kGhPitch + 2 * zx + r0;
-        const float v0 = row[0], v1 = row[2];
+        float v0 = row[0], v1 = row[2];
+        if (SIGN) {
+          v0 = v0 > 0.f ? 1.f : (v0 < 0.f ? -1.f : 0.f);
+          v1 = v1 > 0.f ? 1.f : (v1 < 0.f ? -1.f : 0.f);
+        }
         const uint32_t hi = pack_bf2(v0, v1);
         ahi[f] = hi;
-        alo[f] = pack_bf2(v0 - bf_lo(hi), v1 - bf_hi(hi));
+        if (!SIGN) alo[f] = pack_bf2(v0 - bf_lo(hi), v1 - bf_hi(hi));
       }
 #pragma unroll
       for (int np = 0; np < 2; ++np) {
@@ -312,12 +330,18 @@ __global__ void __launch_bounds__(256, 2) tail_corr_kernel(const float* __restri
                      : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
                      : "r"(addr));
         mma16816(acc[2 * np], ahi, b0, b1);
-        mma16816(acc[2 * np], alo, b0, b1);
+        if (!SIGN) mma16816(acc[2 * np], alo, b0, b1);
         mma16816(acc[2 * np + 1], ahi, b2, b3);
-        mma16816(acc[2 * np + 1], alo, b2, b3);
+        if (!SIGN) mma16816(acc[2 * np + 1], alo, b2, b3);
       }
     }
     __syncthreads();     // the tile and the halo are overwritten by the next iteration
+  }
+  if (SIGN) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[nt][j] *= scale;
   }
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
@@ -728,16 +752,22 @@ int launch_tail_zero_sums(void* scratch, cudaStream_t s) {
 }
 
 int launch_tail_dx(const float* g, const void* scratch, void* dx_bf16, long long n_img, int H1, int W1, int num_sms,
-                   cudaStream_t s) {
+                   cudaStream_t s, float sign_scale) {
   if (n_img <= 0) return 0;
   const float* f = static_cast<const float*>(scratch);
   const int tiles_x = (W1 + kTW - 1) / kTW, tiles_y = (H1 + kTH - 1) / kTH;
   const long long total = n_img * tiles_x * tiles_y;
   if (total >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
   const long long cap = 4LL * (num_sms > 0 ? num_sms : 148);
-  tail_dx_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, tail_pad_bytes(), s>>>(
-      g, reinterpret_cast<const __nv_bfloat16*>(f + kTailUT), static_cast<__nv_bfloat16*>(dx_bf16), static_cast<int>(n_img),
-      H1, W1, tiles_x, tiles_y);
+  const unsigned grid = static_cast<unsigned>(total < cap ? total : cap);
+  if (sign_scale != 0.f)
+    tail_dx_kernel<true><<<grid, 256, tail_pad_bytes(), s>>>(g, reinterpret_cast<const __nv_bfloat16*>(f + kTailUT),
+                                                             static_cast<__nv_bfloat16*>(dx_bf16), static_cast<int>(n_img),
+                                                             H1, W1, tiles_x, tiles_y, sign_scale);
+  else
+    tail_dx_kernel<false><<<grid, 256, tail_pad_bytes(), s>>>(g, reinterpret_cast<const __nv_bfloat16*>(f + kTailUT),
+                                                              static_cast<__nv_bfloat16*>(dx_bf16), static_cast<int>(n_img),
+                                                              H1, W1, tiles_x, tiles_y, 1.f);
   int e = static_cast<int>(cudaGetLastError());
   if (e) return e;
   const long long threads = n_img * border_count(H1, W1) * 64;
@@ -748,16 +778,22 @@ int launch_tail_dx(const float* g, const void* scratch, void* dx_bf16, long long
 }
 
 int launch_tail_corr(const float* g, const void* x_bf16, void* scratch, long long n_img, int H1, int W1, int num_sms,
-                     cudaStream_t s) {
+                     cudaStream_t s, float sign_scale) {
   if (n_img <= 0) return 0;
   float* f = static_cast<float*>(scratch);
   const int tiles_x = (W1 + kTW - 1) / kTW, tiles_y = (H1 + kTH - 1) / kTH;
   const long long total = n_img * tiles_x * tiles_y;
   if (total >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
   const long long cap = 2LL * (num_sms > 0 ? num_sms : 148);
-  tail_corr_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, tail_pad_bytes(), s>>>(
-      g, static_cast<const __nv_bfloat16*>(x_bf16), f + kTailS, f + kTailG, static_cast<int>(n_img), H1, W1, tiles_x,
-      tiles_y);
+  const unsigned nblk = static_cast<unsigned>(total < cap ? total : cap);
+  if (sign_scale != 0.f)
+    tail_corr_kernel<true><<<nblk, 256, tail_pad_bytes(), s>>>(g, static_cast<const __nv_bfloat16*>(x_bf16), f + kTailS,
+                                                               f + kTailG, static_cast<int>(n_img), H1, W1, tiles_x, tiles_y,
+                                                               sign_scale);
+  else
+    tail_corr_kernel<false><<<nblk, 256, tail_pad_bytes(), s>>>(g, static_cast<const __nv_bfloat16*>(x_bf16), f + kTailS,
+                                                                f + kTailG, static_cast<int>(n_img), H1, W1, tiles_x, tiles_y,
+                                                                1.f);
   int e = static_cast<int>(cudaGetLastError());
   if (e) return e;
   const int chunk = 64;

@@ -33,7 +33,7 @@ class _RefineNetFunction(torch.autograd.Function):
         bufs = engine.grad_buffers()
         for b in bufs.values():
             b.zero_()
-        engine.backward(pl, bufs)
+        engine.backward(pl, bufs, generic=True)
         grads = []
         for k in ctx.names:
             # fresh tensors: autograd may keep them as .grad, the buffers are reused by the next backward

@@ -245,9 +245,11 @@ class RefineNetEngine:
         n, _, h, w = x0.shape
         return self.plan_for(n, len(inputs), h, w, True, x0.device, train=True)
 
-    def backward(self, pl, grads):
+    def backward(self, pl, grads, generic=False):
         """Enqueues the backward pass of the last `run(pl)`; pl.dout holds dL/d(out).  `grads`: {parameter name:
-        fp32 tensor} accumulated in place (+=)."""
+        fp32 tensor} accumulated in place (+=).  generic=True: pl.dout is an arbitrary gradient (autograd path)."""
+        if generic:
+            L.check(pl.lib.pvsr_plan_set_sign_gradient(pl.handle, None, 0), "pvsr_plan_set_sign_gradient")
         P, keep = self._params_struct()
         G = self._fill_struct(L.NetGrads(), grads, keep)
         L.check(pl.lib.pvsr_plan_backward(pl.handle, C.byref(P), L.ptr(pl.packed), L.ptr(pl.lr), L.ptr(pl.pos),
@@ -270,6 +272,7 @@ class RefineNetEngine:
         out = self.run(pl)
         S = pl.n_lists // 3
         n_per_list = pl.T * pl.cfg.batch * pl.Hs * pl.Ws
+        sign_scales = None
         if loss_weights is None:
             key = ("lw", pl.n_lists, n_per_list, str(pl.device))
             loss_weights = self._aux.get(key)
@@ -277,6 +280,11 @@ class RefineNetEngine:
                 w = [0.5 ** (S - k // 3 - 1) / n_per_list for k in range(pl.n_lists)]
                 loss_weights = torch.tensor(w, dtype=torch.float32, device=pl.device)
                 self._aux[key] = loss_weights
+                self._aux[key + ("host",)] = (C.c_float * pl.n_lists)(*loss_weights.cpu().tolist())
+            sign_scales = self._aux[key + ("host",)]
+        # dout = w_k * sign(out - target): tell the plan, so the tail adjoint can use the exact sign (include/pvsr.h)
+        L.check(pl.lib.pvsr_plan_set_sign_gradient(pl.handle, sign_scales, pl.n_lists if sign_scales is not None else 0),
+                "pvsr_plan_set_sign_gradient")
         loss = torch.zeros((), dtype=torch.float32, device=pl.device)
         L.check(pl.lib.pvsr_l1_multistage(L.ptr(out), L.ptr(pl.target), L.ptr(loss_weights), pl.n_lists, n_per_list,
                                           L.ptr(loss), L.ptr(pl.dout), L.current_stream()), "pvsr_l1_multistage")

@@ -110,6 +110,7 @@ SIGNATURES = {
     "pvsr_head_tail_bwd": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_void_p]),
     "pvsr_debug_dump_trace": (c_int, []),
     "pvsr_debug_clear_trace": (None, []),
+    "pvsr_plan_set_sign_gradient": (c_int, [c_void_p, c_void_p, c_int]),
     "pvsr_set_tail_fwd": (c_int, [c_int]),
     "pvsr_get_tail_fwd": (c_int, []),
     "pvsr_head_tail_fwd_table_bytes": (c_int64, []),

@@ -416,6 +416,11 @@ typedef struct pvsr_net_grads {
 int pvsr_plan_backward(pvsr_plan* p, const pvsr_net_params* params, const void* packed, const float* lr,
                        const float* pos, const float* dout, const pvsr_net_grads* grads, void* workspace,
                        int use_graph, void* stream);
+/* Promise about the NEXT pvsr_plan_backward calls of this plan: dL/d(out) of list k is scales[k] * {-1, 0, +1} element
+ * by element (what pvsr_l1_multistage writes: the L1 gradient w_k sign(out - target)).  The rank-1 tail adjoint then uses
+ * the exact sign as its bf16 operand and drops the hi/lo split of an arbitrary fp32 gradient (half the MMAs).  scales =
+ * NULL (or n_lists = 0) withdraws the promise (arbitrary gradients: the autograd path).  Host pointer, copied. */
+int pvsr_plan_set_sign_gradient(pvsr_plan* plan, const float* scales, int n_lists);
 int64_t pvsr_plan_num_launches_bwd(const pvsr_plan* p);
 double pvsr_plan_flops_bwd(const pvsr_plan* p);
 /* Backward launch classes: 0 head last-conv adjoints, 1 head dgrad, 2 head wgrad, 3 refine dgrad, 4 refine wgrad,
