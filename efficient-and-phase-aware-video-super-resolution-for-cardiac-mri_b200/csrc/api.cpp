@@ -230,15 +230,15 @@ int pvsr_get_tail_rank1(void) { return get_tail_rank1(); }
 int64_t pvsr_head_tail_scratch_bytes(void) { return static_cast<int64_t>(tail_scratch_bytes()); }
 int pvsr_head_tail_bwd(const float* dout, const void* x_bf16, const float* w2, const float* b2, const float* w3,
                        void* dx_bf16, float* dw2, float* db2, float* dw3, float* db3, void* scratch, int64_t n_img,
-                       int H1, int W1, void* stream) {
+                       int H1, int W1, float sign_scale, void* stream) {
   if (!dout || !x_bf16 || !w2 || !b2 || !w3 || !dx_bf16 || !scratch) return set_error(-2, "null argument");
   if (n_img < 0 || H1 < 1 || W1 < 1) return set_error(-2, "bad shape");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int sms = device_num_sms();
   int e = launch_tail_tables(w2, w3, scratch, s);
   if (!e) e = launch_tail_zero_sums(scratch, s);
-  if (!e) e = launch_tail_dx(dout, scratch, dx_bf16, n_img, H1, W1, sms, s);
-  if (!e) e = launch_tail_corr(dout, x_bf16, scratch, n_img, H1, W1, sms, s);
+  if (!e) e = launch_tail_dx(dout, scratch, dx_bf16, n_img, H1, W1, sms, s, sign_scale);
+  if (!e) e = launch_tail_corr(dout, x_bf16, scratch, n_img, H1, W1, sms, s, sign_scale);
   if (!e) e = launch_tail_finish(scratch, w2, b2, w3, dw2, db2, dw3, db3, s);
   return check_cuda(e, "head_tail_bwd");
 }

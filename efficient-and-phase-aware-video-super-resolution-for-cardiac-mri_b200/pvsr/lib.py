@@ -107,7 +107,7 @@ SIGNATURES = {
     "pvsr_set_tail_rank1": (c_int, [c_int]),
     "pvsr_get_tail_rank1": (c_int, []),
     "pvsr_head_tail_scratch_bytes": (c_int64, []),
-    "pvsr_head_tail_bwd": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_void_p]),
+    "pvsr_head_tail_bwd": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, C.c_float, c_void_p]),
     "pvsr_debug_dump_trace": (c_int, []),
     "pvsr_debug_clear_trace": (None, []),
     "pvsr_plan_set_sign_gradient": (c_int, [c_void_p, c_void_p, c_int]),

@@ -310,7 +310,7 @@ def head_conv_last_bwd(x, w, dout):
     return din, dw, db
 
 
-def head_tail_bwd(x, w2, b2, w3, dout):
+def head_tail_bwd(x, w2, b2, w3, dout, sign_scale=0.0):
     """Rank-1 adjoint of conv3x3 (64 -> 256) + PixelShuffle(2) + conv3x3 (64 -> 1) (csrc/tail_rank1.cu).
     x bf16 [n,H1,W1,64], w2 (256,64,3,3), b2 (256), w3 (1,64,3,3), dout fp32 [n,2 H1,2 W1]
     -> (dx bf16 [n,H1,W1,64], dw2, db2, dw3, db3)."""
@@ -323,7 +323,7 @@ def head_tail_bwd(x, w2, b2, w3, dout):
     scratch = torch.empty(lib.pvsr_head_tail_scratch_bytes(), dtype=torch.uint8, device=x.device)
     L.check(lib.pvsr_head_tail_bwd(L.ptr(dout.contiguous()), L.ptr(x), L.ptr(w2.contiguous()), L.ptr(b2.contiguous()),
                                    L.ptr(w3.contiguous()), L.ptr(dx), L.ptr(dw2), L.ptr(db2), L.ptr(dw3), L.ptr(db3),
-                                   L.ptr(scratch), n, H1, W1, L.current_stream()), "head_tail_bwd")
+                                   L.ptr(scratch), n, H1, W1, float(sign_scale), L.current_stream()), "head_tail_bwd")
     return dx, dw2, db2, dw3, db3
 
 

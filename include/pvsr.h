@@ -307,11 +307,12 @@ int pvsr_add_bf16(const void* a, const void* b, void* out, int64_t n_elems, void
  * (refine_net.py:201-205 under autograd), exploiting that the last conv has ONE output channel (csrc/tail_rank1.cu):
  *   dout fp32 [n_img][2 H1][2 W1], x bf16 NHWC [n_img][H1][W1][64], w2 fp32 (256,64,3,3), b2 (256), w3 (1,64,3,3)
  *   -> dx bf16 NHWC [n_img][H1][W1][64] (written), dw2 / db2 / dw3 / db3 (parameter layout, ACCUMULATED; NULL = skip).
- * scratch: pvsr_head_tail_scratch_bytes() bytes of device memory. */
+ * scratch: pvsr_head_tail_scratch_bytes() bytes of device memory.  sign_scale != 0: the caller promises
+ * dout = sign_scale * {-1, 0, +1} element by element (see pvsr_plan_set_sign_gradient); 0 = arbitrary gradient. */
 int64_t pvsr_head_tail_scratch_bytes(void);
 int pvsr_head_tail_bwd(const float* dout, const void* x_bf16, const float* w2, const float* b2, const float* w3,
                        void* dx_bf16, float* dw2, float* db2, float* dw3, float* db3, void* scratch, int64_t n_img,
-                       int H1, int W1, void* stream);
+                       int H1, int W1, float sign_scale, void* stream);
 /* Training plans use that form for the last conv + PixelShuffle(2) + final conv of x4 / x8 heads instead of the
  * tcgen05 dgrad / wgrad launches of the 64 -> 256 conv and the two adjoint kernels of the 64 -> 1 conv.
  * 1 = on (default), 0 = the conv-by-conv backward (A/B switch; env PVSR_TAIL_RANK1). */
