@@ -61,11 +61,22 @@ __device__ __forceinline__ int border_class(int zy, int zx, int H1, int W1) {
 }
 
 // g halo of one tile -> shared memory (zero outside the HR image): gh[r][c] = g[2*y0 + kOmin + r][2*x0 + kOmin + c]
+// (all loads of a thread are issued before its first shared-memory store: the one-load-one-store loop spent 30 % of the
+// kernel's samples on the store's long-scoreboard wait, profiles/r02/stalls_r02_tail_dx_kernel.txt)
 __device__ __forceinline__ void load_g_halo(const float* __restrict__ gimg, int y0, int x0, int Hs, int Ws, float* gh) {
-  for (int i = threadIdx.x; i < kGhH * kGhW; i += blockDim.x) {
+  constexpr int kIters = (kGhH * kGhW + 255) / 256;      // 256 threads per block
+  float v[kIters];
+#pragma unroll
+  for (int k = 0; k < kIters; ++k) {
+    const int i = threadIdx.x + k * 256;
     const int r = i / kGhW, c = i - r * kGhW;
     const int y = 2 * y0 + kOmin + r, x = 2 * x0 + kOmin + c;
-    gh[r * kGhPitch + c] = (y >= 0 && y < Hs && x >= 0 && x < Ws) ? __ldg(gimg + static_cast<size_t>(y) * Ws + x) : 0.f;
+    v[k] = (i < kGhH * kGhW && y >= 0 && y < Hs && x >= 0 && x < Ws) ? __ldg(gimg + static_cast<size_t>(y) * Ws + x) : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < kIters; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < kGhH * kGhW) gh[(i / kGhW) * kGhPitch + (i % kGhW)] = v[k];
   }
 }
 
@@ -248,6 +259,87 @@ __global__ void __launch_bounds__(256) tail_dx_edge_kernel(const float* __restri
   dX[(static_cast<size_t>(img) * H1 * W1 + static_cast<size_t>(zy) * W1 + zx) * 64 + ci] = __float2bfloat16(sum);
 }
 
+// Fast form for images of at least 4 x 4 pixels: the four border runs WITHOUT their corners (top / bottom row, left /
+// right column) have one border class each, so a thread (channel ci, 8 pixels of a 16-pixel run segment) reads each
+// table entry U[cls][o][ci] once for its 8 pixels; the g stencils of the segment are staged in shared memory.  The first
+// form above re-read the 16 KB class table per pixel (L1-bound: 0.1 ms per launch, as long as tail_dx_kernel itself);
+// it still serves the 4 corners (grid = corners only) and small images.
+constexpr int kRunSeg = 16;
+__global__ void __launch_bounds__(128) tail_dx_runs_kernel(const float* __restrict__ g, const float* __restrict__ U,
+                                                           __nv_bfloat16* __restrict__ dX, int H1, int W1, int segs_row,
+                                                           int segs_col) {
+  __shared__ float gp[kRunSeg][kNO];
+  const int img = blockIdx.y;
+  int b = blockIdx.x;
+  int run, seg;                       // run 0 top row, 1 bottom row, 2 left column, 3 right column
+  if (b < 2 * segs_row) { run = b / segs_row; seg = b - run * segs_row; }
+  else { b -= 2 * segs_row; run = 2 + b / segs_col; seg = b - (run - 2) * segs_col; }
+  const int len = run < 2 ? W1 - 2 : H1 - 2;
+  const int p0 = 1 + seg * kRunSeg;                      // first pixel of the segment along the run (corners excluded)
+  const int n = len - seg * kRunSeg < kRunSeg ? len - seg * kRunSeg : kRunSeg;
+  const int Hs = 2 * H1, Ws = 2 * W1;
+  const float* gimg = g + static_cast<size_t>(img) * Hs * Ws;
+  auto pix = [&](int i, int* zy, int* zx) {
+    if (run == 0) { *zy = 0; *zx = p0 + i; }
+    else if (run == 1) { *zy = H1 - 1; *zx = p0 + i; }
+    else if (run == 2) { *zy = p0 + i; *zx = 0; }
+    else { *zy = p0 + i; *zx = W1 - 1; }
+  };
+  for (int i = threadIdx.x; i < kRunSeg * kNO; i += 128) {
+    const int pi = i >> 6, o = i & 63;
+    float v = 0.f;
+    if (pi < n) {
+      int zy, zx;
+      pix(pi, &zy, &zx);
+      const int y = 2 * zy + kOmin + (o >> 3), x = 2 * zx + kOmin + (o & 7);
+      if (y >= 0 && y < Hs && x >= 0 && x < Ws) v = __ldg(gimg + static_cast<size_t>(y) * Ws + x);
+    }
+    gp[pi][o] = v;
+  }
+  __syncthreads();
+  const int ci = threadIdx.x & 63, pg = threadIdx.x >> 6;     // pixels [8 pg, 8 pg + 8) of the segment
+  int zy0, zx0;
+  pix(0, &zy0, &zx0);
+  const float* Uc = U + static_cast<size_t>(border_class(zy0, zx0, H1, W1)) * kNO * 64 + ci;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 4
+  for (int o = 0; o < kNO; ++o) {
+    const float u = __ldg(Uc + o * 64);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = fmaf(gp[pg * 8 + k][o], u, acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int pi = pg * 8 + k;
+    if (pi < n) {
+      int zy, zx;
+      pix(pi, &zy, &zx);
+      dX[(static_cast<size_t>(img) * H1 * W1 + static_cast<size_t>(zy) * W1 + zx) * 64 + ci] = __float2bfloat16(acc[k]);
+    }
+  }
+}
+
+// The four corners of every image (first form's arithmetic).  Thread = (image, corner, channel).
+__global__ void __launch_bounds__(256) tail_dx_corners_kernel(const float* __restrict__ g, const float* __restrict__ U,
+                                                              __nv_bfloat16* __restrict__ dX, long long n_img, int H1, int W1) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_img * 4 * 64) return;
+  const int ci = static_cast<int>(i & 63), cor = static_cast<int>((i >> 6) & 3);
+  const long long img = i >> 8;
+  const int zy = cor < 2 ? 0 : H1 - 1, zx = (cor & 1) ? W1 - 1 : 0;
+  const int Hs = 2 * H1, Ws = 2 * W1;
+  const float* gimg = g + static_cast<size_t>(img) * Hs * Ws;
+  const float* Uc = U + static_cast<size_t>(border_class(zy, zx, H1, W1)) * kNO * 64 + ci;
+  float sum = 0.f;
+  for (int o = 0; o < kNO; ++o) {
+    const int y = 2 * zy + kOmin + (o >> 3), x = 2 * zx + kOmin + (o & 7);
+    if (y >= 0 && y < Hs && x >= 0 && x < Ws) sum = fmaf(__ldg(gimg + static_cast<size_t>(y) * Ws + x), __ldg(Uc + o * 64), sum);
+  }
+  dX[(static_cast<size_t>(img) * H1 * W1 + static_cast<size_t>(zy) * W1 + zx) * 64 + ci] = __float2bfloat16(sum);
+}
+
 // ------------------------------------------------------------------------------------------------
 // S[o][ci] += sum_z g[2 z + o] * X[z][ci]  and  Gs[o] += sum_z g[2 z + o]  over all pixels of all images: an
 // [64 offsets x pixels] x [pixels x 64 channels] product on mma.sync (K = pixels).  Persistent blocks walk 8 x 16 pixel
@@ -356,43 +448,60 @@ __global__ void __launch_bounds__(256, 2) tail_corr_kernel(const float* __restri
 
 // Edge sums E[set][o][ci]: the same correlation restricted to one edge set of pixels.  set 0 first row, 1 last row,
 // 2 first column, 3 last column, 4..7 the corners (0,0), (0,W1-1), (H1-1,0), (H1-1,W1-1).  blockIdx.y = set,
-// blockIdx.x walks chunks of that set's pixels over all images; thread = (channel, group of 16 offsets).
+// blockIdx.x walks chunks of `chunk` pixels of that set over all images; per sub-chunk of 32 pixels the g stencils and
+// the X rows are staged in shared memory, then thread (channel, group of 16 offsets) accumulates from there
+// (the first form looped over global loads per pixel: 0.2 ms per launch, more than the main correlation kernel).
+constexpr int kEdgeSub = 32;
 __global__ void __launch_bounds__(256) tail_corr_edge_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ X,
                                                              float* __restrict__ E, long long n_img, int H1, int W1,
                                                              int chunk) {
+  __shared__ float gp[kEdgeSub][kNO];
+  __shared__ float xs[kEdgeSub][64];
   const int set = blockIdx.y;
   const int per_img = set < 2 ? W1 : (set < 4 ? H1 : 1);
   const long long n_pix = n_img * per_img;
   const long long p0 = static_cast<long long>(blockIdx.x) * chunk;
   if (p0 >= n_pix) return;
   const long long p1 = p0 + chunk < n_pix ? p0 + chunk : n_pix;
-  const int ci = threadIdx.x & 63, og = threadIdx.x >> 6;      // offsets [16 og, 16 og + 16) = oy indices 2 og, 2 og + 1
+  const int ci = threadIdx.x & 63, og = threadIdx.x >> 6;      // offsets [16 og, 16 og + 16)
   const int Hs = 2 * H1, Ws = 2 * W1;
   float acc[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-  for (long long p = p0; p < p1; ++p) {
-    const long long img = p / per_img;
-    const int e = static_cast<int>(p - img * per_img);
-    int zy, zx;
-    switch (set) {
-      case 0: zy = 0; zx = e; break;
-      case 1: zy = H1 - 1; zx = e; break;
-      case 2: zy = e; zx = 0; break;
-      case 3: zy = e; zx = W1 - 1; break;
-      case 4: zy = 0; zx = 0; break;
-      case 5: zy = 0; zx = W1 - 1; break;
-      case 6: zy = H1 - 1; zx = 0; break;
-      default: zy = H1 - 1; zx = W1 - 1; break;
+  for (long long q0 = p0; q0 < p1; q0 += kEdgeSub) {
+    const int n = static_cast<int>(p1 - q0 < kEdgeSub ? p1 - q0 : kEdgeSub);
+    for (int i = threadIdx.x; i < kEdgeSub * kNO; i += 256) {
+      const int pi = i >> 6, c = i & 63;
+      float gv = 0.f, xv = 0.f;
+      if (pi < n) {
+        const long long p = q0 + pi;
+        const long long img = p / per_img;
+        const int e = static_cast<int>(p - img * per_img);
+        int zy, zx;
+        switch (set) {
+          case 0: zy = 0; zx = e; break;
+          case 1: zy = H1 - 1; zx = e; break;
+          case 2: zy = e; zx = 0; break;
+          case 3: zy = e; zx = W1 - 1; break;
+          case 4: zy = 0; zx = 0; break;
+          case 5: zy = 0; zx = W1 - 1; break;
+          case 6: zy = H1 - 1; zx = 0; break;
+          default: zy = H1 - 1; zx = W1 - 1; break;
+        }
+        const int yy = 2 * zy + kOmin + (c >> 3), xx = 2 * zx + kOmin + (c & 7);
+        if (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) gv = __ldg(g + static_cast<size_t>(img) * Hs * Ws + static_cast<size_t>(yy) * Ws + xx);
+        xv = __bfloat162float(X[(static_cast<size_t>(img) * H1 * W1 + static_cast<size_t>(zy) * W1 + zx) * 64 + c]);
+      }
+      gp[pi][c] = gv;
+      xs[pi][c] = xv;
     }
-    const float x = __bfloat162float(X[(static_cast<size_t>(img) * H1 * W1 + static_cast<size_t>(zy) * W1 + zx) * 64 + ci]);
-    const float* gimg = g + static_cast<size_t>(img) * Hs * Ws;
+    __syncthreads();
+    for (int pi = 0; pi < n; ++pi) {
+      const float x = xs[pi][ci];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int yy = 2 * zy + kOmin + 2 * og + (k >> 3), xx = 2 * zx + kOmin + (k & 7);
-      const float gv = (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) ? __ldg(gimg + static_cast<size_t>(yy) * Ws + xx) : 0.f;
-      acc[k] = fmaf(gv, x, acc[k]);
+      for (int k = 0; k < 16; ++k) acc[k] = fmaf(gp[pi][og * 16 + k], x, acc[k]);
     }
+    __syncthreads();
   }
   float* dst = E + (static_cast<size_t>(set) * kNO + og * 16) * 64 + ci;
 #pragma unroll
@@ -694,31 +803,69 @@ __global__ void __launch_bounds__(256) tail36_weights_kernel(const float* __rest
   Wc[i] = __float2bfloat16(s);          // packed operand layout: [K block = tap t'][N = 48][64 channels]
 }
 
-// out[img][py][px] = b3 + sum_t B[z'][(q',t)],  (2 z' + q') = (py, px) + t inside the HR image.  Thread = HR pixel.
-__global__ void __launch_bounds__(256) tail36_gather_kernel(const float* __restrict__ B, const float* __restrict__ b3,
-                                                            float* __restrict__ out, long long n_px, int H1, int W1) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n_px) return;
-  const int Hs = 2 * H1, Ws = 2 * W1;
-  const int px = static_cast<int>(i % Ws);
-  const long long r = i / Ws;
-  const int py = static_cast<int>(r % Hs);
-  const long long img = r / Hs;
-  const float* Bimg = B + static_cast<size_t>(img) * H1 * W1 * 48;
-  float s = b3[0];
-#pragma unroll
-  for (int ty = -1; ty <= 1; ++ty) {
-    const int y = py + ty;
-    if (y < 0 || y >= Hs) continue;
-#pragma unroll
-    for (int tx = -1; tx <= 1; ++tx) {
-      const int x = px + tx;
-      if (x < 0 || x >= Ws) continue;
-      const int n = ((y & 1) * 2 + (x & 1)) * 9 + (ty + 1) * 3 + (tx + 1);
-      s += __ldg(Bimg + (static_cast<size_t>(y >> 1) * W1 + (x >> 1)) * 48 + n);
-    }
+// out[img][py][px] = b3 + sum_t B[z'][(q',t)],  (2 z' + q') = (py, px) + t inside the HR image.
+// B is bf16 [n_img][H1][W1][48] (the fp32 accumulator rounded once, like the 64-channel HR map it replaces was).  A block
+// stages the records of an 8 x 32 input-pixel tile + a one-pixel ring in shared memory with 16-byte loads (the first
+// form gathered nine scattered 4-byte values per thread straight from global memory: 99 % L1 throughput, 0.66 ms per
+// inference step under ncu), then every thread sums the nine values of four output pixels from there.
+constexpr int kGTH = 8, kGTW = 32;                       // input pixels per tile
+constexpr int kGRW = kGTW + 2, kGRH = kGTH + 2;          // staged records
+constexpr int kGRec = 48;                                // bf16 per record
+__global__ void __launch_bounds__(256) tail36_gather_kernel(const __nv_bfloat16* __restrict__ B, const float* __restrict__ b3,
+                                                            float* __restrict__ out, int H1, int W1, int tiles_x,
+                                                            int tiles_y) {
+  __shared__ __align__(16) __nv_bfloat16 rec[kGRH * kGRW * kGRec];      // 32 640 B
+  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y;
+  const long long img = blockIdx.x / (tiles_x * tiles_y);
+  const int y0 = ty * kGTH, x0 = tx * kGTW;
+  const __nv_bfloat16* Bimg = B + static_cast<size_t>(img) * H1 * W1 * kGRec;
+  for (int i = threadIdx.x; i < kGRH * kGRW * 6; i += 256) {            // 6 x 16 bytes per record
+    const int r = i / 6, ck = i - r * 6;
+    const int zy = y0 - 1 + r / kGRW, zx = x0 - 1 + r % kGRW;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (zy >= 0 && zy < H1 && zx >= 0 && zx < W1)
+      v = __ldg(reinterpret_cast<const uint4*>(Bimg + (static_cast<size_t>(zy) * W1 + zx) * kGRec) + ck);
+    reinterpret_cast<uint4*>(rec + r * kGRec)[ck] = v;
   }
-  out[i] = s;
+  __syncthreads();
+  const int Hs = 2 * H1, Ws = 2 * W1;
+  const float bias = b3[0];
+  float* oimg = out + static_cast<size_t>(img) * Hs * Ws;
+  // 16 x 64 output pixels per tile, thread = (row ly, 4 consecutive columns)
+  const int ly = threadIdx.x >> 4, lx0 = (threadIdx.x & 15) * 4;
+  const int py = 2 * y0 + ly;
+  if (py >= Hs) return;
+  float o4[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int lx = lx0 + k;
+    float sacc = bias;
+#pragma unroll
+    for (int tyy = -1; tyy <= 1; ++tyy) {
+      const int y = ly + tyy;                       // tile-local HR row of the contributing position, -1 .. 16
+      const int gy = py + tyy;
+      if (gy < 0 || gy >= Hs) continue;
+      const int ry = (y + 2) >> 1;                  // staged record row: input row y0 - 1 + ry
+#pragma unroll
+      for (int txx = -1; txx <= 1; ++txx) {
+        const int x = lx + txx;
+        const int gx = 2 * x0 + x;
+        if (gx < 0 || gx >= Ws) continue;
+        const int rx = (x + 2) >> 1;
+        const int n = ((gy & 1) * 2 + (gx & 1)) * 9 + (tyy + 1) * 3 + (txx + 1);
+        sacc += __bfloat162float(rec[(ry * kGRW + rx) * kGRec + n]);
+      }
+    }
+    o4[k] = sacc;
+  }
+  const int px = 2 * x0 + lx0;
+  if (px + 3 < Ws && (Ws & 3) == 0) {
+    *reinterpret_cast<float4*>(oimg + static_cast<size_t>(py) * Ws + px) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (px + k < Ws) oimg[static_cast<size_t>(py) * Ws + px + k] = o4[k];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -770,6 +917,16 @@ int launch_tail_dx(const float* g, const void* scratch, void* dx_bf16, long long
                                                               H1, W1, tiles_x, tiles_y, 1.f);
   int e = static_cast<int>(cudaGetLastError());
   if (e) return e;
+  if (H1 >= 4 && W1 >= 4 && n_img <= 65535) {
+    const int segs_row = (W1 - 2 + kRunSeg - 1) / kRunSeg, segs_col = (H1 - 2 + kRunSeg - 1) / kRunSeg;
+    dim3 grid(static_cast<unsigned>(2 * segs_row + 2 * segs_col), static_cast<unsigned>(n_img));
+    tail_dx_runs_kernel<<<grid, 128, 0, s>>>(g, f + kTailU, static_cast<__nv_bfloat16*>(dx_bf16), H1, W1, segs_row, segs_col);
+    e = static_cast<int>(cudaGetLastError());
+    if (e) return e;
+    tail_dx_corners_kernel<<<static_cast<unsigned>((n_img * 256 + 255) / 256), 256, 0, s>>>(
+        g, f + kTailU, static_cast<__nv_bfloat16*>(dx_bf16), n_img, H1, W1);
+    return static_cast<int>(cudaGetLastError());
+  }
   const long long threads = n_img * border_count(H1, W1) * 64;
   tail_dx_edge_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(g, f + kTailU,
                                                                                   static_cast<__nv_bfloat16*>(dx_bf16),
@@ -796,7 +953,7 @@ int launch_tail_corr(const float* g, const void* x_bf16, void* scratch, long lon
                                                                 1.f);
   int e = static_cast<int>(cudaGetLastError());
   if (e) return e;
-  const int chunk = 64;
+  const int chunk = 256;
   const long long longest = n_img * (H1 > W1 ? H1 : W1);
   dim3 grid(static_cast<unsigned>((longest + chunk - 1) / chunk), 8);
   tail_corr_edge_kernel<<<grid, 256, 0, s>>>(g, static_cast<const __nv_bfloat16*>(x_bf16), f + kTailE, n_img, H1, W1, chunk);
@@ -859,10 +1016,13 @@ int launch_tail36_weights(const float* W2, const float* b2, const float* w3, voi
   tail36_weights_kernel<<<(9 * 48 * 64 + 255) / 256, 256, 0, s>>>(W2, b2, w3, static_cast<__nv_bfloat16*>(wc_bf16), bias48);
   return static_cast<int>(cudaGetLastError());
 }
-int launch_tail36_gather(const float* B, const float* b3, float* out, long long n_img, int H1, int W1, cudaStream_t s) {
-  const long long n_px = n_img * 4 * H1 * W1;
-  if (n_px <= 0) return 0;
-  tail36_gather_kernel<<<static_cast<unsigned>((n_px + 255) / 256), 256, 0, s>>>(B, b3, out, n_px, H1, W1);
+int launch_tail36_gather(const void* B_bf16, const float* b3, float* out, long long n_img, int H1, int W1, cudaStream_t s) {
+  if (n_img <= 0) return 0;
+  const int tiles_x = (W1 + kGTW - 1) / kGTW, tiles_y = (H1 + kGTH - 1) / kGTH;
+  const long long blocks = n_img * tiles_x * tiles_y;
+  if (blocks >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
+  tail36_gather_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(B_bf16), b3, out, H1, W1,
+                                                                    tiles_x, tiles_y);
   return static_cast<int>(cudaGetLastError());
 }
 
