@@ -76,7 +76,8 @@ int launch_tail_fwd(const void* x_bf16, const void* tables, float* out, long lon
 // ... and as a 64 -> 36 channel tcgen05 conv + 9-tap gather (packed operand [9][48][64] bf16, bias fp32 [48])
 size_t tail36_weight_bytes();
 int launch_tail36_weights(const float* W2, const float* b2, const float* w3, void* wc_bf16, float* bias48, cudaStream_t s);
-int launch_tail36_gather(const void* B_bf16, const float* b3, float* out, long long n_img, int H1, int W1, cudaStream_t s);
+int launch_tail36_gather(const void* B, int fp32_records, const float* b3, float* out, long long n_img, int H1, int W1,
+                         cudaStream_t s);
 int launch_cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t s);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                 float wd, float grad_scale, float* state, int num_sms, cudaStream_t s);

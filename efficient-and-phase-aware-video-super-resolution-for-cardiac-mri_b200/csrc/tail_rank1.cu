@@ -808,19 +808,28 @@ __global__ void __launch_bounds__(256) tail36_weights_kernel(const float* __rest
 // stages the records of an 8 x 32 input-pixel tile + a one-pixel ring in shared memory with 16-byte loads (the first
 // form gathered nine scattered 4-byte values per thread straight from global memory: 99 % L1 throughput, 0.66 ms per
 // inference step under ncu), then every thread sums the nine values of four output pixels from there.
-constexpr int kGTH = 8, kGTW = 32;                       // input pixels per tile
-constexpr int kGRW = kGTW + 2, kGRH = kGTH + 2;          // staged records
-constexpr int kGRec = 48;                                // bf16 per record
-__global__ void __launch_bounds__(256) tail36_gather_kernel(const __nv_bfloat16* __restrict__ B, const float* __restrict__ b3,
-                                                            float* __restrict__ out, int H1, int W1, int tiles_x,
-                                                            int tiles_y) {
-  __shared__ __align__(16) __nv_bfloat16 rec[kGRH * kGRW * kGRec];      // 32 640 B
+constexpr int kGTH = 8;                                  // input rows per tile
+constexpr int kGRH = kGTH + 2;                           // staged record rows
+constexpr int kGRec = 48;                                // values per record
+__device__ __forceinline__ float rec_value(const __nv_bfloat16& v) { return __bfloat162float(v); }
+__device__ __forceinline__ float rec_value(const float& v) { return v; }
+// T = bf16 (inference plans: 96 B per record) or float (training plans: the loss gradient is sign(out - target), so the
+// records keep the fp32 accumulator - 8 x 16 input pixels per tile to stay inside 48 KB of static shared memory).
+template <typename T, int kGTW>
+__global__ void __launch_bounds__(8 * kGTW) tail36_gather_kernel(const T* __restrict__ B, const float* __restrict__ b3,
+                                                                 float* __restrict__ out, int H1, int W1, int tiles_x,
+                                                                 int tiles_y) {
+  constexpr int kGRW = kGTW + 2;
+  constexpr int kVec = 16 / static_cast<int>(sizeof(T));                // values per 16-byte load
+  constexpr int kChunks = kGRec / kVec;                                 // 16-byte loads per record
+  constexpr int kThreads = 8 * kGTW;
+  __shared__ __align__(16) T rec[kGRH * kGRW * kGRec];                  // 32 640 B (bf16, 32 wide) / 34 560 B (fp32, 16 wide)
   const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y;
   const long long img = blockIdx.x / (tiles_x * tiles_y);
   const int y0 = ty * kGTH, x0 = tx * kGTW;
-  const __nv_bfloat16* Bimg = B + static_cast<size_t>(img) * H1 * W1 * kGRec;
-  for (int i = threadIdx.x; i < kGRH * kGRW * 6; i += 256) {            // 6 x 16 bytes per record
-    const int r = i / 6, ck = i - r * 6;
+  const T* Bimg = B + static_cast<size_t>(img) * H1 * W1 * kGRec;
+  for (int i = threadIdx.x; i < kGRH * kGRW * kChunks; i += kThreads) {
+    const int r = i / kChunks, ck = i - r * kChunks;
     const int zy = y0 - 1 + r / kGRW, zx = x0 - 1 + r % kGRW;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (zy >= 0 && zy < H1 && zx >= 0 && zx < W1)
@@ -831,8 +840,9 @@ __global__ void __launch_bounds__(256) tail36_gather_kernel(const __nv_bfloat16*
   const int Hs = 2 * H1, Ws = 2 * W1;
   const float bias = b3[0];
   float* oimg = out + static_cast<size_t>(img) * Hs * Ws;
-  // 16 x 64 output pixels per tile, thread = (row ly, 4 consecutive columns)
-  const int ly = threadIdx.x >> 4, lx0 = (threadIdx.x & 15) * 4;
+  // 16 x 2 kGTW output pixels per tile, thread = (row ly, 4 consecutive columns)
+  constexpr int kThreadsPerRow = kGTW / 2;
+  const int ly = threadIdx.x / kThreadsPerRow, lx0 = (threadIdx.x % kThreadsPerRow) * 4;
   const int py = 2 * y0 + ly;
   if (py >= Hs) return;
   float o4[4];
@@ -853,7 +863,7 @@ __global__ void __launch_bounds__(256) tail36_gather_kernel(const __nv_bfloat16*
         if (gx < 0 || gx >= Ws) continue;
         const int rx = (x + 2) >> 1;
         const int n = ((gy & 1) * 2 + (gx & 1)) * 9 + (tyy + 1) * 3 + (txx + 1);
-        sacc += __bfloat162float(rec[(ry * kGRW + rx) * kGRec + n]);
+        sacc += rec_value(rec[(ry * kGRW + rx) * kGRec + n]);
       }
     }
     o4[k] = sacc;
@@ -1016,14 +1026,20 @@ int launch_tail36_weights(const float* W2, const float* b2, const float* w3, voi
   tail36_weights_kernel<<<(9 * 48 * 64 + 255) / 256, 256, 0, s>>>(W2, b2, w3, static_cast<__nv_bfloat16*>(wc_bf16), bias48);
   return static_cast<int>(cudaGetLastError());
 }
-int launch_tail36_gather(const void* B_bf16, const float* b3, float* out, long long n_img, int H1, int W1, cudaStream_t s) {
-  if (n_img <= 0) return 0;
+template <typename T, int kGTW>
+static int launch_tail36_gather_t(const void* B, const float* b3, float* out, long long n_img, int H1, int W1, cudaStream_t s) {
   const int tiles_x = (W1 + kGTW - 1) / kGTW, tiles_y = (H1 + kGTH - 1) / kGTH;
   const long long blocks = n_img * tiles_x * tiles_y;
   if (blocks >= (1LL << 31)) return static_cast<int>(cudaErrorInvalidValue);
-  tail36_gather_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(B_bf16), b3, out, H1, W1,
-                                                                    tiles_x, tiles_y);
+  tail36_gather_kernel<T, kGTW><<<static_cast<unsigned>(blocks), 8 * kGTW, 0, s>>>(static_cast<const T*>(B), b3, out, H1, W1,
+                                                                                   tiles_x, tiles_y);
   return static_cast<int>(cudaGetLastError());
+}
+int launch_tail36_gather(const void* B, int fp32_records, const float* b3, float* out, long long n_img, int H1, int W1,
+                         cudaStream_t s) {
+  if (n_img <= 0) return 0;
+  return fp32_records ? launch_tail36_gather_t<float, 16>(B, b3, out, n_img, H1, W1, s)
+                      : launch_tail36_gather_t<__nv_bfloat16, 32>(B, b3, out, n_img, H1, W1, s);
 }
 
 }  // namespace pvsr
