@@ -66,6 +66,7 @@ int fill_conv_params(const pvsr_conv_desc* d, ConvParams* p) {
   p->grad_split = d->grad_split;
   p->relu = d->relu;
   p->out_scale = d->out_scale;
+  p->prelu = d->prelu;
   if (d->ps_r > 0) p->ps_ch = p->n_total / (d->ps_r * d->ps_r);
   ConvProblem& pr = p->prob[0];
   pr.n_src = d->n_src;
@@ -584,6 +585,16 @@ int pvsr_refine_posterm_bwd(const void* g, const float* pos, float* sums, float*
                                        static_cast<cudaStream_t>(stream)), "posterm_bwd");
 }
 
+int pvsr_prelu_fwd_bf16(const void* z, const float* slope, void* y, int64_t n, void* stream) {
+  if (n % 8 != 0) return set_error(-2, "prelu: n must be a multiple of 8");
+  return check_cuda(launch_prelu_fwd(z, slope, y, n, device_num_sms(), static_cast<cudaStream_t>(stream)), "prelu_fwd");
+}
+int pvsr_prelu_bwd_bf16(const void* g, const void* z, const float* slope, void* dz, float* dslope, int64_t n,
+                        void* stream) {
+  if (n % 8 != 0) return set_error(-2, "prelu: n must be a multiple of 8");
+  return check_cuda(launch_prelu_bwd(g, z, slope, dz, dslope, n, device_num_sms(), static_cast<cudaStream_t>(stream)),
+                    "prelu_bwd");
+}
 int pvsr_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream) {
   if (n % 8 != 0) return set_error(-2, "cast needs a multiple of 8 elements");
   return check_cuda(launch_cast_f32_bf16(in, out, n, static_cast<cudaStream_t>(stream)), "cast_f32_bf16");

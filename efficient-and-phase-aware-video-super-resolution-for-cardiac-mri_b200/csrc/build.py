@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["conv3x3_tc.cu", "wgrad.cu", "simt_kernels.cu", "simt_bwd.cu", "tail_rank1.cu", "data_kernels.cu", "tensormap.cpp", "api.cpp", "plan.cpp"]
+SOURCES = ["conv3x3_tc.cu", "wgrad.cu", "simt_kernels.cu", "simt_bwd.cu", "tail_rank1.cu", "data_kernels.cu", "drf_kernels.cu", "tensormap.cpp", "api.cpp", "plan.cpp"]
 HEADERS = ["conv.h", "wgrad.h", "ptx.cuh", "stencil.cuh", "simt.h", "internal.h", os.path.join("..", "..", "include", "pvsr.h")]
 OUT = os.path.join(HERE, "libpvsr.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -77,6 +77,8 @@ struct ConvParams {
   int grad_split;    // EPI_GRAD column routing (see ConvProblem)
   int relu;          // EPI_STORE: max(x, 0) after the bias, before mask / residual (edsr_net.py:50 relu1)
   float out_scale;   // EPI_STORE: (acc + bias) * out_scale before mask / residual; 0 = 1 (edsr_net.py:56 res_scale)
+  const float* prelu; // EPI_STORE / EPI_PS: device scalar a of nn.PReLU(num_parameters=1): x > 0 ? x : a x after the bias
+                      // (drf_net.py:55-57,65,82-105), or nullptr
   int ps_ch;         // EPI_PS: channels per shuffled pixel (0 = 64): column q * ps_ch + c -> sub-pixel q, channel c
   int halo;          // != 0: padded-raster slab kernel (below); tiles_x = 1, tiles_y = pr_tiles
   int pr_wp;         // padded row pitch Wp >= W + 1: output position p = y * Wp + x, tile t covers [128 t, 128 t + 128)

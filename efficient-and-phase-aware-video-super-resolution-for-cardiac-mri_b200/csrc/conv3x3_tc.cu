@@ -273,6 +273,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvPro
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
+        if (p.prelu) {
+          const float a = __ldg(p.prelu);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : a * f[j];
+        }
         if (pr.mask) {
           float mf[16];
           const uint4* mp = reinterpret_cast<const uint4*>(pr.mask + off);

@@ -79,6 +79,10 @@ int launch_tail36_weights(const float* W2, const float* b2, const float* w3, voi
 int launch_tail36_gather(const void* B, int fp32_records, const float* b3, float* out, long long n_img, int H1, int W1,
                          cudaStream_t s);
 int launch_cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t s);
+// drf_kernels.cu: nn.PReLU(num_parameters=1) on bf16 streams (n a multiple of 8)
+int launch_prelu_fwd(const void* z, const float* slope, void* y, long long n, int num_sms, cudaStream_t s);
+int launch_prelu_bwd(const void* g, const void* z, const float* slope, void* dz, float* dslope, long long n, int num_sms,
+                     cudaStream_t s);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                 float wd, float grad_scale, float* state, int num_sms, cudaStream_t s);
 

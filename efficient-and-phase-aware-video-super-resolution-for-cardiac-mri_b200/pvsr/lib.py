@@ -42,7 +42,7 @@ class ConvDesc(C.Structure):
                 ("posterm", c_void_p), ("out_ch", c_int), ("n_store", c_int), ("ps_r", c_int),
                 ("grad0", c_void_p), ("grad1", c_void_p), ("grad_split", c_int),
                 ("c_in", c_void_p), ("c_out", c_void_p), ("h_out", c_void_p), ("gates_out", c_void_p),
-                ("relu", c_int), ("mask", c_void_p), ("out_scale", C.c_float)]
+                ("relu", c_int), ("mask", c_void_p), ("out_scale", C.c_float), ("prelu", c_void_p)]
 
 
 MAX_DY = 36
@@ -162,6 +162,8 @@ SIGNATURES = {
                                        c_int64, c_int, c_int, c_void_p]),
     "pvsr_refine_posterm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 11 + [c_void_p]),
     "pvsr_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "pvsr_prelu_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pvsr_prelu_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "pvsr_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, C.c_float, C.c_float, C.c_float,
                                C.c_float, C.c_float, C.c_float, c_void_p, c_void_p]),
     "pvsr_plan_backward": (c_int, [c_void_p, C.POINTER(NetParams), c_void_p, c_void_p, c_void_p, c_void_p,

@@ -103,7 +103,7 @@ def in_conv_prelu(x, w, b, slope):
 def conv3x3(act, srcs, n_img, w_packed, bn, epi=L.EPI_STORE, kb_per_src=1, k16_last=4, taps=9, bias=None,
             n_tiles_n=1, w_row_base=0, out_bf16=None, out_f32=None, res=None, posterm=None, out_ch=None,
             n_store=None, ps_r=0, c_in=None, c_out=None, h_out=None, gates_out=None, grad0=None, grad1=None,
-            grad_split=0, out_hw=None, relu=0, mask=None, out_scale=0.0):
+            grad_split=0, out_hw=None, relu=0, mask=None, out_scale=0.0, prelu=None):
     """Generic launch of the tcgen05 implicit-GEMM conv.
 
     act  : one bf16 tensor [images, H, W, C], or a list of views (tensor, mul) - mul > 1 reads the pixel-unshuffled
@@ -137,7 +137,7 @@ def conv3x3(act, srcs, n_img, w_packed, bn, epi=L.EPI_STORE, kb_per_src=1, k16_l
     d.n_tiles_n = n_tiles_n
     for name, t in (("bias", bias), ("out_bf16", out_bf16), ("out_f32", out_f32), ("res", res),
                     ("posterm", posterm), ("c_in", c_in), ("c_out", c_out), ("h_out", h_out),
-                    ("gates_out", gates_out), ("grad0", grad0), ("grad1", grad1), ("mask", mask)):
+                    ("gates_out", gates_out), ("grad0", grad0), ("grad1", grad1), ("mask", mask), ("prelu", prelu)):
         setattr(d, name, None if t is None else t.data_ptr())
     d.out_ch = out_ch if out_ch is not None else bn * n_tiles_n
     d.n_store = n_store if n_store is not None else bn

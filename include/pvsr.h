@@ -175,6 +175,9 @@ typedef struct pvsr_conv_desc {
   int relu;                /* 1: max(x, 0) after the bias (conv1 + relu1) */
   const void* mask;        /* bf16, shape of out_bf16: result zeroed where mask <= 0 (adjoint of relu1), or NULL */
   float out_scale;         /* (acc + bias) * out_scale before relu / mask / residual; 0 = 1 (res_scale, :56) */
+  /* PVSR_EPI_STORE / PVSR_EPI_PS: nn.PReLU(num_parameters=1) fused behind the bias (DRFNet, drf_net.py:55-57,65-105):
+   * device pointer to the slope a (x > 0 ? x : a x, before mask / residual), or NULL */
+  const float* prelu;
 } pvsr_conv_desc;
 int pvsr_conv3x3_fwd(const pvsr_conv_desc* d, void* stream);
 /* Weight (+ bias) gradient of a conv described like pvsr_conv_desc: X sources (source, tap, channel block) against
@@ -358,6 +361,12 @@ int pvsr_refine_posterm_bwd(const void* g_bf16, const float* pos, float* sums, f
                             int frame0, int window, int H, int W, int c_out, int c_in, int feat2, int ch,
                             void* stream);
 int pvsr_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+/* nn.PReLU(num_parameters=1) of the DRFNet row (drf_net.py:55-57,65,82-105) on bf16 streams, n a multiple of 8.
+ * Inference fuses it into the conv epilogue (pvsr_conv_desc.prelu); training stores the pre-activation z and runs
+ *   fwd: y = z > 0 ? z : a z        bwd: dz = g (z > 0 ? 1 : a)  (dz may alias g),  dslope[0] += sum g min(z, 0). */
+int pvsr_prelu_fwd_bf16(const void* z_bf16, const float* slope, void* y_bf16, int64_t n, void* stream);
+int pvsr_prelu_bwd_bf16(const void* g_bf16, const void* z_bf16, const float* slope, void* dz_bf16, float* dslope,
+                        int64_t n, void* stream);
 /* torch.optim.Adam.step (amsgrad off) on flat fp32 buffers of n elements (n % 4 == 0); g is scaled by grad_scale
  * first (1/world_size for averaged data-parallel gradients); state[0] (device float) is the step counter. */
 int pvsr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
