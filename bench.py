@@ -35,8 +35,11 @@ T_FRAMES, U_FRAMES, LR_H, LR_W, SCALE = 30, 6, 54, 63, 4
 WORKLOADS = {"acdc_x4": (54, 63, 4, "ACDCSR"), "acdc_x3": (72, 84, 3, "ACDCSR"), "acdc_x2": (108, 126, 2, "ACDCSR"),
              "dsb15_x4": (63, 48, 4, "DSB15SR"),
              # EDSRNet x4 of configs/{train,test}/edsr_net/exp1_x4.yaml on the same conv core
-             "edsr_x4": (54, 63, 4, "ACDCSR")}
+             "edsr_x4": (54, 63, 4, "ACDCSR"),
+             # ... and DRFNet x4 (src/model/nets/drf_net.py; 64 features, 6 projection groups)
+             "drfnet_x4": (54, 63, 4, "ACDCSR")}
 EDSR_FRAMES = 60
+DRF_SEQS, DRF_FRAMES = 16, 30
 NET_KW = dict(in_channels=1, out_channels=1, num_features=[64, 64, 64], upscale_factor=SCALE, num_stages=3,
               update_memory=True, num_updated_frames=U_FRAMES, refine_window_size=5, positional_encoding=True)
 METRIC = "SR frames/s at x4"
@@ -249,6 +252,76 @@ def run_edsr(args, rank, world):
         dt, cores = edsr_cpu_time(2)
         line["cpu_baseline"] = {"value": 2 / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "2 LR frames 54x63 through the fp32 torch CPU oracle (oracle/edsr_oracle.py)"}
+    print(json.dumps(line), flush=True)
+
+
+def drf_cpu_time(frames):
+    """CPU oracle of DRFNet x4 (64 features, 6 groups) on one ACDCSR-shaped sequence of `frames` LR frames: (s, cores)."""
+    from oracle import drf_oracle as O
+    from src.model.nets import DRFNet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = DRFNet(in_channels=1, out_channels=1, num_features=64, num_groups=6, upscale_factor=4).state_dict()
+    g = torch.Generator().manual_seed(1234)
+    xs = [torch.randn(1, 1, LR_H, LR_W, generator=g) for _ in range(frames)]
+    with torch.no_grad():
+        O.drf_forward(sd, xs[:1], 6, 4)
+        t0 = time.perf_counter()
+        O.drf_forward(sd, xs, 6, 4)
+        return time.perf_counter() - t0, cores
+
+
+def run_drf(args, rank, world):
+    """`--workload drfnet_x4`: single-GPU line for the DRFNet widening row (profiles/bench_drf.py does the device timing)."""
+    if rank != 0:
+        return
+    metric = "SR frames/s at x4 (DRFNet 64 x 6)"
+    cfg = {"workload": f"DRFNet x4 inference (64 features, 6 projection groups, 3.66 M parameters, random init), "
+                       f"{DRF_SEQS} synthetic ACDCSR-shaped cine sequences of {DRF_FRAMES} LR frames {LR_H}x{LR_W} per "
+                       "step -> SR frames 216x252; the frame recurrence is sequential, the sequences are batched",
+           "name": "drfnet_x4", "frames_per_step": DRF_SEQS * DRF_FRAMES, "parallelism": "single GPU",
+           "l2": "256 MiB flush write between steps"}
+    cpu_frames = 6
+    sample = (f"one sequence of {cpu_frames} LR frames {LR_H}x{LR_W} through the fp32 torch CPU oracle "
+              "(oracle/drf_oracle.py, pinned to the unmodified reference by tests/golden/drfnet_*.npz)")
+    if args.impl == "reference":
+        times = []
+        for _ in range(max(1, args.steps)):
+            dt, cores = drf_cpu_time(cpu_frames)
+            times.append(dt)
+        value = cpu_frames * len(times) / sum(times)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": len(times), "warmup": 1, "ms_per_step": 1e3 * sum(times) / len(times),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": dict(cfg, frames_per_step=cpu_frames),
+                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import bench_drf
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    res = bench_drf.measure(argparse.Namespace(seqs=DRF_SEQS, frames=DRF_FRAMES, steps=args.steps, warmup=args.warmup))
+    clocks = sampler.stop()
+    inf = res["inference"]
+    line = {"metric": metric, "value": inf["frames_per_s"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": inf["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "e2e": {"value": inf["e2e_frames_per_s"], "unit": UNIT, "h2d_bytes_per_step": inf["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": inf["d2h_bytes_per_step"], "ms_per_step": inf["ms_per_step_e2e"]},
+            "gpu_launches": inf["launches_per_step"] * args.steps, "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "conv3x3_halo_kernel / conv3x3_kernel <256 | 64, EPI_STORE> (every "
+                                                      "launch of a step: 3x3 phase-stacked projection units + 1x1 convs)",
+                         "achieved": inf["tflops"], "peak": res["peak_tflops"], "unit": "TFLOP/s",
+                         "frac": inf["frac_of_peak"], "traffic": None, "peak_source": res["peak_source"],
+                         "executed_tflops": inf["executed_tflops"], "executed_frac": inf["executed_frac_of_peak"],
+                         "note": "achieved = ALGORITHMIC FLOPs of the reference's k x k ConvTranspose2d / strided Conv2d; "
+                                 "the phase-stacked 3x3 forms execute 9 s^2 / k^2 = 2.25x as many"},
+            "train_step": res["train_step"]}
+    if not args.no_cpu_baseline:
+        dt, cores = drf_cpu_time(cpu_frames)
+        line["cpu_baseline"] = {"value": cpu_frames / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
 
 
@@ -516,6 +589,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload == "edsr_x4":
         run_edsr(args, rank, world)
+        return
+    if args.workload == "drfnet_x4":
+        run_drf(args, rank, world)
         return
     if args.impl == "reference":
         run_reference(args, rank)

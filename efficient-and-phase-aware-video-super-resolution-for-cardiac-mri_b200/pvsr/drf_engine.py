@@ -255,6 +255,29 @@ class DRFEngine:
     def params_changed(self):
         self._packed_version = None
 
+    def flatten_parameters(self):
+        """One flat fp32 parameter buffer + one flat gradient buffer (single all-reduce / single Adam kernel), as
+        RefineNetEngine.flatten_parameters."""
+        if self._flat is not None:
+            return self._flat
+        params = list(self.net.parameters())
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                n = p.numel()
+                flat_p[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = flat_p[o:o + n].view(p.shape)
+                p.grad = flat_g[o:o + n].view(p.shape)
+        self._flat = (flat_p, flat_g)
+        self.params_changed()
+        return self._flat
+
     def _upload_table(self, jobs):
         arr = (L.TableJob * len(jobs))(*jobs)
         t = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
@@ -658,8 +681,11 @@ class DRFEngine:
                 p.grad = torch.zeros_like(p)
             grads[k] = p.grad
         if zero_grads:
-            for t in grads.values():
-                t.zero_()
+            if self._flat is not None:
+                self._flat[1].zero_()
+            else:
+                for t in grads.values():
+                    t.zero_()
         self.backward(g, grads)
         return g.loss.clone(), outs
 
