@@ -75,7 +75,7 @@ class AcdcVSRRefineNetPredictor(BasePredictor):
                      else self._allocate_data(collate([it for _, it in items])))
             inputs, targets, pos_codes, _ = self._get_inputs_targets(batch)
             with torch.no_grad():
-                outputs = self.net(inputs, pos_codes)[-1]           # T x (n, 1, H, W)
+                outputs = self._forward(inputs, pos_codes)          # T x (n, 1, H, W)
                 per_seq = self._per_sequence(outputs, targets, idx)
             for n, (index, losses, metrics, sr) in enumerate(per_seq):
                 T = losses.shape[0]
@@ -107,6 +107,10 @@ class AcdcVSRRefineNetPredictor(BasePredictor):
         log = {k: v / max(count, 1) for k, v in log.items()}
         logging.info(f'Test log: {log}.')
         return log
+
+    def _forward(self, inputs, pos_codes):
+        """The SR frames the scores are computed on: the last output list (:62)."""
+        return self.net(inputs, pos_codes)[-1]
 
     def _get_inputs_targets(self, batch):
         return batch['lr_imgs'], batch['hr_imgs'], batch['pos_code'], batch['index']

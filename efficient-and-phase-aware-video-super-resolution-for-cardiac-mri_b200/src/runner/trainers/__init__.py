@@ -3,5 +3,7 @@ from .base_trainer import BaseTrainer
 from .acdc_vsr_refinenet_trainer import AcdcVSRRefineNetTrainer, Dsb15VSRRefineNetTrainer
 
 from .acdc_sisr_trainer import AcdcSISRTrainer, Dsb15SISRTrainer
+from .acdc_vsr_trainer import AcdcVSRTrainer, Dsb15VSRTrainer
 
-__all__ = ['BaseTrainer', 'AcdcVSRRefineNetTrainer', 'Dsb15VSRRefineNetTrainer', 'AcdcSISRTrainer', 'Dsb15SISRTrainer']
+__all__ = ['BaseTrainer', 'AcdcVSRRefineNetTrainer', 'Dsb15VSRRefineNetTrainer', 'AcdcSISRTrainer', 'Dsb15SISRTrainer',
+           'AcdcVSRTrainer', 'Dsb15VSRTrainer']

@@ -53,7 +53,7 @@ class AcdcVSRRefineNetTrainer(BaseTrainer):
             if training and self._fused:
                 outputs, loss, losses = self._fused_step(inputs, targets, pos_codes)
             elif training:
-                outputs = self.net(inputs, pos_codes)
+                outputs = self._forward(inputs, pos_codes)
                 losses = self._compute_losses(outputs, targets)
                 loss = (torch.stack(losses) * self.loss_weights).sum()
                 self.optimizer.zero_grad()
@@ -61,7 +61,7 @@ class AcdcVSRRefineNetTrainer(BaseTrainer):
                 self._optimizer_step()
             else:
                 with torch.no_grad():
-                    outputs = self.net(inputs, pos_codes)
+                    outputs = self._forward(inputs, pos_codes)
                     losses = self._compute_losses(outputs, targets)
                     loss = (torch.stack(losses) * self.loss_weights).sum()
             metrics = self._compute_metrics(outputs, targets)
@@ -77,6 +77,10 @@ class AcdcVSRRefineNetTrainer(BaseTrainer):
         log = dict(zip(names, acc.tolist()))
         log, count = parallel.reduce_log(log, count, self.device)
         return {k: v / max(count, 1) for k, v in log.items()}, batch, outputs[-1] if outputs is not None else None
+
+    def _forward(self, inputs, pos_codes):
+        """The tuple of output lists of the net (:44,51)."""
+        return self.net(inputs, pos_codes)
 
     def _optimizer_step(self):
         if self._dp is not None:

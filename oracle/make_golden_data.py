@@ -1,7 +1,8 @@
 """ORACLE TOOLING - pins the INPUT PIPELINE to the reference: runs the UNMODIFIED reference
 `src/data/transforms.py` (Normalize :100-168, ToTensor :74-97, RandomHorizontalFlip / RandomVerticalFlip :321-376,
 RandomCropPatch :379-450) and `src/data/datasets/acdc_vsr_refinenet_dataset.py` (`__getitem__` :49-89) in the build
-container and records what they return -> tests/golden/data_pipeline.npz.
+container and records what they return -> tests/golden/data_pipeline.npz; the items of the plain video-SR dataset
+(`src/data/datasets/acdc_vsr_dataset.py` :49-88, both temporal orders) on the same volumes -> tests/golden/data_vsr.npz.
 
     python oracle/make_golden_data.py
 
@@ -151,6 +152,34 @@ def main():
                 meta["items"].append({"kind": kind, "index": index, "seed": seed,
                                       "n_lr": len(item["lr_imgs"]), "n_hr": len(item["hr_imgs"]),
                                       "lr_shape": list(item["lr_imgs"][0].shape), "hr_shape": list(item["hr_imgs"][0].shape)})
+        # ---- the plain video-SR dataset (acdc_vsr_dataset.py:49-88) on the SAME volumes -> data_vsr.npz (items only)
+        vds = importlib.import_module("src.data.datasets.acdc_vsr_dataset")
+        vrec, vmeta = {}, {"num_frames": NUM_FRAMES, "items": []}
+        for order in ("last", "middle"):
+            for kind in ("train", "valid"):
+                def fake_load(path, kind=kind):
+                    parts = Path(path).parts
+                    i = parts.index(kind)
+                    return _FakeImage(VOLUMES_BY_KEY["/".join(parts[i:])])
+                sys.modules["nibabel"].load = fake_load
+                dset = vds.AcdcVSRDataset(downscale_factor=SCALE, transforms=cfg_t, augments=cfg_a, num_frames=NUM_FRAMES,
+                                          temporal_order=order, data_dir=Path(td), type=kind)
+                vmeta[f"len_{kind}"] = len(dset)
+                picks = [0, 1, 3, 7, 8, 9, 18, len(dset) - 1] if kind == "train" else list(range(len(dset)))
+                for j, index in enumerate(picks):
+                    seed = 3000 + 11 * j + (0 if kind == "train" else 500) + (0 if order == "last" else 97)
+                    random.seed(seed)
+                    item = dset[index]
+                    tag = f"{order}_{kind}_{index}"
+                    vrec[f"item_lr::{tag}"] = torch.stack(item["lr_imgs"]).numpy()
+                    vrec[f"item_hr::{tag}"] = torch.stack(item["hr_imgs"]).numpy()
+                    assert item["index"] == index and sorted(item) == ["hr_imgs", "index", "lr_imgs"]
+                    vmeta["items"].append({"order": order, "kind": kind, "index": index, "seed": seed,
+                                           "n": len(item["lr_imgs"])})
+        vrec["meta"] = np.array(json.dumps(vmeta))
+        vpath = os.path.join(OUT, "data_vsr.npz")
+        np.savez_compressed(vpath, **vrec)
+        print("wrote", vpath, os.path.getsize(vpath), "bytes;", len(vmeta["items"]), "plain-VSR dataset items")
     rec["meta"] = np.array(json.dumps(meta))
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, "data_pipeline.npz")

@@ -227,6 +227,35 @@ def test_host_dataset_reproduces_the_reference_items(tmp_path):
         assert item["index"] == it["index"]
 
 
+def test_plain_vsr_dataset_reproduces_the_reference_items(tmp_path):
+    """AcdcVSRDataset.__getitem__ ('last' and 'middle' windows incl. the wrap-around at both ends of the cycle, and
+    whole-cycle items) against the dicts the UNMODIFIED reference dataset returned on the same volumes and `random.seed`
+    (acdc_vsr_dataset.py:49-88): bit-exact."""
+    from src.data.datasets import AcdcVSRDataset
+    z, meta = _load_data_golden()
+    _golden_tree(tmp_path, z, meta)
+    v = np.load(os.path.join(os.path.dirname(GOLDEN_DATA), "data_vsr.npz"), allow_pickle=False)
+    vmeta = json.loads(str(v["meta"]))
+    sets = {}
+    for it in vmeta["items"]:
+        key = (it["order"], it["kind"])
+        if key not in sets:
+            sets[key] = AcdcVSRDataset(
+                data_dir=tmp_path, type=it["kind"], downscale_factor=meta["scale"], temporal_order=it["order"],
+                transforms=[dict(name='Normalize', kwargs=dict(means=meta["means"], stds=meta["stds"])), dict(name='ToTensor')],
+                augments=[dict(name='RandomHorizontalFlip'), dict(name='RandomVerticalFlip'),
+                          dict(name='RandomCropPatch', kwargs=dict(size=meta["patch"], ratio=meta["scale"]))],
+                num_frames=vmeta["num_frames"])
+            assert len(sets[key]) == vmeta[f"len_{it['kind']}"]
+        random.seed(it["seed"])
+        item = sets[key][it["index"]]
+        tag = f"{it['order']}_{it['kind']}_{it['index']}"
+        assert sorted(item) == ["hr_imgs", "index", "lr_imgs"] and item["index"] == it["index"]
+        assert len(item["lr_imgs"]) == it["n"] == len(item["hr_imgs"])
+        assert np.array_equal(torch.stack(item["lr_imgs"]).numpy(), v[f"item_lr::{tag}"]), tag
+        assert np.array_equal(torch.stack(item["hr_imgs"]).numpy(), v[f"item_hr::{tag}"]), tag
+
+
 @pytest.mark.gpu
 def test_device_loader_reproduces_the_reference_items(tmp_path, pvsr_lib):
     """DeviceDataloader (volumes resident in HBM, one pvsr_cine_gather launch per resolution) against the same

@@ -163,3 +163,55 @@ def test_main_trains_and_tests_edsr(pvsr_lib, tmp_path, optimizer):
         assert abs(float(row[1]) - float(RO.psnr(RO.denormalize(o), RO.denormalize(hr)))) <= 0.01
         l1 = float((o - hr).abs().mean())
         assert abs(float(row[3]) - l1) <= 2e-3 * l1
+
+
+# ------------------------------------------------------------------------------------------------ DRFNet
+DRF_NET = {'name': 'DRFNet', 'kwargs': dict(in_channels=1, out_channels=1, num_features=64, num_groups=2, upscale_factor=4)}
+DRF_DATA = dict(DATA, num_updated_frames=0)          # plain VSR items: n LR frames, n HR frames (acdc_vsr_dataset.py)
+
+
+@pytest.mark.parametrize("optimizer", ["Adam", "FusedAdam"])
+def test_main_drfnet_train_then_test(pvsr_lib, tmp_path, optimizer):
+    """`src.main` with the reference's plain-VSR runner names (AcdcVSRTrainer / AcdcVSRPredictor) around DRFNet."""
+    cfg = _train_cfg(tmp_path, optimizer)
+    cfg['dataset'] = {'name': 'SyntheticCineDataset', 'kwargs': dict(DRF_DATA, data_dir=None)}
+    cfg['net'] = DRF_NET
+    cfg['trainer'] = {'name': 'AcdcVSRTrainer', 'kwargs': {'device': 'cuda:0', 'num_epochs': 2}}
+    _run_main(cfg, tmp_path, 'train')
+    ck_dir = tmp_path / 'train' / 'checkpoints'
+    ck = torch.load(ck_dir / 'model_2.pth', weights_only=False)
+    first = torch.load(ck_dir / 'model_1.pth', weights_only=False)['net']
+    assert ck['epoch'] == 2 and list(ck['net']) == list(first)
+    moved = sum(float((ck['net'][k] - first[k]).abs().sum()) for k in first)
+    assert moved > 0 and all(torch.isfinite(v).all() for v in ck['net'].values())
+    assert all(float((ck['net'][k] - first[k]).abs().sum()) > 0 for k in first if 'prelu' in k)     # every slope trains
+
+    test_cfg = {'main': {'saved_dir': str(tmp_path / 'test'), 'loaded_path': str(ck_dir / 'model_best.pth')},
+                'dataset': cfg['dataset'], 'dataloader': {'name': 'Dataloader', 'kwargs': {'batch_size': 1,
+                                                                                          'shuffle': False,
+                                                                                          'num_workers': 0}},
+                'net': DRF_NET, 'losses': cfg['losses'], 'metrics': cfg['metrics'],
+                'predictor': {'name': 'AcdcVSRPredictor',
+                              'kwargs': {'device': 'cuda:0', 'saved_dir': str(tmp_path / 'test'), 'exported': True,
+                                         'sequences_per_launch': 2}}}
+    _run_main(test_cfg, tmp_path, 'test', test=True)
+    with open(tmp_path / 'test' / 'results.csv') as f:
+        rows = list(csv.reader(f))
+    assert rows[0] == ['name', 'PSNR', 'SSIM', 'L1Loss'] and len(rows) == 1 + 3 * 6
+
+    from oracle import drf_oracle as DO
+    from oracle import refinenet_oracle as O
+    from src.data.datasets import SyntheticCineDataset
+    item = SyntheticCineDataset(type='test', **DRF_DATA)[0]
+    sd = {k: v.cpu() for k, v in torch.load(ck_dir / 'model_best.pth', weights_only=False)['net'].items()}
+    with torch.no_grad():
+        ref = DO.drf_forward(sd, [x.unsqueeze(0) for x in item['lr_imgs']], 2, 4)
+    got = {r[0]: r for r in rows[1:]}
+    for t, (o, hr) in enumerate(zip(ref, item['hr_imgs'])):
+        hr = hr.unsqueeze(0)
+        row = got[f'synthetic000_2d_slice00_frame{t + 1:0>2d}']
+        psnr = float(O.psnr(O.denormalize(o), O.denormalize(hr)))
+        ssim = float(O.ssim(O.denormalize(o), O.denormalize(hr)))
+        l1 = float((o - hr).abs().mean())
+        assert abs(float(row[1]) - psnr) <= 0.01 and abs(float(row[2]) - ssim) <= 1e-3, (t, row, psnr, ssim)
+        assert abs(float(row[3]) - l1) <= 2e-3 * l1
