@@ -554,7 +554,6 @@ int pvsr_lstm_cell_bwd_pointwise(const float* dh, const void* gates, const float
 
 int pvsr_l1_multistage(const float* out, const float* target, const float* w, int n_lists, int64_t n_per_list,
                        float* loss, float* dout, void* stream) {
-  if (n_per_list % 4 != 0) return set_error(-2, "n_per_list must be a multiple of 4");
   return check_cuda(launch_l1_multistage(out, target, w, n_lists, n_per_list, loss, dout, device_num_sms(),
                                          static_cast<cudaStream_t>(stream)), "l1_multistage");
 }

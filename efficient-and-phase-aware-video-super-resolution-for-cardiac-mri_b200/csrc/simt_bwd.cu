@@ -208,13 +208,46 @@ __global__ void __launch_bounds__(256) l1_multistage_kernel(const float4* __rest
   }
 }
 
+// Element-wise form for list lengths that are not a multiple of 4 (x3 with odd LR sizes and odd T * N: the lists of the
+// output tensor then start at addresses that are not 16-byte aligned).
+__global__ void __launch_bounds__(256) l1_multistage_scalar_kernel(const float* __restrict__ out,
+                                                                   const float* __restrict__ target,
+                                                                   const float* __restrict__ w, int n_lists, long long n,
+                                                                   float* __restrict__ loss, float* __restrict__ dout) {
+  float acc = 0.f;
+  const long long total = n * n_lists;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i / n);
+    const float wk = w[k];
+    const float d = out[i] - __ldg(target + (i - k * n));
+    acc += wk * fabsf(d);
+    if (dout) dout[i] = d > 0.f ? wk : (d < 0.f ? -wk : 0.f);
+  }
+  __shared__ float part[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = part[threadIdx.x];
+#pragma unroll
+    for (int d = 4; d > 0; d >>= 1) v += __shfl_xor_sync(0xffu, v, d);
+    if (threadIdx.x == 0) atomicAdd(loss, v);
+  }
+}
+
 int launch_l1_multistage(const float* out, const float* target, const float* w, int n_lists, long long n_per_list,
                          float* loss, float* dout, int num_sms, cudaStream_t s) {
-  if (n_per_list % 4 != 0) return static_cast<int>(cudaErrorInvalidValue);
-  const long long n4 = n_per_list / 4;
-  if (n4 == 0 || n_lists == 0) return 0;
-  long long blocks = (n4 * n_lists + 255) / 256;
+  if (n_per_list <= 0 || n_lists == 0) return 0;
   const long long cap = 8LL * (num_sms > 0 ? num_sms : 148);
+  if (n_per_list % 4 != 0) {
+    long long blocks = (n_per_list * n_lists + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    l1_multistage_scalar_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(out, target, w, n_lists, n_per_list, loss, dout);
+    return static_cast<int>(cudaGetLastError());
+  }
+  const long long n4 = n_per_list / 4;
+  long long blocks = (n4 * n_lists + 255) / 256;
   if (blocks > cap) blocks = cap;
   l1_multistage_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
       reinterpret_cast<const float4*>(out), reinterpret_cast<const float4*>(target), w, n_lists, n4, loss,

@@ -666,8 +666,6 @@ class DRFEngine:
         for t, tg in enumerate(targets):
             g.target[t].copy_(tg.reshape(g.target[t].shape))
         n = g.out.numel()
-        if n % 4 != 0:
-            raise L.PvsrError('fused L1 needs T*N*H*W to be a multiple of 4')
         w = getattr(self, '_lw', {}).get(n)
         if w is None:
             self._lw = getattr(self, '_lw', {})

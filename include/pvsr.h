@@ -343,7 +343,7 @@ int pvsr_lstm_cell_bwd_pointwise(const float* dh, const void* gates, const float
                                  int dc_zero, void* dgates, int64_t n_img, int H, int W, void* stream);
 /* Trainer loss (acdc_vsr_refinenet_trainer.py:83-100 with nn.L1Loss): out fp32 [n_lists][n_per_list], target fp32
  * [n_per_list], w fp32 [n_lists] (device) = per-list weight discount/(T*N*H*W).  *loss += sum_k w_k*sum|out_k - t|;
- * dout (may be NULL) = w_k * sign(out_k - target).  n_per_list must be a multiple of 4. */
+ * dout (may be NULL) = w_k * sign(out_k - target).  Any n_per_list (16-byte vector form when it is a multiple of 4). */
 int pvsr_l1_multistage(const float* out, const float* target, const float* w, int n_lists, int64_t n_per_list,
                        float* loss, float* dout, void* stream);
 /* _OutBlock last conv backward: dout fp32 [n_img][H][W] -> din bf16 [n_img][H][W][64]; dw (1,64,3,3), db (1) +=. */

@@ -1,6 +1,6 @@
 """Profiling target: exactly two eager (no CUDA graph) passes of the bench workload, so that an ncu launch list of
 this command shows every kernel of a step by name and `profiles/ncu_capture.sh` can pick representative launches
-for the `--set full` captures.  python profiles/ncu_target.py infer|train|edsr_infer|edsr_train [batch]"""
+for the `--set full` captures.  python profiles/ncu_target.py infer|train|edsr_infer|edsr_train|drf_infer|drf_train [batch]"""
 import os
 import sys
 
@@ -45,6 +45,26 @@ def main():
         for _ in range(2):
             dl.fetch(list(range(32)))
             torch.cuda.synchronize()
+    elif mode.startswith("drf"):
+        # DRFNet x4, 64 features x 6 groups: 16 ACDCSR-shaped sequences, 3 frames of the recurrence
+        from src.model.nets import DRFNet
+        net = DRFNet(in_channels=1, out_channels=1, num_features=64, num_groups=6, upscale_factor=4).to(dev)
+        net.engine.use_graph = False
+        g = torch.Generator().manual_seed(1234)
+        if mode == "drf_infer":
+            xs = [torch.randn(16, 1, 54, 63, generator=g).to(dev) for _ in range(3)]
+            net.eval()
+            with torch.no_grad():
+                for _ in range(2):
+                    net(xs)
+                    torch.cuda.synchronize()
+        else:
+            net.train()
+            xs = [torch.randn(16, 1, 32, 32, generator=g).to(dev) for _ in range(3)]
+            ts = [torch.randn(16, 1, 128, 128, generator=g).to(dev) for _ in range(3)]
+            for _ in range(2):
+                net.engine.loss_and_grads(xs, ts)
+                torch.cuda.synchronize()
     elif mode.startswith("edsr"):
         # EDSR x4, 32 blocks x 256 features (configs/{train,test}/edsr_net/exp1_x4.yaml) - SURVEY 8 f3
         from src.model.nets import EDSRNet

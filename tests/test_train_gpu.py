@@ -86,11 +86,12 @@ def test_lstm_bwd_pointwise(pvsr_lib, n, H, W, first):
     assert torch.allclose(ops.lstm_state_to_nchw(dc2, n, H, W), ref_dc0, atol=1e-5, rtol=1e-5)
 
 
-def test_l1_multistage(pvsr_lib):
+@pytest.mark.parametrize("shape", [(3, 2, 16, 20), (3, 1, 9, 7)])       # 189 elements per list: the element-wise form
+def test_l1_multistage(pvsr_lib, shape):
     from pvsr import ops
     g = torch.Generator(device="cuda").manual_seed(32)
-    out = torch.randn(9, 3, 2, 16, 20, generator=g, device="cuda", requires_grad=True)
-    tgt = torch.randn(3, 2, 16, 20, generator=g, device="cuda")
+    out = torch.randn(9, *shape, generator=g, device="cuda", requires_grad=True)
+    tgt = torch.randn(*shape, generator=g, device="cuda")
     out.data[0, 0, 0, 0, :4] = tgt[0, 0, 0, :4]            # exact ties -> zero gradient, like torch
     w = torch.tensor([0.5 ** (3 - k // 3 - 1) / tgt.numel() for k in range(9)], device="cuda")
     loss, dout = ops.l1_multistage(out.detach(), tgt, w)
@@ -344,6 +345,30 @@ def test_fused_step_matches_autograd_and_adam(pvsr_lib):
         # Adam normalises each element by sqrt(v): tiny gradient differences move single elements by up to ~lr
         assert (pa - pb).abs().max().item() <= 3 * 1e-3 + 1e-6, k
         assert rel_l2(pb.detach(), pa.detach()) < 2e-2, (k, rel_l2(pb.detach(), pa.detach()))
+
+
+def test_fused_step_odd_sizes_x3(pvsr_lib):
+    """x3 with odd LR sizes and odd T * N: T*N*H*W = 3*1*27*21 is not a multiple of 4 (the fused L1 used to refuse it).
+    The fused step must equal the generic autograd path on the same module."""
+    from oracle import refinenet_oracle as O
+    from pvsr.synthetic import cine_batch
+    kw = dict(in_channels=1, out_channels=1, num_features=[64, 64], upscale_factor=3, num_stages=2, update_memory=True,
+              num_updated_frames=2, refine_window_size=5, positional_encoding=True)
+    inputs, pos, targets = cine_batch(1, T=3, U=2, h=9, w=7, scale=3, seed=11, end_systole=1, with_targets=True)
+    inputs, pos, targets = [x.cuda() for x in inputs], pos.cuda(), [t.cuda() for t in targets]
+    assert (len(targets) * targets[0].numel()) % 4 != 0
+    net = build_net(kw).cuda().train()
+    out = net(inputs, pos)
+    loss_a = O.trainer_loss(out, targets, training=True)
+    loss_a.backward()
+    ref = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+    net.zero_grad()
+    loss_b, _ = net.engine.loss_and_grads(inputs, pos, targets)
+    torch.cuda.synchronize()
+    assert abs(loss_a.item() - loss_b.item()) <= 1e-5 * abs(loss_a.item())
+    for k, p in net.named_parameters():
+        if k in ref:
+            assert rel_l2(p.grad, ref[k]) < 5e-3 and cosine(p.grad, ref[k]) > 0.9999, (k, rel_l2(p.grad, ref[k]))
 
 
 def test_training_shape_vs_oracle(pvsr_lib):
