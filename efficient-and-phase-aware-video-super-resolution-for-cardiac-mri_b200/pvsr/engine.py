@@ -86,6 +86,10 @@ class RefineNetEngine:
     """Runs RefineNet.forward / backward (reference refine_net.py:61-135) for a module exposing the reference's
     parameters."""
 
+    # parameters the reference registers but never reads (refine_net.py:147 builds `_RefineBlock.prelu`, forward :157-185
+    # never applies it): their grad stays None in torch, so optimisers must leave them alone (pvsr.optim.FusedAdam)
+    dead_parameters = ('refine_block.prelu.weight',)
+
     def __init__(self, net):
         self.net = net
         self.plans = {}

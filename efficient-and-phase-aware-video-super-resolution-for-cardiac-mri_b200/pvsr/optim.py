@@ -9,9 +9,9 @@ from . import lib as L
 class FusedAdam(torch.optim.Optimizer):
     """Drop-in for torch.optim.Adam(net.parameters(), ...) when the parameters were flattened with
     `net.engine.flatten_parameters()`.  amsgrad / maximize are not supported (the reference configs do not use
-    them).  Parameters that never receive a gradient (the dead refine-block PReLU) see g = 0 and do not move,
-    which equals torch skipping `grad is None` as long as weight_decay == 0 (the reference configs); with weight decay
-    the dead slot would decay here and not in torch - its value is never read by the forward."""
+    them).  Parameters that never receive a gradient (the dead refine-block PReLU, `engine.dead_parameters`) see
+    g = 0 and do not move as long as weight_decay == 0 (the reference configs); with weight decay their slots are put
+    back after the kernel (value and moments), which equals torch skipping `grad is None`."""
 
     def __init__(self, params, flat_param, flat_grad, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
@@ -22,12 +22,17 @@ class FusedAdam(torch.optim.Optimizer):
         self.step_count = torch.zeros(1, dtype=torch.float32, device=flat_param.device)
         self.grad_scale = 1.0
         self.engine = None
+        self.frozen = []          # (offset, numel) of parameters that never receive a gradient (see for_net)
 
     @classmethod
     def for_net(cls, net, **kw):
         flat_p, flat_g = net.engine.flatten_parameters()
         opt = cls(net.parameters(), flat_p, flat_g, **kw)
         opt.engine = net.engine
+        dead = set(getattr(net.engine, 'dead_parameters', ()))
+        named = dict(net.named_parameters())
+        es, base = flat_p.element_size(), flat_p.data_ptr()
+        opt.frozen = [((named[k].data_ptr() - base) // es, named[k].numel()) for k in dead if k in named]
         return opt
 
     def zero_grad(self, set_to_none=False):
@@ -91,9 +96,17 @@ class FusedAdam(torch.optim.Optimizer):
     def step(self, closure=None):
         g = self.param_groups[0]
         lib = L.load()
+        keep = [(o, n, self.flat_param[o:o + n].clone()) for o, n in self.frozen] if g["weight_decay"] != 0 else []
+        self._adam_kernel(lib, g)
+        for o, n, v in keep:      # torch.optim.Adam skips parameters whose grad is None: no decay, no state
+            self.flat_param[o:o + n].copy_(v)
+            self.exp_avg[o:o + n].zero_()
+            self.exp_avg_sq[o:o + n].zero_()
+        if self.engine is not None:
+            self.engine.params_changed()     # torch's version counters cannot see the kernel's in-place update
+
+    def _adam_kernel(self, lib, g):
         L.check(lib.pvsr_adam_step(L.ptr(self.flat_param), L.ptr(self.flat_grad), L.ptr(self.exp_avg),
                                    L.ptr(self.exp_avg_sq), self.flat_param.numel(), g["lr"], g["betas"][0],
                                    g["betas"][1], g["eps"], g["weight_decay"], self.grad_scale,
                                    L.ptr(self.step_count), L.current_stream()), "pvsr_adam_step")
-        if self.engine is not None:
-            self.engine.params_changed()     # torch's version counters cannot see the kernel's in-place update

@@ -347,6 +347,33 @@ def test_fused_step_matches_autograd_and_adam(pvsr_lib):
         assert rel_l2(pb.detach(), pa.detach()) < 2e-2, (k, rel_l2(pb.detach(), pa.detach()))
 
 
+def test_fused_adam_weight_decay_skips_dead_parameter(pvsr_lib):
+    """torch.optim.Adam skips parameters whose grad is None (the refine block's unused PReLU): with weight decay the
+    fused optimiser must not decay that slot either, and must decay everything else like torch."""
+    from pvsr.optim import FusedAdam
+    z, meta = load_golden("x4_pos")
+    kw = meta["kwargs"]
+    inputs = [torch.from_numpy(x).cuda() for x in z["inputs"]]
+    pos = torch.from_numpy(z["pos"]).cuda()
+    targets = [torch.from_numpy(t).cuda() for t in z["targets"]]
+    net = build_net(kw).cuda().train()
+    ref = build_net(kw).cuda().train()
+    opt = FusedAdam.for_net(net, lr=1e-3, weight_decay=0.1)
+    ref_opt = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=0.1)
+    assert opt.frozen and opt.frozen[0][1] == 1
+    net.engine.loss_and_grads(inputs, pos, targets)
+    for (k, p), q in zip(net.named_parameters(), ref.parameters()):
+        q.grad = None if k in net.engine.dead_parameters else p.grad.detach().clone()
+    opt.step()
+    ref_opt.step()
+    torch.cuda.synchronize()
+    assert float(net.refine_block.prelu.weight) == float(ref.refine_block.prelu.weight) == pytest.approx(0.2)
+    for (k, p), q in zip(net.named_parameters(), ref.parameters()):
+        assert (p - q).abs().max().item() <= 2e-6, k
+    sd = opt.state_dict()
+    assert float(sd["state"][list(dict(net.named_parameters())).index("refine_block.prelu.weight")]["exp_avg"].abs().sum()) == 0.0
+
+
 def test_fused_step_odd_sizes_x3(pvsr_lib):
     """x3 with odd LR sizes and odd T * N: T*N*H*W = 3*1*27*21 is not a multiple of 4 (the fused L1 used to refuse it).
     The fused step must equal the generic autograd path on the same module."""
