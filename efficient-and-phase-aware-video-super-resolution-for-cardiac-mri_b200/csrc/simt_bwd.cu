@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "conv.h"
 #include "ptx.cuh"
@@ -154,6 +155,123 @@ __global__ void __launch_bounds__(256, 3) lstm_bwd_pointwise_kernel(const __grid
   }
 }
 
+// Second form (round 2): the first one reads the tile-transposed tensors with 8 different 128-byte lines per warp
+// request (4 row quads x 8 channel groups), and ncu put it at 75 % L1 throughput / 47 % DRAM / 3.9 TB/s.  Here a lane
+// IS a tile row (pixel), exactly like the tcgen05 epilogue that wrote those tensors: every load / store of gates, c,
+// c_prev and dc is one fully used 128-byte (fp32) or 64-byte (bf16) line per warp request.  The two NHWC tensors are
+// transposed through shared memory instead: dh (128 rows x 32 channels of this block, fp32, pitch 36 floats: the
+// per-row float4 reads are conflict-free) is staged with 128-byte row reads; the bf16 gate gradients are collected in
+// [row][4 gates x 32 channels] (pitch 132: the 8-byte per-lane writes are conflict-free) and leave as 64-byte pieces.
+// Block = one tile x 32 channels (256 threads: 4 pixel groups x 2 channel groups of 16); same arithmetic per element
+// as the first form (bit-identical results).
+constexpr int kLb2DhPitch = 36;     // floats
+constexpr int kLb2DgPitch = 132;    // bf16
+constexpr int kLb2Smem = 128 * kLb2DhPitch * 4 + 128 * kLb2DgPitch * 2 + 128 * 8;
+__device__ __forceinline__ float bf16_scalar(const unsigned short* p) { return __uint_as_float(static_cast<uint32_t>(*p) << 16); }
+
+__global__ void __launch_bounds__(256, 4) lstm_bwd_pointwise_v2_kernel(const __grid_constant__ LstmBwdParams p) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  extern __shared__ __align__(16) unsigned char lb2_smem[];
+  float* s_dh = reinterpret_cast<float*>(lb2_smem);
+  __nv_bfloat16* s_dg = reinterpret_cast<__nv_bfloat16*>(lb2_smem + 128 * kLb2DhPitch * 4);
+  long long* s_pix = reinterpret_cast<long long*>(lb2_smem + 128 * kLb2DhPitch * 4 + 128 * kLb2DgPitch * 2);
+  const LstmBwdProb& pr = p.prob[blockIdx.y];
+  const int tile = blockIdx.x >> 1;
+  const int ch_blk = (blockIdx.x & 1) * 32;                 // this block's 32 channels
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 128) {                                          // NHWC pixel index of every tile row (-1: padding)
+    int y, x, img;
+    if (p.wp > 0) {
+      img = tile / p.tiles_per_img;
+      const int pos = (tile - img * p.tiles_per_img) * 128 + tid;
+      y = pos / p.wp;
+      x = pos - y * p.wp;
+    } else {
+      int t = tile;
+      const int tx = t % p.tiles_x;
+      t /= p.tiles_x;
+      const int ty = t % p.tiles_y;
+      img = t / p.tiles_y;
+      const int TW = 1 << p.tw_log2;
+      y = ty * (128 >> p.tw_log2) + (tid >> p.tw_log2);
+      x = (tx << p.tw_log2) + (tid & (TW - 1));
+    }
+    s_pix[tid] = (y < p.H && x < p.W) ? (static_cast<long long>(img) * p.H + y) * p.W + x : -1;
+  }
+  __syncthreads();
+  // dh -> shared memory: a row's 32 channels = 128 contiguous bytes, 8 lanes x 16 bytes
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int row = pass * 32 + (tid >> 3), sub = tid & 7;
+    const long long px = s_pix[row];
+    const float4 v = px >= 0 ? *reinterpret_cast<const float4*>(pr.dh + px * 64 + ch_blk + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(s_dh + row * kLb2DhPitch + sub * 4) = v;
+  }
+  const int row = (warp & 3) * 32 + lane;                   // this thread's tile row
+  const int ch_thr = (warp >> 2) * 16;                      // its 16 channels inside the block's 32
+  const unsigned short* gt = static_cast<const unsigned short*>(pr.gates) + static_cast<size_t>(tile) * 256 * 128 + row;
+  const float* ct = pr.c + static_cast<size_t>(tile) * 64 * 128 + row;
+  const float* cpt = pr.c_prev ? pr.c_prev + static_cast<size_t>(tile) * 64 * 128 + row : nullptr;
+  float* dct = pr.dc + static_cast<size_t>(tile) * 64 * 128 + row;
+  __syncthreads();
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const int lc = ch_thr + 4 * k;                          // channel inside the block
+    const int ch = ch_blk + lc;
+    float gi[4], gf[4], go[4], gg[4], cn[4], cp[4], dcin[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                           // 28 independent requests in flight
+      gi[j] = bf16_scalar(gt + (ch + j) * 128);
+      gf[j] = bf16_scalar(gt + (64 + ch + j) * 128);
+      go[j] = bf16_scalar(gt + (128 + ch + j) * 128);
+      gg[j] = bf16_scalar(gt + (192 + ch + j) * 128);
+      cn[j] = ct[(ch + j) * 128];
+      cp[j] = cpt ? cpt[(ch + j) * 128] : 0.f;
+      dcin[j] = pr.dc_zero ? 0.f : dct[(ch + j) * 128];
+    }
+    const float4 d4 = *reinterpret_cast<const float4*>(s_dh + row * kLb2DhPitch + lc);
+    const float dh[4] = {d4.x, d4.y, d4.z, d4.w};
+    float ai[4], af[4], ao[4], ag[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float tc = tanh_mufu(cn[j]);
+      const float dcv = fmaf(dh[j] * go[j], 1.f - tc * tc, dcin[j]);
+      ao[j] = dh[j] * tc * go[j] * (1.f - go[j]);
+      ai[j] = dcv * gg[j] * gi[j] * (1.f - gi[j]);
+      af[j] = dcv * cp[j] * gf[j] * (1.f - gf[j]);
+      ag[j] = dcv * gi[j] * (1.f - gg[j] * gg[j]);
+      dct[(ch + j) * 128] = dcv * gf[j];
+    }
+    __nv_bfloat16* dst = s_dg + row * kLb2DgPitch + lc;
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(ai[0], ai[1]), pack2(ai[2], ai[3]));
+    *reinterpret_cast<uint2*>(dst + 32) = make_uint2(pack2(af[0], af[1]), pack2(af[2], af[3]));
+    *reinterpret_cast<uint2*>(dst + 64) = make_uint2(pack2(ao[0], ao[1]), pack2(ao[2], ao[3]));
+    *reinterpret_cast<uint2*>(dst + 96) = make_uint2(pack2(ag[0], ag[1]), pack2(ag[2], ag[3]));
+  }
+  __syncthreads();
+  // gate gradients -> NHWC [pixel][256]: one warp per row per pass, lane = (gate, 8-byte piece of its 64 bytes)
+#pragma unroll 4
+  for (int pass = 0; pass < 16; ++pass) {
+    const int r = pass * 8 + warp;
+    const long long px = s_pix[r];
+    if (px < 0) continue;
+    const uint2 v = *reinterpret_cast<const uint2*>(s_dg + r * kLb2DgPitch + lane * 4);
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(pr.dgates) + px * 256 + (lane >> 3) * 64 + ch_blk + (lane & 7) * 4;
+    *reinterpret_cast<uint2*>(dst) = v;
+  }
+}
+
+// A/B switch (PVSR_LSTM_BWD_V1=1 selects the first form)
+static int lstm_bwd_form() {
+  static int form = -1;
+  if (form < 0) {
+    const char* e = getenv("PVSR_LSTM_BWD_V1");
+    form = (e && e[0] == '1') ? 1 : 2;
+  }
+  return form;
+}
+
 int launch_lstm_bwd_pointwise(const LstmBwdParams& p, cudaStream_t s) {
   if (p.n_prob <= 0 || p.n_img <= 0) return 0;
   const int tiles = p.wp > 0 ? p.tiles_per_img : p.tiles_x * p.tiles_y;
@@ -167,6 +285,16 @@ int launch_lstm_bwd_pointwise(const LstmBwdParams& p, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = get_pdl() ? 1 : 0;
+  if (lstm_bwd_form() == 2) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(lstm_bwd_pointwise_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLb2Smem);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      attr_set = true;
+    }
+    cfg.dynamicSmemBytes = kLb2Smem;
+    return static_cast<int>(cudaLaunchKernelEx(&cfg, lstm_bwd_pointwise_v2_kernel, p));
+  }
   return static_cast<int>(cudaLaunchKernelEx(&cfg, lstm_bwd_pointwise_kernel, p));
 }
 

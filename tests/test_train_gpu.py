@@ -367,7 +367,7 @@ def test_fused_adam_weight_decay_skips_dead_parameter(pvsr_lib):
     opt.step()
     ref_opt.step()
     torch.cuda.synchronize()
-    assert float(net.refine_block.prelu.weight) == float(ref.refine_block.prelu.weight) == pytest.approx(0.2)
+    assert float(net.refine_block.prelu.weight.detach()) == float(ref.refine_block.prelu.weight.detach()) == pytest.approx(0.2)
     for (k, p), q in zip(net.named_parameters(), ref.parameters()):
         assert (p - q).abs().max().item() <= 2e-6, k
     sd = opt.state_dict()
