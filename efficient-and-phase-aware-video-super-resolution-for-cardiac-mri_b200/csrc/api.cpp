@@ -210,6 +210,7 @@ int pvsr_set_halo_mode(int mode) {
 int pvsr_get_halo_mode(void) { return get_halo_mode(); }
 int pvsr_set_pdl(int enable) {
   set_pdl(enable);
+  set_pdl_explicit();
   return 0;
 }
 int pvsr_get_pdl(void) { return get_pdl(); }

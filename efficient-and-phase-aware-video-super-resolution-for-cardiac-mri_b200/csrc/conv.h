@@ -100,6 +100,9 @@ inline int cta_pair_factor() { return get_cta_pair() ? 2 : 1; }
 // Programmatic dependent launch (griddepcontrol) on the tcgen05 launches and the LSTM gate-adjoint kernel: 0 = off.
 void set_pdl(int enable);
 int get_pdl();
+void set_pdl_explicit();      // the caller chose (pvsr_set_pdl): plans no longer pick PDL for small batches themselves
+int pdl_is_explicit();
+constexpr long long kPdlAutoPixels = 8192;   // B * h * w up to which an inference plan captures its graph with PDL
 
 // Resident weight operand of narrow slab launches (conv3x3_tc.cu: halo_resident_blocks).  1 = on (default).
 void set_w_resident(int enable);

@@ -908,9 +908,16 @@ static int g_halo = 1;   // 0: nine shifted TMA boxes per source, 1: one slab pe
 void set_halo_mode(int mode) { g_halo = mode; }
 int get_halo_mode() { return g_halo; }
 
-static int g_pdl = 0;   // programmatic dependent launch between consecutive kernels (measured: no gain; off)
+// Programmatic dependent launch between consecutive kernels.  Measured (profiles/r02/README.md): +3.5 % at one sequence
+// per step (143 dependent launches of <= 162 tiles: the prologue of launch n + 1 hides behind the tail of launch n),
+// -1.7 % at 8 sequences, nothing at 32 - so it is off, and inference plans of <= kPdlAutoPixels pixels per frame batch
+// switch it on for their own graph capture unless the caller took the decision (pvsr_set_pdl / PVSR_PDL).
+static int g_pdl = 0;
+static int g_pdl_explicit = 0;
 void set_pdl(int enable) { g_pdl = enable ? 1 : 0; }
 int get_pdl() { return g_pdl; }
+void set_pdl_explicit() { g_pdl_explicit = 1; }
+int pdl_is_explicit() { return g_pdl_explicit; }
 
 static int g_w_resident = 1;   // resident weight operand for launches where it fits (halo_resident_blocks)
 void set_w_resident(int enable) { g_w_resident = enable ? 1 : 0; }

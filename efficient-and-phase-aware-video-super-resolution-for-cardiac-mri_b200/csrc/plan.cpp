@@ -1242,7 +1242,12 @@ static int run_or_replay(pvsr_plan* p, const GraphKey& key, int use_graph, cudaS
   cudaGraph_t graph = nullptr;
   e = cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal);
   if (e) return check_cuda(e, "begin capture");
+  // small inference plans are launch-latency bound: their graph is captured with programmatic dependent launch
+  const bool auto_pdl = !p->train && !pdl_is_explicit() && get_pdl() == 0 &&
+                        static_cast<long long>(p->B) * p->h * p->w <= kPdlAutoPixels;
+  if (auto_pdl) set_pdl(1);
   rc = eager(p->cap_stream, two ? p->cap_side : nullptr);
+  if (auto_pdl) set_pdl(0);
   e = cudaStreamEndCapture(p->cap_stream, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
   if (e) return check_cuda(e, "end capture");

@@ -47,9 +47,11 @@ int pvsr_get_cta_pair(void);
 int pvsr_set_halo_mode(int mode);
 int pvsr_get_halo_mode(void);
 /* Programmatic dependent launch (griddepcontrol) between consecutive launches of a schedule: the next kernel's prologue
- * (barrier init, TMEM allocation) overlaps the tail of the previous one.  Default off (no measurable gain under CUDA-graph
- * replay on B200: profiles/r01); set BEFORE the first run of a
- * plan (captured CUDA graphs keep the setting they were captured with).  Process-wide. */
+ * (barrier init, TMEM allocation) overlaps the tail of the previous one.  Default off (no gain under CUDA-graph replay at
+ * 8+ sequences per step on B200: profiles/r01, r02); inference plans of at most 8192 LR pixels per frame batch (one or two
+ * ACDC sequences: 143 dependent launches of <= 162 tiles, +3.5 %) capture their graph with it on their own unless this
+ * function was called (the caller's choice then holds for every plan).  Set BEFORE the first run of a plan (captured
+ * CUDA graphs keep the setting they were captured with).  Process-wide. */
 int pvsr_set_pdl(int enable);
 int pvsr_get_pdl(void);
 /* Resident weight operand: slab launches with one problem and one N tile whose packed weights fit next to two activation
