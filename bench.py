@@ -161,6 +161,13 @@ def cpu_oracle_time(n_seq_steps, warmup, threads):
 GATES = {"max_abs": 2e-2, "rel_l2": 1.5e-2, "psnr_delta_db": 0.01, "ssim_delta": 1e-4}
 
 
+def gates_for_scale(scale):
+    """SSIM gate = 2x the drift of the REFERENCE ITSELF under torch.autocast(bf16) against its own fp32 run on the same
+    sequence and synthetic target (tests/test_model_gpu.py: x4 54x63 4.9e-5 -> 1e-4; x2 108x126 1.02e-4 -> 2e-4: noise
+    targets 4x the LR grid, where single uint8 flips move the 11x11-window SSIM more)."""
+    return dict(GATES, ssim_delta=2e-4 if scale == 2 else GATES["ssim_delta"])
+
+
 def inference_parity(frames_host, inputs_h, pos_h, hr_h, seqs, state_dict, threads):
     """Checks SR frames of the LAST TIMED e2e step (host copy read back through the HostFrameRing: B sequences x CUDA
     graph replay x rotating output buffers) against the CPU implementation run on the same sequences' own inputs.
@@ -184,8 +191,9 @@ def inference_parity(frames_host, inputs_h, pos_h, hr_h, seqs, state_dict, threa
                 dg, dr = O.denormalize(g, dataset), O.denormalize(r, dataset)
                 worst["psnr_delta_db"] = max(worst["psnr_delta_db"], abs(float(O.psnr(dg, tgt)) - float(O.psnr(dr, tgt))))
                 worst["ssim_delta"] = max(worst["ssim_delta"], abs(float(O.ssim(dg, tgt)) - float(O.ssim(dr, tgt))))
-    ok = all(worst[k] <= GATES[k] for k in GATES)
-    par = dict(worst, ok=ok, gates=GATES, checked_against=kind,
+    gates = gates_for_scale(SCALE)
+    ok = all(worst[k] <= gates[k] for k in gates)
+    par = dict(worst, ok=ok, gates=gates, checked_against=kind,
                what=f"SR frames of sequences {list(seqs)} of the last timed e2e step (graph replay, output ring, D2H) "
                     f"vs the CPU {kind} on the same inputs; PSNR / SSIM deltas against a synthetic HR target")
     return par, times, kind
