@@ -744,12 +744,12 @@ def main():
                     continue
                 pb = eng.plan_for(b, len(inputs_d), LR_H, LR_W, False, dev)
                 eng.stage_inputs(pb, [x[:b] for x in inputs_d], pos_d[:b])
-                for _ in range(args.warmup):
+                for _ in range(args.warmup + 2):            # eager, eager + capture, first replays (graph upload)
                     flush.fill_(1)
                     eng.run(pb)
                 torch.cuda.synchronize()
                 g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                n_rep = max(args.steps, 10)
+                n_rep = max(args.steps, 10) * (4 if b == 1 else 1)      # 4 ms steps: average over enough of them
                 g0.record()
                 for _ in range(n_rep):
                     flush.fill_(1)
