@@ -15,7 +15,8 @@ class _RefineNetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, pl, names, *params):
         out = engine.run(pl).clone()          # the plan's output buffer is reused by the next step
-        ctx.engine, ctx.pl, ctx.names = engine, pl, names
+        pl.fwd_serial = getattr(pl, 'fwd_serial', 0) + 1
+        ctx.engine, ctx.pl, ctx.names, ctx.serial = engine, pl, names, pl.fwd_serial
         ctx.shape = out.shape
         # one differentiable tensor per output frame (views of `out`), list-major
         return tuple(out[l, t].unsqueeze(1) for l in range(out.shape[0]) for t in range(out.shape[1]))
@@ -23,6 +24,9 @@ class _RefineNetFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grad_outs):
         engine, pl = ctx.engine, ctx.pl
+        if pl.fwd_serial != ctx.serial:
+            from .lib import PvsrError
+            raise PvsrError('the activations saved by this forward were overwritten by a later forward of the same shape (the plan keeps ONE set of training buffers per shape): call backward before the next forward')
         n_lists, T = ctx.shape[0], ctx.shape[1]
         dout = pl.dout.view(n_lists * T, *ctx.shape[2:])
         for i, g in enumerate(grad_outs):

@@ -697,12 +697,15 @@ class _DRFFunction(torch.autograd.Function):
     def forward(ctx, engine, T, names, *rest):
         inputs, params = rest[:T], rest[T:]
         outs, g = engine.forward(list(inputs), train=True, clone=True)
-        ctx.engine, ctx.g, ctx.names, ctx.T = engine, g, names, T
+        g.fwd_serial = getattr(g, 'fwd_serial', 0) + 1
+        ctx.engine, ctx.g, ctx.names, ctx.T, ctx.serial = engine, g, names, T, g.fwd_serial
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *grad_outs):
         engine, g = ctx.engine, ctx.g
+        if g.fwd_serial != ctx.serial:
+            raise L.PvsrError('the activations saved by this forward were overwritten by a later forward of the same shape (the plan keeps ONE set of training buffers per shape): call backward before the next forward')
         for t, go in enumerate(grad_outs):
             if go is None:
                 g.dout[t].zero_()

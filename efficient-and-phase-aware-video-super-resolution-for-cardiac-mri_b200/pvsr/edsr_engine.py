@@ -476,12 +476,15 @@ class _EDSRFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, x, names, *params):
         out, g = engine.forward(x, train=True, clone=True)
-        ctx.engine, ctx.g, ctx.names = engine, g, names
+        g.fwd_serial = getattr(g, 'fwd_serial', 0) + 1
+        ctx.engine, ctx.g, ctx.names, ctx.serial = engine, g, names, g.fwd_serial
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         engine, g = ctx.engine, ctx.g
+        if g.fwd_serial != ctx.serial:
+            raise L.PvsrError('the activations saved by this forward were overwritten by a later forward of the same shape (the plan keeps ONE set of training buffers per shape): call backward before the next forward')
         g.dout.copy_(grad_out.reshape(g.dout.shape))
         bufs = engine.grad_buffers()
         for b in bufs.values():

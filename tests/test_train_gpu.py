@@ -374,6 +374,24 @@ def test_fused_adam_weight_decay_skips_dead_parameter(pvsr_lib):
     assert float(sd["state"][list(dict(net.named_parameters())).index("refine_block.prelu.weight")]["exp_avg"].abs().sum()) == 0.0
 
 
+def test_backward_after_a_later_forward_is_refused(pvsr_lib):
+    """One set of training buffers per shape: a backward through a forward whose activations were overwritten by a
+    later forward of the same shape must raise instead of returning the wrong gradients."""
+    from oracle import refinenet_oracle as O
+    from pvsr.lib import PvsrError
+    z, meta = load_golden("x4_pos")
+    net = build_net(meta["kwargs"]).cuda().train()
+    inputs = [torch.from_numpy(x).cuda() for x in z["inputs"]]
+    pos = torch.from_numpy(z["pos"]).cuda()
+    targets = [torch.from_numpy(t).cuda() for t in z["targets"]]
+    first = O.trainer_loss(net(inputs, pos), targets, training=True)
+    second = O.trainer_loss(net(inputs, pos), targets, training=True)
+    with pytest.raises(PvsrError):
+        first.backward()
+    second.backward()
+    assert net.in_block.conv.weight.grad is not None
+
+
 def test_fused_step_odd_sizes_x3(pvsr_lib):
     """x3 with odd LR sizes and odd T * N: T*N*H*W = 3*1*27*21 is not a multiple of 4 (the fused L1 used to refuse it).
     The fused step must equal the generic autograd path on the same module."""
