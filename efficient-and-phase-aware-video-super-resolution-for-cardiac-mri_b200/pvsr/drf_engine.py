@@ -20,6 +20,7 @@ weight gradients batched over T*n images per conv.  torch carries device memory 
 PyTorch fallback.
 """
 import ctypes as C
+import gc
 
 import numpy as np
 import torch
@@ -96,6 +97,20 @@ def table_reduce(F, k, s, p):
     idx = ((col * F + cb * 64 + c) * k + ky) * k + kx
     idx = np.where((ky >= 0) & (ky < k) & (kx >= 0) & (kx < k), idx, -1)
     return idx.reshape(9 * P * kb, F, 64).astype(np.int32)
+
+
+def projection_pairs(kind, k, s, p):
+    """[(tap, phase q, ky, kx)] of the non-zero (tap, phase) blocks of a phase-stacked projection conv ('expand' =
+    deconv, 'reduce' = strided conv): exactly k*k pairs, one per kernel tap of the k x k parameter."""
+    out = []
+    for tap in range(9):
+        dy, dx = tap // 3 - 1, tap % 3 - 1
+        for q in range(s * s):
+            ry, rx = q // s, q % s
+            ky, kx = (ry + p - s * dy, rx + p - s * dx) if kind == 'expand' else (s * dy + ry + p, s * dx + rx + p)
+            if 0 <= ky < k and 0 <= kx < k:
+                out.append((tap, q, ky, kx))
+    return out
 
 
 class _Node:
@@ -558,6 +573,67 @@ class DRFEngine:
             scatter.append(L.TableJob(base + 4 * (off + n_w), nd.idx_b.data_ptr(), grads[nd.name + '.bias'].data_ptr(),
                                       nd.n_total, 1.0, L.TJ_SCATTER))
 
+        def projection_wgrad(nd, x_t, x_base, dz_t, dz_base):
+            """Weight gradient of a phase-stacked projection conv WITHOUT its structural zeros: one (tap, phase) block per
+            kernel tap of the k x k parameter (k*k of the 9 s*s blocks the dense 3x3 form reduces), as single-tap sources
+            shifted by the tap offset.  All descriptors of a node ride in one launch."""
+            k, s_, p_ = self.proj
+            kbF = F // 64
+            off = g.dw_off[nd.name]
+            n_w = nd.n_kb * nd.n_total * 64
+            pairs = projection_pairs(nd.kind, k, s_, p_)
+            views = [(x_t, 1), (dz_t, 1)]
+            descs, o, ob = [], off, off + n_w
+            wname, bname = grads[nd.name + '.weight'].data_ptr(), grads[nd.name + '.bias'].data_ptr()
+            cb, c64 = np.meshgrid(np.arange(kbF), np.arange(64), indexing='ij')
+            kch = (cb * 64 + c64)                                    # K channel of (cb, c)
+            if nd.kind == 'reduce':
+                # X = phase-stacked map (source = phase q's F channels shifted by the tap), dY = dz (F columns)
+                for g0 in range(0, len(pairs), 10):
+                    grp = pairs[g0:g0 + 10]
+                    srcs = [(0, x_base, q * F, tap % 3 - 1, tap // 3 - 1) for tap, q, _, _ in grp]
+                    dys = [(1, dz_base, 64 * c, 0, 0) for c in range(kbF)]
+                    first = g0 == 0
+                    descs.append(self._wg_desc(g, nd.name, 0, views, srcs, dys, hw, TN, kbF, 1, F, o, ob, with_bias=int(first)))
+                    idx = np.empty((len(grp), kbF, F, 64), dtype=np.int64)
+                    col = np.arange(F)[None, :, None]
+                    for si, (_, _, ky, kx) in enumerate(grp):
+                        idx[si] = ((col * F + kch[:, None, :]) * k + ky) * k + kx
+                    t = torch.from_numpy(idx.reshape(-1).astype(np.int32)).to(self.device)
+                    keep.append(t)
+                    scatter.append(L.TableJob(base + 4 * o, t.data_ptr(), wname, t.numel(), 1.0, L.TJ_SCATTER))
+                    o += t.numel()
+                scatter.append(L.TableJob(base + 4 * ob, nd.idx_b.data_ptr(), bname, F, 1.0, L.TJ_SCATTER))
+            else:
+                # X = the F-channel input shifted by the tap, dY = the phases of dz that tap reaches
+                per = max(1, MAX_DY // kbF)
+                for tap in range(9):
+                    qs = [(q, ky, kx) for t_, q, ky, kx in pairs if t_ == tap]
+                    for g0 in range(0, len(qs), per):
+                        grp = qs[g0:g0 + per]
+                        cols = len(grp) * F
+                        srcs = [(0, x_base, 0, tap % 3 - 1, tap // 3 - 1)]
+                        dys = [(1, dz_base, q * F + 64 * c, 0, 0) for q, _, _ in grp for c in range(kbF)]
+                        centre = tap == 4                            # the centre tap reaches every phase once: bias gradient
+                        descs.append(self._wg_desc(g, nd.name, 0, views, srcs, dys, hw, TN, kbF, 1, cols, o, ob,
+                                                   with_bias=int(centre)))
+                        idx = np.empty((kbF, len(grp), F, 64), dtype=np.int64)
+                        ch = np.arange(F)[None, :, None]
+                        for gi, (_, ky, kx) in enumerate(grp):
+                            idx[:, gi] = ((kch[:, None, :] * F + ch) * k + ky) * k + kx
+                        t = torch.from_numpy(idx.reshape(-1).astype(np.int32)).to(self.device)
+                        keep.append(t)
+                        scatter.append(L.TableJob(base + 4 * o, t.data_ptr(), wname, t.numel(), 1.0, L.TJ_SCATTER))
+                        o += t.numel()
+                        if centre:
+                            tb = torch.from_numpy(np.tile(np.arange(F), len(grp)).astype(np.int32)).to(self.device)
+                            keep.append(tb)
+                            scatter.append(L.TableJob(base + 4 * ob, tb.data_ptr(), bname, cols, 1.0, L.TJ_SCATTER))
+                            ob += cols
+            assert o <= off + n_w and ob <= off + n_w + nd.n_total
+            add(descs)
+
+        keep = []
         hw = (g.h, g.w)
         P = self.proj[1] ** 2
         hwp = (g.h, g.w * P)
@@ -576,14 +652,14 @@ class DRFEngine:
                                   grads[nd.name + '.bias'].data_ptr(), F, 1.0, L.TJ_SCATTER))
         for i in range(G):
             if i == 0:
-                node_wgrad(N[('up', 0)], Y['lr'], [0], (Gd['hr'], 0), hw)
-                node_wgrad(N[('down', 0)], Y['hr'], [0], (Gd['lr'], TN), hw)
+                projection_wgrad(N[('up', 0)], Y['lr'], 0, Gd['hr'], 0)
+                projection_wgrad(N[('down', 0)], Y['hr'], 0, Gd['lr'], TN)
             else:
                 node_wgrad(N[('upc', i)], Y['lr'], [j * TN for j in range(i + 1)], (Gd['m'], i * TN), hw)
-                node_wgrad(N[('up', i)], Y['m'], [i * TN], (Gd['hr'], i * TN), hw)
+                projection_wgrad(N[('up', i)], Y['m'], i * TN, Gd['hr'], i * TN)
                 node_wgrad(N[('downc', i)], self._phase(Y['hr']), [j * TN for j in range(i + 1)],
                            (self._phase(Gd['d']), i * TN), hwp)
-                node_wgrad(N[('down', i)], Y['d'], [i * TN], (Gd['lr'], (i + 1) * TN), hw)
+                projection_wgrad(N[('down', i)], Y['d'], i * TN, Gd['lr'], (i + 1) * TN)
         node_wgrad(N['fout'], Y['lr'], [j * TN for j in range(1, G + 1)], (Gd['hid'], n), hw)
         # _OutBlock convs (as edsr_engine: tail against g64, up-samplers against pixel-unshuffled views of dup)
         H, W = g.sizes[-1]
@@ -609,6 +685,7 @@ class DRFEngine:
             scatter.append(L.TableJob(base + 4 * (off + n_w), l.idx_b.data_ptr(), grads[l.name + '.bias'].data_ptr(),
                                       l.n_total, 1.0, L.TJ_SCATTER))
         g.wg_launches = launches
+        g.wg_keep = keep                        # scatter indices of the projection convs (referenced by the table)
         g.scatter_table, g.scatter_max = self._upload_table(scatter)
         g.scatter_jobs = len(scatter)
 
@@ -626,8 +703,18 @@ class DRFEngine:
             fn()
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                fn()
+            # No garbage collection while capturing: a cycle collection that happens to run inside the capture may
+            # destroy CUDA graphs / tensors of dead engines (cudaGraphExecDestroy, cudaFree), which CUDA forbids on a
+            # capturing thread and which invalidates the capture (seen as a rare "operation not permitted when stream is
+            # capturing").  thread_local: other threads (a DataLoader's pin-memory thread) may keep calling the runtime.
+            gc_was_enabled = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                    fn()
+            finally:
+                if gc_was_enabled:
+                    gc.enable()
             setattr(g, attr, graph)
         else:
             state.replay()

@@ -17,6 +17,7 @@ fp32 parameter-layout gradient (`pvsr_scatter_add[_scaled]`).  torch carries dev
 replays the launch sequence as a CUDA graph; there is no CPU / PyTorch fallback.
 """
 import ctypes as C
+import gc
 import math
 
 import torch
@@ -410,8 +411,18 @@ class EDSREngine:
             fn()
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                fn()
+            # No garbage collection while capturing: a cycle collection that happens to run inside the capture may
+            # destroy CUDA graphs / tensors of dead engines (cudaGraphExecDestroy, cudaFree), which CUDA forbids on a
+            # capturing thread and which invalidates the capture (seen as a rare "operation not permitted when stream is
+            # capturing").  thread_local: other threads (a DataLoader's pin-memory thread) may keep calling the runtime.
+            gc_was_enabled = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                    fn()
+            finally:
+                if gc_was_enabled:
+                    gc.enable()
             setattr(g, attr, graph)
         else:
             state.replay()
