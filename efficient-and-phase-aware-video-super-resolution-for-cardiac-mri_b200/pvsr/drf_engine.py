@@ -513,7 +513,7 @@ class DRFEngine:
             L.check(lib.pvsr_conv3x3_wgrad_multi(C.cast(arr, C.c_void_p), n_desc, 0, st), 'wgrad')
         L.check(lib.pvsr_run_table(L.ptr(g.scatter_table), g.scatter_jobs, g.scatter_max, st), 'scatter table')
 
-    def _wg_desc(self, g, name, n_kb_total, views, srcs, dys, out_hw, n_img, kb, taps, n_total, dw_elem_off, db_elem_off,
+    def _wg_desc(self, g, views, srcs, dys, out_hw, n_img, kb, taps, n_total, dw_elem_off, db_elem_off,
                  with_bias=1):
         d = L.WgradDesc()
         d.H, d.W = out_hw
@@ -562,7 +562,7 @@ class DRFEngine:
             for c0, c1, idx, _ in nd.fwd.groups:
                 cols = c1 - c0
                 dys = [(1, dy_t[1], c, 0, 0) for c in range(c0, c1, 64)]
-                descs.append(self._wg_desc(g, nd.name, nd.n_kb, [(x_view, 1), (dy_t[0], 1)],
+                descs.append(self._wg_desc(g, [(x_view, 1), (dy_t[0], 1)],
                                            [(0, b, 0, 0, 0) for b in srcs], dys, out_hw, TN, nd.kb, nd.taps, cols,
                                            o, off + n_w + c0))
                 scatter.append(L.TableJob(base + 4 * o, idx.data_ptr(), grads[nd.name + '.weight'].data_ptr(),
@@ -594,7 +594,7 @@ class DRFEngine:
                     srcs = [(0, x_base, q * F, tap % 3 - 1, tap // 3 - 1) for tap, q, _, _ in grp]
                     dys = [(1, dz_base, 64 * c, 0, 0) for c in range(kbF)]
                     first = g0 == 0
-                    descs.append(self._wg_desc(g, nd.name, 0, views, srcs, dys, hw, TN, kbF, 1, F, o, ob, with_bias=int(first)))
+                    descs.append(self._wg_desc(g, views, srcs, dys, hw, TN, kbF, 1, F, o, ob, with_bias=int(first)))
                     idx = np.empty((len(grp), kbF, F, 64), dtype=np.int64)
                     col = np.arange(F)[None, :, None]
                     for si, (_, _, ky, kx) in enumerate(grp):
@@ -615,7 +615,7 @@ class DRFEngine:
                         srcs = [(0, x_base, 0, tap % 3 - 1, tap // 3 - 1)]
                         dys = [(1, dz_base, q * F + 64 * c, 0, 0) for q, _, _ in grp for c in range(kbF)]
                         centre = tap == 4                            # the centre tap reaches every phase once: bias gradient
-                        descs.append(self._wg_desc(g, nd.name, 0, views, srcs, dys, hw, TN, kbF, 1, cols, o, ob,
+                        descs.append(self._wg_desc(g, views, srcs, dys, hw, TN, kbF, 1, cols, o, ob,
                                                    with_bias=int(centre)))
                         idx = np.empty((kbF, len(grp), F, 64), dtype=np.int64)
                         ch = np.arange(F)[None, :, None]
@@ -642,7 +642,7 @@ class DRFEngine:
         # fin: sources a[t], hid[t] for all t; dY = gradient of lr slot 0
         off = g.dw_off[N['fin'].name]
         nd = N['fin']
-        d = self._wg_desc(g, nd.name, nd.n_kb, [(Y['a'], 1), (Y['hid'], 1), (Gd['lr'], 1)],
+        d = self._wg_desc(g, [(Y['a'], 1), (Y['hid'], 1), (Gd['lr'], 1)],
                           [(0, 0, 0, 0, 0), (1, 0, 0, 0, 0)], [(2, 0, 64 * c, 0, 0) for c in range(F // 64)], hw, TN, nd.kb, 1,
                           F, off, off + nd.n_kb * F * 64)
         add([d])
@@ -667,7 +667,7 @@ class DRFEngine:
         tail = self.head_layers[-1]
         off = g.dw_off[tail.name]
         n_w = tail.n_kb * tail.n_total * 64
-        add([self._wg_desc(g, tail.name, tail.n_kb, [(g.up[-1], 1), (g.g64, 1)], [(0, 0, 0, 0, 0)], [(1, 0, 0, 0, 0)],
+        add([self._wg_desc(g, [(g.up[-1], 1), (g.g64, 1)], [(0, 0, 0, 0, 0)], [(1, 0, 0, 0, 0)],
                            (H, W), TN, tail.fwd.kb_per_src, 9, tail.n_total, off, off + n_w)])
         for k, r in enumerate(self.factors):
             l = self.head_layers[k]
@@ -675,7 +675,7 @@ class DRFEngine:
             off = g.dw_off[l.name]
             n_w = l.n_kb * l.n_total * 64
             dys = [(1, 0, c * 64, q % r, q // r) for q in range(r * r) for c in range(cb)]
-            add([self._wg_desc(g, l.name, l.n_kb, [(x_in, 1), (g.dup[k], r)], [(0, 0, 0, 0, 0)], dys, g.sizes[k], TN,
+            add([self._wg_desc(g, [(x_in, 1), (g.dup[k], r)], [(0, 0, 0, 0, 0)], dys, g.sizes[k], TN,
                                l.fwd.kb_per_src, 9, l.n_total, off, off + n_w)])
         for l in self.head_layers:
             off = g.dw_off[l.name]
