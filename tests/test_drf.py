@@ -115,6 +115,34 @@ def test_projection_tables_equal_torch_convs(s):
     assert np.abs(got - want).max() <= 1e-10
 
 
+@pytest.mark.parametrize("s", [2, 3, 4, 8])
+def test_projection_pairs_cover_every_kernel_tap_once(s):
+    """The sparse weight-gradient form: the non-zero (tap, phase) blocks of the phase-stacked convs are exactly the
+    k*k taps of the k x k parameter, each once, and they are exactly the non-zero blocks of the dense tables."""
+    from pvsr.drf_engine import PROJECTION, projection_pairs, table_expand, table_reduce
+    k, _, p = PROJECTION[s]
+    F, P = 64, s * s
+    for kind, table in (("expand", table_expand(F, k, s, p)), ("reduce", table_reduce(F, k, s, p))):
+        pairs = projection_pairs(kind, k, s, p)
+        assert len(pairs) == k * k and sorted((ky, kx) for _, _, ky, kx in pairs) == [(a, b) for a in range(k) for b in range(k)]
+        nz = set()
+        if kind == "expand":            # table [tap][q * F + ch][c]
+            t = table.reshape(9, P, F, 64)
+            for tap in range(9):
+                for q in range(P):
+                    if (t[tap, q] >= 0).any():
+                        assert (t[tap, q] >= 0).all()
+                        nz.add((tap, q))
+        else:                           # table [tap * P + q][col][c]
+            t = table.reshape(9, P, F, 64)
+            for tap in range(9):
+                for q in range(P):
+                    if (t[tap, q] >= 0).any():
+                        assert (t[tap, q] >= 0).all()
+                        nz.add((tap, q))
+        assert nz == {(tap, q) for tap, q, _, _ in pairs}
+
+
 def test_pointwise_tables():
     from pvsr.drf_engine import table_pointwise, table_pointwise_T
     F, n_src = 64, 3
