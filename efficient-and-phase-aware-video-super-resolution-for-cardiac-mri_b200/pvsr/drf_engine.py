@@ -27,7 +27,7 @@ import torch
 
 from . import lib as L
 from . import ops
-from .edsr_engine import _Layer, up_factors
+from .edsr_engine import _Layer, flatten_module_parameters, up_factors
 
 PROJECTION = {2: (6, 2, 2), 3: (7, 3, 2), 4: (8, 4, 2), 8: (12, 8, 2)}     # drf_net.py:69-76
 MAX_DY = 32                                                               # dY chunks per wgrad descriptor (<= PVSR_MAX_DY)
@@ -273,24 +273,9 @@ class DRFEngine:
     def flatten_parameters(self):
         """One flat fp32 parameter buffer + one flat gradient buffer (single all-reduce / single Adam kernel), as
         RefineNetEngine.flatten_parameters."""
-        if self._flat is not None:
-            return self._flat
-        params = list(self.net.parameters())
-        dev = params[0].device
-        offs, total = [], 0
-        for p in params:
-            offs.append(total)
-            total += (p.numel() + 3) // 4 * 4
-        flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
-        with torch.no_grad():
-            for p, o in zip(params, offs):
-                n = p.numel()
-                flat_p[o:o + n].copy_(p.detach().reshape(-1))
-                p.data = flat_p[o:o + n].view(p.shape)
-                p.grad = flat_g[o:o + n].view(p.shape)
-        self._flat = (flat_p, flat_g)
-        self.params_changed()
+        if self._flat is None:
+            self._flat = flatten_module_parameters(self.net)
+            self.params_changed()
         return self._flat
 
     def _upload_table(self, jobs):

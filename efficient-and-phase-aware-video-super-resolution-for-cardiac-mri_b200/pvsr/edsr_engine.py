@@ -26,6 +26,26 @@ from . import lib as L
 from . import ops
 
 
+def flatten_module_parameters(net):
+    """Re-homes every parameter of `net` (and its .grad) as a view of ONE flat fp32 buffer each, 16-byte aligned per
+    parameter; returns (flat_param, flat_grad).  Shared by the EDSR and DRFNet engines."""
+    params = list(net.parameters())
+    dev = params[0].device
+    offs, total = [], 0
+    for p in params:
+        offs.append(total)
+        total += (p.numel() + 3) // 4 * 4
+    flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+    flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+    with torch.no_grad():
+        for p, o in zip(params, offs):
+            n = p.numel()
+            flat_p[o:o + n].copy_(p.detach().reshape(-1))
+            p.data = flat_p[o:o + n].view(p.shape)
+            p.grad = flat_g[o:o + n].view(p.shape)
+    return flat_p, flat_g
+
+
 def up_factors(upscale_factor):
     if (math.log(upscale_factor, 2) % 1) == 0:
         return [2] * int(math.log(upscale_factor, 2))
@@ -172,24 +192,9 @@ class EDSREngine:
     def flatten_parameters(self):
         """One flat fp32 parameter buffer + one flat gradient buffer (single all-reduce / single Adam kernel), as
         RefineNetEngine.flatten_parameters."""
-        if self._flat is not None:
-            return self._flat
-        params = list(self.net.parameters())
-        dev = params[0].device
-        offs, total = [], 0
-        for p in params:
-            offs.append(total)
-            total += (p.numel() + 3) // 4 * 4
-        flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
-        with torch.no_grad():
-            for p, o in zip(params, offs):
-                n = p.numel()
-                flat_p[o:o + n].copy_(p.detach().reshape(-1))
-                p.data = flat_p[o:o + n].view(p.shape)
-                p.grad = flat_g[o:o + n].view(p.shape)
-        self._flat = (flat_p, flat_g)
-        self.params_changed()
+        if self._flat is None:
+            self._flat = flatten_module_parameters(self.net)
+            self.params_changed()
         return self._flat
 
     def _upload_table(self, jobs):
