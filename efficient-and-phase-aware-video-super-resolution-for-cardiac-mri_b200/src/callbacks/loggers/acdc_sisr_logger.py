@@ -13,3 +13,14 @@ class AcdcSISRLogger(BaseLogger):
 
 class Dsb15SISRLogger(AcdcSISRLogger):
     pass
+
+
+class AcdcSISRSRFBLogger(AcdcSISRLogger):
+    """Iterated nets (reference acdc_sisr_srfb_logger.py:13-31): the panel shows the last of the `num_steps` outputs."""
+
+    def _add_images(self, epoch, train_batch, train_outputs, valid_batch, valid_outputs):
+        super()._add_images(epoch, train_batch, train_outputs[-1], valid_batch, valid_outputs[-1])
+
+
+class Dsb15SISRSRFBLogger(AcdcSISRSRFBLogger):
+    pass

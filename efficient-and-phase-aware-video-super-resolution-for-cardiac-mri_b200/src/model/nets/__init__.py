@@ -3,4 +3,4 @@ from .base_net import BaseNet
 from .refine_net import RefineNet
 from .edsr_net import EDSRNet
 from .bicubic import Bicubic
-from .drf_net import DRFNet
+from .drf_net import DRFNet, DRFSISRNet

@@ -112,3 +112,19 @@ class DRFNet(BaseNet):
             return drf_train_forward(self, inputs)
         outs, _ = self.engine.forward(inputs, train=False, clone=not self.reuse_output_buffers)
         return outs
+
+
+class DRFSISRNet(DRFNet):
+    """DRFSISRNet - drop-in for the reference's src/model/nets/drf_sisr_net.py (class at :8, forward at :38-49): the same
+    three blocks (identical `state_dict` keys and construction order) iterated `num_steps` times on ONE image,
+    `forward(input) -> list of num_steps tensors (N, 1, s*h, s*w)`.  On this path it is the DRFNet engine fed with the
+    image repeated `num_steps` times."""
+
+    def __init__(self, in_channels, out_channels, num_steps, num_features, num_groups, upscale_factor):
+        super().__init__(in_channels, out_channels, num_features, num_groups, upscale_factor)
+        if num_steps < 1:
+            raise ValueError(f'The number of the iterations should be positive. Got {num_steps}.')
+        self.num_steps = num_steps
+
+    def forward(self, input):
+        return super().forward([input] * self.num_steps)

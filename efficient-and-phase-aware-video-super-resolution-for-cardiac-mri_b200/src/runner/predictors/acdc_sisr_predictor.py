@@ -31,6 +31,9 @@ class AcdcSISRPredictor(BasePredictor):
         self.frames_per_launch = max(1, int(frames_per_launch))
         self._denormalize = functools.partial(denormalize, dataset=self.dataset_name)
 
+    def _outputs(self, lr):
+        return [self.net(lr)]
+
     def _name(self, index):
         filename = Path(self.test_dataloader.dataset.data[index][0]).parts[-1].split('.')[0]
         patient, _, sid, fid = filename.split('_')
@@ -61,11 +64,16 @@ class AcdcSISRPredictor(BasePredictor):
             lr = torch.stack([it['lr_img'] for _, it in items]).to(self.device, non_blocking=True)
             hr = torch.stack([it['hr_img'] for _, it in items]).to(self.device, non_blocking=True)
             with torch.no_grad():
-                sr = self.net(lr)
+                outs = self._outputs(lr)             # [net(lr)]; the SRFB variant: the num_steps outputs
+                sr = outs[-1]
                 srd, hrd = self._denormalize(sr), self._denormalize(hr)
                 patients = [self._name(index)[1] for index, _ in items]
                 losses, metrics = per_sample_scores(self.loss_fns, self.metric_fns, sr, hr, srd, hrd, patients,
                                                     dataset=self.dataset_name)
+                if len(outs) > 1:                    # losses averaged over the steps (acdc_sisr_srfb_predictor.py:103-107)
+                    per_step = [losses] + [per_sample_scores(self.loss_fns, [], o, hr, None, None, patients,
+                                                             dataset=self.dataset_name)[0] for o in outs[:-1]]
+                    losses = torch.stack(per_step).mean(dim=0)
                 flat = torch.cat([metrics, losses], dim=1).cpu()
                 imgs = srd[:, 0].to(torch.uint8).cpu().numpy() if self.exported else None
             nm = len(self.metric_fns)
@@ -113,4 +121,16 @@ class AcdcSISRPredictor(BasePredictor):
 
 
 class Dsb15SISRPredictor(AcdcSISRPredictor):
+    dataset_name = 'dsb15'
+
+
+class AcdcSISRSRFBPredictor(AcdcSISRPredictor):
+    """Iterated single-image nets - DRFSISRNet on this path (reference acdc_sisr_srfb_predictor.py:13-127): losses are
+    averaged over the `num_steps` outputs, metrics and exports use the last one."""
+
+    def _outputs(self, lr):
+        return list(self.net(lr))
+
+
+class Dsb15SISRSRFBPredictor(AcdcSISRSRFBPredictor):
     dataset_name = 'dsb15'

@@ -48,7 +48,7 @@ class AcdcSISRTrainer(BaseTrainer):
             batch = self._allocate_data(batch)
             inputs, targets = self._get_inputs_targets(batch)
             if training and self._fused:
-                loss, outputs = self.net.engine.loss_and_grads(inputs, targets)
+                loss, outputs = self._fused_step(inputs, targets)
                 losses = [loss]
                 loss = loss * self.loss_weights[0]
                 if float(self.loss_weights[0]) != 1.0:
@@ -66,7 +66,7 @@ class AcdcSISRTrainer(BaseTrainer):
                     outputs = self.net(inputs)
                     losses = self._compute_losses(outputs, targets)
                     loss = (torch.stack(losses) * self.loss_weights).sum()
-            metrics = self._compute_metrics(outputs.detach(), targets)
+            metrics = self._compute_metrics(self._detached(outputs), targets)
             batch_size = dataloader.batch_size
             # weighted sums stay on the device; they cross PCIe every `log_every` steps (the reference's per-step
             # .item() calls serialise host and GPU)
@@ -79,6 +79,13 @@ class AcdcSISRTrainer(BaseTrainer):
         log = dict(zip(names, acc.tolist()))
         log, count = parallel.reduce_log(log, count, self.device)
         return {k: v / max(count, 1) for k, v in log.items()}, batch, outputs
+
+    def _fused_step(self, inputs, targets):
+        return self.net.engine.loss_and_grads(inputs, targets)
+
+    @staticmethod
+    def _detached(outputs):
+        return outputs.detach()
 
     def _optimizer_step(self):
         if self._dp is not None:

@@ -168,6 +168,73 @@ def test_constructor_contract():
         net.eval()([torch.zeros(1, 1, 8, 8)])                        # no CPU fallback
 
 
+# ------------------------------------------------------------------------------------------------ DRFSISRNet
+SISR_CASES = sorted(os.path.basename(p)[len("drfsisr_"):-4] for p in glob.glob(os.path.join(GOLDEN, "drfsisr_*.npz")))
+
+
+def _load_sisr(name):
+    z = np.load(os.path.join(GOLDEN, f"drfsisr_{name}.npz"), allow_pickle=False)
+    return z, json.loads(str(z["meta"]))
+
+
+def _sisr_net(kwargs):
+    from src.model.nets import DRFSISRNet
+    torch.manual_seed(0)
+    return DRFSISRNet(**kwargs)
+
+
+@pytest.mark.parametrize("name", SISR_CASES)
+def test_drfsisr_module_and_oracle_match_reference_golden(name):
+    """DRFSISRNet (drf_sisr_net.py): same seed -> the reference's weights; the oracle (the DRFNet restatement fed with the
+    image repeated num_steps times) reproduces the reference's outputs, SRFB-trainer loss and gradients."""
+    from oracle import drf_oracle as O
+    z, meta = _load_sisr(name)
+    kw = meta["kwargs"]
+    sd = _sisr_net(kw).state_dict()
+    assert list(sd.keys()) == list(meta["params"].keys())
+    for k, (shape, s, sa) in meta["params"].items():
+        assert list(sd[k].shape) == shape and float(sd[k].double().sum()) == pytest.approx(s, rel=1e-9, abs=1e-9)
+    x, target = torch.from_numpy(z["input"]), torch.from_numpy(z["target"])
+    S = kw["num_steps"]
+    outs, loss, grads = O.drf_loss_and_grads(sd, [x] * S, [target] * S, kw["num_groups"], kw["upscale_factor"])
+    for o, w in zip(outs, z["outputs"]):
+        assert (o - torch.from_numpy(w)).abs().max().item() <= 2e-6
+    assert abs(loss.item() - float(z["loss"])) <= 1e-6
+    for k, (norm, total) in meta["grads"].items():
+        assert float(grads[k].double().norm()) == pytest.approx(norm, rel=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SISR_CASES)
+def test_drfsisr_matches_golden(name, pvsr_lib):
+    """Inference and the SRFB trainer's sequence (acdc_sisr_srfb_trainer.py:22-26) through the autograd bridge."""
+    z, meta = _load_sisr(name)
+    kw = meta["kwargs"]
+    x, target = torch.from_numpy(z["input"]).cuda(), torch.from_numpy(z["target"]).cuda()
+    net = _sisr_net(kw).cuda().eval()
+    with torch.no_grad():
+        outs = net(x)
+    assert len(outs) == kw["num_steps"]
+    for o, w in zip(outs, z["outputs"]):
+        _check_out(o.cpu(), torch.from_numpy(w))
+    net.train()
+    for _ in range(3):
+        net.zero_grad()
+        outs = net(x)
+        loss = torch.stack([torch.nn.L1Loss()(o, target) for o in outs]).mean()
+        loss.backward()
+    assert loss.item() == pytest.approx(float(z["loss"]), rel=2e-3)
+    for k, p in net.named_parameters():
+        if p.numel() > 1:
+            norm, _ = meta["grads"][k]
+            want = torch.from_numpy(z["grad::" + k])
+            g = p.grad.detach().float().cpu()
+            got = g if g.dim() == 1 else g.reshape(-1)[::meta["stride"]]
+            assert float(g.double().norm()) == pytest.approx(norm, rel=0.12), k
+            if want.numel() >= 8:
+                assert ((got - want).norm() / want.norm()).item() <= 0.12, k
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _check_out(out, want):
     d = (out - want)

@@ -215,3 +215,57 @@ def test_main_drfnet_train_then_test(pvsr_lib, tmp_path, optimizer):
         l1 = float((o - hr).abs().mean())
         assert abs(float(row[1]) - psnr) <= 0.01 and abs(float(row[2]) - ssim) <= 1e-3, (t, row, psnr, ssim)
         assert abs(float(row[3]) - l1) <= 2e-3 * l1
+
+
+# ------------------------------------------------------------------------------------------------ DRFSISRNet
+DRFSISR = {'name': 'DRFSISRNet', 'kwargs': dict(in_channels=1, out_channels=1, num_steps=3, num_features=64, num_groups=2,
+                                                upscale_factor=4)}
+
+
+@pytest.mark.parametrize("optimizer", ["Adam", "FusedAdam"])
+def test_main_trains_and_tests_drfsisr(pvsr_lib, tmp_path, optimizer):
+    """The reference's iterated-SISR runner names (AcdcSISRSRFBTrainer / Predictor / Logger) around DRFSISRNet."""
+    cfg = {'main': {'random_seed': 'vsr', 'saved_dir': str(tmp_path / 'train')},
+           'dataset': {'name': 'SyntheticSISRDataset', 'kwargs': dict(SISR_DATA, data_dir=None)},
+           'dataloader': {'name': 'Dataloader', 'kwargs': {'train_batch_size': 4, 'valid_batch_size': 1,
+                                                           'shuffle': True, 'num_workers': 0}},
+           'net': DRFSISR, 'losses': [{'name': 'L1Loss', 'weight': 1.0}], 'metrics': [{'name': 'PSNR'}, {'name': 'SSIM'}],
+           'optimizer': {'name': optimizer, 'kwargs': {'lr': 1e-3, 'weight_decay': 0}},
+           'logger': {'name': 'AcdcSISRSRFBLogger', 'kwargs': {'dummy_input': [4, 1, 12, 10]}},
+           'monitor': {'name': 'Monitor', 'kwargs': {'mode': 'min', 'target': 'Loss', 'saved_freq': 1, 'early_stop': 0}},
+           'trainer': {'name': 'AcdcSISRSRFBTrainer', 'kwargs': {'device': 'cuda:0', 'num_epochs': 2}}}
+    _run_main(cfg, tmp_path, 'train')
+    ck_dir = tmp_path / 'train' / 'checkpoints'
+    ck = torch.load(ck_dir / 'model_2.pth', weights_only=False)
+    first = torch.load(ck_dir / 'model_1.pth', weights_only=False)['net']
+    assert ck['epoch'] == 2 and sum(float((ck['net'][k] - first[k]).abs().sum()) for k in first) > 0
+    assert all(torch.isfinite(v).all() for v in ck['net'].values())
+
+    test_cfg = {'main': {'saved_dir': str(tmp_path / 'test'), 'loaded_path': str(ck_dir / 'model_best.pth')},
+                'dataset': cfg['dataset'],
+                'dataloader': {'name': 'Dataloader', 'kwargs': {'batch_size': 1, 'shuffle': False, 'num_workers': 0}},
+                'net': DRFSISR, 'losses': cfg['losses'], 'metrics': cfg['metrics'],
+                'predictor': {'name': 'AcdcSISRSRFBPredictor',
+                              'kwargs': {'device': 'cuda:0', 'saved_dir': str(tmp_path / 'test'), 'exported': True,
+                                         'frames_per_launch': 5}}}
+    _run_main(test_cfg, tmp_path, 'test', test=True)
+    with open(tmp_path / 'test' / 'results.csv') as f:
+        rows = list(csv.reader(f))
+    assert rows[0] == ['name', 'PSNR', 'SSIM', 'L1Loss'] and len(rows) == 1 + 12
+
+    from oracle import drf_oracle as O
+    from oracle import refinenet_oracle as RO
+    from src.data.datasets import SyntheticSISRDataset
+    ds = SyntheticSISRDataset(type='test', **SISR_DATA)
+    sd = {k: v.cpu() for k, v in torch.load(ck_dir / 'model_best.pth', weights_only=False)['net'].items()}
+    got = {r[0]: r for r in rows[1:]}
+    for index in (0, 7):
+        item = ds[index]
+        with torch.no_grad():
+            outs = O.drf_forward(sd, [item['lr_img'].unsqueeze(0)] * 3, 2, 4)
+        hr = item['hr_img'].unsqueeze(0)
+        row = got[ds.data[index][0].name.split('.')[0]]
+        # metrics on the last step, the loss averaged over the steps (acdc_sisr_srfb_predictor.py:103-107,120)
+        assert abs(float(row[1]) - float(RO.psnr(RO.denormalize(outs[-1]), RO.denormalize(hr)))) <= 0.01
+        l1 = sum(float((o - hr).abs().mean()) for o in outs) / 3
+        assert abs(float(row[3]) - l1) <= 2e-3 * l1
