@@ -187,3 +187,79 @@ def test_two_gpu_edsr_data_parallel_matches_single_gpu(pvsr_lib):
             assert rel <= 5e-3, (k, rel)
         assert torch.equal(res[0][2][k], res[1][2][k])
         assert torch.equal(res[0][3][k], res[1][3][k]), k        # ranks stay in lock-step
+
+
+# ------------------------------------------------------------------------------------------------ DRFNet
+DRF_KW = dict(in_channels=1, out_channels=1, num_features=64, num_groups=2, upscale_factor=4)
+
+
+def _drf_batch(n, T=3):
+    g = torch.Generator().manual_seed(23)
+    return ([torch.randn(n, 1, 12, 10, generator=g) for _ in range(T)],
+            [torch.randn(n, 1, 48, 40, generator=g) for _ in range(T)])
+
+
+def _drf_worker(rank, world, port, q):
+    import sys
+    for p in (PKG, ROOT, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    from pvsr import parallel
+    from pvsr.optim import FusedAdam
+    from src.model.nets import DRFNet
+    parallel.init()
+    dev = torch.device("cuda", rank)
+    xs, ts = _drf_batch(2 * world)
+    sl = slice(2 * rank, 2 * rank + 2)
+    torch.manual_seed(rank)                                  # different seeds: the broadcast must equalise them
+    net = DRFNet(**DRF_KW).to(dev).train()
+    opt = FusedAdam.for_net(net, lr=1e-3)
+    dp = parallel.DataParallelStep(net, opt)
+    loss, _ = net.engine.loss_and_grads([x[sl].to(dev) for x in xs], [t[sl].to(dev) for t in ts])
+    parallel.allreduce_sum_(dp.flat_grad)
+    grads = {k: (p.grad / world).cpu() for k, p in net.named_parameters()}
+    opt.step()
+    net.engine.params_changed()
+    torch.cuda.synchronize()
+    weights = {k: p.detach().cpu() for k, p in net.named_parameters()}
+    q.put((rank, loss.item(), grads, weights))
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_gpu_drfnet_data_parallel_matches_single_gpu(pvsr_lib):
+    """Averaged BPTT gradients of two ranks (two sequences each) equal the single-GPU gradients of the four sequences;
+    the ranks stay bit-identical after the fused Adam step."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from pvsr.optim import FusedAdam
+    from src.model.nets import DRFNet
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_drf_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(60)
+    assert all(p.exitcode == 0 for p in procs)
+    xs, ts = _drf_batch(2 * world)
+    torch.manual_seed(0)
+    net = DRFNet(**DRF_KW).cuda().train()
+    FusedAdam.for_net(net, lr=1e-3)
+    loss, _ = net.engine.loss_and_grads([x.cuda() for x in xs], [t.cuda() for t in ts])
+    torch.cuda.synchronize()
+    assert abs(sum(r[1] for r in res) / world - loss.item()) <= 1e-4 * abs(loss.item())
+    for k, p in net.named_parameters():
+        g = p.grad.cpu()
+        if p.numel() > 1:                                    # slope gradients are cancellation-dominated scalars
+            for r in res:
+                rel = ((r[2][k] - g).norm() / g.norm()).item()
+                assert rel <= 2e-2, (k, rel)
+        assert torch.equal(res[0][2][k], res[1][2][k])
+        assert torch.equal(res[0][3][k], res[1][3][k]), k        # ranks stay in lock-step
